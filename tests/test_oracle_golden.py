@@ -1,0 +1,73 @@
+"""Pins the CPU oracle (oracle/port.py) to what the unmodified reference computed
+(tests/golden/*.npz, produced by oracle/make_golden.py from /root/reference)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import port
+from tests.helpers import golden_setup, load_golden
+
+CACHED_CASES = ["g1_greedy_16_384", "g3_greedy_eos_16_224", "g4_beam3_keep3_16_224", "g6_greedy_32_384",
+                "g7_greedy_dec12_16_224", "g9_greedy_refinit_16_224"]
+
+
+def _run(name, algorithm):
+    z, meta = load_golden(name)
+    cfg, sd, data, extra = golden_setup(meta)
+    pm = port.PortModel(cfg, sd)
+    info, trace = {}, []
+    if meta["torch_seed"] is not None:
+        torch.manual_seed(meta["torch_seed"])
+    with torch.no_grad():
+        ids, lp = port.caption(pm, data, extra, algorithm=algorithm, info=info, trace=trace)
+    return z, meta, cfg, ids, lp, info, trace
+
+
+@pytest.mark.parametrize("name", CACHED_CASES)
+def test_cached_port_matches_reference(name):
+    z, meta, cfg, ids, lp, info, trace = _run(name, "cached")
+    assert np.array_equal(ids.numpy(), z["ids"])
+    np.testing.assert_allclose(lp.numpy(), z["logprobs"], rtol=0, atol=5e-5)
+    logit, prob, idx, n = info["tag"]
+    assert np.array_equal(idx.numpy(), z["tag_topk_idx"])
+    np.testing.assert_allclose(prob.numpy(), z["tag_topk_prob"], atol=1e-5)
+    assert np.array_equal(n.numpy(), z["tag_topk_len"])
+    np.testing.assert_allclose(logit[:, :512].numpy(), z["tag_logit_head"], atol=2e-5)
+    np.testing.assert_allclose(info["img_feats"][:, ::29, ::37].numpy(), z["img_feats_s"], atol=1e-5)
+    np.testing.assert_allclose(info["cap"][:, ::29, ::37].numpy(), z["cap_feats_s"], atol=5e-4, rtol=1e-4)
+    np.testing.assert_allclose(info["tag_feats"][:, ::29, ::37].numpy(), z["tag_feats_s"], atol=5e-4, rtol=1e-4)
+    if meta["decode"].get("num_beams", 1) == 1:
+        # per-step top-4 logits of the step the reference actually ran
+        for s, t in enumerate(trace):
+            v, i = t.topk(4, dim=-1)
+            np.testing.assert_allclose(v.numpy(), z["step_top_val"][s], atol=5e-5)
+
+
+def test_cached_port_beam4_16_384():
+    z, meta, cfg, ids, lp, info, trace = _run("g2_beam4_16_384", "cached")
+    assert np.array_equal(ids.numpy(), z["ids"])
+    np.testing.assert_allclose(lp.numpy(), z["logprobs"], atol=5e-5)
+
+
+@pytest.mark.parametrize("name", ["g5_sample5_16_224", "g8_sample_filtered_16_224"])
+def test_sampling_semantics_with_torch_multinomial(name):
+    """do_sample path: same torch.manual_seed + torch.multinomial => same draws as the reference
+    (only meaningful on the torch build that made the golden)."""
+    z, meta = load_golden(name)
+    if meta["torch"] != torch.__version__:
+        pytest.skip("golden was drawn with torch %s" % meta["torch"])
+    z, meta, cfg, ids, lp, info, trace = _run(name, "cached")
+    assert ids.shape == z["ids"].shape == (meta["batch"] * meta["decode"]["num_return_sequences"], 1, 20)
+    assert np.array_equal(ids.numpy(), z["ids"])
+    np.testing.assert_allclose(lp.numpy(), z["logprobs"], atol=5e-5)
+
+
+@pytest.mark.parametrize("name", ["g6_greedy_32_384", "g4_beam3_keep3_16_224"])
+def test_faithful_port_matches_reference(name):
+    """The uncached restatement (what bench.py times as the CPU baseline) reproduces the reference,
+    including the number of full-model calls (19 for a 20-token caption: no KV cache is live,
+    modeling_bert.py:1072-1073)."""
+    z, meta, cfg, ids, lp, info, trace = _run(name, "faithful")
+    assert np.array_equal(ids.numpy(), z["ids"])
+    np.testing.assert_allclose(lp.numpy(), z["logprobs"], atol=5e-5)
+    assert info["n_calls"] == meta["n_model_calls"]

@@ -1,0 +1,278 @@
+// bf16 GEMM on the 5th-gen tensor cores:  out[M,N] = act(A[M,K] * W[N,K]^T + bias) (+ resid)
+//
+//   * A (activations) and W (nn.Linear weight, [out_features, in_features]) are both K-major, so both
+//     operands are staged by TMA into 128B-swizzled K-major shared-memory tiles and fed to
+//     tcgen05.mma.kind::f16 through shared-memory descriptors; the fp32 accumulator lives in TMEM.
+//   * persistent, warp-specialised CTA (one per SM): warp0 = TMA producer, warp1 = MMA issuer (one elected
+//     thread), warps 2-5 = epilogue (tcgen05.ld -> bias/activation/residual -> global). The accumulator is
+//     double-buffered in TMEM so the epilogue of tile i overlaps the main loop of tile i+1.
+//   * replaces the cuBLAS calls behind nn.Linear in vision_transformer.py:152-210 (qkv/proj/fc1/fc2) and
+//     modeling_bert.py:303-419, 524-563 (q/k/v/dense/intermediate/output/pooler/heads).
+#include "common.cuh"
+
+namespace vc {
+
+enum { ACT_NONE = 0, ACT_GELU = 1, ACT_TANH = 2 };
+
+template <int BN> struct GemmCfg {
+  static constexpr int BM = 128;
+  static constexpr int BK = 64;                         // 64 bf16 = one 128-byte swizzle row
+  static constexpr int A_BYTES = BM * BK * 2;           // 16 KB
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int TMEM_COLS = 2 * BN;              // two accumulator stages
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, int ACT, bool OUT_F32, bool RESID>
+__global__ void __launch_bounds__(192, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const float* __restrict__ bias, void* __restrict__ out, int ldo,
+               const float* resid, int ldr, int M, int N, int K) {
+  using C = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + C::STAGES;
+  uint64_t* tmem_full = bars + 2 * C::STAGES;
+  uint64_t* tmem_empty = bars + 2 * C::STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m_tiles = (M + C::BM - 1) / C::BM;
+  const int n_tiles = (N + BN - 1) / BN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int num_kb = K / C::BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int i = 0; i < C::STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);   // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<C::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_tiles) * C::BM;
+        const int n0 = (tile % n_tiles) * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * C::STAGE_BYTES;
+          uint8_t* sb = sa + C::A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * C::BK, m0);
+          tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * C::BK, n0);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(C::BM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint32_t sb = sa + C::A_BYTES;
+          const uint64_t adesc = make_smem_desc_sw128(sa, 16, 1024);
+          const uint64_t bdesc = make_smem_desc_sw128(sb, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < C::BK / 16; ++k) {
+            // advance 16 bf16 (32 B) along K inside the swizzle atom: +2 in the (addr >> 4) field
+            umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);     // frees the smem stage once these MMAs retire
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[as]);          // accumulator complete -> epilogue
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quad = warp & 3;                // TMEM lane quadrant this warp may access
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / n_tiles) * C::BM;
+      const int n0 = (tile % n_tiles) * BN;
+      const int row = m0 + quad * 32 + lane;
+      const bool row_ok = row < M;
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = n0 + c * 32;
+        if (col0 >= N) break;
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + as * BN + c * 32, r);
+        tmem_ld_wait();
+        const bool full = (col0 + 32 <= N);
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (full) {
+          if (bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 b = __ldg(reinterpret_cast<const float4*>(bias + col0 + j));
+              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+            }
+          }
+          if (ACT == ACT_GELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+          } else if (ACT == ACT_TANH) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
+          }
+          if (row_ok) {
+            if (RESID) {
+              const float* rp = resid + (size_t)row * ldr + col0;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                float4 t = *reinterpret_cast<const float4*>(rp + j);
+                v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+              }
+            }
+            if (OUT_F32) {
+              float* op = reinterpret_cast<float*>(out) + (size_t)row * ldo + col0;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+              bf16* op = reinterpret_cast<bf16*>(out) + (size_t)row * ldo + col0;
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) store8<bf16>(op + j, v + j);
+            }
+          }
+        } else if (row_ok) {
+          // ragged N tail (e.g. the 30522-wide vocabulary): scalar, predicated
+          for (int j = 0; j < 32; ++j) {
+            const int col = col0 + j;
+            if (col < N) {
+              float x = v[j] + (bias != nullptr ? __ldg(bias + col) : 0.f);
+              if (ACT == ACT_GELU) x = gelu_erf(x);
+              else if (ACT == ACT_TANH) x = tanhf(x);
+              if (RESID) x += resid[(size_t)row * ldr + col];
+              if (OUT_F32) reinterpret_cast<float*>(out)[(size_t)row * ldo + col] = x;
+              else reinterpret_cast<bf16*>(out)[(size_t)row * ldo + col] = __float2bfloat16_rn(x);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<C::TMEM_COLS>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------
+// host launcher
+// ------------------------------------------------------------------------------------------
+template <int BN, int ACT, bool OUT_F32, bool RESID>
+static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const float* bias, void* out, int ldo,
+                      const float* resid, int ldr, int M, int N, int K, cudaStream_t stream) {
+  using C = GemmCfg<BN>;
+  auto kern = gemm_tc_kernel<BN, ACT, OUT_F32, RESID>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) { set_last_error("gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return VC_ERR_LAUNCH; }
+    configured = true;
+  }
+  const int tiles = ((M + C::BM - 1) / C::BM) * ((N + BN - 1) / BN);
+  int grid = tiles < sm_count() ? tiles : sm_count();
+  kern<<<grid, 192, C::SMEM_BYTES, stream>>>(ta, tb, bias, out, ldo, resid, ldr, M, N, K);
+  return check_launch("gemm_tc");
+}
+
+template <int BN, int ACT>
+static int launch_act(const CUtensorMap& ta, const CUtensorMap& tb, const float* bias, void* out, int ldo, int out_f32,
+                      const float* resid, int ldr, int M, int N, int K, cudaStream_t s) {
+  if (out_f32) {
+    if (resid) return launch_one<BN, ACT, true, true>(ta, tb, bias, out, ldo, resid, ldr, M, N, K, s);
+    return launch_one<BN, ACT, true, false>(ta, tb, bias, out, ldo, resid, ldr, M, N, K, s);
+  }
+  if (resid) return launch_one<BN, ACT, false, true>(ta, tb, bias, out, ldo, resid, ldr, M, N, K, s);
+  return launch_one<BN, ACT, false, false>(ta, tb, bias, out, ldo, resid, ldr, M, N, K, s);
+}
+
+template <int BN>
+static int launch_bn(const CUtensorMap& ta, const CUtensorMap& tb, const float* bias, void* out, int ldo, int out_f32,
+                     int act, const float* resid, int ldr, int M, int N, int K, cudaStream_t s) {
+  switch (act) {
+    case ACT_NONE: return launch_act<BN, ACT_NONE>(ta, tb, bias, out, ldo, out_f32, resid, ldr, M, N, K, s);
+    case ACT_GELU: return launch_act<BN, ACT_GELU>(ta, tb, bias, out, ldo, out_f32, resid, ldr, M, N, K, s);
+    case ACT_TANH: return launch_act<BN, ACT_TANH>(ta, tb, bias, out, ldo, out_f32, resid, ldr, M, N, K, s);
+  }
+  set_last_error("gemm_tc: unknown activation %d", act);
+  return VC_ERR_BAD_ARG;
+}
+
+int gemm_bf16_tc(const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldo, int out_f32,
+                 int act, const float* resid, int ldr, int M, int N, int K, int force_bn, cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0 || (K % 64) != 0) { set_last_error("gemm_tc: need K %% 64 == 0 (K=%d)", K); return VC_ERR_BAD_ARG; }
+  if ((lda % 8) || (ldw % 8) || (ldo % 8) || (resid && (ldr % 4)) ||
+      (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(W) & 15) ||
+      (reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(resid) & 15) ||
+      (reinterpret_cast<uintptr_t>(bias) & 15)) {
+    set_last_error("gemm_tc: pointers must be 16-byte aligned and pitches multiples of 8 elements");
+    return VC_ERR_BAD_ARG;
+  }
+  // tile width: the widest N tile that still gives every SM work
+  int bn = force_bn;
+  if (bn == 0) {
+    const int mt = (M + 127) / 128;
+    bn = 256;
+    while (bn > 64 && mt * ((N + bn - 1) / bn) < sm_count()) bn >>= 1;
+  }
+  CUtensorMap ta, tb;
+  int rc = get_tmap_2d_bf16(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 128, 64);
+  if (rc) return rc;
+  rc = get_tmap_2d_bf16(&tb, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)bn, 64);
+  if (rc) return rc;
+  switch (bn) {
+    case 256: return launch_bn<256>(ta, tb, bias, out, ldo, out_f32, act, resid, ldr, M, N, K, stream);
+    case 128: return launch_bn<128>(ta, tb, bias, out, ldo, out_f32, act, resid, ldr, M, N, K, stream);
+    case 64: return launch_bn<64>(ta, tb, bias, out, ldo, out_f32, act, resid, ldr, M, N, K, stream);
+  }
+  set_last_error("gemm_tc: unsupported tile width %d", bn);
+  return VC_ERR_BAD_ARG;
+}
+
+}  // namespace vc
