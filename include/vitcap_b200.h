@@ -1,0 +1,127 @@
+/* vitcap_b200 -- C ABI of the B200-native ViTCAP caption-generation hot path.
+ *
+ * The reference (jacobswan1/ViTCAP) is 100 % Python/PyTorch: it has no FFI of its own. Each entry point below
+ * therefore names the reference *operator* (file:line under /root/reference) whose ATen call sequence it replaces;
+ * a Python host (vitcap_b200/ops.py, via ctypes) binds them exactly as listed. INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - every pointer is a CUDA device pointer owned by the caller; kernels never allocate; nothing is retained
+ *     after the call returns except cached TMA descriptors keyed by (pointer, shape)
+ *   - `stream` is a cudaStream_t passed as void*; all work is asynchronous on it, no host sync, graph-capturable
+ *   - return 0 on success, negative on error (VC_ERR_*); vc_last_error() gives the message (thread local)
+ *   - `bf16` flags select the storage/operand type of activations and weights: 1 = bfloat16 operands on the
+ *     tcgen05 tensor cores (fast mode), 0 = fp32 operands on CUDA cores (exact mode). Accumulation, LayerNorm
+ *     statistics, softmax and the residual stream are fp32 in both modes.
+ *   - matrices are row-major; `ld*` are row pitches in elements
+ */
+#ifndef VITCAP_B200_H
+#define VITCAP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VC_OK 0
+#define VC_ERR_BAD_ARG (-1)
+#define VC_ERR_UNSUPPORTED (-2)
+#define VC_ERR_LAUNCH (-3)
+#define VC_ERR_DRIVER (-4)
+
+#define VC_ACT_NONE 0
+#define VC_ACT_GELU 1 /* exact erf GELU: activations.py:16-23, nn.GELU in vision_transformer.py:143 */
+#define VC_ACT_TANH 2 /* BertPooler, modeling_bert.py:524-527 */
+
+const char* vc_last_error(void);
+int vc_abi_version(void);
+/* number of kernels launched through this library since the last vc_reset_launch_count() (bench.py gpu_launches) */
+long long vc_launch_count(void);
+void vc_reset_launch_count(void);
+
+/* out[M,N] = act(A[M,K] * W[N,K]^T + bias[N]) (+ resid[M,N]);  replaces torch.nn.functional.linear behind
+ *   vision_transformer.py:152-158 (Mlp fc1/fc2), :169-201 (Attention qkv/proj), :267-275 (PatchEmbed conv as GEMM),
+ *   modeling_bert.py:307-313 (query/key/value), :353-357, :402-405, :415-419 (dense layers), :524-563 (pooler, heads).
+ * bf16=1: A, W bfloat16, tcgen05.mma kind::f16 with TMA-fed 128B-swizzled smem tiles, fp32 accumulator in TMEM
+ *         (requires K % 64 == 0, 16-byte aligned pointers, pitches % 8 == 0).
+ * bf16=0: A, W fp32, CUDA-core FFMA tiles (K % 16 == 0).
+ * out_f32: output element type (1 = fp32, 0 = bf16 in fast mode / fp32 in exact mode is selected by the caller).
+ * bias may be NULL; resid (fp32, pitch ldr) may be NULL and may alias out when out_f32 = 1. */
+int vc_linear(int bf16, const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldo, int out_f32,
+              int act, const float* resid, int ldr, int M, int N, int K, void* stream);
+/* same contract, forcing the CUDA-core kernel for bf16 operands (cross-check of the tensor-core kernel in tests) */
+int vc_linear_simt(int in_bf16, const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldo,
+                   int out_f32, int act, const float* resid, int ldr, int M, int N, int K, void* stream);
+/* tcgen05 kernel with an explicit N-tile width (64/128/256; 0 = heuristic) -- for tests and tuning */
+int vc_linear_tc(const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldo, int out_f32, int act,
+                 const float* resid, int ldr, int M, int N, int K, int tile_n, void* stream);
+
+/* image fp32 [B,3,S,S] -> patch matrix [B*(S/p)^2, 3*p*p] (column order = Conv2d weight.flatten(1));
+ * PatchEmbed.forward, vision_transformer.py:267-275 */
+int vc_patchify(int bf16, const float* image, void* out, int B, int img_size, int patch, void* stream);
+/* x[b,0] = cls + pos[0]; x[b,1+i] = patch_out[b*P+i] + pos[1+i]; forward_features, vision_transformer.py:423-427 */
+int vc_assemble_tokens(const float* patch_out, const float* cls, const float* pos, float* x, int B, int P, int H, void* stream);
+
+/* LayerNorm over the last dim of fp32 rows (nn.LayerNorm eps 1e-6 in ViT blocks, vision_transformer.py:218/229/352;
+ * eps 1e-12 in BERT layers/heads, modeling_bert.py:219/350/412/538). out_t: operand copy (bf16 or fp32), may be NULL;
+ * out_f: fp32 copy, may be NULL. */
+int vc_layernorm(int bf16, const float* in, int ld_in, const float* gamma, const float* beta, float eps, void* out_t, int ld_t,
+                 float* out_f, int ld_f, int rows, int H, void* stream);
+/* out[r,:] = cast(in[r*row_stride : +H]) -- e.g. hidden_states[:, 0] of BertPooler (modeling_bert.py:524) */
+int vc_gather_rows(int bf16, const float* in, size_t row_stride, void* out, int ld_out, int rows, int H, void* stream);
+/* ctx[b] = [tag_feats[b,0] ; cap_feats[b,0..N-1]] (modeling_bert.py:1493), fp32 copy + operand copy */
+int vc_assemble_ctx(int bf16, const float* cap, const float* tag, float* ctx_f, void* ctx_t, int B, int N, int H, void* stream);
+
+/* softmax(Q K^T * scale) V for packed qkv [B,N,3*heads*64] -> out [B,N,heads*64]; scores stay on chip.
+ * Attention.forward vision_transformer.py:174-200 (mask is all-zero, modeling_bert.py:1415) and BertSelfAttention
+ * modeling_bert.py:303-340 over the context rows. bf16=1: tcgen05 flash kernel; bf16=0: CUDA-core kernel. */
+int vc_attention(int bf16, const void* qkv, void* out, int B, int N, int heads, float scale, void* stream);
+int vc_attention_simt(int bf16, const void* qkv, void* out, int B, int N, int heads, float scale, void* stream);
+
+/* concept head selection: sigmoid -> topk(K) sorted desc -> count(prob >= thresh); modeling_bert.py:1429-1432 */
+int vc_tag_topk(const float* logits, int ld, int rows, int V, int K, float thresh, int* out_idx, float* out_prob, int* out_len,
+                void* stream);
+
+/* decode-step text embedding, BertEmbeddings.forward modeling_bert.py:222-237 for rows [last token @ cur_len-1, MASK @ cur_len]
+ * of each of R sequences; ids int32 [R,max_len]; out_f fp32 [2R,H], out_t operand copy */
+int vc_embed_ln(int bf16, const int* ids, int max_len, int cur_len, int mask_id, const float* word, const float* pos,
+                const float* type0, const float* gamma, const float* beta, float eps, float* out_f, void* out_t, int R, int H,
+                void* stream);
+
+/* one decoder self-attention step over the KV cache (BertSelfAttention with history, modeling_bert.py:303-340; mask
+ * semantics of modeling_bert.py:1494-1501 / dataset.py:371-390 encoded structurally). ctx_qkv [B,C,3H]: prefill QKV of the
+ * context rows; step_qkv [max_len, 2*B*E, 3H]: per-step QKV rows (2r = token, 2r+1 = MASK); anc int32 [max_len, B*E]
+ * ancestor rows for beam search (NULL = identity); out [2*B*E, H]. E = beams*samples per image. */
+int vc_decode_attention(int bf16, const void* ctx_qkv, const void* step_qkv, const int* anc, void* out, int B, int C, int heads,
+                        int E, int cur_len, float scale, void* stream);
+
+/* greedy / sampled next token + log-prob + state update for `rows` sequences, modeling_utils.py:839-862.
+ * logits fp32 [rows, ld]; sampling = Gumbel-max with Philox4x32-10 noise keyed by (seed; vocab idx/4, row, cur_len). */
+int vc_token_step(const float* logits, int ld, int rows, int V, int do_sample, float temperature, uint64_t seed, int cur_len,
+                  int max_len, int pad_id, const int* eos_ids, int n_eos, int* ids, int* unfinished, float* sum_lp, int* n_steps,
+                  void* stream);
+/* modeling_utils.py:869-886: force EOS, mean log-prob, int64 ids [R,max_len] */
+int vc_greedy_finalize(const int* ids, const int* unfinished, const float* sum_lp, const int* n_steps, int eos0, int max_len, int R,
+                       long long* out_ids, float* out_lp, void* stream);
+
+/* beam search step, modeling_utils.py:988-1065: (1) per-row log-sum-exp + top-(2*beams) logits, (2) per-image candidate
+ * walk, hypothesis pool (BeamHypotheses, :1138-1180), next beams, ancestor table update. */
+int vc_beam_row_topk(const float* logits, int ld, int rows, int V, int K, float* cand_val, int* cand_idx, float* row_max,
+                     float* row_logsum, void* stream);
+int vc_beam_advance(int* ids, float* beam_scores, int* done, int* anc, double* hyp_score, int* hyp_len, int* hyp_ids,
+                    int* hyp_count, double* worst, const float* cand_val, const int* cand_idx, const float* row_max,
+                    const float* row_logsum, int B, int num_beams, int V, int cur_len, int max_len, int keep,
+                    double length_penalty, int pad_id, const int* eos_ids, int n_eos, void* stream);
+/* modeling_utils.py:1074-1100 */
+int vc_beam_finalize(const double* hyp_score, const int* hyp_len, const int* hyp_ids, const int* hyp_count, int B, int keep,
+                     int max_len, int pad_id, int eos0, long long* out_ids, float* out_lp, void* stream);
+
+/* top_k_top_p_filtering, modeling_utils.py:1103-1135, in place on fp32 logits (after the 1/temperature scaling) */
+int vc_filter_logits(float* logits, int ld, int rows, int V, float inv_temperature, int top_k, float top_p,
+                     int min_tokens_to_keep, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VITCAP_B200_H */

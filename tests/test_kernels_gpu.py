@@ -1,0 +1,232 @@
+"""Per-kernel parity on the GPU: every C-ABI entry point against a plain torch fp32 expression of the same
+reference operator (tolerances stated per test; integer outputs are compared bit-exactly)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from vitcap_b200 import ops  # noqa: E402
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def rnd(*shape, seed=0, scale=1.0, dtype=torch.float32):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(dtype).to(dev())
+
+
+def ref_linear(a, w, bias, act, resid):
+    y = a.float() @ w.float().t()
+    if bias is not None:
+        y = y + bias
+    if act == ops.ACT_GELU:
+        y = y * 0.5 * (1 + torch.erf(y / math.sqrt(2)))
+    elif act == ops.ACT_TANH:
+        y = torch.tanh(y)
+    if resid is not None:
+        y = y + resid
+    return y
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 200, 64), (128, 768, 768), (577 * 2, 2304, 768), (77, 30522 // 16, 128)])
+@pytest.mark.parametrize("act", [ops.ACT_NONE, ops.ACT_GELU, ops.ACT_TANH])
+def test_linear_exact_fp32(M, N, K, act):
+    a, w, b = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=0.05), rnd(N, seed=3)
+    resid = rnd(M, N, seed=4)
+    ldo = (N + 7) // 8 * 8
+    out = torch.zeros(M, ldo, device=dev())
+    ops.linear(a, w, b, out[:, :N], act=act, resid=resid, ldo=ldo)
+    ref = ref_linear(a, w, b, act, resid)
+    torch.testing.assert_close(out[:, :N], ref, rtol=1e-4, atol=1e-4)
+
+
+TC_SHAPES = [(128, 256, 64), (128, 256, 768), (256, 512, 128), (300, 200, 64), (577 * 2, 2304, 768), (1154, 768, 3072),
+             (64, 1000, 768), (1024, 768, 768)]
+
+
+@pytest.mark.parametrize("tile_n", [256, 128, 64])
+@pytest.mark.parametrize("M,N,K", TC_SHAPES)
+def test_linear_tc_bf16_plain(M, N, K, tile_n):
+    """tcgen05 GEMM, bf16 out, bias only. Tolerance: bf16 output rounding (2^-8 relative) on fp32-accumulated sums."""
+    a, w, b = rnd(M, K, seed=1, dtype=torch.bfloat16), rnd(N, K, seed=2, scale=0.05, dtype=torch.bfloat16), rnd(N, seed=3)
+    ldo = (N + 7) // 8 * 8
+    out = torch.zeros(M, ldo, device=dev(), dtype=torch.bfloat16)
+    ops.linear(a, w, b, out[:, :N], ldo=ldo, impl="tc", tile_n=tile_n)
+    ref = ref_linear(a, w, b, ops.ACT_NONE, None)
+    torch.testing.assert_close(out[:, :N].float(), ref, rtol=1e-2, atol=2e-2)
+    if ldo > N:
+        assert float(out[:, N:].abs().max()) == 0.0          # never writes past N
+
+
+@pytest.mark.parametrize("act", [ops.ACT_NONE, ops.ACT_GELU, ops.ACT_TANH])
+@pytest.mark.parametrize("out_f32,with_resid", [(True, True), (True, False), (False, False)])
+def test_linear_tc_epilogues(act, out_f32, with_resid):
+    M, N, K = 577 * 3, 768, 768
+    a, w, b = rnd(M, K, seed=5, dtype=torch.bfloat16), rnd(N, K, seed=6, scale=0.03, dtype=torch.bfloat16), rnd(N, seed=7)
+    resid = rnd(M, N, seed=8) if with_resid else None
+    out = torch.zeros(M, N, device=dev(), dtype=torch.float32 if out_f32 else torch.bfloat16)
+    ops.linear(a, w, b, out, act=act, resid=resid)
+    ref = ref_linear(a, w, b, act, resid)
+    if out_f32:
+        torch.testing.assert_close(out, ref, rtol=2e-4, atol=2e-4)   # fp32 accumulate of exact bf16 products
+    else:
+        torch.testing.assert_close(out.float(), ref, rtol=1e-2, atol=1e-2)
+
+
+def test_linear_tc_inplace_residual_stream():
+    """x = x + proj(h): out aliases resid (vision_transformer.py:246)."""
+    M, N, K = 1154, 768, 768
+    a, w, b = rnd(M, K, seed=5, dtype=torch.bfloat16), rnd(N, K, seed=6, scale=0.03, dtype=torch.bfloat16), rnd(N, seed=7)
+    x = rnd(M, N, seed=9)
+    ref = ref_linear(a, w, b, ops.ACT_NONE, x.clone())
+    ops.linear(a, w, b, x, resid=x)
+    torch.testing.assert_close(x, ref, rtol=2e-4, atol=2e-4)
+
+
+def test_linear_tc_strided_rows_and_vocab_tail():
+    """A rows taken with a pitch (the MASK rows 1::2 of the decode buffer) and the ragged 30522-wide vocabulary."""
+    R, K, V = 96, 768, 30522
+    buf = rnd(2 * R, K, seed=11, dtype=torch.bfloat16)
+    w = rnd(V, K, seed=12, scale=0.02, dtype=torch.bfloat16)
+    bias = rnd(V, seed=13)
+    ldl = (V + 63) // 64 * 64
+    logits = torch.full((R, ldl), -7.0, device=dev())
+    ops.linear(buf[1::2], w, bias, logits[:, :V], M=R, lda=2 * K, ldo=ldl)
+    ref = ref_linear(buf[1::2], w, bias, ops.ACT_NONE, None)
+    torch.testing.assert_close(logits[:, :V], ref, rtol=2e-4, atol=2e-4)
+    assert bool((logits[:, V:] == -7.0).all())
+
+
+def test_linear_tc_matches_simt_bf16_bitwise_inputs():
+    """Independent on-device cross-check: CUDA-core kernel on the same bf16 operands."""
+    M, N, K = 640, 512, 1024
+    a, w = rnd(M, K, seed=21, dtype=torch.bfloat16), rnd(N, K, seed=22, scale=0.05, dtype=torch.bfloat16)
+    o1 = torch.zeros(M, N, device=dev())
+    o2 = torch.zeros(M, N, device=dev())
+    ops.linear(a, w, None, o1, impl="tc")
+    ops.linear(a, w, None, o2, impl="simt")
+    torch.testing.assert_close(o1, o2, rtol=1e-4, atol=1e-4)
+
+
+def ref_attention(qkv, heads, scale):
+    B, N, H3 = qkv.shape
+    H = H3 // 3
+    q, k, v = qkv.float().view(B, N, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    a = torch.softmax((q @ k.transpose(-1, -2)) * scale, dim=-1)
+    return (a @ v).transpose(1, 2).reshape(B, N, H)
+
+
+@pytest.mark.parametrize("B,N,heads", [(2, 577, 12), (3, 197, 12), (1, 578, 12), (2, 145, 12), (2, 17, 2), (1, 128, 1), (1, 129, 1)])
+def test_attention_exact_fp32(B, N, heads):
+    qkv = rnd(B, N, 3 * heads * 64, seed=3)
+    out = torch.zeros(B, N, heads * 64, device=dev())
+    ops.attention(qkv, out, B, N, heads, 0.125)
+    torch.testing.assert_close(out, ref_attention(qkv, heads, 0.125), rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("impl", ["auto", "simt"])
+@pytest.mark.parametrize("B,N,heads", [(2, 577, 12), (3, 197, 12), (1, 578, 12), (2, 145, 12), (2, 17, 2), (1, 128, 1), (1, 129, 1), (1, 256, 3)])
+def test_attention_bf16(B, N, heads, impl):
+    """bf16 operands; P is rounded to bf16 before the PV product (as any flash kernel does): 2e-2 abs on O(1) outputs."""
+    qkv = rnd(B, N, 3 * heads * 64, seed=3, dtype=torch.bfloat16)
+    out = torch.zeros(B, N, heads * 64, device=dev(), dtype=torch.bfloat16)
+    ops.attention(qkv, out, B, N, heads, 0.125, impl=impl)
+    ref = ref_attention(qkv, heads, 0.125)
+    torch.testing.assert_close(out.float(), ref, rtol=2e-2, atol=2e-2)
+
+
+def test_attention_bf16_peaky_scores():
+    """Large-magnitude scores (online-softmax rescaling across chunks must stay exact)."""
+    B, N, heads = 1, 577, 2
+    qkv = rnd(B, N, 3 * heads * 64, seed=4, scale=3.0, dtype=torch.bfloat16)
+    out = torch.zeros(B, N, heads * 64, device=dev(), dtype=torch.bfloat16)
+    ops.attention(qkv, out, B, N, heads, 0.125)
+    torch.testing.assert_close(out.float(), ref_attention(qkv, heads, 0.125), rtol=3e-2, atol=6e-2)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("eps", [1e-6, 1e-12])
+def test_layernorm(dtype, eps):
+    rows, H = 1000, 768
+    x, g, b = rnd(rows, H, seed=1, scale=2.0), rnd(H, seed=2), rnd(H, seed=3)
+    o_t = torch.zeros(rows, H, device=dev(), dtype=dtype)
+    o_f = torch.zeros(rows, H, device=dev())
+    ops.layernorm(x, g, b, eps, out_t=o_t, out_f=o_f)
+    ref = F.layer_norm(x, (H,), g, b, eps)
+    torch.testing.assert_close(o_f, ref, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(o_t.float(), ref, rtol=1e-2 if dtype == torch.bfloat16 else 1e-5, atol=1e-2 if dtype == torch.bfloat16 else 1e-5)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_patchify_and_tokens(dtype):
+    B, S, p, H = 2, 64, 16, 768
+    img = rnd(B, 3, S, S, seed=1)
+    P = (S // p) ** 2
+    a = torch.zeros(B * P, 3 * p * p, device=dev(), dtype=dtype)
+    ops.patchify(img, a, p)
+    ref = F.unfold(img, kernel_size=p, stride=p).transpose(1, 2).reshape(B * P, 3 * p * p)
+    assert torch.equal(a.float(), ref.to(dtype).float())
+    po, cls, pos = rnd(B * P, H, seed=2), rnd(H, seed=3), rnd(P + 1, H, seed=4)
+    x = torch.zeros(B, P + 1, H, device=dev())
+    ops.assemble_tokens(po, cls, pos, x, B, P, H)
+    ref = torch.cat([cls.view(1, 1, H).expand(B, 1, H), po.view(B, P, H)], 1) + pos
+    assert torch.equal(x, ref)
+
+
+def test_gather_rows_and_ctx():
+    B, N, H = 3, 17, 768
+    cap, tag = rnd(B, N, H, seed=1), rnd(B, N, H, seed=2)
+    o = torch.zeros(B, H, device=dev(), dtype=torch.bfloat16)
+    ops.gather_rows(tag, N * H, o, B, H)
+    assert torch.equal(o, tag[:, 0].to(torch.bfloat16))
+    cf = torch.zeros(B, N + 1, H, device=dev())
+    ct = torch.zeros(B, N + 1, H, device=dev(), dtype=torch.bfloat16)
+    ops.assemble_ctx(cap, tag, cf, ct, B, N, H)
+    ref = torch.cat([tag[:, 0:1], cap], 1)
+    assert torch.equal(cf, ref) and torch.equal(ct, ref.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("scale", [1.0, 4.0])
+def test_tag_topk_matches_torch(scale):
+    """sigmoid -> topk(50) -> count(prob >= 0.2) (modeling_bert.py:1429-1432). Selection runs on the logits: where
+    sigmoid saturates in fp32 (scale 4: logits ~ 17) torch's topk-on-probabilities sees exact ties whose order is
+    implementation-defined, so there the index comparison is against topk of the logits and the probabilities are
+    compared as sorted values."""
+    B, V, K = 37, 30522, 50
+    logits = rnd(B, V, seed=5, scale=scale)
+    ld = 30528
+    buf = torch.zeros(B, ld, device=dev())
+    buf[:, :V] = logits
+    idx = torch.zeros(B, K, device=dev(), dtype=torch.int32)
+    prob = torch.zeros(B, K, device=dev())
+    n = torch.zeros(B, device=dev(), dtype=torch.int32)
+    ops.tag_topk(buf, V, K, 0.2, idx, prob, n)
+    rp, ri = torch.sigmoid(logits).topk(K, dim=1)
+    lv, li = logits.topk(K, dim=1)
+    assert torch.equal(idx.long(), li)
+    torch.testing.assert_close(prob, rp, rtol=1e-6, atol=1e-7)
+    assert torch.equal(n.long(), (rp >= 0.2).sum(1))
+    if scale == 1.0:
+        assert torch.equal(idx.long(), ri)
+
+
+def test_tag_topk_ties_and_small_rows():
+    V, K = 100, 50
+    logits = torch.zeros(2, 104, device=dev())
+    logits[0, :V] = torch.arange(V, device=dev()).float() % 7          # heavy ties
+    logits[1, :V] = -torch.arange(V, device=dev()).float()
+    idx = torch.zeros(2, K, device=dev(), dtype=torch.int32)
+    prob = torch.zeros(2, K, device=dev())
+    n = torch.zeros(2, device=dev(), dtype=torch.int32)
+    ops.tag_topk(logits, V, K, 0.2, idx, prob, n)
+    v0 = logits[0, :V]
+    # sorted by value desc, ties by lowest index first
+    order = sorted(range(V), key=lambda i: (-float(v0[i]), i))[:K]
+    assert idx[0].tolist() == order
+    assert idx[1].tolist() == list(range(K))

@@ -1,0 +1,88 @@
+"""Builds libvitcap_b200.so (sm_100a) in-tree with nvcc. No torch involvement: the library is a plain C-ABI
+shared object (include/vitcap_b200.h) that links only the static CUDA runtime."""
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIBDIR = os.path.join(HERE, "lib")
+OBJDIR = os.path.join(HERE, "build")
+LIB = os.path.join(LIBDIR, "libvitcap_b200.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr",
+]
+
+
+def _nvcc():
+    p = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(p):
+        raise RuntimeError("nvcc not found")
+    return p
+
+
+def _sources():
+    return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def _digest(path):
+    h = hashlib.sha1()
+    for extra in ("common.cuh",):
+        with open(os.path.join(CSRC, extra), "rb") as f:
+            h.update(f.read())
+    with open(os.path.join(os.path.dirname(HERE), "include", "vitcap_b200.h"), "rb") as f:
+        h.update(f.read())
+    with open(path, "rb") as f:
+        h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def _compile(src, verbose):
+    path = os.path.join(CSRC, src)
+    obj = os.path.join(OBJDIR, src[:-3] + ".o")
+    stamp = obj + ".sha1"
+    dg = _digest(path)
+    if os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == dg:
+        return obj, False, ""
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-c", path, "-o", obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
+    with open(stamp, "w") as f:
+        f.write(dg)
+    return obj, True, r.stderr
+
+
+def build(verbose=False, force=False):
+    os.makedirs(LIBDIR, exist_ok=True)
+    os.makedirs(OBJDIR, exist_ok=True)
+    if force:
+        for f in os.listdir(OBJDIR):
+            os.remove(os.path.join(OBJDIR, f))
+    srcs = _sources()
+    with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
+        results = list(ex.map(lambda s: _compile(s, verbose), srcs))
+    objs = [o for o, _, _ in results]
+    changed = any(c for _, c, _ in results)
+    log = "\n".join("== %s ==\n%s" % (s, l) for s, (_, c, l) in zip(srcs, results) if c and l)
+    if log:
+        with open(os.path.join(OBJDIR, "ptxas.log"), "w") as f:
+            f.write(log)
+        if verbose:
+            print(log)
+    if changed or not os.path.exists(LIB):
+        cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-cudart", "static", "-Xcompiler", "-fPIC"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(verbose="-v" in sys.argv, force="-f" in sys.argv))

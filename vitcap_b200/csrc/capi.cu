@@ -1,0 +1,137 @@
+// extern "C" surface of libvitcap_b200.so (declared in include/vitcap_b200.h). Pure marshalling: plain pointers and
+// sizes in, error code out; every function forwards to one kernel launcher.
+#include "common.cuh"
+#include "../../include/vitcap_b200.h"
+
+#include <atomic>
+
+namespace vc {
+const char* last_error();
+int gemm_bf16_tc(const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldo, int out_f32, int act,
+                 const float* resid, int ldr, int M, int N, int K, int force_bn, cudaStream_t stream);
+int gemm_simt(int in_bf16, const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldo, int out_f32,
+              int act, const float* resid, int ldr, int M, int N, int K, cudaStream_t s);
+int patchify(int out_bf16, const float* img, void* out, int B, int img_size, int patch, cudaStream_t s);
+int assemble_tokens(const float* patch_out, const float* cls, const float* pos, float* x, int B, int P, int H, cudaStream_t s);
+int layernorm(int out_bf16, const float* in, int ld_in, const float* gamma, const float* beta, float eps, void* out_t, int ld_t,
+              float* out_f, int ld_f, int rows, int H, cudaStream_t s);
+int gather_rows(int out_bf16, const float* in, size_t row_stride, void* out, int ld_out, int rows, int H, cudaStream_t s);
+int assemble_ctx(int out_bf16, const float* cap, const float* tag, float* ctx_f, void* ctx_t, int B, int N, int H, cudaStream_t s);
+int attention_simt(int is_bf16, const void* qkv, void* out, int B, int N, int heads, float scale, cudaStream_t s);
+int attention_tc(const void* qkv, void* out, int B, int N, int heads, float scale, cudaStream_t s);
+int tag_topk(const float* logits, int ld, int rows, int V, int K, float thresh, int* out_idx, float* out_prob, int* out_len,
+             cudaStream_t s);
+int embed_ln(int out_bf16, const int* ids, int max_len, int cur_len, int mask_id, const float* word, const float* pos,
+             const float* type0, const float* gamma, const float* beta, float eps, float* out_f, void* out_t, int R, int H,
+             cudaStream_t s);
+int decode_attention(int is_bf16, const void* ctx_qkv, const void* step_qkv, const int* anc, void* out, int B, int C, int heads,
+                     int E, int cur_len, float scale, cudaStream_t s);
+int token_step(const float* logits, int ld, int rows, int V, int do_sample, float temperature, uint64_t seed, int cur_len,
+               int max_len, int pad_id, const int* eos_ids, int n_eos, int* ids, int* unfinished, float* sum_lp, int* n_steps,
+               cudaStream_t s);
+int greedy_finalize(const int* ids, const int* unfinished, const float* sum_lp, const int* n_steps, int eos0, int max_len, int R,
+                    long long* out_ids, float* out_lp, cudaStream_t s);
+int beam_row_topk(const float* logits, int ld, int rows, int V, int K, float* cand_val, int* cand_idx, float* row_max,
+                  float* row_logsum, cudaStream_t s);
+int beam_advance(int* ids, float* beam_scores, int* done, int* anc, double* hyp_score, int* hyp_len, int* hyp_ids, int* hyp_count,
+                 double* worst, const float* cand_val, const int* cand_idx, const float* row_max, const float* row_logsum, int B,
+                 int nb, int V, int cur_len, int max_len, int keep, double length_penalty, int pad_id, const int* eos_ids,
+                 int n_eos, cudaStream_t s);
+int beam_finalize(const double* hyp_score, const int* hyp_len, const int* hyp_ids, const int* hyp_count, int B, int keep, int max_len,
+                  int pad_id, int eos0, long long* out_ids, float* out_lp, cudaStream_t s);
+int filter_logits(float* logits, int ld, int rows, int V, float inv_temperature, int top_k, float top_p, int min_tokens_to_keep,
+                  cudaStream_t s);
+}  // namespace vc
+
+static std::atomic<long long> g_launches{0};
+#define VC_COUNT(n, expr) do { int rc__ = (expr); if (rc__ == 0) g_launches += (n); return rc__; } while (0)
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" {
+
+const char* vc_last_error(void) { return vc::last_error(); }
+int vc_abi_version(void) { return 1; }
+long long vc_launch_count(void) { return g_launches.load(); }
+void vc_reset_launch_count(void) { g_launches = 0; }
+
+int vc_linear(int bf16, const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldo, int out_f32, int act,
+              const float* resid, int ldr, int M, int N, int K, void* stream) {
+  if (bf16) VC_COUNT(1, vc::gemm_bf16_tc(A, lda, W, ldw, bias, out, ldo, out_f32, act, resid, ldr, M, N, K, 0, ST(stream)));
+  VC_COUNT(1, vc::gemm_simt(0, A, lda, W, ldw, bias, out, ldo, 1, act, resid, ldr, M, N, K, ST(stream)));
+}
+int vc_linear_simt(int in_bf16, const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldo, int out_f32,
+                   int act, const float* resid, int ldr, int M, int N, int K, void* stream) {
+  VC_COUNT(1, vc::gemm_simt(in_bf16, A, lda, W, ldw, bias, out, ldo, out_f32, act, resid, ldr, M, N, K, ST(stream)));
+}
+int vc_linear_tc(const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldo, int out_f32, int act,
+                 const float* resid, int ldr, int M, int N, int K, int tile_n, void* stream) {
+  VC_COUNT(1, vc::gemm_bf16_tc(A, lda, W, ldw, bias, out, ldo, out_f32, act, resid, ldr, M, N, K, tile_n, ST(stream)));
+}
+int vc_patchify(int bf16, const float* image, void* out, int B, int img_size, int patch, void* stream) {
+  VC_COUNT(1, vc::patchify(bf16, image, out, B, img_size, patch, ST(stream)));
+}
+int vc_assemble_tokens(const float* patch_out, const float* cls, const float* pos, float* x, int B, int P, int H, void* stream) {
+  VC_COUNT(1, vc::assemble_tokens(patch_out, cls, pos, x, B, P, H, ST(stream)));
+}
+int vc_layernorm(int bf16, const float* in, int ld_in, const float* gamma, const float* beta, float eps, void* out_t, int ld_t,
+                 float* out_f, int ld_f, int rows, int H, void* stream) {
+  VC_COUNT(1, vc::layernorm(bf16, in, ld_in, gamma, beta, eps, out_t, ld_t, out_f, ld_f, rows, H, ST(stream)));
+}
+int vc_gather_rows(int bf16, const float* in, size_t row_stride, void* out, int ld_out, int rows, int H, void* stream) {
+  VC_COUNT(1, vc::gather_rows(bf16, in, row_stride, out, ld_out, rows, H, ST(stream)));
+}
+int vc_assemble_ctx(int bf16, const float* cap, const float* tag, float* ctx_f, void* ctx_t, int B, int N, int H, void* stream) {
+  VC_COUNT(1, vc::assemble_ctx(bf16, cap, tag, ctx_f, ctx_t, B, N, H, ST(stream)));
+}
+int vc_attention(int bf16, const void* qkv, void* out, int B, int N, int heads, float scale, void* stream) {
+  if (bf16) VC_COUNT(1, vc::attention_tc(qkv, out, B, N, heads, scale, ST(stream)));
+  VC_COUNT(1, vc::attention_simt(0, qkv, out, B, N, heads, scale, ST(stream)));
+}
+int vc_attention_simt(int bf16, const void* qkv, void* out, int B, int N, int heads, float scale, void* stream) {
+  VC_COUNT(1, vc::attention_simt(bf16, qkv, out, B, N, heads, scale, ST(stream)));
+}
+int vc_tag_topk(const float* logits, int ld, int rows, int V, int K, float thresh, int* out_idx, float* out_prob, int* out_len,
+                void* stream) {
+  VC_COUNT(1, vc::tag_topk(logits, ld, rows, V, K, thresh, out_idx, out_prob, out_len, ST(stream)));
+}
+int vc_embed_ln(int bf16, const int* ids, int max_len, int cur_len, int mask_id, const float* word, const float* pos,
+                const float* type0, const float* gamma, const float* beta, float eps, float* out_f, void* out_t, int R, int H,
+                void* stream) {
+  VC_COUNT(1, vc::embed_ln(bf16, ids, max_len, cur_len, mask_id, word, pos, type0, gamma, beta, eps, out_f, out_t, R, H, ST(stream)));
+}
+int vc_decode_attention(int bf16, const void* ctx_qkv, const void* step_qkv, const int* anc, void* out, int B, int C, int heads,
+                        int E, int cur_len, float scale, void* stream) {
+  VC_COUNT(1, vc::decode_attention(bf16, ctx_qkv, step_qkv, anc, out, B, C, heads, E, cur_len, scale, ST(stream)));
+}
+int vc_token_step(const float* logits, int ld, int rows, int V, int do_sample, float temperature, uint64_t seed, int cur_len,
+                  int max_len, int pad_id, const int* eos_ids, int n_eos, int* ids, int* unfinished, float* sum_lp, int* n_steps,
+                  void* stream) {
+  VC_COUNT(1, vc::token_step(logits, ld, rows, V, do_sample, temperature, seed, cur_len, max_len, pad_id, eos_ids, n_eos, ids,
+                             unfinished, sum_lp, n_steps, ST(stream)));
+}
+int vc_greedy_finalize(const int* ids, const int* unfinished, const float* sum_lp, const int* n_steps, int eos0, int max_len, int R,
+                       long long* out_ids, float* out_lp, void* stream) {
+  VC_COUNT(1, vc::greedy_finalize(ids, unfinished, sum_lp, n_steps, eos0, max_len, R, out_ids, out_lp, ST(stream)));
+}
+int vc_beam_row_topk(const float* logits, int ld, int rows, int V, int K, float* cand_val, int* cand_idx, float* row_max,
+                     float* row_logsum, void* stream) {
+  VC_COUNT(1, vc::beam_row_topk(logits, ld, rows, V, K, cand_val, cand_idx, row_max, row_logsum, ST(stream)));
+}
+int vc_beam_advance(int* ids, float* beam_scores, int* done, int* anc, double* hyp_score, int* hyp_len, int* hyp_ids, int* hyp_count,
+                    double* worst, const float* cand_val, const int* cand_idx, const float* row_max, const float* row_logsum, int B,
+                    int num_beams, int V, int cur_len, int max_len, int keep, double length_penalty, int pad_id,
+                    const int* eos_ids, int n_eos, void* stream) {
+  VC_COUNT(1, vc::beam_advance(ids, beam_scores, done, anc, hyp_score, hyp_len, hyp_ids, hyp_count, worst, cand_val, cand_idx,
+                               row_max, row_logsum, B, num_beams, V, cur_len, max_len, keep, length_penalty, pad_id, eos_ids, n_eos,
+                               ST(stream)));
+}
+int vc_beam_finalize(const double* hyp_score, const int* hyp_len, const int* hyp_ids, const int* hyp_count, int B, int keep,
+                     int max_len, int pad_id, int eos0, long long* out_ids, float* out_lp, void* stream) {
+  VC_COUNT(1, vc::beam_finalize(hyp_score, hyp_len, hyp_ids, hyp_count, B, keep, max_len, pad_id, eos0, out_ids, out_lp, ST(stream)));
+}
+int vc_filter_logits(float* logits, int ld, int rows, int V, float inv_temperature, int top_k, float top_p, int min_tokens_to_keep,
+                     void* stream) {
+  VC_COUNT(1, vc::filter_logits(logits, ld, rows, V, inv_temperature, top_k, top_p, min_tokens_to_keep, ST(stream)));
+}
+
+}  // extern "C"

@@ -128,8 +128,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Bounded spin: a protocol bug must surface as a trapped launch (sticky CUDA error), never as a hung GPU.
+#ifndef VC_SPIN_LIMIT
+#define VC_SPIN_LIMIT (1u << 22)
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
+    if (++spins > VC_SPIN_LIMIT) __trap();
   }
 }
 

@@ -1,0 +1,255 @@
+// Bandwidth-bound helper kernels of the caption path: patch extraction, token/context assembly,
+// LayerNorm, row gathers, decode-step embedding. All use 128-bit global accesses and warp-shuffle
+// reductions; one warp owns one row of the hidden dimension.
+#include "common.cuh"
+
+namespace vc {
+
+// ------------------------------------------------------------------------------------------
+// patchify: image fp32 NCHW -> A[B*P, 3*p*p] (column order c,i,j == Conv2d weight.flatten(1));
+// the conv of PatchEmbed (vision_transformer.py:267-275) then is a plain GEMM.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void patchify_kernel(const float* __restrict__ img, T* __restrict__ out, int B, int HW, int p) {
+  const int g = HW / p;                      // patches per side
+  const int kdim = 3 * p * p;
+  const int groups = kdim / 8;               // 8 consecutive j within one (c,i) row
+  const size_t total = (size_t)B * g * g * groups;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int gi = (int)(idx % groups);
+    const size_t prow = idx / groups;        // b*P + py*g + px
+    const int px = (int)(prow % g);
+    const int py = (int)((prow / g) % g);
+    const int b = (int)(prow / ((size_t)g * g));
+    const int k = gi * 8;
+    const int c = k / (p * p), i = (k / p) % p, j = k % p;
+    const float* src = img + (((size_t)b * 3 + c) * HW + (py * p + i)) * HW + px * p + j;
+    float f[8];
+    load8<float>(src, f);
+    store8<T>(out + prow * kdim + k, f);
+  }
+}
+
+int patchify(int out_bf16, const float* img, void* out, int B, int img_size, int patch, cudaStream_t s) {
+  if (patch % 8 || img_size % patch) { set_last_error("patchify: patch %% 8 and img %% patch required"); return VC_ERR_BAD_ARG; }
+  const size_t total = (size_t)B * (img_size / patch) * (img_size / patch) * (3 * patch * patch / 8);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (out_bf16) patchify_kernel<bf16><<<blocks, 256, 0, s>>>(img, (bf16*)out, B, img_size, patch);
+  else patchify_kernel<float><<<blocks, 256, 0, s>>>(img, (float*)out, B, img_size, patch);
+  return check_launch("patchify");
+}
+
+// ------------------------------------------------------------------------------------------
+// assemble_tokens: x[b,0]=cls+pos[0]; x[b,1+p]=patch_out[b*P+p]+pos[1+p]  (vision_transformer.py:423-427)
+// ------------------------------------------------------------------------------------------
+__global__ void assemble_tokens_kernel(const float* __restrict__ patch_out, const float* __restrict__ cls,
+                                       const float* __restrict__ pos, float* __restrict__ x, int B, int P, int H) {
+  const int hv = H / 4;
+  const size_t total = (size_t)B * (P + 1) * hv;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % hv) * 4;
+    const size_t row = idx / hv;
+    const int t = (int)(row % (P + 1));
+    const int b = (int)(row / (P + 1));
+    float4 a = (t == 0) ? *reinterpret_cast<const float4*>(cls + c)
+                        : *reinterpret_cast<const float4*>(patch_out + ((size_t)b * P + t - 1) * H + c);
+    float4 q = *reinterpret_cast<const float4*>(pos + (size_t)t * H + c);
+    *reinterpret_cast<float4*>(x + row * H + c) = make_float4(a.x + q.x, a.y + q.y, a.z + q.z, a.w + q.w);
+  }
+}
+
+int assemble_tokens(const float* patch_out, const float* cls, const float* pos, float* x, int B, int P, int H, cudaStream_t s) {
+  const size_t total = (size_t)B * (P + 1) * (H / 4);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  assemble_tokens_kernel<<<blocks, 256, 0, s>>>(patch_out, cls, pos, x, B, P, H);
+  return check_launch("assemble_tokens");
+}
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm over the last dim (H % 128 == 0, H <= 1024); fp32 in; one warp per row.
+// out_t: T copy (GEMM operand), out_f: optional fp32 copy (residual stream of the post-LN decoder).
+// Two-pass mean/variance in registers (matches torch's fp32 LayerNorm to ~1 ulp).
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ in, int ld_in, const float* __restrict__ gamma, const float* __restrict__ beta,
+                 float eps, T* __restrict__ out_t, int ld_t, float* __restrict__ out_f, int ld_f, int rows, int H) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const int nv = H / 128;                    // float4 per lane
+  float4 v[8];
+  const float* ip = in + (size_t)warp * ld_in;
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (i < nv) {
+      v[i] = *reinterpret_cast<const float4*>(ip + (i * 32 + lane) * 4);
+      s += v[i].x + v[i].y + v[i].z + v[i].w;
+    }
+  const float mean = warp_sum(s) / (float)H;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (i < nv) {
+      float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      q += a * a + b * b + c * c + d * d;
+    }
+  const float rstd = rsqrtf(warp_sum(q) / (float)H + eps);
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (i < nv) {
+      const int c = (i * 32 + lane) * 4;
+      float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+      float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
+      float4 o = make_float4((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y,
+                             (v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
+      if (out_f) *reinterpret_cast<float4*>(out_f + (size_t)warp * ld_f + c) = o;
+      if (out_t) {
+        if (sizeof(T) == 4) {
+          *reinterpret_cast<float4*>(reinterpret_cast<float*>(out_t) + (size_t)warp * ld_t + c) = o;
+        } else {
+          uint2 pk = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+          *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(out_t) + (size_t)warp * ld_t + c) = pk;
+        }
+      }
+    }
+}
+
+int layernorm(int out_bf16, const float* in, int ld_in, const float* gamma, const float* beta, float eps, void* out_t, int ld_t,
+              float* out_f, int ld_f, int rows, int H, cudaStream_t s) {
+  if (H % 128 || H > 1024 || rows <= 0 || (ld_in % 4) || (ld_t % 4) || (out_f && (ld_f % 4))) {
+    set_last_error("layernorm: need H %% 128 == 0, H <= 1024, pitches %% 4 (H=%d)", H);
+    return VC_ERR_BAD_ARG;
+  }
+  const int blocks = (rows + 7) / 8;
+  if (out_bf16) layernorm_kernel<bf16><<<blocks, 256, 0, s>>>(in, ld_in, gamma, beta, eps, (bf16*)out_t, ld_t, out_f, ld_f, rows, H);
+  else layernorm_kernel<float><<<blocks, 256, 0, s>>>(in, ld_in, gamma, beta, eps, (float*)out_t, ld_t, out_f, ld_f, rows, H);
+  return check_launch("layernorm");
+}
+
+// ------------------------------------------------------------------------------------------
+// gather_rows: out[r, :] = cast(in[r * row_stride + :H])  (e.g. the CLS row of every image)
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void gather_rows_kernel(const float* __restrict__ in, size_t row_stride, T* __restrict__ out, int ld_out, int rows, int H) {
+  const int hv = H / 8;
+  const size_t total = (size_t)rows * hv;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % hv) * 8;
+    const size_t r = idx / hv;
+    float f[8];
+    load8<float>(in + r * row_stride + c, f);
+    store8<T>(out + r * ld_out + c, f);
+  }
+}
+
+int gather_rows(int out_bf16, const float* in, size_t row_stride, void* out, int ld_out, int rows, int H, cudaStream_t s) {
+  if (H % 8 || (row_stride % 4) || (ld_out % 8)) { set_last_error("gather_rows: alignment"); return VC_ERR_BAD_ARG; }
+  const size_t total = (size_t)rows * (H / 8);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (out_bf16) gather_rows_kernel<bf16><<<blocks, 256, 0, s>>>(in, row_stride, (bf16*)out, ld_out, rows, H);
+  else gather_rows_kernel<float><<<blocks, 256, 0, s>>>(in, row_stride, (float*)out, ld_out, rows, H);
+  return check_launch("gather_rows");
+}
+
+// ------------------------------------------------------------------------------------------
+// assemble_ctx: ctx[b] = [ tag_stream[b,0] ; cap_stream[b,0..N-1] ]  (modeling_bert.py:1493) as fp32 residual
+// copy + T operand copy. No LayerNorm / position / type embedding is applied to these rows.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void assemble_ctx_kernel(const float* __restrict__ cap, const float* __restrict__ tag, float* __restrict__ ctx_f,
+                                    T* __restrict__ ctx_t, int B, int N, int H) {
+  const int hv = H / 8;
+  const size_t total = (size_t)B * (N + 1) * hv;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % hv) * 8;
+    const size_t row = idx / hv;
+    const int t = (int)(row % (N + 1));
+    const size_t b = row / (N + 1);
+    const float* src = (t == 0) ? tag + (b * N) * H + c : cap + (b * N + t - 1) * H + c;
+    float f[8];
+    load8<float>(src, f);
+    store8<float>(ctx_f + row * H + c, f);
+    if (sizeof(T) == 2) store8<T>(ctx_t + row * H + c, f);
+  }
+}
+
+int assemble_ctx(int out_bf16, const float* cap, const float* tag, float* ctx_f, void* ctx_t, int B, int N, int H, cudaStream_t s) {
+  if (H % 8) { set_last_error("assemble_ctx: H %% 8"); return VC_ERR_BAD_ARG; }
+  const size_t total = (size_t)B * (N + 1) * (H / 8);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (out_bf16) assemble_ctx_kernel<bf16><<<blocks, 256, 0, s>>>(cap, tag, ctx_f, (bf16*)ctx_t, B, N, H);
+  else assemble_ctx_kernel<float><<<blocks, 256, 0, s>>>(cap, tag, ctx_f, (float*)ctx_t, B, N, H);
+  return check_launch("assemble_ctx");
+}
+
+// ------------------------------------------------------------------------------------------
+// embed_ln: decode-step text embedding (BertEmbeddings.forward, modeling_bert.py:222-237) for the two rows of
+// every sequence: [last generated token @ pos cur_len-1, MASK @ pos cur_len]; token type 0.
+// ids: int32 [R, max_len] running token buffer. One warp per output row.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+embed_ln_kernel(const int* __restrict__ ids, int max_len, int cur_len, int mask_id, const float* __restrict__ word,
+                const float* __restrict__ pos, const float* __restrict__ type0, const float* __restrict__ gamma,
+                const float* __restrict__ beta, float eps, float* __restrict__ out_f, T* __restrict__ out_t, int R, int H) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= 2 * R) return;
+  const int r = warp >> 1, which = warp & 1;
+  const int tok = which ? mask_id : ids[(size_t)r * max_len + cur_len - 1];
+  const int p = which ? cur_len : cur_len - 1;
+  const int nv = H / 128;
+  float4 v[8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (i < nv) {
+      const int c = (i * 32 + lane) * 4;
+      float4 a = __ldg(reinterpret_cast<const float4*>(word + (size_t)tok * H + c));
+      float4 b = __ldg(reinterpret_cast<const float4*>(pos + (size_t)p * H + c));
+      float4 t = __ldg(reinterpret_cast<const float4*>(type0 + c));
+      v[i] = make_float4(a.x + b.x + t.x, a.y + b.y + t.y, a.z + b.z + t.z, a.w + b.w + t.w);
+      s += v[i].x + v[i].y + v[i].z + v[i].w;
+    }
+  const float mean = warp_sum(s) / (float)H;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (i < nv) {
+      float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      q += a * a + b * b + c * c + d * d;
+    }
+  const float rstd = rsqrtf(warp_sum(q) / (float)H + eps);
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (i < nv) {
+      const int c = (i * 32 + lane) * 4;
+      float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+      float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
+      float4 o = make_float4((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y,
+                             (v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
+      *reinterpret_cast<float4*>(out_f + (size_t)warp * H + c) = o;
+      if (sizeof(T) == 2) {
+        uint2 pk = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+        *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(out_t) + (size_t)warp * H + c) = pk;
+      }
+    }
+}
+
+int embed_ln(int out_bf16, const int* ids, int max_len, int cur_len, int mask_id, const float* word, const float* pos,
+             const float* type0, const float* gamma, const float* beta, float eps, float* out_f, void* out_t, int R, int H,
+             cudaStream_t s) {
+  if (H % 128 || H > 1024 || cur_len < 1 || cur_len >= max_len) { set_last_error("embed_ln: bad args"); return VC_ERR_BAD_ARG; }
+  const int blocks = (2 * R + 7) / 8;
+  if (out_bf16) embed_ln_kernel<bf16><<<blocks, 256, 0, s>>>(ids, max_len, cur_len, mask_id, word, pos, type0, gamma, beta, eps, out_f, (bf16*)out_t, R, H);
+  else embed_ln_kernel<float><<<blocks, 256, 0, s>>>(ids, max_len, cur_len, mask_id, word, pos, type0, gamma, beta, eps, out_f, (float*)out_t, R, H);
+  return check_launch("embed_ln");
+}
+
+}  // namespace vc

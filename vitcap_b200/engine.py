@@ -1,0 +1,408 @@
+"""Device-side execution plan of the caption path: owns packed weights and workspaces in HBM and issues the
+C-ABI kernels (vitcap_b200.ops) in the order of SURVEY.md section 7.1:
+
+    patch embed -> 8 shared ViT blocks -> {4 caption blocks, 4 tag blocks} -> tag head + top-k
+    -> context = [tag-CLS | caption features] prefilled ONCE through the decoder (K/V cached per layer)
+    -> 19 decode steps of 2 rows per sequence (greedy / sampling / beam), captured in a CUDA graph.
+
+What the reference recomputes every step (all 16 ViT blocks, the tag head, 50 dead od/tag slots and the decoder
+over all ~648 rows; modeling_bert.py:845-876 with past=None) is computed exactly once here.
+
+HBM layout (T = bf16 in fast mode, fp32 in exact mode; all row-major, rows = tokens):
+    x, xt        fp32 [B*N, H]       residual streams of the caption / tag branches (never rounded to bf16)
+    ln, att      T    [B*C, H]       LayerNorm output (GEMM A operand), attention output
+    qkv          T    [B*N, 3H]      packed q|k|v of the current ViT block
+    hid          T    [B*C, F]       MLP hidden
+    ctx_qkv      T    [L, B*C, 3H]   prefill q|k|v of the 578 context rows per decoder layer == the KV cache
+    step_qkv     T    [L, max_len, 2R, 3H]  q|k|v rows of every decode step == caption-token KV cache
+    logits       fp32 [R, ldl]       vocabulary logits of the MASK rows (ldl = vocab rounded up to 64)
+"""
+import math
+
+import torch
+
+from . import ops
+from .config import VitCapConfig
+
+
+def _round_up(a, b):
+    return (a + b - 1) // b * b
+
+
+class PackedWeights:
+    """Weights re-laid for the kernels from a reference-layout state_dict (fp32 masters stay in the nn.Module)."""
+
+    def __init__(self, cfg: VitCapConfig, sd, mode, device):
+        self.cfg = cfg
+        self.mode = mode
+        wt = torch.bfloat16 if mode == "bf16" else torch.float32
+        self.wt = wt
+
+        def W(key):
+            return sd[key].detach().to(device=device, dtype=wt).contiguous()
+
+        def Fp(key):
+            return sd[key].detach().to(device=device, dtype=torch.float32).contiguous()
+
+        H = cfg.hidden
+        ie = "image_encoder.module."
+        self.patch_w = sd[ie + "patch_embed.proj.weight"].detach().reshape(H, cfg.patch_dim).to(device=device, dtype=wt).contiguous()
+        self.patch_b = Fp(ie + "patch_embed.proj.bias")
+        self.cls_token = Fp(ie + "cls_token").reshape(H).contiguous()
+        self.pos_embed = Fp(ie + "pos_embed").reshape(cfg.n_tokens, H).contiguous()
+
+        def block(prefix):
+            return {
+                "n1w": Fp(prefix + "norm1.weight"), "n1b": Fp(prefix + "norm1.bias"),
+                "qkv_w": W(prefix + "attn.qkv.weight"), "qkv_b": Fp(prefix + "attn.qkv.bias"),
+                "proj_w": W(prefix + "attn.proj.weight"), "proj_b": Fp(prefix + "attn.proj.bias"),
+                "n2w": Fp(prefix + "norm2.weight"), "n2b": Fp(prefix + "norm2.bias"),
+                "fc1_w": W(prefix + "mlp.fc1.weight"), "fc1_b": Fp(prefix + "mlp.fc1.bias"),
+                "fc2_w": W(prefix + "mlp.fc2.weight"), "fc2_b": Fp(prefix + "mlp.fc2.bias"),
+            }
+        self.blocks = [block("module.bert.encoder.blocks.%d." % i) for i in range(cfg.enc_blocks)]
+        self.tag_blocks = [block("module.bert.encoder.tag_blocks.%d." % i) for i in range(cfg.split_blocks)]
+
+        self.pool_w, self.pool_b = W("module.bert.pooler.dense.weight"), Fp("module.bert.pooler.dense.bias")
+
+        def head(prefix):
+            return {
+                "t_w": W(prefix + "transform.dense.weight"), "t_b": Fp(prefix + "transform.dense.bias"),
+                "ln_w": Fp(prefix + "transform.LayerNorm.weight"), "ln_b": Fp(prefix + "transform.LayerNorm.bias"),
+                "dec_w": W(prefix + "decoder.weight"), "bias": Fp(prefix + "bias"),
+            }
+        self.tag_head = head("module.bert.tag_logit.predictions.")
+        self.cls_head = head("module.cls.predictions.")
+
+        e = "module.bert.embeddings."
+        self.word = Fp(e + "word_embeddings.weight")
+        self.pos = Fp(e + "position_embeddings.weight")
+        self.type0 = Fp(e + "token_type_embeddings.weight")[0].contiguous()
+        self.emb_ln_w, self.emb_ln_b = Fp(e + "LayerNorm.weight"), Fp(e + "LayerNorm.bias")
+
+        self.dec = []
+        for i in range(cfg.dec_layers):
+            p = "module.bert.decoder.layer.%d." % i
+            qkv_w = torch.cat([sd[p + "attention.self.%s.weight" % n].detach() for n in ("query", "key", "value")], 0)
+            qkv_b = torch.cat([sd[p + "attention.self.%s.bias" % n].detach() for n in ("query", "key", "value")], 0)
+            self.dec.append({
+                "qkv_w": qkv_w.to(device=device, dtype=wt).contiguous(),
+                "qkv_b": qkv_b.to(device=device, dtype=torch.float32).contiguous(),
+                "o_w": W(p + "attention.output.dense.weight"), "o_b": Fp(p + "attention.output.dense.bias"),
+                "ln1_w": Fp(p + "attention.output.LayerNorm.weight"), "ln1_b": Fp(p + "attention.output.LayerNorm.bias"),
+                "i_w": W(p + "intermediate.dense.weight"), "i_b": Fp(p + "intermediate.dense.bias"),
+                "f_w": W(p + "output.dense.weight"), "f_b": Fp(p + "output.dense.bias"),
+                "ln2_w": Fp(p + "output.LayerNorm.weight"), "ln2_b": Fp(p + "output.LayerNorm.bias"),
+            })
+
+
+class CaptionEngine:
+    def __init__(self, cfg: VitCapConfig, weights: PackedWeights, device, use_cuda_graph=True):
+        self.cfg = cfg
+        self.w = weights
+        self.mode = weights.mode
+        self.T = weights.wt
+        self.dev = device
+        self.use_cuda_graph = use_cuda_graph
+        self.ldl = _round_up(cfg.vocab, 64)
+        self._enc_ws = None
+        self._dec_ws = {}
+        self._graphs = {}
+        self.attn_impl = "auto"
+        self.stats = {}
+
+    # ------------------------------------------------------------------ workspaces
+    def _alloc(self, *shape, dtype=None):
+        return torch.empty(*shape, device=self.dev, dtype=dtype or self.T)
+
+    def _encoder_ws(self, B):
+        ws = self._enc_ws
+        if ws is not None and ws["B"] >= B:
+            return ws
+        cfg = self.cfg
+        N, C, H, F, L = cfg.n_tokens, cfg.n_ctx, cfg.hidden, cfg.inter, cfg.dec_layers
+        f32 = torch.float32
+        ws = {"B": B}
+        ws["patches"] = self._alloc(B * cfg.n_patches, cfg.patch_dim)
+        ws["patch_out"] = self._alloc(B * cfg.n_patches, H, dtype=f32)
+        ws["x"] = self._alloc(B * N, H, dtype=f32)
+        ws["xt"] = self._alloc(B * N, H, dtype=f32)
+        ws["ln"] = self._alloc(B * C, H)
+        ws["qkv"] = self._alloc(B * N, 3 * H)
+        ws["att"] = self._alloc(B * C, H)
+        ws["hid"] = self._alloc(B * C, F)
+        ws["ctx_f"] = self._alloc(B * C, H, dtype=f32)
+        ws["ctx_t"] = ws["ctx_f"] if self.T == f32 else self._alloc(B * C, H)
+        ws["tmp_f"] = self._alloc(B * C, H, dtype=f32)
+        ws["a_f"] = self._alloc(B * C, H, dtype=f32)
+        ws["ctx_qkv"] = self._alloc(L, B * C, 3 * H)
+        # tag head
+        ws["cls_t"] = self._alloc(B, H)
+        ws["pooled"] = self._alloc(B, H, dtype=f32 if self.T == f32 else self.T)
+        ws["th_f"] = self._alloc(B, H, dtype=f32)
+        ws["th_t"] = self._alloc(B, H)
+        ws["tag_logits"] = self._alloc(B, self.ldl, dtype=f32)
+        ws["tag_idx"] = self._alloc(B, cfg.topk, dtype=torch.int32)
+        ws["tag_prob"] = self._alloc(B, cfg.topk, dtype=f32)
+        ws["tag_len"] = self._alloc(B, dtype=torch.int32)
+        self._enc_ws = ws
+        self._dec_ws = {}
+        self._graphs = {}
+        return ws
+
+    def _decoder_ws(self, B, E, max_len):
+        key = (B, E, max_len)
+        if key in self._dec_ws:
+            return self._dec_ws[key]
+        cfg = self.cfg
+        H, F, L = cfg.hidden, cfg.inter, cfg.dec_layers
+        R = B * E
+        f32, i32 = torch.float32, torch.int32
+        ws = {"B": B, "E": E, "R": R, "max_len": max_len}
+        ws["e_f"] = self._alloc(2 * R, H, dtype=f32)
+        ws["e_t"] = ws["e_f"] if self.T == f32 else self._alloc(2 * R, H)
+        ws["att"] = self._alloc(2 * R, H)
+        ws["tmp"] = self._alloc(2 * R, H, dtype=f32)
+        ws["a_f"] = self._alloc(2 * R, H, dtype=f32)
+        ws["a_t"] = ws["a_f"] if self.T == f32 else self._alloc(2 * R, H)
+        ws["hid"] = self._alloc(2 * R, F)
+        ws["step_qkv"] = self._alloc(L, max_len, 2 * R, 3 * H)
+        ws["head_f"] = self._alloc(R, H, dtype=f32)
+        ws["head_t"] = ws["head_f"] if self.T == f32 else self._alloc(R, H)
+        ws["logits"] = self._alloc(R, self.ldl, dtype=f32)
+        ws["ids"] = torch.zeros(R, max_len, device=self.dev, dtype=i32)
+        ws["unfinished"] = torch.ones(R, device=self.dev, dtype=i32)
+        ws["sum_lp"] = torch.zeros(R, device=self.dev, dtype=f32)
+        ws["n_steps"] = torch.zeros(R, device=self.dev, dtype=i32)
+        ws["out_ids"] = torch.zeros(R, max_len, device=self.dev, dtype=torch.int64)
+        ws["out_lp"] = torch.zeros(R, device=self.dev, dtype=f32)
+        self._dec_ws = {key: ws}          # keep one decode workspace alive at a time
+        self._graphs = {}
+        return ws
+
+    # ------------------------------------------------------------------ building blocks
+    def _ln(self, x, g, b, eps, out_t, out_f=None, rows=None):
+        """LayerNorm of fp32 rows -> operand copy (and optional fp32 copy). In exact mode both are the same buffer."""
+        if self.T == torch.float32:
+            tgt = out_f if out_f is not None else out_t
+            ops.layernorm(x, g, b, eps, out_t=None, out_f=tgt, rows=rows)
+            return tgt
+        ops.layernorm(x, g, b, eps, out_t=out_t, out_f=out_f, rows=rows)
+        return out_t
+
+    def _vit_block(self, p, x, rows, B, N, ws):
+        """Pre-LN ViT block on the fp32 stream x (in place). vision_transformer.py:233-250."""
+        cfg = self.cfg
+        H = cfg.hidden
+        ln, qkv, att, hid = ws["ln"][:rows], ws["qkv"][:rows], ws["att"][:rows], ws["hid"][:rows]
+        h = self._ln(x, p["n1w"], p["n1b"], cfg.vit_ln_eps, ln, rows=rows)
+        ops.linear(h, p["qkv_w"], p["qkv_b"], qkv, M=rows)
+        ops.attention(qkv, att, B, N, cfg.heads, cfg.head_dim ** -0.5, impl=self.attn_impl)
+        ops.linear(att, p["proj_w"], p["proj_b"], x, resid=x, M=rows)
+        h = self._ln(x, p["n2w"], p["n2b"], cfg.vit_ln_eps, ln, rows=rows)
+        ops.linear(h, p["fc1_w"], p["fc1_b"], hid, act=ops.ACT_GELU, M=rows)
+        ops.linear(hid, p["fc2_w"], p["fc2_b"], x, resid=x, M=rows)
+
+    # ------------------------------------------------------------------ stages
+    def patch_embed(self, image):
+        """image fp32 [B,3,S,S] (device) -> img_feats fp32 [B,N,H] (a view of the trunk stream buffer)."""
+        cfg, w = self.cfg, self.w
+        B = image.shape[0]
+        ws = self._encoder_ws(B)
+        P, H, N = cfg.n_patches, cfg.hidden, cfg.n_tokens
+        patches = ws["patches"][:B * P]
+        po = ws["patch_out"][:B * P]
+        ops.patchify(image, patches, cfg.patch)
+        ops.linear(patches, w.patch_w, w.patch_b, po, M=B * P)
+        x = ws["x"][:B * N]
+        ops.assemble_tokens(po, w.cls_token, w.pos_embed, x, B, P, H)
+        return x.view(B, N, H)
+
+    def encode(self, img_feats, caption_branch=True):
+        """TIMMVitSplitEncoder.forward (modeling_bert.py:458-478): returns (caption feats, tag feats) fp32 [B,N,H]."""
+        cfg, w = self.cfg, self.w
+        B, N, H = img_feats.shape
+        ws = self._encoder_ws(B)
+        rows = B * N
+        x = ws["x"][:rows]
+        if img_feats.data_ptr() != x.data_ptr():
+            x.copy_(img_feats.reshape(rows, H))
+        xt = ws["xt"][:rows]
+        split_at = cfg.enc_blocks - cfg.split_blocks
+        for i in range(split_at):
+            self._vit_block(w.blocks[i], x, rows, B, N, ws)
+        xt.copy_(x)                                    # fork: both branches start from the block-8 input
+        if caption_branch:
+            for i in range(split_at, cfg.enc_blocks):
+                self._vit_block(w.blocks[i], x, rows, B, N, ws)
+        for j in range(cfg.split_blocks):
+            self._vit_block(w.tag_blocks[j], xt, rows, B, N, ws)
+        return x.view(B, N, H), xt.view(B, N, H)
+
+    def _head(self, hp, a_t, rows, th_f, th_t, logits):
+        """BertLMPredictionHead (modeling_bert.py:540-563): dense + gelu -> LN(1e-12) -> tied/untied decoder + bias."""
+        cfg = self.cfg
+        ops.linear(a_t, hp["t_w"], hp["t_b"], th_f, act=ops.ACT_GELU, M=rows, lda=a_t.stride(0))
+        t = self._ln(th_f, hp["ln_w"], hp["ln_b"], cfg.bert_ln_eps, th_t, rows=rows)
+        ops.linear(t, hp["dec_w"], hp["bias"], logits[:, :cfg.vocab], M=rows, ldo=logits.stride(0))
+
+    def tag_head(self, B):
+        """pooler -> tag_logit -> sigmoid -> topk -> len (modeling_bert.py:1424-1432) on the tag stream."""
+        cfg, w = self.cfg, self.w
+        ws = self._encoder_ws(B)
+        N, H = cfg.n_tokens, cfg.hidden
+        cls_t, pooled = ws["cls_t"][:B], ws["pooled"][:B]
+        ops.gather_rows(ws["xt"], N * H, cls_t, B, H)
+        ops.linear(cls_t, w.pool_w, w.pool_b, pooled, act=ops.ACT_TANH, M=B)
+        logits = ws["tag_logits"][:B]
+        self._head(w.tag_head, pooled, B, ws["th_f"][:B], ws["th_t"][:B], logits)
+        ops.tag_topk(logits, cfg.vocab, cfg.topk, cfg.tag_thresh, ws["tag_idx"], ws["tag_prob"], ws["tag_len"], rows=B)
+        return logits[:, :cfg.vocab], ws["tag_idx"][:B], ws["tag_prob"][:B], ws["tag_len"][:B]
+
+    def prefill(self, B):
+        """Context rows [tag-CLS | caption feats] through the decoder once; per-layer q|k|v stay in ctx_qkv (KV cache).
+        BertLayer, modeling_bert.py:303-437, bidirectional over the context (image rows only see image columns,
+        pipeline file lines 57-85)."""
+        cfg, w = self.cfg, self.w
+        ws = self._encoder_ws(B)
+        N, C, H = cfg.n_tokens, cfg.n_ctx, cfg.hidden
+        rows = B * C
+        ctx_f, ctx_t = ws["ctx_f"][:rows], ws["ctx_t"][:rows]
+        ops.assemble_ctx(ws["x"], ws["xt"], ctx_f, ctx_t, B, N, H)
+        att, hid, tmp, a_f, ln = ws["att"][:rows], ws["hid"][:rows], ws["tmp_f"][:rows], ws["a_f"][:rows], ws["ln"][:rows]
+        for l, p in enumerate(w.dec):
+            qkv = ws["ctx_qkv"][l][:rows]
+            last = (l == cfg.dec_layers - 1)
+            if last:
+                # only K and V of the last layer are ever used: project the k|v two thirds of the fused weight
+                ops.linear(ctx_t, p["qkv_w"][H:], p["qkv_b"][H:], qkv[:, H:], M=rows, ldo=3 * H)
+                break
+            ops.linear(ctx_t, p["qkv_w"], p["qkv_b"], qkv, M=rows)
+            ops.attention(qkv, att, B, C, cfg.heads, 1.0 / math.sqrt(cfg.head_dim), impl=self.attn_impl)
+            ops.linear(att, p["o_w"], p["o_b"], tmp, resid=ctx_f, M=rows)
+            a_t = self._ln(tmp, p["ln1_w"], p["ln1_b"], cfg.bert_ln_eps, ln, out_f=a_f, rows=rows)
+            ops.linear(a_t, p["i_w"], p["i_b"], hid, act=ops.ACT_GELU, M=rows)
+            ops.linear(hid, p["f_w"], p["f_b"], tmp, resid=a_f, M=rows)
+            self._ln(tmp, p["ln2_w"], p["ln2_b"], cfg.bert_ln_eps, ctx_t, out_f=ctx_f, rows=rows)
+
+    def _decode_layers(self, ws, B, E, cur_len, anc, mask_id):
+        """One decode step up to the vocabulary logits of the MASK rows."""
+        cfg, w = self.cfg, self.w
+        R, H = ws["R"], cfg.hidden
+        C = cfg.n_ctx
+        enc = self._enc_ws
+        e_f, e_t = ws["e_f"], ws["e_t"]
+        ops.embed_ln(ws["ids"], cur_len, mask_id, w.word, w.pos, w.type0, w.emb_ln_w, w.emb_ln_b, cfg.bert_ln_eps, e_f, e_t, R)
+        scale = 1.0 / math.sqrt(cfg.head_dim)
+        for l, p in enumerate(w.dec):
+            sq = ws["step_qkv"][l]
+            ops.linear(e_t, p["qkv_w"], p["qkv_b"], sq[cur_len - 1], M=2 * R)
+            ops.decode_attention(enc["ctx_qkv"][l], sq, anc, ws["att"], B, C, cfg.heads, E, cur_len, scale)
+            ops.linear(ws["att"], p["o_w"], p["o_b"], ws["tmp"], resid=e_f, M=2 * R)
+            a_t = self._ln(ws["tmp"], p["ln1_w"], p["ln1_b"], cfg.bert_ln_eps, ws["a_t"], out_f=ws["a_f"], rows=2 * R)
+            ops.linear(a_t, p["i_w"], p["i_b"], ws["hid"], act=ops.ACT_GELU, M=2 * R)
+            ops.linear(ws["hid"], p["f_w"], p["f_b"], ws["tmp"], resid=ws["a_f"], M=2 * R)
+            self._ln(ws["tmp"], p["ln2_w"], p["ln2_b"], cfg.bert_ln_eps, e_t, out_f=e_f, rows=2 * R)
+        # vocabulary head on the MASK rows only (rows 1::2); the reference runs it over all T text rows
+        # (modeling_bert.py:809-810) and keeps one
+        mask_rows = e_t[1::2]
+        self._head(w.cls_head, mask_rows, R, ws["head_f"], ws["head_t"], ws["logits"])
+
+    # ------------------------------------------------------------------ search drivers
+    def _maybe_graph(self, key, fn):
+        """Runs fn() eagerly once (warm-up: lazy kernel attribute setup, descriptor cache), then captures and replays it."""
+        if not self.use_cuda_graph:
+            fn()
+            return
+        g = self._graphs.get(key)
+        if g is None:
+            fn()                                         # warm-up / first execution is the real one
+            torch.cuda.current_stream().synchronize()
+            g = torch.cuda.CUDAGraph()
+            before = ops.launch_count()
+            with torch.cuda.graph(g):
+                fn()
+            self.stats["graph_kernels"] = ops.launch_count() - before
+            self._graphs[key] = g
+            return "captured_after_eager"
+        g.replay()
+        self.stats["graph_replays"] = self.stats.get("graph_replays", 0) + 1
+
+    def greedy_or_sample(self, B, E, max_len, bos, pad, eos_ids, mask_id, do_sample=False, temperature=1.0, top_k=0,
+                         top_p=1.0, seed=0):
+        """_generate_no_beam_search (modeling_utils.py:768-886) for R = B*E sequences; returns (ids int64 [R,1,max_len],
+        logprob fp32 [R,1])."""
+        cfg = self.cfg
+        ws = self._decoder_ws(B, E, max_len)
+        R = ws["R"]
+        eos = torch.tensor(list(eos_ids), device=self.dev, dtype=torch.int32)
+        filt = do_sample and (top_k > 0 or top_p < 1.0)
+
+        def reset():
+            ws["ids"].zero_()
+            ws["ids"][:, 0] = bos
+            ws["unfinished"].fill_(1)
+            ws["sum_lp"].zero_()
+            ws["n_steps"].zero_()
+
+        def run():
+            reset()
+            for cur_len in range(1, max_len):
+                self._decode_layers(ws, B, E, cur_len, None, mask_id)
+                t = temperature
+                if filt:
+                    ops.filter_logits(ws["logits"], cfg.vocab, R, 1.0 / temperature, top_k, top_p)
+                    t = 1.0
+                ops.token_step(ws["logits"], cfg.vocab, R, do_sample, t, seed, cur_len, pad, eos, ws["ids"], ws["unfinished"],
+                               ws["sum_lp"], ws["n_steps"])
+            ops.greedy_finalize(ws["ids"], ws["unfinished"], ws["sum_lp"], ws["n_steps"], int(eos_ids[0]), R, ws["out_ids"],
+                                ws["out_lp"])
+
+        ws["_eos"] = eos
+        self._maybe_graph(("tok", B, E, max_len, do_sample, temperature, top_k, top_p, seed, bos, pad, tuple(eos_ids), mask_id), run)
+        return ws["out_ids"].view(R, 1, max_len).clone(), ws["out_lp"].view(R, 1).clone()
+
+    def beam_search(self, B, nb, max_len, bos, pad, eos_ids, mask_id, length_penalty=1.0, keep=1):
+        """_generate_beam_search (modeling_utils.py:888-1100), do_sample=False. Returns (ids int64 [B,keep,max_len],
+        logprob fp32 [B,keep])."""
+        cfg = self.cfg
+        ws = self._decoder_ws(B, nb, max_len)
+        R, K = ws["R"], 2 * nb
+        f32, i32 = torch.float32, torch.int32
+        if "beam" not in ws or ws["beam"]["keep"] != keep:
+            ws["beam"] = {
+                "keep": keep,
+                "ids": ws["ids"], "beam_scores": torch.zeros(R, device=self.dev, dtype=f32),
+                "done": torch.zeros(B, device=self.dev, dtype=i32), "anc": torch.zeros(max_len, R, device=self.dev, dtype=i32),
+                "hyp_score": torch.zeros(B, keep, device=self.dev, dtype=torch.float64),
+                "hyp_len": torch.zeros(B, keep, device=self.dev, dtype=i32),
+                "hyp_ids": torch.zeros(B, keep, max_len, device=self.dev, dtype=i32),
+                "hyp_count": torch.zeros(B, device=self.dev, dtype=i32),
+                "worst": torch.zeros(B, device=self.dev, dtype=torch.float64),
+                "cand_val": torch.zeros(R, K, device=self.dev, dtype=f32), "cand_idx": torch.zeros(R, K, device=self.dev, dtype=i32),
+                "row_max": torch.zeros(R, device=self.dev, dtype=f32), "row_logsum": torch.zeros(R, device=self.dev, dtype=f32),
+                "out_ids": torch.zeros(B, keep, max_len, device=self.dev, dtype=torch.int64),
+                "out_lp": torch.zeros(B, keep, device=self.dev, dtype=f32),
+                "init_scores": torch.tensor(([0.0] + [-1e9] * (nb - 1)) * B, device=self.dev, dtype=f32),
+            }
+        st = ws["beam"]
+        eos = torch.tensor(list(eos_ids), device=self.dev, dtype=torch.int32)
+        st["_eos"] = eos
+
+        def run():
+            st["ids"].zero_()
+            st["ids"][:, 0] = bos
+            st["beam_scores"].copy_(st["init_scores"])       # [0, -1e9, ...] per image (modeling_utils.py:922-924)
+            st["done"].zero_()
+            st["anc"].zero_()
+            st["hyp_count"].zero_()
+            st["worst"].fill_(1e9)
+            for cur_len in range(1, max_len):
+                self._decode_layers(ws, B, nb, cur_len, st["anc"], mask_id)
+                ops.beam_row_topk(ws["logits"], cfg.vocab, R, K, st["cand_val"], st["cand_idx"], st["row_max"], st["row_logsum"])
+                ops.beam_advance(st, st["cand_val"], st["cand_idx"], st["row_max"], st["row_logsum"], B, nb, cfg.vocab, cur_len,
+                                 keep, length_penalty, pad, eos)
+            ops.beam_finalize(st, B, keep, pad, int(eos_ids[0]), st["out_ids"], st["out_lp"])
+
+        self._maybe_graph(("beam", B, nb, max_len, keep, float(length_penalty), bos, pad, tuple(eos_ids), mask_id), run)
+        return st["out_ids"].clone(), st["out_lp"].clone()

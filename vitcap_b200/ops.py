@@ -1,0 +1,220 @@
+"""ctypes binding of libvitcap_b200.so (the C ABI declared in include/vitcap_b200.h).
+
+PyTorch is used for device memory and streams only: every wrapper passes ``tensor.data_ptr()`` and the
+current CUDA stream handle; no torch type crosses the boundary. There is no fallback: if the shared library
+cannot be loaded the import of a compute entry point raises.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libvitcap_b200.so")
+
+ACT_NONE, ACT_GELU, ACT_TANH = 0, 1, 2
+
+_c = ctypes
+_P, _I, _F, _D, _SZ, _U64, _LL = _c.c_void_p, _c.c_int, _c.c_float, _c.c_double, _c.c_size_t, _c.c_uint64, _c.c_longlong
+
+# name -> argtypes; must list every symbol the header declares (checked by tests/test_abi.py)
+SIGNATURES = {
+    "vc_linear": [_I, _P, _I, _P, _I, _P, _P, _I, _I, _I, _P, _I, _I, _I, _I, _P],
+    "vc_linear_simt": [_I, _P, _I, _P, _I, _P, _P, _I, _I, _I, _P, _I, _I, _I, _I, _P],
+    "vc_linear_tc": [_P, _I, _P, _I, _P, _P, _I, _I, _I, _P, _I, _I, _I, _I, _I, _P],
+    "vc_patchify": [_I, _P, _P, _I, _I, _I, _P],
+    "vc_assemble_tokens": [_P, _P, _P, _P, _I, _I, _I, _P],
+    "vc_layernorm": [_I, _P, _I, _P, _P, _F, _P, _I, _P, _I, _I, _I, _P],
+    "vc_gather_rows": [_I, _P, _SZ, _P, _I, _I, _I, _P],
+    "vc_assemble_ctx": [_I, _P, _P, _P, _P, _I, _I, _I, _P],
+    "vc_attention": [_I, _P, _P, _I, _I, _I, _F, _P],
+    "vc_attention_simt": [_I, _P, _P, _I, _I, _I, _F, _P],
+    "vc_tag_topk": [_P, _I, _I, _I, _I, _F, _P, _P, _P, _P],
+    "vc_embed_ln": [_I, _P, _I, _I, _I, _P, _P, _P, _P, _P, _F, _P, _P, _I, _I, _P],
+    "vc_decode_attention": [_I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
+    "vc_token_step": [_P, _I, _I, _I, _I, _F, _U64, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P],
+    "vc_greedy_finalize": [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P],
+    "vc_beam_row_topk": [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P],
+    "vc_beam_advance": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _D, _I, _P, _I, _P],
+    "vc_beam_finalize": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P],
+    "vc_filter_logits": [_P, _I, _I, _I, _F, _I, _F, _I, _P],
+}
+
+_lib = None
+
+
+def load_library(path=None):
+    """Loads the shared library (no GPU needed) and declares all prototypes."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise RuntimeError(
+            "vitcap_b200: %s is missing -- build it with `python -m vitcap_b200.build` "
+            "(there is no CPU or PyTorch fallback for the caption path)" % p)
+    lib = ctypes.CDLL(p)
+    for name, args in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = _I
+    lib.vc_last_error.restype = ctypes.c_char_p
+    lib.vc_last_error.argtypes = []
+    lib.vc_abi_version.restype = _I
+    lib.vc_launch_count.restype = _LL
+    lib.vc_reset_launch_count.restype = None
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def _check(rc, name):
+    if rc != 0:
+        msg = load_library().vc_last_error().decode("utf-8", "replace")
+        raise RuntimeError("%s failed (%d): %s" % (name, rc, msg))
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    assert t.is_cuda, "vitcap_b200 kernels need CUDA tensors"
+    return t.data_ptr()
+
+
+def launch_count():
+    return int(load_library().vc_launch_count())
+
+
+def reset_launch_count():
+    load_library().vc_reset_launch_count()
+
+
+def _is_bf16(t):
+    return 1 if t.dtype == torch.bfloat16 else 0
+
+
+def linear(a, w, bias, out, act=ACT_NONE, resid=None, M=None, lda=None, ldo=None, impl="auto", tile_n=0):
+    """out[M,N] = act(a[M,K] @ w[N,K]^T + bias) (+ resid). a/w: both bf16 (tensor cores) or both fp32 (exact mode).
+    ``a`` and ``out`` may be strided row views (pitch = stride(0))."""
+    lib = load_library()
+    K = w.shape[1]
+    N = w.shape[0]
+    M = a.shape[0] if M is None else M
+    lda = a.stride(0) if lda is None else lda
+    ldo = out.stride(0) if ldo is None else ldo
+    assert a.dtype == w.dtype and a.stride(-1) == 1 and w.stride(-1) == 1 and out.stride(-1) == 1
+    out_f32 = 1 if out.dtype == torch.float32 else 0
+    ldr = resid.stride(0) if resid is not None else 0
+    if resid is not None:
+        assert resid.dtype == torch.float32 and out_f32
+    args = (_ptr(a), lda, _ptr(w), w.stride(0), _ptr(bias), _ptr(out), ldo, out_f32, act, _ptr(resid), ldr, M, N, K)
+    if impl == "simt":
+        _check(lib.vc_linear_simt(_is_bf16(a), *args, _stream()), "vc_linear_simt")
+    elif impl == "tc":
+        assert a.dtype == torch.bfloat16
+        _check(lib.vc_linear_tc(*args, tile_n, _stream()), "vc_linear_tc")
+    else:
+        if a.dtype == torch.float32:
+            assert out_f32, "exact mode writes fp32"
+        _check(lib.vc_linear(_is_bf16(a), *args, _stream()), "vc_linear")
+    return out
+
+
+def patchify(image, out, patch):
+    B, _, S, _ = image.shape
+    assert image.dtype == torch.float32 and image.is_contiguous()
+    _check(load_library().vc_patchify(_is_bf16(out), _ptr(image), _ptr(out), B, S, patch, _stream()), "vc_patchify")
+    return out
+
+
+def assemble_tokens(patch_out, cls, pos, x, B, P, H):
+    _check(load_library().vc_assemble_tokens(_ptr(patch_out), _ptr(cls), _ptr(pos), _ptr(x), B, P, H, _stream()),
+           "vc_assemble_tokens")
+    return x
+
+
+def layernorm(x, gamma, beta, eps, out_t=None, out_f=None, rows=None):
+    rows = x.shape[0] if rows is None else rows
+    H = x.shape[-1]
+    bf = _is_bf16(out_t) if out_t is not None else 0
+    _check(load_library().vc_layernorm(bf, _ptr(x), x.stride(0), _ptr(gamma), _ptr(beta), float(eps), _ptr(out_t),
+                                       out_t.stride(0) if out_t is not None else 0, _ptr(out_f),
+                                       out_f.stride(0) if out_f is not None else 0, rows, H, _stream()), "vc_layernorm")
+
+
+def gather_rows(x, row_stride, out, rows, H):
+    _check(load_library().vc_gather_rows(_is_bf16(out), _ptr(x), row_stride, _ptr(out), out.stride(0), rows, H, _stream()),
+           "vc_gather_rows")
+    return out
+
+
+def assemble_ctx(cap, tag, ctx_f, ctx_t, B, N, H):
+    _check(load_library().vc_assemble_ctx(_is_bf16(ctx_t), _ptr(cap), _ptr(tag), _ptr(ctx_f), _ptr(ctx_t), B, N, H, _stream()),
+           "vc_assemble_ctx")
+
+
+def attention(qkv, out, B, N, heads, scale, impl="auto"):
+    lib = load_library()
+    if impl == "simt":
+        _check(lib.vc_attention_simt(_is_bf16(qkv), _ptr(qkv), _ptr(out), B, N, heads, float(scale), _stream()), "vc_attention_simt")
+    else:
+        _check(lib.vc_attention(_is_bf16(qkv), _ptr(qkv), _ptr(out), B, N, heads, float(scale), _stream()), "vc_attention")
+    return out
+
+
+def tag_topk(logits, V, K, thresh, out_idx, out_prob, out_len, rows=None):
+    rows = logits.shape[0] if rows is None else rows
+    _check(load_library().vc_tag_topk(_ptr(logits), logits.stride(0), rows, V, K, float(thresh), _ptr(out_idx), _ptr(out_prob),
+                                      _ptr(out_len), _stream()), "vc_tag_topk")
+
+
+def embed_ln(ids, cur_len, mask_id, word, pos, type0, gamma, beta, eps, out_f, out_t, R):
+    H = word.shape[1]
+    _check(load_library().vc_embed_ln(_is_bf16(out_t), _ptr(ids), ids.shape[1], cur_len, mask_id, _ptr(word), _ptr(pos),
+                                      _ptr(type0), _ptr(gamma), _ptr(beta), float(eps), _ptr(out_f), _ptr(out_t), R, H,
+                                      _stream()), "vc_embed_ln")
+
+
+def decode_attention(ctx_qkv, step_qkv, anc, out, B, C, heads, E, cur_len, scale):
+    _check(load_library().vc_decode_attention(_is_bf16(ctx_qkv), _ptr(ctx_qkv), _ptr(step_qkv), _ptr(anc), _ptr(out), B, C,
+                                              heads, E, cur_len, float(scale), _stream()), "vc_decode_attention")
+
+
+def token_step(logits, V, rows, do_sample, temperature, seed, cur_len, pad_id, eos_ids, ids, unfinished, sum_lp, n_steps):
+    _check(load_library().vc_token_step(_ptr(logits), logits.stride(0), rows, V, int(do_sample), float(temperature),
+                                        int(seed) & 0xFFFFFFFFFFFFFFFF, cur_len, ids.shape[1], pad_id, _ptr(eos_ids),
+                                        eos_ids.numel(), _ptr(ids), _ptr(unfinished), _ptr(sum_lp), _ptr(n_steps), _stream()),
+           "vc_token_step")
+
+
+def greedy_finalize(ids, unfinished, sum_lp, n_steps, eos0, R, out_ids, out_lp):
+    _check(load_library().vc_greedy_finalize(_ptr(ids), _ptr(unfinished), _ptr(sum_lp), _ptr(n_steps), eos0, ids.shape[1], R,
+                                             _ptr(out_ids), _ptr(out_lp), _stream()), "vc_greedy_finalize")
+
+
+def beam_row_topk(logits, V, rows, K, cand_val, cand_idx, row_max, row_logsum):
+    _check(load_library().vc_beam_row_topk(_ptr(logits), logits.stride(0), rows, V, K, _ptr(cand_val), _ptr(cand_idx),
+                                           _ptr(row_max), _ptr(row_logsum), _stream()), "vc_beam_row_topk")
+
+
+def beam_advance(st, cand_val, cand_idx, row_max, row_logsum, B, nb, V, cur_len, keep, length_penalty, pad_id, eos_ids):
+    _check(load_library().vc_beam_advance(_ptr(st["ids"]), _ptr(st["beam_scores"]), _ptr(st["done"]), _ptr(st["anc"]),
+                                          _ptr(st["hyp_score"]), _ptr(st["hyp_len"]), _ptr(st["hyp_ids"]), _ptr(st["hyp_count"]),
+                                          _ptr(st["worst"]), _ptr(cand_val), _ptr(cand_idx), _ptr(row_max), _ptr(row_logsum),
+                                          B, nb, V, cur_len, st["ids"].shape[1], keep, float(length_penalty), pad_id,
+                                          _ptr(eos_ids), eos_ids.numel(), _stream()), "vc_beam_advance")
+
+
+def beam_finalize(st, B, keep, pad_id, eos0, out_ids, out_lp):
+    _check(load_library().vc_beam_finalize(_ptr(st["hyp_score"]), _ptr(st["hyp_len"]), _ptr(st["hyp_ids"]), _ptr(st["hyp_count"]),
+                                           B, keep, st["ids"].shape[1], pad_id, eos0, _ptr(out_ids), _ptr(out_lp), _stream()),
+           "vc_beam_finalize")
+
+
+def filter_logits(logits, V, rows, inv_temperature, top_k, top_p, min_tokens_to_keep=1):
+    _check(load_library().vc_filter_logits(_ptr(logits), logits.stride(0), rows, V, float(inv_temperature), int(top_k),
+                                           float(top_p), int(min_tokens_to_keep), _stream()), "vc_filter_logits")
