@@ -1,0 +1,96 @@
+"""CPU-only checks of the host side: state_dict layout, C-ABI surface, argument validation, sharding."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from vitcap_b200 import config as vcfg
+from vitcap_b200 import ops, synth
+from vitcap_b200.model import FastImageCaptioning
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_state_dict_layout_matches_reference_names():
+    """Same 288 keys / shapes as ImageCaptioning(ViTCAP) of the reference, same order."""
+    cfg = vcfg.variant("16_384")
+    m = FastImageCaptioning(cfg)
+    sd = m.state_dict()
+    spec = synth.state_dict_spec(cfg)
+    assert len(sd) == len(spec) == 288
+    assert list(sd.keys()) == [k for k, _, _ in spec]
+    for k, shape, _ in spec:
+        assert tuple(sd[k].shape) == tuple(shape), k
+    # tied vocabulary matrix (modeling_bert.py:728-730)
+    assert sd["module.cls.predictions.decoder.weight"].data_ptr() == sd["module.bert.embeddings.word_embeddings.weight"].data_ptr()
+
+
+def test_state_dict_roundtrip_tiny():
+    cfg = vcfg.tiny()
+    sd = synth.make_state_dict(cfg, seed=3)
+    m = FastImageCaptioning(cfg)
+    r = m.load_state_dict(sd, strict=True)
+    assert not r.missing_keys and not r.unexpected_keys
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, sd[k]), k
+    # checkpoint written by the reference Checkpointer: {'model': state_dict} with a leading 'module.' (DDP) is the
+    # caller's concern; names below the wrapper are identical
+    assert all(k.startswith(("module.", "image_encoder.module.")) for k in sd)
+
+
+def test_header_symbols_are_exported_and_bound():
+    """Every function declared in include/vitcap_b200.h is exported by the shared library and has a ctypes prototype."""
+    hdr = open(os.path.join(ROOT, "include", "vitcap_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b(vc_[a-z0-9_]+)\s*\(", hdr))
+    assert len(names) >= 20
+    lib = ops.load_library()
+    for n in names:
+        assert hasattr(lib, n), n
+    simple = {"vc_last_error", "vc_abi_version", "vc_launch_count", "vc_reset_launch_count"}
+    assert names - simple == set(ops.SIGNATURES), (names - simple) ^ set(ops.SIGNATURES)
+    assert lib.vc_abi_version() == 1
+    assert isinstance(lib.vc_last_error(), bytes)
+
+
+def test_library_has_no_torch_or_libcuda_link_dependency():
+    import subprocess
+    out = subprocess.run(["ldd", ops.LIB_PATH], capture_output=True, text=True).stdout
+    assert "torch" not in out and "libcuda.so" not in out and "c10" not in out
+
+
+def test_missing_library_fails_loudly(tmp_path):
+    with pytest.raises(RuntimeError, match="no CPU or PyTorch fallback"):
+        ops.load_library(str(tmp_path / "nope.so"))
+
+
+def test_cpu_module_refuses_to_run():
+    cfg = vcfg.tiny()
+    m = FastImageCaptioning(cfg)
+    data = synth.make_text_inputs(cfg, 1)
+    data["image"] = synth.make_images(cfg, 1)
+    with pytest.raises(RuntimeError, match="CUDA device only"):
+        m(data)
+
+
+def test_unsupported_flags_raise():
+    cfg = vcfg.tiny()
+    m = FastImageCaptioning(cfg)
+    feats = torch.zeros(1, cfg.n_tokens, cfg.hidden)
+    base = dict(synth.default_test_extra_input(cfg), input_ids=synth.make_text_inputs(cfg, 1)["input_ids"])
+    for bad in (dict(use_cbs=True), dict(repetition_penalty=1.2), dict(num_beams=2, do_sample=True),
+                dict(num_keep_best=2), dict(head_mask=torch.ones(1))):
+        kw = dict(base)
+        kw.update(bad)
+        with pytest.raises((NotImplementedError, AssertionError)):
+            m.module(feats, **kw)
+    with pytest.raises(NotImplementedError):
+        m.module(feats, is_decode=False)
+    # a mask with a visible label region is refused, not silently mis-computed
+    ti = synth.make_text_inputs(cfg, 1)
+    ti["attention_mask"][:, :20, 20:] = 1
+    with pytest.raises(NotImplementedError, match="visible od/tag"):
+        m._check_canonical_mask(ti["attention_mask"], ti["input_ids"], 20)
+    m._check_canonical_mask(synth.make_text_inputs(cfg, 2)["attention_mask"], ti["input_ids"].repeat(2, 1), 20)

@@ -1,0 +1,361 @@
+"""Drop-in replacement for the reference's eval model
+``ImageCaptioning(ViTCAP(config), test_extra_input, image_encoder=InputAsDict(timm ViT))``
+(tagger_caption_uni_pipeline_expanding_bertemb.py:23-189, 566-618; modeling_bert.py:695-1059, 1307-1516).
+
+Same call contract:  ``model(data) -> (ids int64 (B*K, num_keep_best, max_length), logprobs fp32 (B*K, num_keep_best))``
+with ``data`` = {'image', 'input_ids', 'attention_mask', 'token_type_ids', 'masked_pos', 'key'} and the decode flags
+of ``test_extra_input``. Same parameter names, so ``state_dict`` / ``Checkpointer.load`` work unchanged.
+All compute runs in the sm_100a kernels of libvitcap_b200.so; this file only holds parameters and orchestration.
+"""
+import torch
+import torch.nn as nn
+
+from . import ops, synth
+from .config import VitCapConfig
+from .engine import CaptionEngine, PackedWeights
+
+
+# --------------------------------------------------------------------------- parameter containers (never "called")
+class _Mlp(nn.Module):
+    def __init__(self, h, f):
+        super().__init__()
+        self.fc1 = nn.Linear(h, f)
+        self.fc2 = nn.Linear(f, h)
+
+
+class _Attn(nn.Module):
+    def __init__(self, h):
+        super().__init__()
+        self.qkv = nn.Linear(h, 3 * h)
+        self.proj = nn.Linear(h, h)
+
+
+class _Block(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(cfg.hidden, eps=cfg.vit_ln_eps)
+        self.attn = _Attn(cfg.hidden)
+        self.norm2 = nn.LayerNorm(cfg.hidden, eps=cfg.vit_ln_eps)
+        self.mlp = _Mlp(cfg.hidden, cfg.inter)
+
+
+class _SplitEncoder(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        self.blocks = nn.ModuleList([_Block(cfg) for _ in range(cfg.enc_blocks)])
+        self.tag_blocks = nn.ModuleList([_Block(cfg) for _ in range(cfg.split_blocks)])
+
+
+class _Embeddings(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        self.word_embeddings = nn.Embedding(cfg.vocab, cfg.hidden)
+        self.position_embeddings = nn.Embedding(cfg.max_pos, cfg.hidden)
+        self.token_type_embeddings = nn.Embedding(cfg.type_vocab, cfg.hidden)
+        self.LayerNorm = nn.LayerNorm(cfg.hidden, eps=cfg.bert_ln_eps)
+
+
+class _Dense(nn.Module):
+    def __init__(self, i, o):
+        super().__init__()
+        self.dense = nn.Linear(i, o)
+
+
+class _DenseLN(nn.Module):
+    def __init__(self, i, o, eps):
+        super().__init__()
+        self.dense = nn.Linear(i, o)
+        self.LayerNorm = nn.LayerNorm(o, eps=eps)
+
+
+class _SelfAttn(nn.Module):
+    def __init__(self, h):
+        super().__init__()
+        self.query = nn.Linear(h, h)
+        self.key = nn.Linear(h, h)
+        self.value = nn.Linear(h, h)
+
+
+class _BertAttention(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        self.self = _SelfAttn(cfg.hidden)
+        self.output = _DenseLN(cfg.hidden, cfg.hidden, cfg.bert_ln_eps)
+
+
+class _BertLayer(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        self.attention = _BertAttention(cfg)
+        self.intermediate = _Dense(cfg.hidden, cfg.inter)
+        self.output = _DenseLN(cfg.inter, cfg.hidden, cfg.bert_ln_eps)
+
+
+class _BertEncoder(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        self.layer = nn.ModuleList([_BertLayer(cfg) for _ in range(cfg.dec_layers)])
+
+
+class _Predictions(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        self.bias = nn.Parameter(torch.zeros(cfg.vocab))
+        self.transform = _DenseLN(cfg.hidden, cfg.hidden, cfg.bert_ln_eps)
+        self.decoder = nn.Linear(cfg.hidden, cfg.vocab, bias=False)
+
+
+class _Heads(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        self.predictions = _Predictions(cfg)
+
+
+class _Bert(nn.Module):
+    """Parameter layout of ViTSplitCLSEmbModel (modeling_bert.py:1307-1365)."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        self.embeddings = _Embeddings(cfg)
+        self.extra_embeddings = _Embeddings(cfg)       # unused when tagemb == 'cls'; kept for checkpoint compatibility
+        self.encoder = _SplitEncoder(cfg)
+        self.caption_pooler = _Dense(cfg.hidden, cfg.hidden)   # dead in eval (modeling_bert.py:1513, result unused)
+        self.pooler = _Dense(cfg.hidden, cfg.hidden)
+        self.tag_logit = _Heads(cfg)
+        self.decoder = _BertEncoder(cfg)
+
+
+class _PatchEmbed(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        self.proj = nn.Conv2d(3, cfg.hidden, kernel_size=cfg.patch, stride=cfg.patch)
+
+
+class _TimmVit(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        self.cls_token = nn.Parameter(torch.zeros(1, 1, cfg.hidden))
+        self.pos_embed = nn.Parameter(torch.zeros(1, cfg.n_tokens, cfg.hidden))
+        self.patch_embed = _PatchEmbed(cfg)
+        self.head = nn.Linear(cfg.hidden, 1000)        # unused classifier head of the timm model
+
+
+_UNSUPPORTED = "vitcap_b200 does not implement %s (the reference path for it is host-side Python; see DESIGN.md)"
+
+
+class FastImageEncoder(nn.Module):
+    """``InputAsDict(timm ViT with blocks=[] and norm=Identity)`` (pipeline file lines 750-778): patch embed + cls + pos."""
+
+    def __init__(self, cfg, owner):
+        super().__init__()
+        self.module = _TimmVit(cfg)
+        self._owner = [owner]          # list: not registered as a sub-module
+
+    def forward(self, data_dict):
+        im = data_dict if isinstance(data_dict, torch.Tensor) else data_dict["image"]
+        return self._owner[0]._patch_embed(im)
+
+
+class FastViTCAP(nn.Module):
+    """``ViTCAP`` (modeling_bert.py:695-1059) with the same ``forward``/``generate`` signatures."""
+
+    def __init__(self, cfg, owner):
+        super().__init__()
+        self.cfg = cfg
+        self.bert = _Bert(cfg)
+        self.cls = _Heads(cfg)
+        self.cls.predictions.decoder.weight = self.bert.embeddings.word_embeddings.weight    # tie_weights, :728-730
+        self._owner = [owner]
+
+    def forward(self, *args, **kwargs):
+        if kwargs.get("inference_mode", ""):
+            raise NotImplementedError(_UNSUPPORTED % "inference_mode='prod'/'prod_no_hidden' (batch-1 paths)")
+        if kwargs.get("is_decode", False):
+            return self.generate(*args, **kwargs)
+        raise NotImplementedError(_UNSUPPORTED % "encode_forward (training / teacher-forced scoring)")
+
+    def generate(self, img_feats, label=None, attention_mask=None, masked_pos=None, token_type_ids=None,
+                 position_ids=None, head_mask=None, input_ids=None, max_length=None, do_sample=None, num_beams=None,
+                 temperature=None, top_k=None, top_p=None, repetition_penalty=None, bos_token_id=None, pad_token_id=None,
+                 eos_token_ids=None, mask_token_id=None, length_penalty=None, num_return_sequences=None, num_keep_best=1,
+                 is_decode=None, add_od_labels=False, od_labels_start_posid=None, use_cbs=False, fsm=None,
+                 num_constraints=None, min_constraints_to_satisfy=None, use_hypo=False, decoding_constraint_flag=None,
+                 bad_ending_ids=None, gen_tag_ratio=None, seed=None):
+        assert is_decode
+        owner = self._owner[0]
+        cfg = self.cfg
+        if use_cbs:
+            raise NotImplementedError(_UNSUPPORTED % "constrained beam search (use_cbs)")
+        if repetition_penalty not in (None, 1, 1.0):
+            raise NotImplementedError(_UNSUPPORTED % "repetition_penalty != 1")
+        if head_mask is not None:
+            raise NotImplementedError(_UNSUPPORTED % "head_mask")
+        if position_ids is not None:
+            raise NotImplementedError(_UNSUPPORTED % "caller-supplied position_ids")
+        num_beams = 1 if num_beams is None else int(num_beams)
+        nret = 1 if num_return_sequences is None else int(num_return_sequences)
+        if num_beams > 1 and do_sample:
+            raise NotImplementedError(_UNSUPPORTED % "beam sampling (num_beams > 1 with do_sample)")
+        if num_beams > 1 and nret != 1:
+            raise NotImplementedError(_UNSUPPORTED % "num_return_sequences > 1 with beam search")
+        if num_beams == 1 and num_keep_best != 1:
+            raise AssertionError("cannot generate >1 sentences in greedy search")      # modeling_utils.py:785
+        B = img_feats.shape[0]
+        assert input_ids is not None and input_ids.shape[0] == B                    # modeling_bert.py:962
+        max_length = int(max_length)
+        if max_length > cfg.max_seq or max_length < 2:
+            raise ValueError("max_length must be in [2, %d]" % cfg.max_seq)
+        owner._check_canonical_mask(attention_mask, input_ids, max_length)
+        return owner._generate(img_feats, max_length=max_length, do_sample=bool(do_sample), num_beams=num_beams,
+                               temperature=float(1.0 if temperature is None else temperature),
+                               top_k=int(top_k or 0), top_p=float(1.0 if top_p is None else top_p),
+                               bos=int(bos_token_id), pad=int(pad_token_id), eos_ids=[int(e) for e in eos_token_ids],
+                               mask_id=int(mask_token_id), length_penalty=float(1.0 if length_penalty is None else length_penalty),
+                               nret=nret, keep=int(num_keep_best), seed=seed)
+
+
+class FastImageCaptioning(nn.Module):
+    """B200-native ``ImageCaptioning`` (eval branch). ``mode``: 'bf16' = tcgen05 tensor cores, bf16 operands, fp32
+    accumulation; 'fp32' = exact mode on CUDA cores (token ids / tag indices match the fp32 reference)."""
+
+    def __init__(self, cfg: VitCapConfig, test_extra_input=None, mode="bf16", tokenizer=None, max_batch=64,
+                 use_cuda_graph=True, sample_seed=0):
+        super().__init__()
+        assert mode in ("bf16", "fp32")
+        self.cfg = cfg
+        self.mode = mode
+        self.module = FastViTCAP(cfg, self)
+        self.image_encoder = FastImageEncoder(cfg, self)
+        self.test_extra_input = dict(test_extra_input) if test_extra_input is not None else synth.default_test_extra_input(cfg)
+        self.tokenizer = tokenizer
+        self.max_batch = max_batch
+        self.use_cuda_graph = use_cuda_graph
+        self.sample_seed = sample_seed
+        self._engine = None
+        self._sample_calls = 0
+        self.register_load_state_dict_post_hook(lambda m, keys: m._invalidate())
+        self.eval()
+
+    # ---- packing -----------------------------------------------------------------------------------------------------
+    def _invalidate(self):
+        self._engine = None
+
+    def pack(self):
+        """(Re)builds the kernel-side weight copies from the current parameters. Called lazily by forward()."""
+        ops.load_library()
+        dev = self.module.bert.embeddings.word_embeddings.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("vitcap_b200 runs on a CUDA device only (no CPU path): move the module with .cuda() first")
+        sd = self.state_dict()
+        w = PackedWeights(self.cfg, sd, self.mode, dev)
+        self._engine = CaptionEngine(self.cfg, w, dev, use_cuda_graph=self.use_cuda_graph)
+        return self
+
+    @property
+    def engine(self):
+        if self._engine is None:
+            self.pack()
+        return self._engine
+
+    # ---- pieces called by the sub-modules ----------------------------------------------------------------------------
+    def _patch_embed(self, image):
+        image = image.to(dtype=torch.float32).contiguous()
+        if image.shape[-1] != self.cfg.img_size or image.shape[-2] != self.cfg.img_size:
+            raise NotImplementedError(_UNSUPPORTED % "position-embedding interpolation for a different image size")
+        return self.engine.patch_embed(image)
+
+    def _check_canonical_mask(self, attention_mask, input_ids, max_length):
+        """The eval pipeline always passes the 70x70 mask whose only non-zeros are the caption triangle
+        (dataset.py:371-390 with text_b == ''), i.e. the 50 od/tag slots are attended by no row.
+        The kernels encode exactly that structure; anything else is refused instead of silently diverging."""
+        if attention_mask is None:
+            return
+        cfg = self.cfg
+        m = attention_mask
+        if m.dim() != 3 or m.shape[1] != m.shape[2]:
+            raise NotImplementedError(_UNSUPPORTED % "attention_mask that is not (B, S, S)")
+        S = m.shape[1]
+        n_img = cfg.n_tokens
+        if S == input_ids.shape[1] + n_img:          # full mask built by construct_attn_mask: check its text block
+            m = m[:, :input_ids.shape[1], :input_ids.shape[1]]
+            S = m.shape[1]
+        a = max_length
+        ref = torch.zeros(S, S, device=m.device, dtype=m.dtype)
+        ref[:a, :a] = torch.tril(torch.ones(a, a, device=m.device, dtype=m.dtype))
+        if not bool((m == ref.unsqueeze(0)).all()):
+            raise NotImplementedError(_UNSUPPORTED % "a text attention mask with a visible od/tag label region")
+
+    def _generate(self, img_feats, max_length, do_sample, num_beams, temperature, top_k, top_p, bos, pad, eos_ids, mask_id,
+                  length_penalty, nret, keep, seed):
+        eng = self.engine
+        B = img_feats.shape[0]
+        outs_i, outs_l = [], []
+        if do_sample:
+            if seed is None:
+                seed = self.sample_seed + self._sample_calls * 0x9E3779B97F4A7C15
+                self._sample_calls += 1
+        for s in range(0, B, self.max_batch):
+            chunk = img_feats[s:s + self.max_batch]
+            b = chunk.shape[0]
+            eng.encode(chunk)
+            eng.tag_head(b)
+            eng.prefill(b)
+            if num_beams > 1:
+                ids, lp = eng.beam_search(b, num_beams, max_length, bos, pad, eos_ids, mask_id, length_penalty, keep)
+            else:
+                ids, lp = eng.greedy_or_sample(b, nret, max_length, bos, pad, eos_ids, mask_id, do_sample, temperature, top_k,
+                                               top_p, seed=(seed + s) if do_sample else 0)
+            outs_i.append(ids)
+            outs_l.append(lp)
+        return torch.cat(outs_i, 0), torch.cat(outs_l, 0)
+
+    # ---- public entry points -----------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, data):
+        """Eval branch of ImageCaptioning.forward (pipeline file lines 87-112, 173-184)."""
+        if self.training:
+            raise NotImplementedError(_UNSUPPORTED % "training mode")
+        data = dict(data.items())
+        data.pop("key", None)
+        image = data.pop("image")
+        B = image.shape[0]
+        extra = dict(self.test_extra_input)
+        ids_all, lp_all = [], []
+        for s in range(0, B, self.max_batch):      # the image stream buffer holds max_batch images
+            sub = {k: (v[s:s + self.max_batch] if torch.is_tensor(v) and v.shape[:1] == (B,) else v) for k, v in data.items()}
+            sub["img_feats"] = self.image_encoder({"image": image[s:s + self.max_batch]})
+            sub["gen_tag_ratio"] = 1
+            sub.update(extra)
+            ids, lp = self.module(**sub)
+            ids_all.append(ids)
+            lp_all.append(lp)
+        return torch.cat(ids_all, 0), torch.cat(lp_all, 0)
+
+    @torch.no_grad()
+    def forward_tags(self, image, caption_branch=True):
+        """Additive API (BASELINE config 2): patch embed -> split encoder -> concept head -> top-k.
+        Returns (tag_logits fp32 [B,V], topk_idx int64 [B,K] sorted by score, topk_prob fp32 [B,K], topk_len int64 [B])
+        = what ``bert(...)`` computes at modeling_bert.py:1415-1432."""
+        eng = self.engine
+        outs = []
+        for s in range(0, image.shape[0], self.max_batch):
+            f = self._patch_embed(image[s:s + self.max_batch])
+            eng.encode(f, caption_branch=caption_branch)
+            lg, idx, pr, n = eng.tag_head(f.shape[0])
+            outs.append((lg.clone(), idx.long(), pr.clone(), n.long()))
+        return tuple(torch.cat([o[i] for o in outs], 0) for i in range(4))
+
+    @torch.no_grad()
+    def encode_features(self, image):
+        """(caption feats, tag feats) fp32 [B,N,H] of the split encoder (modeling_bert.py:458-478), for parity checks."""
+        eng = self.engine
+        assert image.shape[0] <= self.max_batch
+        f = self._patch_embed(image)
+        cap, tag = eng.encode(f)
+        return cap.clone(), tag.clone()
+
+
+def build_from_state_dict(cfg, state_dict, device="cuda", **kw):
+    m = FastImageCaptioning(cfg, **kw)
+    m.load_state_dict(state_dict, strict=True)
+    return m.to(device)

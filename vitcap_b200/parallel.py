@@ -1,0 +1,90 @@
+"""Data-parallel plumbing: one process per GPU, images sharded in contiguous chunks, ONE collective per batch.
+
+The reference shards the test set with a contiguous-chunk ``DistributedSampler`` (src/data_layer/samplers.py:86-146:
+pad by wrapping, rank r takes [r*n, (r+1)*n)), has every rank write ``..._{rank}_{size}.tsv`` and lets rank 0
+concatenate / re-order / de-duplicate the files behind a barrier (uni_pipeline.py:783-831). Here the same sharding
+is kept and the files are replaced by a single all-gather of a packed per-image record
+{ids int32[max_len*keep], logprob f32[keep], tag_idx int32[K], tag_prob f32[K]} (484 B per image at the defaults)
+over NCCL (NVLink 5 / NVSwitch); gloo is used by the CPU tests.
+"""
+import math
+
+import torch
+import torch.distributed as dist
+
+
+def shard_indices(n_items, world_size, rank):
+    """Indices of the reference's non-shuffled DistributedSampler for ``rank`` (samplers.py:127-146)."""
+    num_samples = int(math.ceil(n_items * 1.0 / world_size))
+    total = num_samples * world_size
+    idx = list(range(n_items))
+    assert total - len(idx) <= len(idx), "not implemented (same limit as the reference)"
+    idx += idx[: total - len(idx)]
+    return idx[num_samples * rank: num_samples * (rank + 1)]
+
+
+def pack_records(ids, logprobs, tag_idx=None, tag_prob=None):
+    """(B,keep,L) int64, (B,keep) f32, (B,K) int, (B,K) f32 -> int32 (B, W) record matrix (floats bit-cast)."""
+    B = ids.shape[0]
+    parts = [ids.reshape(B, -1).to(torch.int32), logprobs.reshape(B, -1).float().contiguous().view(torch.int32)]
+    if tag_idx is not None:
+        parts.append(tag_idx.reshape(B, -1).to(torch.int32))
+        parts.append(tag_prob.reshape(B, -1).float().contiguous().view(torch.int32))
+    return torch.cat(parts, dim=1).contiguous()
+
+
+def unpack_records(rec, keep, max_len, topk=None):
+    B = rec.shape[0]
+    o = 0
+    ids = rec[:, o:o + keep * max_len].to(torch.int64).view(B, keep, max_len)
+    o += keep * max_len
+    lp = rec[:, o:o + keep].contiguous().view(torch.float32).view(B, keep)
+    o += keep
+    if topk is None:
+        return ids, lp
+    tag_idx = rec[:, o:o + topk].to(torch.int64)
+    o += topk
+    tag_prob = rec[:, o:o + topk].contiguous().view(torch.float32)
+    return ids, lp, tag_idx, tag_prob
+
+
+def all_gather_records(rec, group=None):
+    """rec int32 (b, W) per rank (same b on every rank) -> (world*b, W), rank-major == dataset order of the
+    contiguous-chunk sharding."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return rec
+    world = dist.get_world_size(group)
+    out = torch.empty(world * rec.shape[0], rec.shape[1], dtype=rec.dtype, device=rec.device)
+    dist.all_gather_into_tensor(out, rec.contiguous(), group=group)
+    return out
+
+
+def gather_in_dataset_order(rec, n_items, group=None):
+    """All-gather + drop the wrap-around padding rows (the reference de-duplicates by key on rank 0, uni_pipeline.py:822-828)."""
+    full = all_gather_records(rec, group)
+    return full[:n_items]
+
+
+class DataParallelCaptioner:
+    """Runs a FastImageCaptioning replica on this rank's shard and returns the gathered results of the whole batch."""
+
+    def __init__(self, model, group=None, with_tags=False):
+        self.model = model
+        self.group = group
+        self.with_tags = with_tags
+
+    @torch.no_grad()
+    def __call__(self, data):
+        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        rank = dist.get_rank(self.group) if dist.is_initialized() else 0
+        n = data["image"].shape[0]
+        idx = shard_indices(n, world, rank)
+        sel = torch.as_tensor(idx, device=data["image"].device)
+        sub = {k: (v.index_select(0, sel) if torch.is_tensor(v) and v.shape[:1] == (n,) else v) for k, v in data.items()}
+        if "key" in data and not torch.is_tensor(data["key"]):
+            sub["key"] = [data["key"][i] for i in idx]
+        ids, lp = self.model(sub)
+        keep, max_len = ids.shape[1], ids.shape[2]
+        rec = pack_records(ids, lp)
+        full = gather_in_dataset_order(rec, n * (ids.shape[0] // len(idx)), self.group)
+        return unpack_records(full, keep, max_len)
