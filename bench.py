@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""Benchmark of the ViTCAP caption hot path on B200 (driver contract: one JSON line on stdout from rank 0).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (bf16, tcgen05)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host CPU cores
+
+A step = one pass of the hot path (patch embed -> split ViT encoder -> concept head/top-50 -> decoder prefill ->
+19 greedy decode steps -> token ids) over one batch of 512 synthetic 384x384 images per GPU (BASELINE.json configs[2],
+the configuration the metric "images/sec captioned" is quoted on). Weak scaling: every rank captions its own 512 images
+and the packed results are all-gathered (the path's only exchange step).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "images/sec captioned (ViT-B/16-384, 20-tok greedy)"
+UNIT = "images/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=512, help="images per GPU per step")
+    ap.add_argument("--variant", default="16_384")
+    ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--dec-layers", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-sample-images", type=int, default=2)
+    return ap.parse_args()
+
+
+def workload_config(args, cfg):
+    return {
+        "workload": "BASELINE.json configs[2]: full ViTCAP greedy captioning, ViT-B/16-%d, %d-layer decoder, max_len 20, "
+                    "batch %d per GPU, data-parallel" % (cfg.img_size, cfg.dec_layers, args.batch),
+        "variant": args.variant, "batch_per_gpu": args.batch, "global_batch": args.batch * max(1, args.gpus),
+        "max_length": 20, "num_beams": 1, "decoder_layers": cfg.dec_layers, "parallelism": "dp%d" % max(1, args.gpus),
+        "weights": "random-init (synth.make_state_dict seed 0, reference layout)",
+        "l2": "inputs larger than L2 (906 MB of images and >10 GB of activations per step vs 126 MB L2)",
+    }
+
+
+# ------------------------------------------------------------------------------------------------ clocks sampling
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        load = [s for s, p in zip(sm, pw) if p > 300] or sm
+        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU baseline
+def cpu_baseline(cfg, sd, n_images, extra):
+    """The reference's algorithm as shipped (every decode step re-runs the ViT trunk, the tag head and the whole decoder;
+    oracle/port.py 'faithful', pinned against the reference's own outputs in tests/golden) on the host cores."""
+    import torch
+    from oracle import port
+    from vitcap_b200 import synth
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    pm = port.PortModel(cfg, sd)
+    data = synth.make_text_inputs(cfg, n_images)
+    data["image"] = synth.make_images(cfg, n_images, seed=1234)
+    t0 = time.time()
+    with torch.no_grad():
+        ids, lp = port.caption(pm, data, extra, algorithm="faithful")
+    dt = time.time() - t0
+    return {"value": n_images / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "%d image(s) of the same workload (ViT-B/16-%d, 20-token greedy, fp32, reference algorithm without KV cache: "
+                      "19 full-model calls), %.1f s" % (n_images, cfg.img_size, dt)}, ids
+
+
+def run_reference_arm(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from vitcap_b200 import config as vcfg
+    from vitcap_b200 import synth
+    from oracle import port
+    cfg = vcfg.variant(args.variant, dec_layers=args.dec_layers)
+    sd = synth.make_state_dict(cfg, seed=0)
+    extra = synth.default_test_extra_input(cfg)
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    pm = port.PortModel(cfg, sd)
+    per_step = 1
+    data = synth.make_text_inputs(cfg, per_step)
+    data["image"] = synth.make_images(cfg, per_step, seed=1234)
+    times = []
+    budget = 240.0
+    t_start = time.time()
+    done_steps = 0
+    for i in range(args.warmup + args.steps):
+        t0 = time.time()
+        with torch.no_grad():
+            port.caption(pm, data, extra, algorithm="faithful")
+        dt = time.time() - t0
+        if i >= args.warmup:
+            times.append(dt)
+            done_steps += 1
+        # keep the whole arm within a few minutes on slow hosts: stop early but never before one timed step
+        if time.time() - t_start > budget and done_steps >= 1:
+            break
+    total = sum(times)
+    value = per_step * len(times) / total
+    sample = "%d timed step(s) of %d image(s) each, reference algorithm (no KV cache, 19 full-model calls per caption), fp32, " \
+             "%d host threads" % (len(times), per_step, threads)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, cfg),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ B200 arm
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+    import torch
+    import torch.distributed as dist
+    from vitcap_b200 import config as vcfg
+    from vitcap_b200 import ops, parallel, synth
+    from vitcap_b200.model import FastImageCaptioning
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the caption path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg = vcfg.variant(args.variant, dec_layers=args.dec_layers)
+    sd = synth.make_state_dict(cfg, seed=0)
+    extra = synth.default_test_extra_input(cfg)
+    B = args.batch
+    model = FastImageCaptioning(cfg, test_extra_input=extra, mode=args.mode, max_batch=B)
+    model.load_state_dict(sd)
+    model = model.to(dev)
+    host = synth.make_text_inputs(cfg, B)
+    # every rank captions different images (seed by rank)
+    img_host = synth.make_images(cfg, B, seed=1234 + rank).pin_memory()
+    text_dev = {k: v.to(dev) for k, v in host.items()}
+    img_dev = img_host.to(dev)
+    data_dev = dict(text_dev, image=img_dev)
+
+    def step_device():
+        ids, lp = model(data_dev)
+        rec = parallel.pack_records(ids, lp, model.engine._enc_ws["tag_idx"][:B], model.engine._enc_ws["tag_prob"][:B])
+        return parallel.all_gather_records(rec)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- GEMM profiler: CUDA events around every eager tensor-core GEMM launch of the timed steps
+    prof = []
+    ops.GEMM_PROFILE = None
+    for _ in range(args.warmup):
+        step_device()
+    sync_all()
+    ops.reset_launch_count()
+    replays0 = model.engine.stats.get("graph_replays", 0)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ops.GEMM_PROFILE = prof
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    ev0.record()
+    for _ in range(args.steps):
+        out = step_device()
+    ev1.record()
+    sync_all()
+    ops.GEMM_PROFILE = None
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    eager = ops.launch_count()
+    replays = model.engine.stats.get("graph_replays", 0) - replays0
+    launches = eager + replays * model.engine.stats.get("graph_kernels", 0)
+    value = world * B * args.steps / (ms_max / 1e3)
+
+    # ---- roofline of the dominant kernel (gemm_tc_kernel): algorithmic FLOPs / measured duration
+    flops = sum(p[0] for p in prof)
+    gemm_ms = sum(p[1].elapsed_time(p[2]) for p in prof)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = peaks.get("bf16_tflops_sustained")
+    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
+    if not peak:
+        peak, peak_src = 1400.0, "fallback (B200_PROFILING.md: ~1.4 PFLOP/s sustained)"
+    achieved = flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    roofline = {
+        "kernel": "gemm_tc_kernel (tcgen05 bf16 GEMM; %d eager launches/step: ViT qkv/proj/fc1/fc2, patch embed, decoder prefill, heads)"
+                  % (len(prof) // max(1, args.steps)),
+        "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+        "peak_source": peak_src, "traffic": None,
+        "share_of_step": gemm_ms / ms if ms > 0 else None,
+        "algorithmic_flops_per_step": flops / max(1, args.steps),
+    }
+
+    # ---- e2e: same step through the public module call with HOST buffers (pinned), H2D + D2H inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        host_data = {k: v.pin_memory() for k, v in host.items()}
+        out_host = torch.empty(world * B, out.shape[1], dtype=out.dtype).pin_memory()
+
+        def step_e2e():
+            d = {k: v.to(dev, non_blocking=True) for k, v in host_data.items()}
+            d["image"] = img_host.to(dev, non_blocking=True)
+            ids, lp = model(d)
+            rec = parallel.pack_records(ids, lp, model.engine._enc_ws["tag_idx"][:B], model.engine._enc_ws["tag_prob"][:B])
+            full = parallel.all_gather_records(rec)
+            out_host.copy_(full, non_blocking=True)
+            torch.cuda.current_stream().synchronize()        # the caller reads the captions on the host
+            return full
+
+        step_e2e()
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_e2e = max(1, min(args.steps, 5))
+        t0 = time.time()
+        e0.record()
+        for _ in range(n_e2e):
+            step_e2e()
+        e1.record()
+        sync_all()
+        wall = time.time() - t0
+        ems = max(e0.elapsed_time(e1), wall * 1e3)
+        te = torch.tensor([ems], device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        h2d = img_host.numel() * 4 + sum(v.numel() * v.element_size() for v in host_data.values())
+        e2e = {"value": world * B * n_e2e / (float(te.item()) / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(out_host.numel() * out_host.element_size()), "steps": n_e2e}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if args.mode == "bf16" else "f32", "data": "synthetic", "config": workload_config(args, cfg),
+        "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cb, _ = cpu_baseline(cfg, sd, args.cpu_sample_images, extra)
+        line["cpu_baseline"] = cb
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

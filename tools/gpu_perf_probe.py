@@ -1,0 +1,115 @@
+"""Per-kernel and per-stage timing on the GPU (CUDA events, warm, inputs larger than L2). Not a bench value: it is the
+map of where a step's time goes, used to pick the next kernel to optimise."""
+import json
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from vitcap_b200 import config as vcfg  # noqa: E402
+from vitcap_b200 import ops, synth  # noqa: E402
+from vitcap_b200.model import FastImageCaptioning  # noqa: E402
+
+dev = torch.device("cuda:0")
+
+
+def timeit(fn, iters=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def gemm_probe(B):
+    M = B * 577
+    res = []
+    for (N, K, act, resid, outf32, name) in [(2304, 768, 0, False, False, "qkv"), (768, 768, 0, True, True, "proj+res"),
+                                             (3072, 768, 1, False, False, "fc1+gelu"), (768, 3072, 0, True, True, "fc2+res")]:
+        a = torch.randn(M, K, device=dev).to(torch.bfloat16)
+        w = (torch.randn(N, K, device=dev) * 0.02).to(torch.bfloat16)
+        b = torch.randn(N, device=dev)
+        out = torch.empty(M, N, device=dev, dtype=torch.float32 if outf32 else torch.bfloat16)
+        r = out if resid else None
+        if resid:
+            out.normal_()
+        for tn in (256, 128):
+            ms = timeit(lambda: ops.linear(a, w, b, out, act=act, resid=r, impl="tc", tile_n=tn))
+            tf = 2.0 * M * N * K / ms / 1e9
+            res.append((name, M, N, K, tn, ms, tf))
+            print("gemm %-9s M=%d N=%d K=%d tile_n=%d: %.3f ms  %.1f TFLOP/s" % (name, M, N, K, tn, ms, tf), flush=True)
+        # torch (cuBLAS) comparator for the plain product
+        ms = timeit(lambda: torch.matmul(a, w.t()))
+        print("     cublas bf16 matmul same shape: %.3f ms  %.1f TFLOP/s" % (ms, 2.0 * M * N * K / ms / 1e9), flush=True)
+        del a, w, out
+    return res
+
+
+def attn_probe(B):
+    N, heads = 577, 12
+    qkv = torch.randn(B, N, 3 * 768, device=dev).to(torch.bfloat16)
+    out = torch.empty(B, N, 768, device=dev, dtype=torch.bfloat16)
+    ms = timeit(lambda: ops.attention(qkv, out, B, N, heads, 0.125))
+    fl = 4.0 * B * heads * N * N * 64
+    print("attention_tc B=%d N=%d: %.3f ms  %.1f TFLOP/s (algorithmic)" % (B, N, ms, fl / ms / 1e9), flush=True)
+    q, k, v = qkv.view(B, N, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    ms2 = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(q, k, v))
+    print("     torch SDPA same shape: %.3f ms  %.1f TFLOP/s" % (ms2, fl / ms2 / 1e9), flush=True)
+
+
+def ln_probe(B):
+    rows = B * 577
+    x = torch.randn(rows, 768, device=dev)
+    g, b = torch.randn(768, device=dev), torch.randn(768, device=dev)
+    o = torch.empty(rows, 768, device=dev, dtype=torch.bfloat16)
+    ms = timeit(lambda: ops.layernorm(x, g, b, 1e-6, out_t=o))
+    print("layernorm rows=%d: %.3f ms  %.0f GB/s" % (rows, ms, rows * 768 * 6 / ms / 1e6), flush=True)
+
+
+def stage_probe(B, variant="16_384"):
+    cfg = vcfg.variant(variant)
+    sd = synth.make_state_dict(cfg, seed=0)
+    m = FastImageCaptioning(cfg, mode="bf16", max_batch=B)
+    m.load_state_dict(sd)
+    m = m.to(dev)
+    img = synth.make_images(cfg, B, seed=1).to(dev)
+    eng = m.engine
+    data = {k: v.to(dev) for k, v in synth.make_text_inputs(cfg, B).items()}
+    data["image"] = img
+    m(data)
+    m(data)
+    torch.cuda.synchronize()
+    t = {}
+    t["patch_embed"] = timeit(lambda: eng.patch_embed(img), iters=3, warm=1)
+    f = eng.patch_embed(img)
+    t["encode(16 blocks)"] = timeit(lambda: eng.encode(f), iters=3, warm=1)
+    t["tag_head"] = timeit(lambda: eng.tag_head(B), iters=3, warm=1)
+    t["prefill"] = timeit(lambda: eng.prefill(B), iters=3, warm=1)
+    ex = m.test_extra_input
+    t["decode(19 steps, graph)"] = timeit(lambda: eng.greedy_or_sample(B, 1, 20, 101, 0, [102], 103), iters=3, warm=1)
+    t["full forward"] = timeit(lambda: m(data), iters=3, warm=1)
+    for k, v in t.items():
+        print("stage %-26s %.2f ms" % (k, v), flush=True)
+    print("images/s (full forward): %.1f" % (B / t["full forward"] * 1e3))
+    print("graph kernels per decode loop:", eng.stats.get("graph_kernels"))
+    return t
+
+
+if __name__ == "__main__":
+    B = int(sys.argv[1]) if len(sys.argv) > 1 else 512
+    what = sys.argv[2] if len(sys.argv) > 2 else "all"
+    print(torch.cuda.get_device_name(0), "B =", B, flush=True)
+    if what in ("all", "gemm"):
+        gemm_probe(B)
+    if what in ("all", "attn"):
+        attn_probe(B)
+        ln_probe(B)
+    if what in ("all", "stage"):
+        stage_probe(B)

@@ -42,6 +42,10 @@ SIGNATURES = {
 
 _lib = None
 
+# bench.py instrumentation: when set to a list, every eager tensor-core GEMM launch is bracketed by CUDA events on the
+# launching stream and (flops, start_event, end_event) is appended (graph-captured launches are skipped).
+GEMM_PROFILE = None
+
 
 def load_library(path=None):
     """Loads the shared library (no GPU needed) and declares all prototypes."""
@@ -120,7 +124,15 @@ def linear(a, w, bias, out, act=ACT_NONE, resid=None, M=None, lda=None, ldo=None
     else:
         if a.dtype == torch.float32:
             assert out_f32, "exact mode writes fp32"
-        _check(lib.vc_linear(_is_bf16(a), *args, _stream()), "vc_linear")
+        prof = GEMM_PROFILE
+        if prof is not None and a.dtype == torch.bfloat16 and not torch.cuda.is_current_stream_capturing():
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _check(lib.vc_linear(1, *args, _stream()), "vc_linear")
+            e1.record()
+            prof.append((2.0 * M * N * K, e0, e1))
+        else:
+            _check(lib.vc_linear(_is_bf16(a), *args, _stream()), "vc_linear")
     return out
 
 
