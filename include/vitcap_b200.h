@@ -47,7 +47,9 @@ void vc_reset_launch_count(void);
  *         (requires K % 64 == 0, 16-byte aligned pointers, pitches % 8 == 0).
  * bf16=0: A, W fp32, CUDA-core FFMA tiles (K % 16 == 0).
  * out_f32: output element type (1 = fp32, 0 = bf16 in fast mode / fp32 in exact mode is selected by the caller).
- * bias may be NULL; resid (fp32, pitch ldr) may be NULL and may alias out when out_f32 = 1. */
+ * bias may be NULL; resid (fp32, pitch ldr) may be NULL and may alias out when out_f32 = 1.
+ * bf16=1 stores tiles with TMA, which clips at 16-byte granularity: if N * sizeof(out element) is not a multiple of 16,
+ * the pad columns up to the next 16-byte boundary of each row (< ldo) are overwritten. */
 int vc_linear(int bf16, const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldo, int out_f32,
               int act, const float* resid, int ldr, int M, int N, int K, void* stream);
 /* same contract, forcing the CUDA-core kernel for bf16 operands (cross-check of the tensor-core kernel in tests) */

@@ -158,6 +158,42 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// smem -> global tile store (bulk async group completion)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N> __device__ __forceinline__ void bulk_wait_all() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// GELU with erf evaluated by an odd polynomial z*P(z^2) on |z| <= 3 (clamped beyond): |erf error| < 5e-5,
+// |gelu error| < 1e-4 absolute -- far below bf16 output resolution; 15 FMA-pipe instructions, no MUFU, no branch.
+// Used only by the bf16 tensor-core epilogue; the exact mode keeps erff.
+__device__ __forceinline__ float gelu_erf_poly(float x) {
+  float z = fminf(fmaxf(x * 0.70710678118654752440f, -3.0f), 3.0f);
+  const float u = z * z;
+  float p = 5.151738646e-08f;
+  p = fmaf(p, u, -2.354642769e-06f);
+  p = fmaf(p, u, 4.747118605e-05f);
+  p = fmaf(p, u, -5.641628908e-04f);
+  p = fmaf(p, u, 4.485614384e-03f);
+  p = fmaf(p, u, -2.576903463e-02f);
+  p = fmaf(p, u, 1.120150662e-01f);
+  p = fmaf(p, u, -3.758994344e-01f);
+  p = fmaf(p, u, 1.128372685e+00f);
+  const float hx = 0.5f * x;
+  return fmaf(hx, p * z, hx);
+}
+
 // ------------------------------------------------------------------------------------------
 // tcgen05 / TMEM
 // ------------------------------------------------------------------------------------------
@@ -239,6 +275,9 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 // 2-D bf16 tensor [rows, cols] with row pitch ld (elements); box = [box_rows, box_cols]; 128B swizzle
 int get_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                      uint32_t box_rows, uint32_t box_cols);
+// same for fp32 elements
+int get_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                    uint32_t box_rows, uint32_t box_cols);
 // 3-D bf16 tensor [d2, d1, d0(cols)] with pitches ld1, ld2 (elements); box = [1, box_rows, box_cols]
 int get_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t d2, uint64_t d1, uint64_t d0, uint64_t ld1,
                      uint64_t ld2, uint32_t box_rows, uint32_t box_cols);

@@ -72,7 +72,8 @@ static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmaps;
 static std::mutex g_tmap_mu;
 
 static int encode(CUtensorMap* out, const TmapKey& key, int rank, const void* base, const cuuint64_t* dims,
-                  const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+                  const cuuint64_t* strides_bytes, const cuuint32_t* box,
+                  CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16) {
   {
     std::lock_guard<std::mutex> g(g_tmap_mu);
     auto it = g_tmaps.find(key);
@@ -81,7 +82,7 @@ static int encode(CUtensorMap* out, const TmapKey& key, int rank, const void* ba
   EncodeTiledFn fn = encode_fn();
   if (!fn) { set_last_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)"); return VC_ERR_DRIVER; }
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
+  CUresult r = fn(out, dtype, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -102,6 +103,15 @@ int get_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t
   cuuint64_t strides[1] = {ld * 2};
   cuuint32_t box[2] = {box_cols, box_rows};
   return encode(out, key, 2, base, dims, strides, box);
+}
+
+int get_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                    uint32_t box_cols) {
+  TmapKey key = {{(uint64_t)(uintptr_t)base, rows, cols, ld, box_rows, box_cols, 2, 4}};
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 4};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  return encode(out, key, 2, base, dims, strides, box, CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
 }
 
 int get_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t d2, uint64_t d1, uint64_t d0, uint64_t ld1, uint64_t ld2,
