@@ -144,6 +144,19 @@ def test_attention_bf16(B, N, heads, impl):
     torch.testing.assert_close(out.float(), ref, rtol=2e-2, atol=2e-2)
 
 
+def test_attention_bf16_many_ctas():
+    """Enough (image, head) work items that CTAs are co-resident and SMs run several waves (pipeline hand-over,
+    TMEM re-allocation, barrier phase bookkeeping across tiles)."""
+    B, N, heads = 48, 577, 12
+    qkv = rnd(B, N, 3 * heads * 64, seed=9, dtype=torch.bfloat16)
+    out = torch.zeros(B, N, heads * 64, device=dev(), dtype=torch.bfloat16)
+    for _ in range(3):
+        ops.attention(qkv, out, B, N, heads, 0.125)
+    torch.cuda.synchronize()
+    ref = ref_attention(qkv, heads, 0.125)
+    torch.testing.assert_close(out.float(), ref, rtol=2e-2, atol=2e-2)
+
+
 def test_attention_bf16_peaky_scores():
     """Large-magnitude scores (online-softmax rescaling across chunks must stay exact)."""
     B, N, heads = 1, 577, 2

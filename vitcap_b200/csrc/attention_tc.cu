@@ -3,61 +3,117 @@
 // Replaces Attention.forward (vision_transformer.py:174-200; the additive mask is all zeros, modeling_bert.py:1415)
 // and BertSelfAttention over the 578 context rows (modeling_bert.py:303-340). The N x N scores never leave the SM.
 //
-// One CTA = one (image, head, 128-query tile). TMEM: S (128 x 128 fp32, columns 0..127) and O (128 x 64 fp32, columns
-// 128..191). Per 128-key chunk:  S = Q K_j^T (tcgen05.mma, both operands K-major smem)  ->  4 softmax warps, one query
-// row per thread: tcgen05.ld S, online max/sum, rescale O in TMEM, P = exp2(.) as bf16 into a 128B-swizzled smem tile
-// ->  O += P V_j (A = P K-major smem, B = V MN-major smem straight from the row-major qkv buffer).
-// K/V chunks are double-buffered by TMA (3-D tensor map over [B, N, 3H]: rows past N are zero-filled by the hardware).
-// Two CTAs are co-resident per SM (112 KB smem, 256 TMEM columns each), so one CTA's softmax overlaps the other's MMAs.
+// One CTA = one (image, head); it walks the 128-query tiles of that head and, inside each tile, the keys in 64-key chunks,
+// as ONE flattened software pipeline (no drain between tiles).
+//   TMEM   : S0, S1 (128 x 64 fp32, ping-pong over chunks) and O0, O1 (128 x 64 fp32, ping-pong over tiles) = 256 columns
+//   smem   : Q 2 x 16 KB (ping-pong over tiles), K ring 3 x 8 KB, V ring 3 x 8 KB, P 2 x 16 KB  (112 KB -> two CTAs per SM)
+//   control warp (1 elected thread): TMA loads (3-D tensor map over [B, N, 3H]; rows past N are zero-filled by hardware),
+//            S_g = Q K_j^T issued two chunks ahead of the softmax, O += P_g V_j (V consumed MN-major straight from the
+//            row-major qkv buffer); the next tile's Q is prefetched while the current tile is being processed
+//   4 softmax warps, one query row per thread: tcgen05.ld S_g, row max, lazy rescale of O (FA4-style: the exponent reference
+//            only moves when the max grew by > 2^8), P_g = exp2(.) as bf16 into a 128B-swizzled tile; per tile epilogue
+//            O / l -> bf16 -> global while the MMAs of the next tile already run.
+// The MUFU (exp2) pipe is the true bound of this d=64 attention (16 exp/clk/SM, measured); round-1 profiles showed the
+// single-buffered per-tile version spending most of its time in the serial MMA -> softmax -> MMA chain and in per-CTA
+// prologues, hence the ping-pong buffers and the persistent tile loop.
 #include "common.cuh"
 
 namespace vc {
 
 namespace {
-constexpr int QT = 128;           // queries per CTA
-constexpr int KT = 128;           // keys per chunk
+constexpr int QT = 128;           // queries per tile
+constexpr int KT = 64;            // keys per chunk
 constexpr int D = 64;             // head dim
-constexpr int TILE_BYTES = 128 * 64 * 2;   // 16 KB: [128 rows][64 bf16], 128B swizzle
-constexpr int SMEM_Q = 0;
-constexpr int SMEM_K = SMEM_Q + TILE_BYTES;              // 2 stages
-constexpr int SMEM_V = SMEM_K + 2 * TILE_BYTES;          // 2 stages
-constexpr int SMEM_P = SMEM_V + 2 * TILE_BYTES;          // 2 sub-tiles of 64 keys
-constexpr int SMEM_BAR = SMEM_P + 2 * TILE_BYTES;
-constexpr int SMEM_TOTAL = SMEM_BAR + 128;
+constexpr int Q_BYTES = 128 * 64 * 2;      // 16 KB  [128 rows][64 bf16], 128B swizzle
+constexpr int KV_BYTES = KT * 64 * 2;      // 8 KB   [64 keys][64 bf16]
+constexpr int P_BYTES = 128 * KT * 2;      // 16 KB  [128 rows][64 keys]
+constexpr int NKV = 3;                     // K/V ring depth
+constexpr int SMEM_Q = 0;                  // 2 buffers
+constexpr int SMEM_K = SMEM_Q + 2 * Q_BYTES;
+constexpr int SMEM_V = SMEM_K + NKV * KV_BYTES;
+constexpr int SMEM_P = SMEM_V + NKV * KV_BYTES;
+constexpr int SMEM_BAR = SMEM_P + 2 * P_BYTES;
+constexpr int SMEM_TOTAL = SMEM_BAR + 256;
 constexpr int TMEM_COLS = 256;
-constexpr int COL_S = 0, COL_O = 128;
+constexpr int COL_S = 0, COL_O = 128;      // S0 | S1 | O0 | O1, 64 columns each
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+
+// rescale the running output row by `corr` (rare: only when the exponent reference moved)
+__device__ __forceinline__ void rescale_o(uint32_t taddr_o, float corr) {
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    uint32_t o[32];
+    tmem_ld_32x32(taddr_o + c * 32, o);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
+    tmem_st_32x32(taddr_o + c * 32, o);
+  }
+  tmem_st_wait();
+}
 }  // namespace
 
-__global__ void __launch_bounds__(160, 2)
-attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, bf16* __restrict__ out, int N, int H, float scale_log2) {
+// per-tile epilogue of one query row: O / l -> bf16 -> out
+__device__ __forceinline__ void store_o_row(uint32_t taddr_o, float l, bf16* op, bool valid, uint64_t* o_free_bar) {
+  uint32_t o[2][32];
+  tmem_ld_32x32(taddr_o, o[0]);
+  tmem_ld_32x32(taddr_o + 32, o[1]);
+  tmem_ld_wait();
+  tc_fence_before();
+  mbar_arrive(o_free_bar);                             // the O buffer may be overwritten by tile+2
+  if (valid) {
+    const float inv = 1.f / l;
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(o[c][i + e]) * inv;
+        store8<bf16>(op + c * 32 + i, f);
+      }
+  }
+}
+
+__global__ void __launch_bounds__(192, 2)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
+                    bf16* __restrict__ out, int N, int H, float scale_log2) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_BAR);
-  uint64_t* bar_q = bars;            // Q tile landed
-  uint64_t* k_full = bars + 1;       // [2]
-  uint64_t* v_full = bars + 3;       // [2]
-  uint64_t* s_full = bars + 5;       // S = QK^T complete (tcgen05.commit)
-  uint64_t* p_full = bars + 6;       // P written + O rescaled (128 arrivals)
-  uint64_t* pv_done = bars + 7;      // O += PV complete (tcgen05.commit)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* q_full = bars;           // [2] Q tile landed
+  uint64_t* k_full = bars + 2;       // [3]
+  uint64_t* v_full = bars + 5;       // [3]
+  uint64_t* s_full = bars + 8;       // [2] S_g complete (tcgen05.commit)
+  uint64_t* p_full = bars + 10;      // [2] P_g written, S_g consumed (128 arrivals)
+  uint64_t* pv_done = bars + 12;     // [2] O += P_g V complete (tcgen05.commit)
+  uint64_t* o_free = bars + 14;      // [2] epilogue finished reading O buffer (128 arrivals)
+  uint64_t* k_free = bars + 16;      // [3] S MMAs that read this K stage retired (tcgen05.commit)
+  uint64_t* v_free = bars + 19;      // [3] PV MMAs that read this V stage retired (tcgen05.commit)
+  uint64_t* q_free = bars + 22;      // [2] every S MMA of the tile that used this Q buffer retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * QT, h = blockIdx.y, b = blockIdx.z;
-  const int nchunks = (N + KT - 1) / KT;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int nch = (N + KT - 1) / KT;                 // key chunks per tile
+  const int nq = (N + QT - 1) / QT;                  // query tiles
+  const int total = nq * nch;                        // flattened pipeline steps
+  const int last_keys = N - (nch - 1) * KT;          // valid keys of the last chunk
+  const int last_kn = last_keys >= KT ? KT : ((last_keys + 15) & ~15);   // rounded to the MMA granularity
 
   if (threadIdx.x == 0) {
     if ((smem_u32(smem) & 1023u) != 0) __trap();    // swizzled tiles need 1024-byte alignment
-    tma_prefetch_desc(&tmap);
-    mbar_init(bar_q, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1); }
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 128);
-    mbar_init(pv_done, 1);
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_kv);
+    for (int i = 0; i < NKV; ++i) { mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1); mbar_init(&k_free[i], 1); mbar_init(&v_free[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1); mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128); mbar_init(&pv_done[i], 1);
+      mbar_init(&o_free[i], 128); mbar_init(&q_free[i], 1);
+    }
     fence_barrier_init();
   }
   if (warp == 4) tmem_alloc<TMEM_COLS>(tmem_slot);
@@ -66,153 +122,231 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, bf16* __restrict__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 4) {
-    // ===================== control warp: TMA loads + MMA issue (one elected thread) =====================
+  if (warp == 5) {
+    // ===================== TMA loader (one elected thread): never on the MMA critical path =====================
     if (lane == 0) {
       const int cq = h * D, ck = H + h * D, cv = 2 * H + h * D;
-      mbar_arrive_expect_tx(bar_q, TILE_BYTES);
-      tma_load_3d(smem + SMEM_Q, &tmap, bar_q, cq, q0, b);
-      for (int j = 0; j < 2 && j < nchunks; ++j) {
-        mbar_arrive_expect_tx(&k_full[j], TILE_BYTES);
-        tma_load_3d(smem + SMEM_K + j * TILE_BYTES, &tmap, &k_full[j], ck, j * KT, b);
-        mbar_arrive_expect_tx(&v_full[j], TILE_BYTES);
-        tma_load_3d(smem + SMEM_V + j * TILE_BYTES, &tmap, &v_full[j], cv, j * KT, b);
+      auto load_q = [&](int tile) {
+        mbar_arrive_expect_tx(&q_full[tile & 1], Q_BYTES);
+        tma_load_3d(smem + SMEM_Q + (tile & 1) * Q_BYTES, &tmap_q, &q_full[tile & 1], cq, tile * QT, b);
+      };
+      auto load_k = [&](int g) {
+        const int st = g % NKV;
+        mbar_arrive_expect_tx(&k_full[st], KV_BYTES);
+        tma_load_3d(smem + SMEM_K + st * KV_BYTES, &tmap_kv, &k_full[st], ck, (g % nch) * KT, b);
+      };
+      auto load_v = [&](int g) {
+        const int st = g % NKV;
+        mbar_arrive_expect_tx(&v_full[st], KV_BYTES);
+        tma_load_3d(smem + SMEM_V + st * KV_BYTES, &tmap_kv, &v_full[st], cv, (g % nch) * KT, b);
+      };
+      load_q(0);
+      for (int g = 0; g < NKV && g < total; ++g) { load_k(g); load_v(g); }
+      if (nq > 1) load_q(1);
+      // classic full/empty rings: every *_free barrier is re-armed only by this thread's own refill, so the loader can
+      // never fall a phase behind (it must not wait on s_full / pv_done, which advance without it)
+      int tile = 0, j = 0;
+      for (int g = 0; g < total; ++g) {
+        if (g + NKV < total) {
+          mbar_wait(&k_free[g % NKV], (g / NKV) & 1);      // S_g retired -> K stage free
+          load_k(g + NKV);
+        }
+        if (j == nch - 1 && tile + 2 < nq) {
+          mbar_wait(&q_free[tile & 1], (tile >> 1) & 1);   // last S of this tile retired -> Q buffer free
+          load_q(tile + 2);
+        }
+        if (g + NKV < total) {
+          mbar_wait(&v_free[g % NKV], (g / NKV) & 1);      // PV_g retired -> V stage free
+          load_v(g + NKV);
+        }
+        if (++j == nch) { j = 0; ++tile; }
       }
-      constexpr uint32_t idesc_s = make_idesc_bf16(128, KT, 0, 0);   // Q (K-major) x K (K-major)
-      constexpr uint32_t idesc_o = make_idesc_bf16(128, D, 0, 1);    // P (K-major) x V (MN-major)
-      const uint32_t sq = smem_u32(smem + SMEM_Q);
-      const uint32_t sp = smem_u32(smem + SMEM_P);
-      const uint64_t qdesc = make_smem_desc_sw128(sq, 16, 1024);
-
-      mbar_wait(bar_q, 0);
-      // S_0
-      mbar_wait(&k_full[0], 0);
-      tc_fence_after();
-      {
-        const uint64_t kdesc = make_smem_desc_sw128(smem_u32(smem + SMEM_K), 16, 1024);
+    }
+  } else if (warp == 4) {
+    // ===================== MMA issuer (one elected thread) =====================
+    if (lane == 0) {
+      // descriptors differ only in their 16-byte-granular start address: precompute bases, add offsets
+      const uint64_t qd0 = make_smem_desc_sw128(smem_u32(smem + SMEM_Q), 16, 1024);
+      const uint64_t kd0 = make_smem_desc_sw128(smem_u32(smem + SMEM_K), 16, 1024);
+      const uint64_t vd0 = make_smem_desc_sw128(smem_u32(smem + SMEM_V), 16, 1024);
+      const uint64_t pd0 = make_smem_desc_sw128(smem_u32(smem + SMEM_P), 16, 1024);
+      const uint32_t idesc_s_full = make_idesc_bf16(128, KT, 0, 0);            // Q (K-major) x K (K-major)
+      const uint32_t idesc_s_last = make_idesc_bf16(128, last_kn, 0, 0);
+      constexpr uint32_t idesc_o = make_idesc_bf16(128, D, 0, 1);              // P (K-major) x V (MN-major)
+      auto issue_s = [&](int g, int tile, int j) {     // S_g = Q_tile K_j^T into S buffer g & 1
+        const int st = g % NKV;
+        if (j == 0) mbar_wait(&q_full[tile & 1], (tile >> 1) & 1);
+        mbar_wait(&k_full[st], (g / NKV) & 1);
+        tc_fence_after();
+        const uint64_t qd = qd0 + (uint64_t)((tile & 1) * (Q_BYTES >> 4));
+        const uint64_t kd = kd0 + (uint64_t)(st * (KV_BYTES >> 4));
+        const uint32_t idesc = (j == nch - 1) ? idesc_s_last : idesc_s_full;
+        const uint32_t d = tmem_base + COL_S + (g & 1) * KT;
 #pragma unroll
-        for (int k = 0; k < D / 16; ++k) umma_f16(tmem_base + COL_S, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
-        umma_commit(s_full);
-      }
-      for (int j = 0; j < nchunks; ++j) {
-        const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        // O += P_j V_j
-        mbar_wait(p_full, j & 1);
-        mbar_wait(&v_full[st], ph);
+        for (int k = 0; k < D / 16; ++k) umma_f16(d, qd + 2 * k, kd + 2 * k, idesc, k != 0);
+        umma_commit(&s_full[g & 1]);
+        umma_commit(&k_free[st]);
+        if (j == nch - 1) umma_commit(&q_free[tile & 1]);
+      };
+      // (tile, j) of steps g, g+1, g+2 are tracked incrementally (no divisions on the critical path)
+      int t0 = 0, j0 = 0;                               // step g
+      int t2 = 0, j2 = 0;                               // step g+2
+      issue_s(0, 0, 0);
+      if (total > 1) { int t1 = 0, j1 = 1; if (j1 == nch) { j1 = 0; t1 = 1; } issue_s(1, t1, j1); }
+      for (int i = 0; i < 2; ++i) if (++j2 == nch) { j2 = 0; ++t2; }
+      for (int g = 0; g < total; ++g) {
+        const int pb = g & 1;
+        mbar_wait(&p_full[pb], (g >> 1) & 1);          // P_g written and S_g consumed
+        // the softmax is waiting for S, nobody waits for O: S_{g+2} first
+        if (g + 2 < total) issue_s(g + 2, t2, j2);
+        // O_tile += P_g V_j
+        mbar_wait(&v_full[g % NKV], (g / NKV) & 1);
+        if (j0 == 0 && t0 >= 2) mbar_wait(&o_free[t0 & 1], ((t0 - 2) >> 1) & 1);   // epilogue of tile-2 has read this O buffer
         tc_fence_after();
         {
-          const uint32_t sv = smem_u32(smem + SMEM_V + st * TILE_BYTES);
+          const uint64_t pd = pd0 + (uint64_t)(pb * (P_BYTES >> 4));
+          const uint64_t vd = vd0 + (uint64_t)((g % NKV) * (KV_BYTES >> 4));
+          const uint32_t d = tmem_base + COL_O + (t0 & 1) * D;
+          const int ksteps = (j0 == nch - 1 ? last_kn : KT) / 16;
+          if (ksteps == 4) {
 #pragma unroll
-          for (int k = 0; k < KT / 16; ++k) {
-            const uint64_t pdesc = make_smem_desc_sw128(sp + (k >> 2) * TILE_BYTES + (k & 3) * 32, 16, 1024);
-            const uint64_t vdesc = make_smem_desc_sw128(sv + k * 2048, 16, 1024);   // 16 keys = 2 groups of 8 rows
-            umma_f16(tmem_base + COL_O, pdesc, vdesc, idesc_o, (j | k) != 0);
+            for (int k = 0; k < 4; ++k) umma_f16(d, pd + 2 * k, vd + 128 * k, idesc_o, (j0 | k) != 0);   // 16 keys = 2048 B of V
+          } else {
+#pragma unroll 1
+            for (int k = 0; k < ksteps; ++k) umma_f16(d, pd + 2 * k, vd + 128 * k, idesc_o, (j0 | k) != 0);
           }
-          umma_commit(pv_done);
+          umma_commit(&pv_done[pb]);
+          umma_commit(&v_free[g % NKV]);
         }
-        // S_{j+1} right behind it (S is free: every softmax thread finished reading S_j before arriving on p_full)
-        if (j + 1 < nchunks) {
-          const int st1 = (j + 1) & 1;
-          mbar_wait(&k_full[st1], ((j + 1) >> 1) & 1);
-          tc_fence_after();
-          const uint64_t kdesc = make_smem_desc_sw128(smem_u32(smem + SMEM_K + st1 * TILE_BYTES), 16, 1024);
-#pragma unroll
-          for (int k = 0; k < D / 16; ++k) umma_f16(tmem_base + COL_S, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
-          umma_commit(s_full);
-        }
-        // refill this K/V stage with chunk j+2 once PV_j has consumed it
-        if (j + 2 < nchunks) {
-          mbar_wait(pv_done, j & 1);
-          mbar_arrive_expect_tx(&k_full[st], TILE_BYTES);
-          tma_load_3d(smem + SMEM_K + st * TILE_BYTES, &tmap, &k_full[st], ck, (j + 2) * KT, b);
-          mbar_arrive_expect_tx(&v_full[st], TILE_BYTES);
-          tma_load_3d(smem + SMEM_V + st * TILE_BYTES, &tmap, &v_full[st], cv, (j + 2) * KT, b);
-        }
+        if (++j0 == nch) { j0 = 0; ++t0; }
+        if (++j2 == nch) { j2 = 0; ++t2; }
       }
     }
   } else {
-    // ===================== softmax warps: thread t owns query row t =====================
+    // ===================== softmax warps: thread t owns query row t of the current tile =====================
     const int t = threadIdx.x;                         // 0..127 == TMEM lane
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-    float m = -INFINITY, l = 0.f;
-    uint8_t* prow = smem + SMEM_P + t * 128;
-    for (int j = 0; j < nchunks; ++j) {
-      mbar_wait(s_full, j & 1);
-      tc_fence_after();
-      uint32_t r[4][32];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld_32x32(tmem_base + lane_base + COL_S + c * 32, r[c]);
-      tmem_ld_wait();
-      const int kbase = j * KT;
-      const bool ragged = (kbase + KT > N);
-      float mx = m;
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float s = __uint_as_float(r[c][i]) * scale_log2;
-          if (ragged && kbase + c * 32 + i >= N) s = -INFINITY;
-          r[c][i] = __float_as_uint(s);
-          mx = fmaxf(mx, s);
-        }
-      const float corr = ex2(m - mx);                  // 0 for the first chunk (m = -inf)
-      m = mx;
-      float sum = 0.f;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-          float p[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) { p[e] = ex2(__uint_as_float(r[c][i + e]) - mx); sum += p[e]; }
-          const int key = c * 32 + i;                  // 8 consecutive keys -> one 16-byte chunk
-          const int sub = key >> 6, chunk = (key & 63) >> 3;
-          uint4 pk = make_uint4(pack_bf16x2(p[0], p[1]), pack_bf16x2(p[2], p[3]), pack_bf16x2(p[4], p[5]), pack_bf16x2(p[6], p[7]));
-          *reinterpret_cast<uint4*>(prow + sub * TILE_BYTES + ((chunk ^ (t & 7)) << 4)) = pk;
-        }
-      }
-      l = l * corr + sum;
-      if (j > 0) {
-        // rescale the running output: PV_{j-1} must have landed in TMEM first
-        mbar_wait(pv_done, (j - 1) & 1);
+    const uint32_t sw = (uint32_t)(t & 7);
+    int g = 0;
+    // deferred epilogue of the previous tile (runs after the first chunk of the next tile, off the critical path)
+    bool pend = false;
+    float pend_l = 0.f;
+    int pend_tile = 0, pend_g = 0;
+    for (int tile = 0; tile < nq; ++tile) {
+      const uint32_t taddr_o = tmem_base + lane_base + COL_O + (tile & 1) * D;
+      float m_ref = -INFINITY;                         // exponent reference (scaled log2 units); lags the true max by < 8
+      float l = 0.f;
+      for (int j = 0; j < nch; ++j, ++g) {
+        const int sb = g & 1;
+        const int lim = N - j * KT;                    // valid keys in this chunk (>= 64 for full chunks)
+        const uint32_t taddr_s = tmem_base + lane_base + COL_S + sb * KT;
+        uint8_t* prow = smem + SMEM_P + sb * P_BYTES + t * 128;
+        mbar_wait(&s_full[sb], (g >> 1) & 1);
         tc_fence_after();
-        uint32_t o[2][32];
-        tmem_ld_32x32(tmem_base + lane_base + COL_O, o[0]);
-        tmem_ld_32x32(tmem_base + lane_base + COL_O + 32, o[1]);
-        tmem_ld_wait();
+        if (lim >= KT) {
+          uint32_t r[2][32];
+          tmem_ld_32x32(taddr_s, r[0]);
+          tmem_ld_32x32(taddr_s + 32, r[1]);
+          tmem_ld_wait();
+          float mx = -INFINITY;
 #pragma unroll
-        for (int c = 0; c < 2; ++c)
+          for (int c = 0; c < 2; ++c)
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[c][i] = __float_as_uint(__uint_as_float(o[c][i]) * corr);
-        tmem_st_32x32(tmem_base + lane_base + COL_O, o[0]);
-        tmem_st_32x32(tmem_base + lane_base + COL_O + 32, o[1]);
-        tmem_st_wait();
-      }
-      fence_proxy_async_smem();                        // P (generic-proxy stores) -> visible to the MMA (async proxy)
-      tc_fence_before();
-      mbar_arrive(p_full);
-    }
-    // epilogue: O / l -> bf16 -> out[b, q0 + t, h*64 ..]
-    mbar_wait(pv_done, (nchunks - 1) & 1);
-    tc_fence_after();
-    uint32_t o[2][32];
-    tmem_ld_32x32(tmem_base + lane_base + COL_O, o[0]);
-    tmem_ld_32x32(tmem_base + lane_base + COL_O + 32, o[1]);
-    tmem_ld_wait();
-    const int q = q0 + t;
-    if (q < N) {
-      const float inv = 1.f / l;
-      bf16* op = out + ((size_t)b * N + q) * H + h * D;
+            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[c][i]));
+          const float mxs = mx * scale_log2;
+          const bool need = mxs > m_ref + 8.0f;
+          const float m_new = need ? mxs : m_ref;
+          if (j > 0 && __any_sync(0xffffffffu, need)) {
+            const float corr = ex2(m_ref - m_new);     // exactly 1 for lanes that keep their reference
+            mbar_wait(&pv_done[(g - 1) & 1], ((g - 1) >> 1) & 1);    // every issued PV has landed in TMEM
+            tc_fence_after();
+            rescale_o(taddr_o, corr);
+            l *= corr;
+          }
+          m_ref = m_new;
+          if (g >= 2) mbar_wait(&pv_done[sb], ((g - 2) >> 1) & 1);   // P buffer still being read by PV_{g-2}?
+          const float neg = -m_ref;
+          float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
-      for (int c = 0; c < 2; ++c)
+          for (int c = 0; c < 2; ++c)
 #pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-          float f[8];
+            for (int i = 0; i < 32; i += 8) {
+              float p[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(o[c][i + e]) * inv;
-          store8<bf16>(op + c * 32 + i, f);
+              for (int e = 0; e < 8; ++e) p[e] = ex2(fmaf(__uint_as_float(r[c][i + e]), scale_log2, neg));
+              sum0 += (p[0] + p[1]) + (p[2] + p[3]);
+              sum1 += (p[4] + p[5]) + (p[6] + p[7]);
+              const int chunk = (c * 32 + i) >> 3;     // 8 consecutive keys -> one 16-byte chunk of the 128-byte row
+              uint4 pk = make_uint4(pack_bf16x2(p[0], p[1]), pack_bf16x2(p[2], p[3]), pack_bf16x2(p[4], p[5]), pack_bf16x2(p[6], p[7]));
+              *reinterpret_cast<uint4*>(prow + ((chunk ^ sw) << 4)) = pk;
+            }
+          l += sum0 + sum1;
+        } else {
+          // ragged last chunk: only `lim` keys are valid; work in 16-column groups, two passes over TMEM
+          const int ng = (lim + 15) >> 4;
+          float mx = -INFINITY;
+          for (int gg = 0; gg < ng; ++gg) {
+            uint32_t r[16];
+            tmem_ld_32x16(taddr_s + gg * 16, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (gg * 16 + i < lim) mx = fmaxf(mx, __uint_as_float(r[i]));
+          }
+          const float mxs = mx * scale_log2;
+          const bool need = mxs > m_ref + 8.0f;
+          const float m_new = need ? mxs : m_ref;
+          if (j > 0 && __any_sync(0xffffffffu, need)) {
+            const float corr = ex2(m_ref - m_new);
+            mbar_wait(&pv_done[(g - 1) & 1], ((g - 1) >> 1) & 1);
+            tc_fence_after();
+            rescale_o(taddr_o, corr);
+            l *= corr;
+          }
+          m_ref = m_new;
+          if (g >= 2) mbar_wait(&pv_done[sb], ((g - 2) >> 1) & 1);
+          const float neg = -m_ref;
+          float sum = 0.f;
+          for (int gg = 0; gg < ng; ++gg) {
+            uint32_t r[16];
+            tmem_ld_32x16(taddr_s + gg * 16, r);
+            tmem_ld_wait();
+            float p[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              p[i] = (gg * 16 + i < lim) ? ex2(fmaf(__uint_as_float(r[i]), scale_log2, neg)) : 0.f;
+              sum += p[i];
+            }
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              uint4 pk = make_uint4(pack_bf16x2(p[8 * hh], p[8 * hh + 1]), pack_bf16x2(p[8 * hh + 2], p[8 * hh + 3]),
+                                    pack_bf16x2(p[8 * hh + 4], p[8 * hh + 5]), pack_bf16x2(p[8 * hh + 6], p[8 * hh + 7]));
+              *reinterpret_cast<uint4*>(prow + (((uint32_t)(gg * 2 + hh) ^ sw) << 4)) = pk;
+            }
+          }
+          l += sum;
         }
+        fence_proxy_async_smem();                      // P (generic-proxy stores) -> visible to the MMA (async proxy)
+        tc_fence_before();
+        mbar_arrive(&p_full[sb]);
+        if (pend && j == 0) {
+          // epilogue of the previous tile, after this tile's first chunk has been handed to the tensor core
+          mbar_wait(&pv_done[pend_g & 1], (pend_g >> 1) & 1);
+          tc_fence_after();
+          const int q = pend_tile * QT + t;
+          store_o_row(tmem_base + lane_base + COL_O + (pend_tile & 1) * D, pend_l,
+                      out + ((size_t)b * N + q) * H + h * D, q < N, &o_free[pend_tile & 1]);
+          pend = false;
+        }
+      }
+      pend = true; pend_l = l; pend_tile = tile; pend_g = g - 1;
+    }
+    if (pend) {
+      mbar_wait(&pv_done[pend_g & 1], (pend_g >> 1) & 1);
+      tc_fence_after();
+      const int q = pend_tile * QT + t;
+      store_o_row(tmem_base + lane_base + COL_O + (pend_tile & 1) * D, pend_l, out + ((size_t)b * N + q) * H + h * D, q < N,
+                  &o_free[pend_tile & 1]);
     }
   }
   tc_fence_before();
@@ -226,18 +360,21 @@ int attention_tc(const void* qkv, void* out, int B, int N, int heads, float scal
   if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(out) & 15)) {
     set_last_error("attention_tc: pointers must be 16-byte aligned"); return VC_ERR_BAD_ARG;
   }
-  CUtensorMap tm;
-  int rc = get_tmap_3d_bf16(&tm, qkv, (uint64_t)B, (uint64_t)N, (uint64_t)3 * H, (uint64_t)3 * H, (uint64_t)N * 3 * H, 128, 64);
+  CUtensorMap tq, tkv;
+  int rc = get_tmap_3d_bf16(&tq, qkv, (uint64_t)B, (uint64_t)N, (uint64_t)3 * H, (uint64_t)3 * H, (uint64_t)N * 3 * H, 128, 64);
+  if (rc) return rc;
+  rc = get_tmap_3d_bf16(&tkv, qkv, (uint64_t)B, (uint64_t)N, (uint64_t)3 * H, (uint64_t)3 * H, (uint64_t)N * 3 * H, KT, 64);
   if (rc) return rc;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (e != cudaSuccess) { set_last_error("attention_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return VC_ERR_LAUNCH; }
     configured = true;
   }
-  dim3 grid((N + QT - 1) / QT, heads, B);
+  dim3 grid(heads, B);
   const float scale_log2 = scale * 1.4426950408889634f;
-  attention_tc_kernel<<<grid, 160, SMEM_TOTAL, s>>>(tm, reinterpret_cast<bf16*>(out), N, H, scale_log2);
+  attention_tc_kernel<<<grid, 192, SMEM_TOTAL, s>>>(tq, tkv, reinterpret_cast<bf16*>(out), N, H, scale_log2);
   return check_launch("attention_tc");
 }
 
