@@ -94,9 +94,15 @@ int vc_embed_ln(int bf16, const int* ids, int max_len, int cur_len, int mask_id,
 /* one decoder self-attention step over the KV cache (BertSelfAttention with history, modeling_bert.py:303-340; mask
  * semantics of modeling_bert.py:1494-1501 / dataset.py:371-390 encoded structurally). ctx_qkv [B,C,3H]: prefill QKV of the
  * context rows; step_qkv [max_len, 2*B*E, 3H]: per-step QKV rows (2r = token, 2r+1 = MASK); anc int32 [max_len, B*E]
- * ancestor rows for beam search (NULL = identity); out [2*B*E, H]. E = beams*samples per image. */
+ * ancestor rows for beam search (NULL = identity); out [2*B*E, H]. E = beams*samples per image.
+ * bf16=1: cp.async-pipelined mma.sync kernel, one CTA per (image, head) covering up to 8 sequences (16 query rows), so the
+ * shared context K/V is read once per image; bf16=0: CUDA-core kernel on fp32 storage. */
 int vc_decode_attention(int bf16, const void* ctx_qkv, const void* step_qkv, const int* anc, void* out, int B, int C, int heads,
                         int E, int cur_len, float scale, void* stream);
+/* same contract on the CUDA-core kernel for either storage type (bf16=0 is what vc_decode_attention runs in exact mode;
+ * bf16=1 cross-checks the mma.sync kernel in tests) */
+int vc_decode_attention_simt(int bf16, const void* ctx_qkv, const void* step_qkv, const int* anc, void* out, int B, int C,
+                             int heads, int E, int cur_len, float scale, void* stream);
 
 /* greedy / sampled next token + log-prob + state update for `rows` sequences, modeling_utils.py:839-862.
  * logits fp32 [rows, ld]; sampling = Gumbel-max with Philox4x32-10 noise keyed by (seed; vocab idx/4, row, cur_len). */

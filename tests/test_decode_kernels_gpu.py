@@ -1,0 +1,283 @@
+"""Kernel-level parity of the decode-step entry points (through the C ABI) against torch expressions / the CPU oracle's
+search loops (oracle/port.py, restating modeling_utils.py:768-1180) driven by identical synthetic logits."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import philox, port  # noqa: E402
+from vitcap_b200 import ops  # noqa: E402
+
+DEV = "cuda:0"
+
+
+def _rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g) * scale
+
+
+# ------------------------------------------------------------------------------------------------ decode attention
+def _decode_attention_ref(ctx, stepq, anc, B, C, heads, E, cur_len, scale):
+    """fp32 torch restatement: rows (2r, 2r+1) = (token, MASK) queries of sequence r = b*E+e (modeling_bert.py:303-340 with the
+    structural mask of modeling_bert.py:1494-1501): context keys of image b, cached caption keys through the ancestor table,
+    this step's token key, and -- for the MASK query only -- this step's MASK key."""
+    H = heads * 64
+    R = B * E
+    step = cur_len - 1
+    ctx = ctx.float().view(B, C, 3, heads, 64)
+    sq = stepq.float().view(stepq.shape[0], 2 * R, 3, heads, 64)
+    out = torch.zeros(2 * R, heads, 64)
+    for r in range(R):
+        b = r // E
+        ks = [ctx[b, :, 1]]
+        vs = [ctx[b, :, 2]]
+        for j in range(step):
+            src = int(anc[j, r]) if anc is not None else r
+            ks.append(sq[j, 2 * src, 1][None])
+            vs.append(sq[j, 2 * src, 2][None])
+        ks.append(sq[step, 2 * r, 1][None]); vs.append(sq[step, 2 * r, 2][None])
+        ks.append(sq[step, 2 * r + 1, 1][None]); vs.append(sq[step, 2 * r + 1, 2][None])
+        K = torch.cat(ks, 0)            # [keys, heads, 64]
+        V = torch.cat(vs, 0)
+        for w in range(2):
+            q = sq[step, 2 * r + w, 0]  # [heads, 64]
+            s = torch.einsum("hd,khd->hk", q, K) * scale
+            if w == 0:
+                s[:, -1] = -1e30
+            p = torch.softmax(s, dim=-1)
+            out[2 * r + w] = torch.einsum("hk,khd->hd", p, V)
+    return out.view(2 * R, H)
+
+
+DA_CASES = [(2, 578, 12, 1, 1), (2, 578, 12, 1, 19), (3, 198, 12, 5, 7), (2, 578, 12, 4, 10), (1, 18, 2, 1, 3),
+            (2, 146, 12, 8, 19), (1, 578, 12, 10, 5), (2, 50, 3, 3, 2), (1, 578, 12, 2, 40)]
+
+
+def _da_inputs(B, C, heads, E, cur_len, dtype, seed=0):
+    H = heads * 64
+    R = B * E
+    max_len = max(20, cur_len + 1)
+    ctx = _rnd(B, C, 3 * H, seed=seed).to(dtype)
+    stepq = _rnd(max_len, 2 * R, 3 * H, seed=seed + 1).to(dtype)
+    g = torch.Generator().manual_seed(seed + 2)
+    anc = torch.zeros(max_len, R, dtype=torch.int32)
+    for j in range(max_len):
+        for r in range(R):
+            b = r // E
+            anc[j, r] = b * E + int(torch.randint(0, E, (1,), generator=g))
+    return ctx, stepq, anc
+
+
+@pytest.mark.parametrize("use_anc", [False, True])
+@pytest.mark.parametrize("B,C,heads,E,cur_len", DA_CASES)
+def test_decode_attention_bf16_mma(B, C, heads, E, cur_len, use_anc):
+    scale = 0.125
+    ctx, stepq, anc = _da_inputs(B, C, heads, E, cur_len, torch.bfloat16)
+    ref = _decode_attention_ref(ctx, stepq, anc if use_anc else None, B, C, heads, E, cur_len, scale)
+    H = heads * 64
+    out = torch.full((2 * B * E, H), float("nan"), dtype=torch.bfloat16, device=DEV)
+    d_anc = anc.to(DEV) if use_anc else None
+    ops.decode_attention(ctx.to(DEV), stepq.to(DEV), d_anc, out, B, C, heads, E, cur_len, scale)
+    torch.cuda.synchronize()
+    got = out.float().cpu()
+    assert torch.isfinite(got).all()
+    # bf16 probabilities and bf16 output rounding: |err| <~ 2^-8 of the value scale (outputs are O(0.1..1))
+    assert float((got - ref).abs().max()) < 2.5e-2, float((got - ref).abs().max())
+    assert float((got - ref).norm() / ref.norm()) < 6e-3
+    # cross-check against the CUDA-core kernel on the same bf16 inputs
+    out2 = torch.empty_like(out)
+    ops.decode_attention(ctx.to(DEV), stepq.to(DEV), d_anc, out2, B, C, heads, E, cur_len, scale, impl="simt")
+    assert float((out2.float().cpu() - ref).abs().max()) < 2.5e-2
+
+
+@pytest.mark.parametrize("B,C,heads,E,cur_len", [(2, 578, 12, 1, 5), (2, 198, 12, 4, 19), (1, 18, 2, 5, 3)])
+def test_decode_attention_fp32_exact(B, C, heads, E, cur_len):
+    scale = 0.125
+    ctx, stepq, anc = _da_inputs(B, C, heads, E, cur_len, torch.float32, seed=5)
+    ref = _decode_attention_ref(ctx, stepq, anc, B, C, heads, E, cur_len, scale)
+    out = torch.empty(2 * B * E, heads * 64, dtype=torch.float32, device=DEV)
+    ops.decode_attention(ctx.to(DEV), stepq.to(DEV), anc.to(DEV), out, B, C, heads, E, cur_len, scale)
+    np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), atol=2e-5, rtol=1e-4)
+
+
+def test_decode_attention_peaky_scores_bf16():
+    """Large score range: the lazy rescale path (running reference moves by more than 2^8) must stay exact."""
+    B, C, heads, E, cur_len = 1, 578, 12, 2, 6
+    ctx, stepq, anc = _da_inputs(B, C, heads, E, cur_len, torch.bfloat16, seed=9)
+    ctx = (ctx.float() * 3.0).to(torch.bfloat16)
+    stepq = (stepq.float() * 3.0).to(torch.bfloat16)
+    ref = _decode_attention_ref(ctx, stepq, anc, B, C, heads, E, cur_len, 0.125)
+    out = torch.empty(2 * B * E, heads * 64, dtype=torch.bfloat16, device=DEV)
+    ops.decode_attention(ctx.to(DEV), stepq.to(DEV), anc.to(DEV), out, B, C, heads, E, cur_len, 0.125)
+    got = out.float().cpu()
+    assert float((got - ref).abs().max()) < 8e-2 and float((got - ref).norm() / ref.norm()) < 8e-3
+
+
+# ------------------------------------------------------------------------------------------------ embedding
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_embed_ln(dtype):
+    R, H, V, L, cur_len, mask_id = 37, 768, 500, 20, 7, 103
+    word, pos, typ = _rnd(V, H, seed=1, scale=0.05), _rnd(64, H, seed=2, scale=0.05), _rnd(H, seed=3, scale=0.05)
+    gam, bet = 1 + _rnd(H, seed=4, scale=0.1), _rnd(H, seed=5, scale=0.1)
+    ids = torch.randint(0, V, (R, L), generator=torch.Generator().manual_seed(6), dtype=torch.int32)
+    out_f = torch.empty(2 * R, H, device=DEV)
+    out_t = out_f if dtype == torch.float32 else torch.empty(2 * R, H, device=DEV, dtype=dtype)
+    ops.embed_ln(ids.to(DEV), cur_len, mask_id, word.to(DEV), pos.to(DEV), typ.to(DEV), gam.to(DEV), bet.to(DEV), 1e-12, out_f, out_t, R)
+    tok = torch.stack([ids[:, cur_len - 1].long(), torch.full((R,), mask_id)], 1).reshape(-1)
+    p = torch.tensor([cur_len - 1, cur_len]).repeat(R)
+    ref = torch.nn.functional.layer_norm(word[tok] + pos[p] + typ, (H,), gam, bet, 1e-12)
+    np.testing.assert_allclose(out_f.cpu().numpy(), ref.numpy(), atol=2e-5)
+    if dtype == torch.bfloat16:
+        np.testing.assert_allclose(out_t.float().cpu().numpy(), ref.numpy(), atol=2e-2)
+
+
+# ------------------------------------------------------------------------------------------------ search loops
+class _TableLogits:
+    """logits(row) = table[hash(prefix ids of the row)]: a pure gather, so the CPU oracle loop and the GPU kernels see
+    bit-identical logits as long as their token prefixes agree -- any divergence in ids / reordering shows up at once."""
+
+    def __init__(self, V, T=509, seed=0, eos=102, eos_boost=6.0, scale=3.0):
+        g = torch.Generator().manual_seed(seed)
+        self.table = torch.randn(T, V, generator=g) * scale
+        boost = torch.rand(T, generator=g) < 0.12
+        self.table[boost, eos] += eos_boost
+        self.T = T
+        self.V = V
+        self._dev = {}
+
+    def index(self, ids):
+        L = ids.shape[1]
+        w = torch.arange(1, L + 1, device=ids.device, dtype=torch.int64) * 7919
+        return ((ids.to(torch.int64) * w).sum(1) + 31 * L) % self.T
+
+    def __call__(self, ids, beam_idx=None):
+        key = str(ids.device)
+        if key not in self._dev:
+            self._dev[key] = self.table.to(ids.device)
+        return self._dev[key][self.index(ids)]
+
+
+def _greedy_kernels(tl, R, max_len, bos, pad, eos_ids, do_sample=False, temperature=1.0, top_k=0, top_p=1.0, seed=0):
+    V = tl.V
+    ldl = (V + 63) // 64 * 64
+    ids = torch.zeros(R, max_len, dtype=torch.int32, device=DEV)
+    ids[:, 0] = bos
+    unf = torch.ones(R, dtype=torch.int32, device=DEV)
+    sum_lp = torch.zeros(R, device=DEV)
+    n_steps = torch.zeros(R, dtype=torch.int32, device=DEV)
+    logits = torch.zeros(R, ldl, device=DEV)
+    eos = torch.tensor(eos_ids, dtype=torch.int32, device=DEV)
+    for cur_len in range(1, max_len):
+        logits[:, :V] = tl(ids[:, :cur_len])
+        t = temperature
+        if do_sample and (top_k > 0 or top_p < 1.0):
+            ops.filter_logits(logits, V, R, 1.0 / temperature, top_k, top_p)
+            t = 1.0
+        ops.token_step(logits, V, R, do_sample, t, seed, cur_len, pad, eos, ids, unf, sum_lp, n_steps)
+    out_ids = torch.zeros(R, max_len, dtype=torch.int64, device=DEV)
+    out_lp = torch.zeros(R, device=DEV)
+    ops.greedy_finalize(ids, unf, sum_lp, n_steps, eos_ids[0], R, out_ids, out_lp)
+    return out_ids.cpu(), out_lp.cpu()
+
+
+@pytest.mark.parametrize("V,R", [(3000, 64), (30522, 16)])
+def test_greedy_kernels_vs_oracle_loop(V, R):
+    tl = _RowTable(_TableLogits(V, seed=V, eos_boost=6.0 if V < 10000 else 14.0), 1)
+    rids, rlp = port.greedy_or_sample(tl, R, 20, 101, 0, [102])
+    ids, lp = _greedy_kernels(tl, R, 20, 101, 0, [102])
+    assert torch.equal(ids, rids[:, 0])
+    np.testing.assert_allclose(lp.numpy(), rlp[:, 0].numpy(), atol=1e-5)
+    assert (ids == 0).any() and (ids[:, -1] == 102).any()      # both early EOS (PAD fill) and forced EOS occur
+
+
+class _RowTable:
+    """Makes the hash depend on the image (row // rows_per_image) too, so different images get different captions."""
+
+    def __init__(self, tl, rows_per_image):
+        self.tl, self.n, self.V = tl, rows_per_image, tl.V
+
+    def __call__(self, ids, beam_idx=None):
+        img = (torch.arange(ids.shape[0], device=ids.device, dtype=ids.dtype).unsqueeze(1) // self.n) % 97
+        return self.tl(torch.cat([img, ids], 1))
+
+
+def test_sampling_kernels_vs_oracle_loop_same_noise():
+    V, R, seed = 3000, 48, 4321
+    tl = _RowTable(_TableLogits(V, seed=3, scale=2.0), 1)
+    for (temp, top_k, top_p) in [(1.0, 0, 1.0), (0.7, 40, 0.9), (1.3, 0, 0.8), (1.0, 5, 1.0)]:
+        rids, rlp = port.greedy_or_sample(tl, R, 20, 101, 0, [102], do_sample=True, temperature=temp, top_k=top_k, top_p=top_p,
+                                          sampler=philox.make_sampler(seed))
+        ids, lp = _greedy_kernels(tl, R, 20, 101, 0, [102], do_sample=True, temperature=temp, top_k=top_k, top_p=top_p, seed=seed)
+        same = (ids == rids[:, 0]).all(1)
+        # Gumbel noise is computed with different log implementations on CPU and GPU: a sample may flip at a near-tie
+        assert float(same.float().mean()) >= 0.9, (temp, top_k, top_p, float(same.float().mean()))
+        np.testing.assert_allclose(lp[same].numpy(), rlp[:, 0][same].numpy(), atol=2e-5)
+
+
+@pytest.mark.parametrize("top_k,top_p,temp", [(50, 1.0, 1.0), (0, 0.9, 1.0), (20, 0.5, 0.7), (1, 1.0, 1.0), (0, 0.05, 2.0)])
+def test_filter_logits_vs_reference_filter(top_k, top_p, temp):
+    R, V = 33, 30522
+    x = _rnd(R, V, seed=11, scale=2.5)
+    ldl = (V + 63) // 64 * 64
+    d = torch.zeros(R, ldl, device=DEV)
+    d[:, :V] = x.to(DEV)
+    ops.filter_logits(d, V, R, 1.0 / temp, top_k, top_p)
+    ref = port.top_k_top_p_filtering(x / temp if temp != 1.0 else x.clone(), top_k=top_k, top_p=top_p)
+    got = d[:, :V].cpu()
+    kept_ref, kept_got = torch.isfinite(ref), torch.isfinite(got)
+    # the top-p boundary is a cumulative fp32 sum: allow the kept set to differ by at most one boundary token per row
+    diff = (kept_ref != kept_got).sum(1)
+    assert int(diff.max()) <= 1, diff
+    both = kept_ref & kept_got
+    np.testing.assert_allclose(got[both].numpy(), ref[both].numpy(), rtol=1e-6, atol=1e-6)
+    if top_p >= 1.0:
+        assert int(diff.max()) == 0
+
+
+def _beam_kernels(tl, B, nb, max_len, bos, pad, eos_ids, keep, length_penalty):
+    V = tl.V
+    R, K = B * nb, 2 * nb
+    ldl = (V + 63) // 64 * 64
+    f32, i32 = torch.float32, torch.int32
+    st = {
+        "ids": torch.zeros(R, max_len, dtype=i32, device=DEV),
+        "beam_scores": torch.tensor(([0.0] + [-1e9] * (nb - 1)) * B, device=DEV, dtype=f32),
+        "done": torch.zeros(B, device=DEV, dtype=i32), "anc": torch.zeros(max_len, R, device=DEV, dtype=i32),
+        "hyp_score": torch.zeros(B, keep, device=DEV, dtype=torch.float64), "hyp_len": torch.zeros(B, keep, device=DEV, dtype=i32),
+        "hyp_ids": torch.zeros(B, keep, max_len, device=DEV, dtype=i32), "hyp_count": torch.zeros(B, device=DEV, dtype=i32),
+        "worst": torch.full((B,), 1e9, device=DEV, dtype=torch.float64),
+    }
+    st["ids"][:, 0] = bos
+    cand_val = torch.zeros(R, K, device=DEV, dtype=f32)
+    cand_idx = torch.zeros(R, K, device=DEV, dtype=i32)
+    row_max, row_logsum = torch.zeros(R, device=DEV), torch.zeros(R, device=DEV)
+    logits = torch.zeros(R, ldl, device=DEV)
+    eos = torch.tensor(eos_ids, dtype=i32, device=DEV)
+    anc_hist = []
+    for cur_len in range(1, max_len):
+        logits[:, :V] = tl(st["ids"][:, :cur_len])
+        ops.beam_row_topk(logits, V, R, K, cand_val, cand_idx, row_max, row_logsum)
+        ops.beam_advance(st, cand_val, cand_idx, row_max, row_logsum, B, nb, V, cur_len, keep, length_penalty, pad, eos)
+        anc_hist.append(st["anc"].clone())
+    out_ids = torch.zeros(B, keep, max_len, dtype=torch.int64, device=DEV)
+    out_lp = torch.zeros(B, keep, device=DEV)
+    ops.beam_finalize(st, B, keep, pad, eos_ids[0], out_ids, out_lp)
+    return out_ids.cpu(), out_lp.cpu(), st
+
+
+@pytest.mark.parametrize("B,nb,keep,lp,V", [(24, 4, 1, 1.0, 3000), (16, 3, 3, 0.6, 3000), (8, 8, 4, 1.4, 3000), (6, 4, 2, 1.0, 30522),
+                                            (12, 2, 1, 0.0, 997)])
+def test_beam_kernels_vs_oracle_loop(B, nb, keep, lp, V):
+    tl = _RowTable(_TableLogits(V, seed=100 + nb, eos_boost=5.0), nb)
+    rids, rlp = port.beam_search(tl, B, 20, 101, 0, [102], nb, V, length_penalty=lp, num_keep_best=keep)
+    ids, glp, st = _beam_kernels(tl, B, nb, 20, 101, 0, [102], keep, lp)
+    assert torch.equal(ids, rids), (ids[0], rids[0])
+    np.testing.assert_allclose(glp.numpy(), rlp.numpy(), atol=2e-5, rtol=1e-5)
+    # the ancestor table must reproduce every live beam's prefix: ids[r, j+1] was generated by row anc[j, r] at step j
+    anc = st["anc"].cpu()
+    assert int(anc.min()) >= 0 and int(anc.max()) < B * nb
+    rows = torch.arange(B * nb)
+    assert torch.equal(anc // nb, (rows // nb).expand_as(anc))        # beams never cross images

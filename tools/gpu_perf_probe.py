@@ -73,6 +73,25 @@ def ln_probe(B):
     print("layernorm rows=%d: %.3f ms  %.0f GB/s" % (rows, ms, rows * 768 * 6 / ms / 1e6), flush=True)
 
 
+def decode_attn_probe(B, E=1, C=578, L=4):
+    """One decode-step attention call per decoder layer over distinct caches (so L2 cannot help): algorithmic bytes =
+    K+V of the visible keys, context rows counted once per image."""
+    heads, H = 12, 768
+    R = B * E
+    ctx = [torch.randn(B, C, 3 * H, device=dev).to(torch.bfloat16) for _ in range(L)]
+    stepq = [torch.randn(20, 2 * R, 3 * H, device=dev).to(torch.bfloat16) for _ in range(L)]
+    out = torch.empty(2 * R, H, device=dev, dtype=torch.bfloat16)
+    for impl in ("auto", "simt"):
+        for cur_len in (1, 10, 19):
+            def run():
+                for l in range(L):
+                    ops.decode_attention(ctx[l], stepq[l], None, out, B, C, heads, E, cur_len, 0.125, impl=impl)
+            ms = timeit(run) / L
+            byt = B * (C + E * (cur_len + 1)) * 2 * H * 2
+            print("decode_attention[%s] B=%d E=%d cur_len=%d: %.1f us  %.0f GB/s (algorithmic)" % (impl, B, E, cur_len, ms * 1e3, byt / ms / 1e6),
+                  flush=True)
+
+
 def stage_probe(B, variant="16_384"):
     cfg = vcfg.variant(variant)
     sd = synth.make_state_dict(cfg, seed=0)
@@ -111,5 +130,8 @@ if __name__ == "__main__":
     if what in ("all", "attn"):
         attn_probe(B)
         ln_probe(B)
+    if what in ("all", "dattn"):
+        decode_attn_probe(B)
+        decode_attn_probe(min(B, 256), E=4)
     if what in ("all", "stage"):
         stage_probe(B)

@@ -26,6 +26,8 @@ int embed_ln(int out_bf16, const int* ids, int max_len, int cur_len, int mask_id
              cudaStream_t s);
 int decode_attention(int is_bf16, const void* ctx_qkv, const void* step_qkv, const int* anc, void* out, int B, int C, int heads,
                      int E, int cur_len, float scale, cudaStream_t s);
+int decode_attention_simt(int is_bf16, const void* ctx_qkv, const void* step_qkv, const int* anc, void* out, int B, int C,
+                          int heads, int E, int cur_len, float scale, cudaStream_t s);
 int token_step(const float* logits, int ld, int rows, int V, int do_sample, float temperature, uint64_t seed, int cur_len,
                int max_len, int pad_id, const int* eos_ids, int n_eos, int* ids, int* unfinished, float* sum_lp, int* n_steps,
                cudaStream_t s);
@@ -102,6 +104,10 @@ int vc_embed_ln(int bf16, const int* ids, int max_len, int cur_len, int mask_id,
 int vc_decode_attention(int bf16, const void* ctx_qkv, const void* step_qkv, const int* anc, void* out, int B, int C, int heads,
                         int E, int cur_len, float scale, void* stream) {
   VC_COUNT(1, vc::decode_attention(bf16, ctx_qkv, step_qkv, anc, out, B, C, heads, E, cur_len, scale, ST(stream)));
+}
+int vc_decode_attention_simt(int bf16, const void* ctx_qkv, const void* step_qkv, const int* anc, void* out, int B, int C,
+                             int heads, int E, int cur_len, float scale, void* stream) {
+  VC_COUNT(1, vc::decode_attention_simt(bf16, ctx_qkv, step_qkv, anc, out, B, C, heads, E, cur_len, scale, ST(stream)));
 }
 int vc_token_step(const float* logits, int ld, int rows, int V, int do_sample, float temperature, uint64_t seed, int cur_len,
                   int max_len, int pad_id, const int* eos_ids, int n_eos, int* ids, int* unfinished, float* sum_lp, int* n_steps,

@@ -15,6 +15,12 @@
 
 namespace vc {
 
+int decode_attention_mma(const void* ctx_qkv, const void* step_qkv, const int* anc, void* out, int B, int C, int heads, int E,
+                         int cur_len, float scale, cudaStream_t s);
+// CUDA-core variant (exact mode, fp32 storage); also instantiable for bf16 as a cross-check of the mma kernel
+int decode_attention_simt(int is_bf16, const void* ctx_qkv, const void* step_qkv, const int* anc, void* out, int B, int C,
+                          int heads, int E, int cur_len, float scale, cudaStream_t s);
+
 template <typename T> __device__ __forceinline__ float fast_exp(float x);
 template <> __device__ __forceinline__ float fast_exp<float>(float x) { return expf(x); }
 template <> __device__ __forceinline__ float fast_exp<bf16>(float x) { return __expf(x); }
@@ -225,6 +231,15 @@ int decode_attention(int is_bf16, const void* ctx_qkv, const void* step_qkv, con
   if (B <= 0 || C <= 0 || heads <= 0 || E <= 0 || cur_len < 1 || B * ((E + 3) / 4) > 65535) {
     set_last_error("decode_attention: bad args B=%d C=%d heads=%d E=%d cur_len=%d", B, C, heads, E, cur_len);
     return VC_ERR_BAD_ARG;
+  }
+  if (is_bf16) return decode_attention_mma(ctx_qkv, step_qkv, anc, out, B, C, heads, E, cur_len, scale, s);
+  return launch_da<float>(ctx_qkv, step_qkv, anc, out, B, C, heads, E, cur_len, scale, s);
+}
+
+int decode_attention_simt(int is_bf16, const void* ctx_qkv, const void* step_qkv, const int* anc, void* out, int B, int C,
+                          int heads, int E, int cur_len, float scale, cudaStream_t s) {
+  if (B <= 0 || C <= 0 || heads <= 0 || E <= 0 || cur_len < 1 || B * ((E + 3) / 4) > 65535) {
+    set_last_error("decode_attention_simt: bad args"); return VC_ERR_BAD_ARG;
   }
   if (is_bf16) return launch_da<bf16>(ctx_qkv, step_qkv, anc, out, B, C, heads, E, cur_len, scale, s);
   return launch_da<float>(ctx_qkv, step_qkv, anc, out, B, C, heads, E, cur_len, scale, s);

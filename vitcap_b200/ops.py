@@ -32,6 +32,7 @@ SIGNATURES = {
     "vc_tag_topk": [_P, _I, _I, _I, _I, _F, _P, _P, _P, _P],
     "vc_embed_ln": [_I, _P, _I, _I, _I, _P, _P, _P, _P, _P, _F, _P, _P, _I, _I, _P],
     "vc_decode_attention": [_I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
+    "vc_decode_attention_simt": [_I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
     "vc_token_step": [_P, _I, _I, _I, _I, _F, _U64, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P],
     "vc_greedy_finalize": [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P],
     "vc_beam_row_topk": [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P],
@@ -191,9 +192,10 @@ def embed_ln(ids, cur_len, mask_id, word, pos, type0, gamma, beta, eps, out_f, o
                                       _stream()), "vc_embed_ln")
 
 
-def decode_attention(ctx_qkv, step_qkv, anc, out, B, C, heads, E, cur_len, scale):
-    _check(load_library().vc_decode_attention(_is_bf16(ctx_qkv), _ptr(ctx_qkv), _ptr(step_qkv), _ptr(anc), _ptr(out), B, C,
-                                              heads, E, cur_len, float(scale), _stream()), "vc_decode_attention")
+def decode_attention(ctx_qkv, step_qkv, anc, out, B, C, heads, E, cur_len, scale, impl="auto"):
+    fn = load_library().vc_decode_attention_simt if impl == "simt" else load_library().vc_decode_attention
+    _check(fn(_is_bf16(ctx_qkv), _ptr(ctx_qkv), _ptr(step_qkv), _ptr(anc), _ptr(out), B, C, heads, E, cur_len, float(scale),
+              _stream()), "vc_decode_attention")
 
 
 def token_step(logits, V, rows, do_sample, temperature, seed, cur_len, pad_id, eos_ids, ids, unfinished, sum_lp, n_steps):
