@@ -43,7 +43,8 @@ void vc_reset_launch_count(void);
 /* out[M,N] = act(A[M,K] * W[N,K]^T + bias[N]) (+ resid[M,N]);  replaces torch.nn.functional.linear behind
  *   vision_transformer.py:152-158 (Mlp fc1/fc2), :169-201 (Attention qkv/proj), :267-275 (PatchEmbed conv as GEMM),
  *   modeling_bert.py:307-313 (query/key/value), :353-357, :402-405, :415-419 (dense layers), :524-563 (pooler, heads).
- * bf16=1: A, W bfloat16, tcgen05.mma kind::f16 with TMA-fed 128B-swizzled smem tiles, fp32 accumulator in TMEM
+ * bf16=1: A, W bfloat16, tcgen05.mma kind::f16 (cta_group::2 on CTA pairs for large M) with TMA-fed 128B-swizzled smem
+ *         tiles, fp32 accumulator in TMEM
  *         (requires K % 64 == 0, 16-byte aligned pointers, pitches % 8 == 0).
  * bf16=0: A, W fp32, CUDA-core FFMA tiles (K % 16 == 0).
  * out_f32: output element type (1 = fp32, 0 = bf16 in fast mode / fp32 in exact mode is selected by the caller).
@@ -55,7 +56,8 @@ int vc_linear(int bf16, const void* A, int lda, const void* W, int ldw, const fl
 /* same contract, forcing the CUDA-core kernel for bf16 operands (cross-check of the tensor-core kernel in tests) */
 int vc_linear_simt(int in_bf16, const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldo,
                    int out_f32, int act, const float* resid, int ldr, int M, int N, int K, void* stream);
-/* tcgen05 kernel with an explicit N-tile width (64/128/256; 0 = heuristic) -- for tests and tuning */
+/* tcgen05 kernel with an explicit N-tile width (64/128/256 = single-CTA kernel, 512 = the CTA-pair kernel with 256x256
+ * tiles; 0 = heuristic: CTA pairs when the problem has at least two rounds of pair tiles) -- for tests and tuning */
 int vc_linear_tc(const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldo, int out_f32, int act,
                  const float* resid, int ldr, int M, int N, int K, int tile_n, void* stream);
 

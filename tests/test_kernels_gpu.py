@@ -50,7 +50,7 @@ TC_SHAPES = [(128, 256, 64), (128, 256, 768), (256, 512, 128), (300, 200, 64), (
              (64, 1000, 768), (1024, 768, 768)]
 
 
-@pytest.mark.parametrize("tile_n", [256, 128, 64])
+@pytest.mark.parametrize("tile_n", [512, 256, 128, 64])
 @pytest.mark.parametrize("M,N,K", TC_SHAPES)
 def test_linear_tc_bf16_plain(M, N, K, tile_n):
     """tcgen05 GEMM, bf16 out, bias only. Tolerance: bf16 output rounding (2^-8 relative) on fp32-accumulated sums."""
@@ -78,6 +78,42 @@ def test_linear_tc_epilogues(act, out_f32, with_resid):
         torch.testing.assert_close(out, ref, rtol=2e-4, atol=2e-4)   # fp32 accumulate of exact bf16 products
     else:
         torch.testing.assert_close(out.float(), ref, rtol=1e-2, atol=1e-2)
+
+
+@pytest.mark.parametrize("M,N,K", [(577 * 3, 768, 768), (20000, 768, 768), (9000, 1024, 3072), (4111, 2304, 768)])
+@pytest.mark.parametrize("act", [ops.ACT_NONE, ops.ACT_GELU, ops.ACT_TANH])
+@pytest.mark.parametrize("out_f32,with_resid", [(True, True), (True, False), (False, False)])
+def test_linear_tc2_cta_pair_epilogues(M, N, K, act, out_f32, with_resid):
+    """CTA-pair kernel (cta_group::2, forced with tile_n=512): several rounds of tiles per cluster (accumulator / stage phase
+    wrap), ragged M, every epilogue. GELU here is the tanh-form fit of erf (|err| <= 3e-5 + MUFU.TANH's 2^-11 relative)."""
+    a, w, b = rnd(M, K, seed=5, dtype=torch.bfloat16), rnd(N, K, seed=6, scale=0.03, dtype=torch.bfloat16), rnd(N, seed=7)
+    resid = rnd(M, N, seed=8) if with_resid else None
+    out = torch.zeros(M, N, device=dev(), dtype=torch.float32 if out_f32 else torch.bfloat16)
+    ops.linear(a, w, b, out, act=act, resid=resid, impl="tc", tile_n=512)
+    ref = ref_linear(a, w, b, act, resid)
+    if out_f32:
+        tol = 2e-3 if act == ops.ACT_GELU else 3e-4
+        torch.testing.assert_close(out, ref, rtol=tol, atol=tol)
+    else:
+        torch.testing.assert_close(out.float(), ref, rtol=1e-2, atol=1e-2)
+
+
+def test_linear_tc2_inplace_residual_and_heuristic():
+    """x = x + proj(h) in place on the CTA-pair kernel; the auto heuristic must pick it for the encoder shape and agree."""
+    M, N, K = 577 * 64, 768, 768
+    a, w, b = rnd(M, K, seed=5, dtype=torch.bfloat16), rnd(N, K, seed=6, scale=0.03, dtype=torch.bfloat16), rnd(N, seed=7)
+    x = rnd(M, N, seed=9)
+    x2 = x.clone()
+    ref = ref_linear(a, w, b, ops.ACT_NONE, x.clone())
+    ops.linear(a, w, b, x, resid=x, impl="tc", tile_n=512)
+    torch.testing.assert_close(x, ref, rtol=3e-4, atol=3e-4)
+    ops.linear(a, w, b, x2, resid=x2)
+    torch.testing.assert_close(x, x2, rtol=0, atol=1e-6)
+    y1 = torch.empty(M, N, device=dev(), dtype=torch.bfloat16)
+    y2 = torch.empty_like(y1)
+    ops.linear(a, w, b, y1, impl="tc", tile_n=512)
+    ops.linear(a, w, b, y2, impl="tc", tile_n=256)
+    assert torch.equal(y1, y2)                       # same products, same accumulation order per output element
 
 
 def test_linear_tc_inplace_residual_stream():

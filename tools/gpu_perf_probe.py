@@ -40,7 +40,7 @@ def gemm_probe(B):
         r = out if resid else None
         if resid:
             out.normal_()
-        for tn in (256, 128):
+        for tn in (512, 256):
             ms = timeit(lambda: ops.linear(a, w, b, out, act=act, resid=r, impl="tc", tile_n=tn))
             tf = 2.0 * M * N * K / ms / 1e9
             res.append((name, M, N, K, tn, ms, tf))

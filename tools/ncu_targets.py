@@ -1,0 +1,52 @@
+"""Launches single hot kernels at the bench shapes (B=512) for `ncu --set full -k regex:...` captures.
+usage: python tools/ncu_targets.py [attn|gemm_qkv|gemm_proj|gemm_fc1|gemm_fc2|dattn|ln] [reps]"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from vitcap_b200 import ops  # noqa: E402
+
+dev = torch.device("cuda:0")
+what = sys.argv[1] if len(sys.argv) > 1 else "attn"
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+B = int(os.environ.get("VC_B", "512"))
+M = B * 577
+
+
+def gemm(N, K, act, resid, outf32):
+    a = torch.randn(M, K, device=dev).to(torch.bfloat16)
+    w = (torch.randn(N, K, device=dev) * 0.02).to(torch.bfloat16)
+    b = torch.randn(N, device=dev)
+    out = torch.randn(M, N, device=dev, dtype=torch.float32 if outf32 else torch.bfloat16)
+    for _ in range(reps):
+        ops.linear(a, w, b, out, act=act, resid=out if resid else None)
+
+
+if what == "attn":
+    qkv = torch.randn(B, 577, 2304, device=dev).to(torch.bfloat16)
+    out = torch.empty(B, 577, 768, device=dev, dtype=torch.bfloat16)
+    for _ in range(reps):
+        ops.attention(qkv, out, B, 577, 12, 0.125)
+elif what == "gemm_qkv":
+    gemm(2304, 768, 0, False, False)
+elif what == "gemm_proj":
+    gemm(768, 768, 0, True, True)
+elif what == "gemm_fc1":
+    gemm(3072, 768, 1, False, False)
+elif what == "gemm_fc2":
+    gemm(768, 3072, 0, True, True)
+elif what == "dattn":
+    ctx = torch.randn(B, 578, 2304, device=dev).to(torch.bfloat16)
+    sq = torch.randn(20, 2 * B, 2304, device=dev).to(torch.bfloat16)
+    out = torch.empty(2 * B, 768, device=dev, dtype=torch.bfloat16)
+    for _ in range(reps):
+        ops.decode_attention(ctx, sq, None, out, B, 578, 12, 1, 10, 0.125)
+elif what == "ln":
+    x = torch.randn(M, 768, device=dev)
+    g, b = torch.randn(768, device=dev), torch.randn(768, device=dev)
+    o = torch.empty(M, 768, device=dev, dtype=torch.bfloat16)
+    for _ in range(reps):
+        ops.layernorm(x, g, b, 1e-6, out_t=o)
+torch.cuda.synchronize()

@@ -315,6 +315,9 @@ static int launch_bn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
   return VC_ERR_BAD_ARG;
 }
 
+int gemm_bf16_tc2(const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldo, int out_f32, int act,
+                  const float* resid, int ldr, int M, int N, int K, cudaStream_t stream);
+
 int gemm_bf16_tc(const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldo, int out_f32,
                  int act, const float* resid, int ldr, int M, int N, int K, int force_bn, cudaStream_t stream) {
   if (M <= 0 || N <= 0 || K <= 0 || (K % 64) != 0) { set_last_error("gemm_tc: need K %% 64 == 0 (K=%d)", K); return VC_ERR_BAD_ARG; }
@@ -325,6 +328,14 @@ int gemm_bf16_tc(const void* A, int lda, const void* W, int ldw, const float* bi
       (reinterpret_cast<uintptr_t>(bias) & 15)) {
     set_last_error("gemm_tc: pointers must be 16-byte aligned and row pitches multiples of 16 bytes");
     return VC_ERR_BAD_ARG;
+  }
+  // large problems run on CTA pairs (gemm_tc2.cu): 256 x 256 tiles, at least two rounds of tiles per cluster
+  {
+    const long pair_tiles = (long)((M + 255) / 256) * ((N + 255) / 256);
+    // (the K <= 768 residual GEMM is bound by its fp32 residual traffic, where the single-CTA kernel measured 3 % faster)
+    const bool hbm_bound_resid = resid != nullptr && K <= 768;
+    if (force_bn == 512 || (force_bn == 0 && N >= 256 && pair_tiles >= 2 * (sm_count() / 2) && !hbm_bound_resid))
+      return gemm_bf16_tc2(A, lda, W, ldw, bias, out, ldo, out_f32, act, resid, ldr, M, N, K, stream);
   }
   // tile width: the widest N tile that still gives every SM work
   int bn = force_bn;

@@ -1,0 +1,391 @@
+// bf16 GEMM on CTA pairs (tcgen05 cta_group::2):  out[M,N] = act(A[M,K] * W[N,K]^T + bias) (+ resid)
+//
+// The large GEMMs of the caption path (M = images x 577 rows) run here; gemm_tc.cu keeps the small-M decode shapes.
+// Compared with the single-CTA kernel:
+//   * a cluster of two CTAs (one per SM of a TPC) owns a 256 x 256 output tile; the leader's single elected thread issues
+//     tcgen05.mma.cta_group::2 (M = 256), each CTA holds its 128 accumulator rows in its own TMEM and stages only its own
+//     128 rows of A and HALF of the W tile, so the operand traffic into shared memory per SM drops from 48 KB to 32 KB per
+//     k-block and the freed space deepens the TMA pipeline to 5-6 stages (round-1 profile: 3-4 stages of 48 KB left the
+//     tensor pipe at 67-78 % on the single-CTA kernel)
+//   * every CTA's TMA loads complete on the LEADER's full barrier (peer bit of the barrier address cleared); the leader's
+//     tcgen05.commit multicasts the stage-free / accumulator-ready arrivals to both CTAs; the peer's epilogue warps release
+//     the accumulator stage by a remote mbarrier arrive on the leader
+//   * epilogue warps come in one or two groups of four (one warp per TMEM lane quadrant and group). Two groups split the
+//     32/64-column chunks of a tile between them, which keeps two warps per scheduler busy on the activation math
+//     (the erf-GELU epilogue was issue/latency bound with a single warp per scheduler)
+//   * GELU is x/2 * (1 + tanh(z * (c0 + c1 z^2 + c2 z^4))), z = x / sqrt(2): a minimax fit of erf(z) by one MUFU.TANH
+//     (|gelu error| < 3e-5 + tanh.approx error, far below the bf16 output resolution), 10 issue slots instead of 17.
+#include "common.cuh"
+
+namespace vc {
+
+namespace {
+
+enum { ACT2_NONE = 0, ACT2_GELU = 1, ACT2_TANH = 2 };
+
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;    // clears the CTA-rank bit of a shared::cluster address -> rank 0 of the pair
+
+template <bool OUT_F32, bool RESID, int G> struct Gemm2Cfg {
+  static constexpr int BM = 128;                        // rows per CTA (256 per pair)
+  static constexpr int BN = 256;                        // columns per pair tile; each CTA stages 128 rows of W
+  static constexpr int BK = 64;
+  static constexpr int A_BYTES = BM * BK * 2;           // 16 KB
+  static constexpr int B_BYTES = (BN / 2) * BK * 2;     // 16 KB
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int EPI_BYTES = 16384;               // staging tile: 128 rows x 128 B
+  static constexpr int NBUF_G = (G == 2) ? 2 : (RESID ? 4 : 2);     // staging tiles per epilogue group
+  static constexpr int NBUF = NBUF_G * G;
+  static constexpr int BUDGET = 227 * 1024 - 1024 - 512 - NBUF * EPI_BYTES;
+  static constexpr int STAGES_MAX = BUDGET / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_MAX > 8 ? 8 : STAGES_MAX;
+  static constexpr int TMEM_COLS = 512;                 // two accumulator stages of 256 columns
+  static constexpr int CW = OUT_F32 ? 32 : 64;          // output columns per staging tile
+  static constexpr int NCH = BN / CW;
+  static constexpr int THREADS = 64 + 128 * G;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NBUF * EPI_BYTES + 1024 + 512;
+  static_assert(!(RESID && G == 2), "the residual epilogue runs with one group (4 staging tiles)");
+  static_assert(STAGES >= 4, "pipeline too shallow");
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load into OWN shared memory whose completion bytes are credited to the barrier at the same offset in CTA rank 0
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & PEER_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+template <int kCols> __device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_slot) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "n"(kCols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int kCols> __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once all prior MMAs of this thread retired) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+// arrive on the barrier at this offset in CTA rank 0 of the pair (local arrive when executed by rank 0)
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 ra;\n"
+      "mapa.shared::cluster.u32 ra, %0, 0;\n"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
+      "}\n"
+      ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// erf(z) ~= tanh(z * (C0 + C1 u + C2 u^2)), u = min(z^2, 30): max |gelu error| 2.5e-5 (fit in DESIGN.md section 4)
+__device__ __forceinline__ float gelu_erf_tanh(float x) {
+  const float z = x * 0.70710678118654752440f;
+  const float u = fminf(z * z, 30.0f);
+  float p = fmaf(-1.988479253896676e-03f, u, 1.0466777301852825e-01f);
+  p = fmaf(p, u, 1.1278464660309704f);
+  const float t = tanh_approx(z * p);
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
+}
+
+template <int ACT> __device__ __forceinline__ float apply_act(float v) {
+  if (ACT == ACT2_GELU) return gelu_erf_tanh(v);
+  if (ACT == ACT2_TANH) return tanhf(v);
+  return v;
+}
+
+}  // namespace
+
+template <int ACT, bool OUT_F32, bool RESID, int G>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 128 * G, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
+                const float* __restrict__ bias, int M, int N, int K) {
+  using C = Gemm2Cfg<OUT_F32, RESID, G>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* epi = smem + C::STAGES * C::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi + C::NBUF * C::EPI_BYTES);
+  uint64_t* full_bar = bars;                            // [STAGES] used in the leader only (both CTAs' TMA bytes land here)
+  uint64_t* empty_bar = bars + C::STAGES;               // [STAGES] per CTA, armed by the leader's multicast commit
+  uint64_t* tmem_full = bars + 2 * C::STAGES;           // [2] per CTA, multicast commit
+  uint64_t* tmem_empty = bars + 2 * C::STAGES + 2;      // [2] leader only: 2 CTAs x 4G warps arrive
+  uint64_t* res_full = bars + 2 * C::STAGES + 4;        // [NBUF] residual tile landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4 + C::NBUF);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+  const int m_tiles = (M + 2 * C::BM - 1) / (2 * C::BM);
+  const int n_tiles = (N + C::BN - 1) / C::BN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int num_kb = K / C::BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    tma_prefetch_desc(&tmap_out);
+    if (RESID) tma_prefetch_desc(&tmap_res);
+    for (int i = 0; i < C::STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 2 * 4 * G);
+    }
+    for (int i = 0; i < C::NBUF; ++i) mbar_init(&res_full[i], 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_pair<C::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  cluster_sync_all();                                   // barriers of both CTAs initialised, TMEM allocated in both
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs: own A rows, own half of the W tile) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int m0 = (tile / n_tiles) * (2 * C::BM) + (int)rank * C::BM;
+        const int n0 = (tile % n_tiles) * C::BN + (int)rank * (C::BN / 2);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * C::STAGE_BYTES;
+          uint8_t* sb = sa + C::A_BYTES;
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
+          tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], kb * C::BK, m0);
+          tma_load_2d_pair(sb, &tmap_b, &full_bar[stage], kb * C::BK, n0);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (rank == 0 && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * C::BM, C::BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        mbar_wait(&tmem_empty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * C::BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint32_t sb = sa + C::A_BYTES;
+          const uint64_t adesc = make_smem_desc_sw128(sa, 16, 1024);
+          const uint64_t bdesc = make_smem_desc_sw128(sb, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < C::BK / 16; ++k) umma_f16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          umma_commit_pair(&empty_bar[stage]);          // frees this stage in both CTAs
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_pair(&tmem_full[as]);               // accumulator complete -> both epilogues
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue: G groups of 4 warps; thread <-> accumulator row of this CTA =====================
+    const int quad = warp & 3;                          // TMEM lane quadrant this warp may access
+    const int grp = (warp - 2) >> 2;                    // epilogue group 0 / 1
+    const int t = quad * 32 + lane;                     // row inside this CTA's half of the pair tile
+    const bool leader = (((warp - 2) & 3) == 0 && lane == 0);
+    const uint32_t sw = (uint32_t)(t & 7);
+    uint8_t* gepi = epi + grp * C::NBUF_G * C::EPI_BYTES;
+    uint64_t* gres = res_full + grp * C::NBUF_G;
+    const int bar_id = 1 + grp;
+    int as = 0;
+    uint32_t aphase = 0;
+    uint32_t g = 0;                                     // this group's running chunk counter (buffer = g % NBUF_G)
+    uint32_t pf_g = 0;                                  // residual prefetch cursor (leader of the group, RESID => G == 1)
+    int pf_tile = cluster_id, pf_c = 0;
+    auto prefetch_resid = [&]() {
+      if (pf_tile >= num_tiles) return;
+      const int pm0 = (pf_tile / n_tiles) * (2 * C::BM) + (int)rank * C::BM;
+      const int pn0 = (pf_tile % n_tiles) * C::BN + pf_c * C::CW;
+      const int b = pf_g % C::NBUF_G;
+      mbar_arrive_expect_tx(&gres[b], C::EPI_BYTES);
+      tma_load_2d(gepi + b * C::EPI_BYTES, &tmap_res, &gres[b], pn0, pm0);
+      ++pf_g;
+      ++pf_c;
+      if (pf_c == C::NCH || (pf_tile % n_tiles) * C::BN + pf_c * C::CW >= N) { pf_c = 0; pf_tile += num_clusters; }
+    };
+    if (RESID && leader) {
+      for (int i = 0; i < C::NBUF_G - 2; ++i) prefetch_resid();
+    }
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      const int m0 = (tile / n_tiles) * (2 * C::BM) + (int)rank * C::BM;
+      const int n0 = (tile % n_tiles) * C::BN;
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = grp; c < C::NCH; c += G) {
+        const int col0 = n0 + c * C::CW;
+        if (col0 >= N) break;
+        const int b = g % C::NBUF_G;
+        uint8_t* ebuf = gepi + b * C::EPI_BYTES;
+        uint8_t* myrow = ebuf + t * 128;
+        // (1) the staging tile written NBUF_G chunks ago must have been read by its TMA store
+        if (leader) {
+          bulk_wait_read<1>();
+          if (RESID) prefetch_resid();
+        }
+        named_bar_sync(bar_id, 128);
+        const bool full = (col0 + C::CW <= N);
+        // (2) accumulator row -> registers -> bias / activation / residual -> swizzled staging row
+#pragma unroll
+        for (int hh = 0; hh < C::CW / 32; ++hh) {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + as * C::BN + c * C::CW + hh * 32, r);
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          const int cb = col0 + hh * 32;
+          if (bias != nullptr) {
+            if (full) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + cb + j));
+                v[j] += bb.x; v[j + 1] += bb.y; v[j + 2] += bb.z; v[j + 3] += bb.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] += (cb + j < N) ? __ldg(bias + cb + j) : 0.f;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = apply_act<ACT>(v[j]);
+          if (OUT_F32) {
+            if (RESID) {
+              mbar_wait(&gres[b], (g / C::NBUF_G) & 1);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 rr = *reinterpret_cast<const float4*>(myrow + ((j ^ sw) << 4));
+                v[4 * j] += rr.x; v[4 * j + 1] += rr.y; v[4 * j + 2] += rr.z; v[4 * j + 3] += rr.w;
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(myrow + ((j ^ sw) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 pk = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                          pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+              *reinterpret_cast<uint4*>(myrow + (((hh * 4 + j) ^ sw) << 4)) = pk;
+            }
+          }
+        }
+        // (3) staging tile -> global (rows >= M and columns >= N are clipped by the tensor map)
+        fence_proxy_async_smem();
+        named_bar_sync(bar_id, 128);
+        if (leader) {
+          tma_store_2d(&tmap_out, ebuf, col0, m0);
+          bulk_commit();
+        }
+        ++g;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tmem_empty[as]);
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+    if (leader) bulk_wait_all<0>();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();                                   // the peer's smem / TMEM stay alive until the leader's MMAs retired
+  if (warp == 1) tmem_dealloc_pair<C::TMEM_COLS>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------
+// host launcher
+// ------------------------------------------------------------------------------------------
+template <int ACT, bool OUT_F32, bool RESID, int G>
+static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr, const float* bias,
+                   int M, int N, int K, cudaStream_t stream) {
+  using C = Gemm2Cfg<OUT_F32, RESID, G>;
+  auto kern = gemm_tc2_kernel<ACT, OUT_F32, RESID, G>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) { set_last_error("gemm_tc2: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return VC_ERR_LAUNCH; }
+    configured = true;
+  }
+  const int tiles = ((M + 2 * C::BM - 1) / (2 * C::BM)) * ((N + C::BN - 1) / C::BN);
+  int clusters = sm_count() / 2;
+  if (tiles < clusters) clusters = tiles;
+  kern<<<2 * clusters, C::THREADS, C::SMEM_BYTES, stream>>>(ta, tb, to, tr, bias, M, N, K);
+  return check_launch("gemm_tc2");
+}
+
+template <int ACT>
+static int launch2_act(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr, const float* bias,
+                       int out_f32, bool resid, int M, int N, int K, cudaStream_t s) {
+  if (out_f32) {
+    if (resid) return launch2<ACT, true, true, 1>(ta, tb, to, tr, bias, M, N, K, s);
+    return launch2<ACT, true, false, 2>(ta, tb, to, tr, bias, M, N, K, s);
+  }
+  return launch2<ACT, false, false, 2>(ta, tb, to, tr, bias, M, N, K, s);
+}
+
+// same contract as gemm_bf16_tc (gemm_tc.cu)
+int gemm_bf16_tc2(const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldo, int out_f32, int act,
+                  const float* resid, int ldr, int M, int N, int K, cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0 || (K % 64) != 0) { set_last_error("gemm_tc2: need K %% 64 == 0 (K=%d)", K); return VC_ERR_BAD_ARG; }
+  if (resid && !out_f32) { set_last_error("gemm_tc2: a residual needs fp32 output"); return VC_ERR_BAD_ARG; }
+  CUtensorMap ta, tb, to, tr;
+  int rc = get_tmap_2d_bf16(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 128, 64);
+  if (rc) return rc;
+  rc = get_tmap_2d_bf16(&tb, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, 128, 64);
+  if (rc) return rc;
+  if (out_f32) rc = get_tmap_2d_f32(&to, out, (uint64_t)M, (uint64_t)N, (uint64_t)ldo, 128, 32);
+  else rc = get_tmap_2d_bf16(&to, out, (uint64_t)M, (uint64_t)N, (uint64_t)ldo, 128, 64);
+  if (rc) return rc;
+  tr = to;
+  if (resid) {
+    rc = get_tmap_2d_f32(&tr, resid, (uint64_t)M, (uint64_t)N, (uint64_t)ldr, 128, 32);
+    if (rc) return rc;
+  }
+  switch (act) {
+    case ACT2_NONE: return launch2_act<ACT2_NONE>(ta, tb, to, tr, bias, out_f32, resid != nullptr, M, N, K, stream);
+    case ACT2_GELU: return launch2_act<ACT2_GELU>(ta, tb, to, tr, bias, out_f32, resid != nullptr, M, N, K, stream);
+    case ACT2_TANH: return launch2_act<ACT2_TANH>(ta, tb, to, tr, bias, out_f32, resid != nullptr, M, N, K, stream);
+  }
+  set_last_error("gemm_tc2: unknown activation %d", act);
+  return VC_ERR_BAD_ARG;
+}
+
+}  // namespace vc
