@@ -277,7 +277,7 @@ def test_beam_kernels_vs_oracle_loop(B, nb, keep, lp, V):
     assert torch.equal(ids, rids), (ids[0], rids[0])
     np.testing.assert_allclose(glp.numpy(), rlp.numpy(), atol=2e-5, rtol=1e-5)
     # the ancestor table must reproduce every live beam's prefix: ids[r, j+1] was generated by row anc[j, r] at step j
-    anc = st["anc"].cpu()
+    anc = st["anc"].cpu()[:19]                                        # one row per decode step (max_len - 1 steps)
     assert int(anc.min()) >= 0 and int(anc.max()) < B * nb
     rows = torch.arange(B * nb)
     assert torch.equal(anc // nb, (rows // nb).expand_as(anc))        # beams never cross images

@@ -127,8 +127,9 @@ __device__ void block_lse(const float* __restrict__ row, int V, float inv_temp, 
   float m = -INFINITY, s = 0.f;
   for (int i = tid; i < V; i += nt) {
     const float x = row[i] * inv_temp;
-    if (x > m) { s = s * expf(m - x) + 1.f; m = x; }
-    else s += expf(x - m);
+    // filtered logits are -inf (modeling_utils.py:1120/1134): they contribute nothing, and exp(-inf - -inf) must not be formed
+    if (x > m) { s = (m == -INFINITY ? 0.f : s * expf(m - x)) + 1.f; m = x; }
+    else if (x != -INFINITY) s += expf(x - m);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
