@@ -4,18 +4,20 @@
 // and BertSelfAttention over the 578 context rows (modeling_bert.py:303-340). The N x N scores never leave the SM.
 //
 // One CTA = one (image, head); it walks the 128-query tiles of that head and, inside each tile, the keys in 64-key chunks,
-// as ONE flattened software pipeline (no drain between tiles).
-//   TMEM   : S0, S1 (128 x 64 fp32, ping-pong over chunks) and O0, O1 (128 x 64 fp32, ping-pong over tiles) = 256 columns
-//   smem   : Q 2 x 16 KB (ping-pong over tiles), K ring 3 x 8 KB, V ring 3 x 8 KB, P 2 x 16 KB  (112 KB -> two CTAs per SM)
-//   control warp (1 elected thread): TMA loads (3-D tensor map over [B, N, 3H]; rows past N are zero-filled by hardware),
-//            S_g = Q K_j^T issued two chunks ahead of the softmax, O += P_g V_j (V consumed MN-major straight from the
-//            row-major qkv buffer); the next tile's Q is prefetched while the current tile is being processed
-//   4 softmax warps, one query row per thread: tcgen05.ld S_g, row max, lazy rescale of O (FA4-style: the exponent reference
-//            only moves when the max grew by > 2^8), P_g = exp2(.) as bf16 into a 128B-swizzled tile; per tile epilogue
-//            O / l -> bf16 -> global while the MMAs of the next tile already run.
-// The MUFU (exp2) pipe is the true bound of this d=64 attention (16 exp/clk/SM, measured); round-1 profiles showed the
-// single-buffered per-tile version spending most of its time in the serial MMA -> softmax -> MMA chain and in per-CTA
-// prologues, hence the ping-pong buffers and the persistent tile loop.
+// as ONE flattened software pipeline (no drain between tiles); two CTAs share an SM.
+//   TMEM   : S0, S1 (128 x 64 fp32, ping-pong over chunks) and O0, O1 (128 x 64 fp32, ping-pong over tiles) = 256 columns.
+//            P_g = exp2(S_g - m) is written back as packed bf16 pairs INTO the first 32 columns of its own S buffer and the
+//            O += P V MMA reads its A operand straight from TMEM: P never touches shared memory (round-1 profile: the P
+//            round trip through smem cost 8 STS + a proxy fence per row and chunk and made the PV MMA smem-read bound).
+//   smem   : Q 2 x 16 KB (ping-pong over tiles), K ring 4 x 8 KB, V ring 4 x 8 KB
+//   warp 0 (1 elected thread): TMA loads (3-D tensor map over [B, N, 3H]; rows past N are zero-filled by hardware)
+//   warp 1 (1 elected thread): MMA issue. Step g: O += P_g V_j (V consumed MN-major straight from the row-major qkv buffer),
+//            then S_{g+2} = Q K^T into the buffer P_g just vacated (the tensor pipe executes in issue order)
+//   warps 2-5 (softmax, one query row per thread; they outrank the role warps in the scheduler's highest-warp-first pick):
+//            tcgen05.ld S_g, row max (FMNMX3, two chains), lazy rescale of O (the exponent reference only moves when the
+//            max grew by > 2^8), P = exp2(.) with packed FFMA2 / FADD2 arithmetic around the MUFU, tcgen05.st P_g;
+//            per tile epilogue O / l -> bf16 -> global while the MMAs of the next tile already run.
+// The MUFU (exp2) pipe is the bound of this d=64 attention: 16 exp/clk/SM.
 #include "common.cuh"
 
 namespace vc {
@@ -26,16 +28,14 @@ constexpr int KT = 64;            // keys per chunk
 constexpr int D = 64;             // head dim
 constexpr int Q_BYTES = 128 * 64 * 2;      // 16 KB  [128 rows][64 bf16], 128B swizzle
 constexpr int KV_BYTES = KT * 64 * 2;      // 8 KB   [64 keys][64 bf16]
-constexpr int P_BYTES = 128 * KT * 2;      // 16 KB  [128 rows][64 keys]
-constexpr int NKV = 3;                     // K/V ring depth
+constexpr int NKV = 4;                     // K/V ring depth
 constexpr int SMEM_Q = 0;                  // 2 buffers
 constexpr int SMEM_K = SMEM_Q + 2 * Q_BYTES;
 constexpr int SMEM_V = SMEM_K + NKV * KV_BYTES;
-constexpr int SMEM_P = SMEM_V + NKV * KV_BYTES;
-constexpr int SMEM_BAR = SMEM_P + 2 * P_BYTES;
+constexpr int SMEM_BAR = SMEM_V + NKV * KV_BYTES;
 constexpr int SMEM_TOTAL = SMEM_BAR + 256;
 constexpr int TMEM_COLS = 256;
-constexpr int COL_S = 0, COL_O = 128;      // S0 | S1 | O0 | O1, 64 columns each
+constexpr int COL_S = 0, COL_O = 128;      // S0 | S1 | O0 | O1, 64 columns each; P_g aliases columns [0, 32) of S_g
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -56,7 +56,6 @@ __device__ __forceinline__ void rescale_o(uint32_t taddr_o, float corr) {
   }
   tmem_st_wait();
 }
-}  // namespace
 
 // per-tile epilogue of one query row: O / l -> bf16 -> out
 __device__ __forceinline__ void store_o_row(uint32_t taddr_o, float l, bf16* op, bool valid, uint64_t* o_free_bar) {
@@ -79,6 +78,7 @@ __device__ __forceinline__ void store_o_row(uint32_t taddr_o, float l, bf16* op,
       }
   }
 }
+}  // namespace
 
 __global__ void __launch_bounds__(192, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
@@ -86,16 +86,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_BAR);
   uint64_t* q_full = bars;           // [2] Q tile landed
-  uint64_t* k_full = bars + 2;       // [3]
-  uint64_t* v_full = bars + 5;       // [3]
-  uint64_t* s_full = bars + 8;       // [2] S_g complete (tcgen05.commit)
-  uint64_t* p_full = bars + 10;      // [2] P_g written, S_g consumed (128 arrivals)
-  uint64_t* pv_done = bars + 12;     // [2] O += P_g V complete (tcgen05.commit)
-  uint64_t* o_free = bars + 14;      // [2] epilogue finished reading O buffer (128 arrivals)
-  uint64_t* k_free = bars + 16;      // [3] S MMAs that read this K stage retired (tcgen05.commit)
-  uint64_t* v_free = bars + 19;      // [3] PV MMAs that read this V stage retired (tcgen05.commit)
-  uint64_t* q_free = bars + 22;      // [2] every S MMA of the tile that used this Q buffer retired
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+  uint64_t* q_free = bars + 2;       // [2] every S MMA of the tile that used this Q buffer retired (tcgen05.commit)
+  uint64_t* s_full = bars + 4;       // [2] S_g complete (tcgen05.commit)
+  uint64_t* p_full = bars + 6;       // [2] P_g written to TMEM (128 arrivals)
+  uint64_t* pv_done = bars + 8;      // [2] O += P_g V complete (tcgen05.commit)
+  uint64_t* o_free = bars + 10;      // [2] epilogue finished reading the O buffer (128 arrivals)
+  uint64_t* k_full = bars + 12;      // [NKV]
+  uint64_t* v_full = k_full + NKV;
+  uint64_t* k_free = v_full + NKV;   // S MMAs that read this K stage retired (tcgen05.commit)
+  uint64_t* v_free = k_free + NKV;   // PV MMAs that read this V stage retired (tcgen05.commit)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(v_free + NKV);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.x, b = blockIdx.y;
@@ -116,13 +116,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     }
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc<TMEM_COLS>(tmem_slot);
+  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 5) {
+  if (warp == 0) {
     // ===================== TMA loader (one elected thread): never on the MMA critical path =====================
     if (lane == 0) {
       const int cq = h * D, ck = H + h * D, cv = 2 * H + h * D;
@@ -162,17 +162,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         if (++j == nch) { j = 0; ++tile; }
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == 1) {
     // ===================== MMA issuer (one elected thread) =====================
     if (lane == 0) {
       // descriptors differ only in their 16-byte-granular start address: precompute bases, add offsets
       const uint64_t qd0 = make_smem_desc_sw128(smem_u32(smem + SMEM_Q), 16, 1024);
       const uint64_t kd0 = make_smem_desc_sw128(smem_u32(smem + SMEM_K), 16, 1024);
       const uint64_t vd0 = make_smem_desc_sw128(smem_u32(smem + SMEM_V), 16, 1024);
-      const uint64_t pd0 = make_smem_desc_sw128(smem_u32(smem + SMEM_P), 16, 1024);
       const uint32_t idesc_s_full = make_idesc_bf16(128, KT, 0, 0);            // Q (K-major) x K (K-major)
       const uint32_t idesc_s_last = make_idesc_bf16(128, last_kn, 0, 0);
-      constexpr uint32_t idesc_o = make_idesc_bf16(128, D, 0, 1);              // P (K-major) x V (MN-major)
+      constexpr uint32_t idesc_o = make_idesc_bf16(128, D, 0, 1);              // P (TMEM) x V (MN-major)
       auto issue_s = [&](int g, int tile, int j) {     // S_g = Q_tile K_j^T into S buffer g & 1
         const int st = g % NKV;
         if (j == 0) mbar_wait(&q_full[tile & 1], (tile >> 1) & 1);
@@ -188,7 +187,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         umma_commit(&k_free[st]);
         if (j == nch - 1) umma_commit(&q_free[tile & 1]);
       };
-      // (tile, j) of steps g, g+1, g+2 are tracked incrementally (no divisions on the critical path)
+      // (tile, j) of steps g and g+2 are tracked incrementally (no divisions on the critical path)
       int t0 = 0, j0 = 0;                               // step g
       int t2 = 0, j2 = 0;                               // step g+2
       issue_s(0, 0, 0);
@@ -196,37 +195,38 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       for (int i = 0; i < 2; ++i) if (++j2 == nch) { j2 = 0; ++t2; }
       for (int g = 0; g < total; ++g) {
         const int pb = g & 1;
-        mbar_wait(&p_full[pb], (g >> 1) & 1);          // P_g written and S_g consumed
-        // the softmax is waiting for S, nobody waits for O: S_{g+2} first
-        if (g + 2 < total) issue_s(g + 2, t2, j2);
-        // O_tile += P_g V_j
+        mbar_wait(&p_full[pb], (g >> 1) & 1);          // P_g sits in TMEM (first 32 columns of S buffer pb)
         mbar_wait(&v_full[g % NKV], (g / NKV) & 1);
         if (j0 == 0 && t0 >= 2) mbar_wait(&o_free[t0 & 1], ((t0 - 2) >> 1) & 1);   // epilogue of tile-2 has read this O buffer
         tc_fence_after();
         {
-          const uint64_t pd = pd0 + (uint64_t)(pb * (P_BYTES >> 4));
+          // O_tile += P_g V_j : A from TMEM (16 keys = 8 columns of bf16 pairs per step), B = 16 keys = 2048 B of V
+          const uint32_t pa = tmem_base + COL_S + pb * KT;
           const uint64_t vd = vd0 + (uint64_t)((g % NKV) * (KV_BYTES >> 4));
           const uint32_t d = tmem_base + COL_O + (t0 & 1) * D;
           const int ksteps = (j0 == nch - 1 ? last_kn : KT) / 16;
           if (ksteps == 4) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_f16(d, pd + 2 * k, vd + 128 * k, idesc_o, (j0 | k) != 0);   // 16 keys = 2048 B of V
+            for (int k = 0; k < 4; ++k) umma_f16_ts(d, pa + 8 * k, vd + 128 * k, idesc_o, (j0 | k) != 0);
           } else {
 #pragma unroll 1
-            for (int k = 0; k < ksteps; ++k) umma_f16(d, pd + 2 * k, vd + 128 * k, idesc_o, (j0 | k) != 0);
+            for (int k = 0; k < ksteps; ++k) umma_f16_ts(d, pa + 8 * k, vd + 128 * k, idesc_o, (j0 | k) != 0);
           }
           umma_commit(&pv_done[pb]);
           umma_commit(&v_free[g % NKV]);
         }
+        // S_{g+2} reuses the buffer P_g occupied: issued after PV_g, the tensor pipe keeps the order
+        if (g + 2 < total) issue_s(g + 2, t2, j2);
         if (++j0 == nch) { j0 = 0; ++t0; }
         if (++j2 == nch) { j2 = 0; ++t2; }
       }
     }
   } else {
-    // ===================== softmax warps: thread t owns query row t of the current tile =====================
-    const int t = threadIdx.x;                         // 0..127 == TMEM lane
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-    const uint32_t sw = (uint32_t)(t & 7);
+    // ===================== softmax warps 2..5: thread t owns query row t of the current tile =====================
+    const int quad = warp & 3;                         // TMEM lane quadrant this warp may access
+    const int t = quad * 32 + lane;                    // 0..127 == TMEM lane == row inside the tile
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    const uint64_t scale2 = pack_f32x2(scale_log2, scale_log2);
     int g = 0;
     // deferred epilogue of the previous tile (runs after the first chunk of the next tile, off the critical path)
     bool pend = false;
@@ -240,93 +240,57 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         const int sb = g & 1;
         const int lim = N - j * KT;                    // valid keys in this chunk (>= 64 for full chunks)
         const uint32_t taddr_s = tmem_base + lane_base + COL_S + sb * KT;
-        uint8_t* prow = smem + SMEM_P + sb * P_BYTES + t * 128;
         mbar_wait(&s_full[sb], (g >> 1) & 1);
         tc_fence_after();
-        if (lim >= KT) {
-          uint32_t r[2][32];
-          tmem_ld_32x32(taddr_s, r[0]);
-          tmem_ld_32x32(taddr_s + 32, r[1]);
-          tmem_ld_wait();
-          float mx = -INFINITY;
+        uint32_t r[64];
+        tmem_ld_32x32(taddr_s, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+        tmem_ld_32x32(taddr_s + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
+        tmem_ld_wait();
+        if (lim < KT) {
+          // ragged last chunk: columns >= lim hold stale scores (or nothing the MMA wrote): exclude them
 #pragma unroll
-          for (int c = 0; c < 2; ++c)
-#pragma unroll
-            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[c][i]));
-          const float mxs = mx * scale_log2;
-          const bool need = mxs > m_ref + 8.0f;
-          const float m_new = need ? mxs : m_ref;
-          if (j > 0 && __any_sync(0xffffffffu, need)) {
-            const float corr = ex2(m_ref - m_new);     // exactly 1 for lanes that keep their reference
-            mbar_wait(&pv_done[(g - 1) & 1], ((g - 1) >> 1) & 1);    // every issued PV has landed in TMEM
-            tc_fence_after();
-            rescale_o(taddr_o, corr);
-            l *= corr;
-          }
-          m_ref = m_new;
-          if (g >= 2) mbar_wait(&pv_done[sb], ((g - 2) >> 1) & 1);   // P buffer still being read by PV_{g-2}?
-          const float neg = -m_ref;
-          float sum0 = 0.f, sum1 = 0.f;
-#pragma unroll
-          for (int c = 0; c < 2; ++c)
-#pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-              float p[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) p[e] = ex2(fmaf(__uint_as_float(r[c][i + e]), scale_log2, neg));
-              sum0 += (p[0] + p[1]) + (p[2] + p[3]);
-              sum1 += (p[4] + p[5]) + (p[6] + p[7]);
-              const int chunk = (c * 32 + i) >> 3;     // 8 consecutive keys -> one 16-byte chunk of the 128-byte row
-              uint4 pk = make_uint4(pack_bf16x2(p[0], p[1]), pack_bf16x2(p[2], p[3]), pack_bf16x2(p[4], p[5]), pack_bf16x2(p[6], p[7]));
-              *reinterpret_cast<uint4*>(prow + ((chunk ^ sw) << 4)) = pk;
-            }
-          l += sum0 + sum1;
-        } else {
-          // ragged last chunk: only `lim` keys are valid; work in 16-column groups, two passes over TMEM
-          const int ng = (lim + 15) >> 4;
-          float mx = -INFINITY;
-          for (int gg = 0; gg < ng; ++gg) {
-            uint32_t r[16];
-            tmem_ld_32x16(taddr_s + gg * 16, r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (gg * 16 + i < lim) mx = fmaxf(mx, __uint_as_float(r[i]));
-          }
-          const float mxs = mx * scale_log2;
-          const bool need = mxs > m_ref + 8.0f;
-          const float m_new = need ? mxs : m_ref;
-          if (j > 0 && __any_sync(0xffffffffu, need)) {
-            const float corr = ex2(m_ref - m_new);
-            mbar_wait(&pv_done[(g - 1) & 1], ((g - 1) >> 1) & 1);
-            tc_fence_after();
-            rescale_o(taddr_o, corr);
-            l *= corr;
-          }
-          m_ref = m_new;
-          if (g >= 2) mbar_wait(&pv_done[sb], ((g - 2) >> 1) & 1);
-          const float neg = -m_ref;
-          float sum = 0.f;
-          for (int gg = 0; gg < ng; ++gg) {
-            uint32_t r[16];
-            tmem_ld_32x16(taddr_s + gg * 16, r);
-            tmem_ld_wait();
-            float p[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              p[i] = (gg * 16 + i < lim) ? ex2(fmaf(__uint_as_float(r[i]), scale_log2, neg)) : 0.f;
-              sum += p[i];
-            }
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-              uint4 pk = make_uint4(pack_bf16x2(p[8 * hh], p[8 * hh + 1]), pack_bf16x2(p[8 * hh + 2], p[8 * hh + 3]),
-                                    pack_bf16x2(p[8 * hh + 4], p[8 * hh + 5]), pack_bf16x2(p[8 * hh + 6], p[8 * hh + 7]));
-              *reinterpret_cast<uint4*>(prow + (((uint32_t)(gg * 2 + hh) ^ sw) << 4)) = pk;
-            }
-          }
-          l += sum;
+          for (int i = 0; i < 64; ++i)
+            if (i >= lim) r[i] = 0xff800000u;          // -inf
         }
-        fence_proxy_async_smem();                      // P (generic-proxy stores) -> visible to the MMA (async proxy)
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 64; i += 4) {
+          mx0 = fmaxf(mx0, fmaxf(__uint_as_float(r[i]), __uint_as_float(r[i + 1])));
+          mx1 = fmaxf(mx1, fmaxf(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])));
+        }
+        const float mxs = fmaxf(mx0, mx1) * scale_log2;
+        const bool need = mxs > m_ref + 8.0f;
+        const float m_new = need ? mxs : m_ref;
+        if (j > 0 && __any_sync(0xffffffffu, need)) {
+          const float corr = ex2(m_ref - m_new);       // exactly 1 for lanes that keep their reference
+          mbar_wait(&pv_done[(g - 1) & 1], ((g - 1) >> 1) & 1);    // every issued PV has landed in TMEM
+          tc_fence_after();
+          rescale_o(taddr_o, corr);
+          l *= corr;
+        }
+        m_ref = m_new;
+        const uint64_t neg2 = pack_f32x2(-m_ref, -m_ref);
+        uint64_t sum_a = 0ull, sum_b = 0ull;           // two packed partial sums (bit pattern of +0.0f pairs)
+        uint32_t pk[32];
+#pragma unroll
+        for (int i = 0; i < 64; i += 4) {
+          float x0, x1, x2, x3;
+          unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), scale2, neg2), x0, x1);
+          unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])), scale2, neg2), x2, x3);
+          const float p0 = ex2(x0), p1 = ex2(x1), p2 = ex2(x2), p3 = ex2(x3);     // ex2(-inf) = 0 for masked columns
+          sum_a = add_f32x2(sum_a, pack_f32x2(p0, p1));
+          sum_b = add_f32x2(sum_b, pack_f32x2(p2, p3));
+          pk[i >> 1] = pack_bf16x2(p0, p1);
+          pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
+        }
+        {
+          float s0, s1, s2, s3;
+          unpack_f32x2(sum_a, s0, s1);
+          unpack_f32x2(sum_b, s2, s3);
+          l += (s0 + s1) + (s2 + s3);
+        }
+        tmem_st_32x32(taddr_s, pk);                    // P_g overwrites the first half of its own S buffer
+        tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&p_full[sb]);
         if (pend && j == 0) {
@@ -351,7 +315,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc<TMEM_COLS>(tmem_base);
+  if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
 int attention_tc(const void* qkv, void* out, int B, int N, int heads, float scale, cudaStream_t s) {
