@@ -5,20 +5,24 @@
 //
 // One CTA = one (image, head); it walks the 128-query tiles of that head and, inside each tile, the keys in 64-key chunks,
 // as ONE flattened software pipeline (no drain between tiles); two CTAs share an SM.
-//   TMEM   : S0, S1 (128 x 64 fp32, ping-pong over chunks) and O0, O1 (128 x 64 fp32, ping-pong over tiles) = 256 columns.
+//   TMEM   : S0, S1, S2 (128 x 64 fp32, rotating over chunks) and O (128 x 64 fp32) = 256 columns. Three S buffers give
+//            the MMA round trip (P_g ready -> PV_g -> S_{g+3} -> softmax) two chunks of slack (with two, the softmax warps
+//            were measured waiting for S).
 //            P_g = exp2(S_g - m) is written back as packed bf16 pairs INTO the first 32 columns of its own S buffer and the
 //            O += P V MMA reads its A operand straight from TMEM: P never touches shared memory (round-1 profile: the P
 //            round trip through smem cost 8 STS + a proxy fence per row and chunk and made the PV MMA smem-read bound).
 //   smem   : Q 2 x 16 KB (ping-pong over tiles), K ring 4 x 8 KB, V ring 4 x 8 KB
 //   warp 0 (1 elected thread): TMA loads (3-D tensor map over [B, N, 3H]; rows past N are zero-filled by hardware)
 //   warp 1 (1 elected thread): MMA issue. Step g: O += P_g V_j (V consumed MN-major straight from the row-major qkv buffer),
-//            then S_{g+2} = Q K^T into the buffer P_g just vacated (the tensor pipe executes in issue order)
+//            then S_{g+3} = Q K^T into the buffer P_g just vacated (the tensor pipe executes in issue order)
 //   warps 2-5 (softmax, one query row per thread; they outrank the role warps in the scheduler's highest-warp-first pick):
 //            tcgen05.ld S_g, row max (FMNMX3, two chains), lazy rescale of O (the exponent reference only moves when the
 //            max grew by > 2^8), P = exp2(.) with packed FFMA2 / FADD2 arithmetic around the MUFU, tcgen05.st P_g;
 //            per tile epilogue O / l -> bf16 -> global while the MMAs of the next tile already run.
 // The MUFU (exp2) pipe is the bound of this d=64 attention: 16 exp/clk/SM.
 #include "common.cuh"
+
+#include <type_traits>
 
 namespace vc {
 
@@ -35,7 +39,8 @@ constexpr int SMEM_V = SMEM_K + NKV * KV_BYTES;
 constexpr int SMEM_BAR = SMEM_V + NKV * KV_BYTES;
 constexpr int SMEM_TOTAL = SMEM_BAR + 256;
 constexpr int TMEM_COLS = 256;
-constexpr int COL_S = 0, COL_O = 128;      // S0 | S1 | O0 | O1, 64 columns each; P_g aliases columns [0, 32) of S_g
+constexpr int NS = 3;                      // S buffers: S_{g+3} is issued when P_g is consumed, two chunks of slack for the MMA round trip
+constexpr int COL_S = 0, COL_O = NS * KT;  // S0 | S1 | S2 | O, 64 columns each; P_g aliases columns [0, 32) of S_g
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -87,11 +92,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_BAR);
   uint64_t* q_full = bars;           // [2] Q tile landed
   uint64_t* q_free = bars + 2;       // [2] every S MMA of the tile that used this Q buffer retired (tcgen05.commit)
-  uint64_t* s_full = bars + 4;       // [2] S_g complete (tcgen05.commit)
-  uint64_t* p_full = bars + 6;       // [2] P_g written to TMEM (128 arrivals)
-  uint64_t* pv_done = bars + 8;      // [2] O += P_g V complete (tcgen05.commit)
-  uint64_t* o_free = bars + 10;      // [2] epilogue finished reading the O buffer (128 arrivals)
-  uint64_t* k_full = bars + 12;      // [NKV]
+  uint64_t* s_full = bars + 4;       // [NS] S_g complete (tcgen05.commit)
+  uint64_t* p_full = bars + 7;       // [NS] P_g written to TMEM (128 arrivals)
+  uint64_t* pv_done = bars + 10;     // [NS] O += P_g V complete (tcgen05.commit)
+  uint64_t* o_free = bars + 13;      // [1] epilogue of the tile finished reading O (128 arrivals)
+  uint64_t* k_full = bars + 14;      // [NKV]
   uint64_t* v_full = k_full + NKV;
   uint64_t* k_free = v_full + NKV;   // S MMAs that read this K stage retired (tcgen05.commit)
   uint64_t* v_free = k_free + NKV;   // PV MMAs that read this V stage retired (tcgen05.commit)
@@ -110,10 +115,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_kv);
     for (int i = 0; i < NKV; ++i) { mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1); mbar_init(&k_free[i], 1); mbar_init(&v_free[i], 1); }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&q_full[i], 1); mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128); mbar_init(&pv_done[i], 1);
-      mbar_init(&o_free[i], 128); mbar_init(&q_free[i], 1);
-    }
+    for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_free[i], 1); }
+    for (int i = 0; i < NS; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128); mbar_init(&pv_done[i], 1); }
+    mbar_init(&o_free[0], 128);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
@@ -172,7 +176,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       const uint32_t idesc_s_full = make_idesc_bf16(128, KT, 0, 0);            // Q (K-major) x K (K-major)
       const uint32_t idesc_s_last = make_idesc_bf16(128, last_kn, 0, 0);
       constexpr uint32_t idesc_o = make_idesc_bf16(128, D, 0, 1);              // P (TMEM) x V (MN-major)
-      auto issue_s = [&](int g, int tile, int j) {     // S_g = Q_tile K_j^T into S buffer g & 1
+      auto issue_s = [&](int g, int sbuf, int tile, int j) {     // S_g = Q_tile K_j^T into S buffer sbuf = g % NS
         const int st = g % NKV;
         if (j == 0) mbar_wait(&q_full[tile & 1], (tile >> 1) & 1);
         mbar_wait(&k_full[st], (g / NKV) & 1);
@@ -180,30 +184,38 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         const uint64_t qd = qd0 + (uint64_t)((tile & 1) * (Q_BYTES >> 4));
         const uint64_t kd = kd0 + (uint64_t)(st * (KV_BYTES >> 4));
         const uint32_t idesc = (j == nch - 1) ? idesc_s_last : idesc_s_full;
-        const uint32_t d = tmem_base + COL_S + (g & 1) * KT;
+        const uint32_t d = tmem_base + COL_S + sbuf * KT;
 #pragma unroll
         for (int k = 0; k < D / 16; ++k) umma_f16(d, qd + 2 * k, kd + 2 * k, idesc, k != 0);
-        umma_commit(&s_full[g & 1]);
+        umma_commit(&s_full[sbuf]);
         umma_commit(&k_free[st]);
         if (j == nch - 1) umma_commit(&q_free[tile & 1]);
       };
-      // (tile, j) of steps g and g+2 are tracked incrementally (no divisions on the critical path)
+      // (tile, j) of steps g and g+NS are tracked incrementally (no divisions on the critical path)
       int t0 = 0, j0 = 0;                               // step g
-      int t2 = 0, j2 = 0;                               // step g+2
-      issue_s(0, 0, 0);
-      if (total > 1) { int t1 = 0, j1 = 1; if (j1 == nch) { j1 = 0; t1 = 1; } issue_s(1, t1, j1); }
-      for (int i = 0; i < 2; ++i) if (++j2 == nch) { j2 = 0; ++t2; }
+      int t3 = 0, j3 = 0;                               // step g+NS
+      for (int i = 0; i < NS && i < total; ++i) {
+        issue_s(i, i, t3, j3);
+        if (++j3 == nch) { j3 = 0; ++t3; }
+      }
+      int pb = 0;                                       // g % NS
+      uint32_t pph = 0;                                 // (g / NS) & 1
       for (int g = 0; g < total; ++g) {
-        const int pb = g & 1;
-        mbar_wait(&p_full[pb], (g >> 1) & 1);          // P_g sits in TMEM (first 32 columns of S buffer pb)
+        // everything the next 8 MMAs need besides P_g is waited for FIRST (it has long arrived), so that the issue follows
+        // the softmax warps' arrival without further round trips
         mbar_wait(&v_full[g % NKV], (g / NKV) & 1);
-        if (j0 == 0 && t0 >= 2) mbar_wait(&o_free[t0 & 1], ((t0 - 2) >> 1) & 1);   // epilogue of tile-2 has read this O buffer
+        if (j0 == 0 && t0 >= 1) mbar_wait(&o_free[0], (t0 - 1) & 1);   // epilogue of the previous tile has read O
+        if (g + NS < total) {
+          if (j3 == 0) mbar_wait(&q_full[t3 & 1], (t3 >> 1) & 1);
+          mbar_wait(&k_full[(g + NS) % NKV], ((g + NS) / NKV) & 1);
+        }
+        mbar_wait(&p_full[pb], pph);                   // P_g sits in TMEM (first 32 columns of S buffer pb)
         tc_fence_after();
         {
           // O_tile += P_g V_j : A from TMEM (16 keys = 8 columns of bf16 pairs per step), B = 16 keys = 2048 B of V
           const uint32_t pa = tmem_base + COL_S + pb * KT;
           const uint64_t vd = vd0 + (uint64_t)((g % NKV) * (KV_BYTES >> 4));
-          const uint32_t d = tmem_base + COL_O + (t0 & 1) * D;
+          const uint32_t d = tmem_base + COL_O;
           const int ksteps = (j0 == nch - 1 ? last_kn : KT) / 16;
           if (ksteps == 4) {
 #pragma unroll
@@ -215,10 +227,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           umma_commit(&pv_done[pb]);
           umma_commit(&v_free[g % NKV]);
         }
-        // S_{g+2} reuses the buffer P_g occupied: issued after PV_g, the tensor pipe keeps the order
-        if (g + 2 < total) issue_s(g + 2, t2, j2);
+        // S_{g+NS} reuses the buffer P_g occupied: issued after PV_g, the tensor pipe keeps the order
+        if (g + NS < total) issue_s(g + NS, pb, t3, j3);
         if (++j0 == nch) { j0 = 0; ++t0; }
-        if (++j2 == nch) { j2 = 0; ++t2; }
+        if (++j3 == nch) { j3 = 0; ++t3; }
+        if (++pb == NS) { pb = 0; pph ^= 1; }
       }
     }
   } else {
@@ -228,89 +241,157 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     const uint64_t scale2 = pack_f32x2(scale_log2, scale_log2);
     int g = 0;
+    int sb = 0, sb_prev = NS - 1;                      // g % NS, (g - 1) % NS
+    uint32_t sph = 0, sph_prev = 1;                    // (g / NS) & 1 and the same for g - 1
     // deferred epilogue of the previous tile (runs after the first chunk of the next tile, off the critical path)
     bool pend = false;
     float pend_l = 0.f;
-    int pend_tile = 0, pend_g = 0;
+    int pend_tile = 0, pend_sb = 0;
+    uint32_t pend_ph = 0;
     for (int tile = 0; tile < nq; ++tile) {
-      const uint32_t taddr_o = tmem_base + lane_base + COL_O + (tile & 1) * D;
+      const uint32_t taddr_o = tmem_base + lane_base + COL_O;
       float m_ref = -INFINITY;                         // exponent reference (scaled log2 units); lags the true max by < 8
       float l = 0.f;
       for (int j = 0; j < nch; ++j, ++g) {
-        const int sb = g & 1;
         const int lim = N - j * KT;                    // valid keys in this chunk (>= 64 for full chunks)
         const uint32_t taddr_s = tmem_base + lane_base + COL_S + sb * KT;
-        mbar_wait(&s_full[sb], (g >> 1) & 1);
+        mbar_wait(&s_full[sb], sph);
         tc_fence_after();
-        uint32_t r[64];
-        tmem_ld_32x32(taddr_s, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
-        tmem_ld_32x32(taddr_s + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
-        tmem_ld_wait();
-        if (lim < KT) {
-          // ragged last chunk: columns >= lim hold stale scores (or nothing the MMA wrote): exclude them
+        if (lim >= KT) {
+          // ------------------------------ full chunk: 64 keys ------------------------------
+          uint32_t r[64];
+          tmem_ld_32x32(taddr_s, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+          tmem_ld_32x32(taddr_s + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
+          tmem_ld_wait();
+          // P = exp2(s * scale - m_ref) as packed bf16 pairs in pk[], row sum in `csum`; WITH_MAX also folds the chunk max
+          // into (mx0, mx1) in the same instruction stream
+          uint32_t pk[32];
+          float csum;
+          float mx0 = -INFINITY, mx1 = -INFINITY;
+          auto exp_pass = [&](float mref, auto with_max) {
+            const uint64_t neg2 = pack_f32x2(-mref, -mref);
+            uint64_t sum_a = 0ull, sum_b = 0ull;       // two packed partial sums (bit pattern of +0.0f pairs)
 #pragma unroll
-          for (int i = 0; i < 64; ++i)
-            if (i >= lim) r[i] = 0xff800000u;          // -inf
-        }
-        float mx0 = -INFINITY, mx1 = -INFINITY;
+            for (int i = 0; i < 64; i += 4) {
+              const float s0 = __uint_as_float(r[i]), s1 = __uint_as_float(r[i + 1]);
+              const float s2 = __uint_as_float(r[i + 2]), s3 = __uint_as_float(r[i + 3]);
+              if (decltype(with_max)::value) {
+                mx0 = fmaxf(mx0, fmaxf(s0, s1));
+                mx1 = fmaxf(mx1, fmaxf(s2, s3));
+              }
+              float x0, x1, x2, x3;
+              unpack_f32x2(fma_f32x2(pack_f32x2(s0, s1), scale2, neg2), x0, x1);
+              unpack_f32x2(fma_f32x2(pack_f32x2(s2, s3), scale2, neg2), x2, x3);
+              const float p0 = ex2(x0), p1 = ex2(x1), p2 = ex2(x2), p3 = ex2(x3);
+              sum_a = add_f32x2(sum_a, pack_f32x2(p0, p1));
+              sum_b = add_f32x2(sum_b, pack_f32x2(p2, p3));
+              pk[i >> 1] = pack_bf16x2(p0, p1);
+              pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
+            }
+            float a0, a1, a2, a3;
+            unpack_f32x2(sum_a, a0, a1);
+            unpack_f32x2(sum_b, a2, a3);
+            csum = (a0 + a1) + (a2 + a3);
+          };
+          bool redo;
+          if (j == 0) {
+            // first chunk of a tile: no reference yet, the max has to come first
 #pragma unroll
-        for (int i = 0; i < 64; i += 4) {
-          mx0 = fmaxf(mx0, fmaxf(__uint_as_float(r[i]), __uint_as_float(r[i + 1])));
-          mx1 = fmaxf(mx1, fmaxf(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])));
-        }
-        const float mxs = fmaxf(mx0, mx1) * scale_log2;
-        const bool need = mxs > m_ref + 8.0f;
-        const float m_new = need ? mxs : m_ref;
-        if (j > 0 && __any_sync(0xffffffffu, need)) {
-          const float corr = ex2(m_ref - m_new);       // exactly 1 for lanes that keep their reference
-          mbar_wait(&pv_done[(g - 1) & 1], ((g - 1) >> 1) & 1);    // every issued PV has landed in TMEM
-          tc_fence_after();
-          rescale_o(taddr_o, corr);
-          l *= corr;
-        }
-        m_ref = m_new;
-        const uint64_t neg2 = pack_f32x2(-m_ref, -m_ref);
-        uint64_t sum_a = 0ull, sum_b = 0ull;           // two packed partial sums (bit pattern of +0.0f pairs)
-        uint32_t pk[32];
+            for (int i = 0; i < 64; i += 4) {
+              mx0 = fmaxf(mx0, fmaxf(__uint_as_float(r[i]), __uint_as_float(r[i + 1])));
+              mx1 = fmaxf(mx1, fmaxf(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])));
+            }
+            m_ref = fmaxf(mx0, mx1) * scale_log2;
+            redo = true;
+          } else {
+            // speculate that the reference holds (it moves only when the chunk max exceeds it by 2^8): the exponentials
+            // run against the old reference while the max chain proceeds beside them, off the MUFU critical path
+            exp_pass(m_ref, std::true_type{});
+            const float mxs = fmaxf(mx0, mx1) * scale_log2;
+            const bool need = mxs > m_ref + 8.0f;
+            redo = __any_sync(0xffffffffu, need);
+            if (redo) {
+              const float m_new = need ? mxs : m_ref;
+              const float corr = ex2(m_ref - m_new);   // exactly 1 for lanes that keep their reference
+              mbar_wait(&pv_done[sb_prev], sph_prev);  // every issued PV has landed in TMEM
+              tc_fence_after();
+              rescale_o(taddr_o, corr);
+              l *= corr;
+              m_ref = m_new;
+            }
+          }
+          if (redo) exp_pass(m_ref, std::false_type{});
+          l += csum;
+          tmem_st_32x32(taddr_s, pk);                  // P_g overwrites the first half of its own S buffer
+        } else {
+          // ------------------------------ ragged last chunk (1 key of 64 at N = 577) ------------------------------
+          // only last_kn / 16 MMA steps exist; columns in [lim, last_kn) are scores of zero-filled keys. Plain order:
+          // max, (rare) rescale, exponentials, 16 columns at a time.
+          const int ng = last_kn >> 4;
+          float mx = -INFINITY;
+          for (int gq = 0; gq < ng; ++gq) {
+            uint32_t r[16];
+            tmem_ld_32x16(taddr_s + gq * 16, r);
+            tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 64; i += 4) {
-          float x0, x1, x2, x3;
-          unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), scale2, neg2), x0, x1);
-          unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])), scale2, neg2), x2, x3);
-          const float p0 = ex2(x0), p1 = ex2(x1), p2 = ex2(x2), p3 = ex2(x3);     // ex2(-inf) = 0 for masked columns
-          sum_a = add_f32x2(sum_a, pack_f32x2(p0, p1));
-          sum_b = add_f32x2(sum_b, pack_f32x2(p2, p3));
-          pk[i >> 1] = pack_bf16x2(p0, p1);
-          pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
+            for (int i = 0; i < 16; ++i)
+              if (gq * 16 + i < lim) mx = fmaxf(mx, __uint_as_float(r[i]));
+          }
+          const float mxs = mx * scale_log2;
+          const bool need = mxs > m_ref + 8.0f;        // also covers j == 0 (m_ref = -inf)
+          if (__any_sync(0xffffffffu, need)) {
+            const float m_new = need ? mxs : m_ref;
+            if (j > 0) {
+              const float corr = ex2(m_ref - m_new);
+              mbar_wait(&pv_done[sb_prev], sph_prev);
+              tc_fence_after();
+              rescale_o(taddr_o, corr);
+              l *= corr;
+            }
+            m_ref = m_new;
+          }
+          const float neg = -m_ref;
+          float sum = 0.f;
+          for (int gq = 0; gq < ng; ++gq) {
+            uint32_t r[16], pq[16];
+            tmem_ld_32x16(taddr_s + gq * 16, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) {
+              const float p0 = (gq * 16 + i < lim) ? ex2(fmaf(__uint_as_float(r[i]), scale_log2, neg)) : 0.f;
+              const float p1 = (gq * 16 + i + 1 < lim) ? ex2(fmaf(__uint_as_float(r[i + 1]), scale_log2, neg)) : 0.f;
+              sum += p0 + p1;
+              pq[i >> 1] = pack_bf16x2(p0, p1);
+            }
+#pragma unroll
+            for (int i = 8; i < 16; ++i) pq[i] = 0u;
+            // group gq's 8 packed columns go to P columns [8 gq, 8 gq + 8); they alias S columns that were read in an
+            // earlier (or this) iteration only if 8 gq + 8 <= 16 gq + 16, which always holds
+            tmem_st_32x16(taddr_s + gq * 8, pq);       // (the upper 8 columns written are rewritten by the next group)
+          }
+          l += sum;
         }
-        {
-          float s0, s1, s2, s3;
-          unpack_f32x2(sum_a, s0, s1);
-          unpack_f32x2(sum_b, s2, s3);
-          l += (s0 + s1) + (s2 + s3);
-        }
-        tmem_st_32x32(taddr_s, pk);                    // P_g overwrites the first half of its own S buffer
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&p_full[sb]);
         if (pend && j == 0) {
           // epilogue of the previous tile, after this tile's first chunk has been handed to the tensor core
-          mbar_wait(&pv_done[pend_g & 1], (pend_g >> 1) & 1);
+          mbar_wait(&pv_done[pend_sb], pend_ph);
           tc_fence_after();
           const int q = pend_tile * QT + t;
-          store_o_row(tmem_base + lane_base + COL_O + (pend_tile & 1) * D, pend_l,
-                      out + ((size_t)b * N + q) * H + h * D, q < N, &o_free[pend_tile & 1]);
+          store_o_row(taddr_o, pend_l, out + ((size_t)b * N + q) * H + h * D, q < N, &o_free[0]);
           pend = false;
         }
+        sb_prev = sb; sph_prev = sph;
+        if (++sb == NS) { sb = 0; sph ^= 1; }
       }
-      pend = true; pend_l = l; pend_tile = tile; pend_g = g - 1;
+      pend = true; pend_l = l; pend_tile = tile; pend_sb = sb_prev; pend_ph = sph_prev;
     }
     if (pend) {
-      mbar_wait(&pv_done[pend_g & 1], (pend_g >> 1) & 1);
+      mbar_wait(&pv_done[pend_sb], pend_ph);
       tc_fence_after();
       const int q = pend_tile * QT + t;
-      store_o_row(tmem_base + lane_base + COL_O + (pend_tile & 1) * D, pend_l, out + ((size_t)b * N + q) * H + h * D, q < N,
-                  &o_free[pend_tile & 1]);
+      store_o_row(tmem_base + lane_base + COL_O, pend_l, out + ((size_t)b * N + q) * H + h * D, q < N, &o_free[0]);
     }
   }
   tc_fence_before();
