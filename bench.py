@@ -270,40 +270,43 @@ def main():
         "algorithmic_flops_per_step": flops / max(1, args.steps),
     }
 
-    # ---- e2e: same step through the public module call with HOST buffers (pinned), H2D + D2H inside the timed region
+    # ---- e2e: the same steps through the public host loop (vitcap_b200.stream.OverlappedCaptioner, the drop-in for the
+    # reference's predict_iter) with HOST buffers: every step uploads its own 512 images from pinned memory and reads its
+    # result records back; the upload of step i+1 overlaps the captioning of step i (double-buffered device staging)
     e2e = None
     if not args.no_e2e:
-        host_data = {k: v.pin_memory() for k, v in host.items()}
-        out_host = torch.empty(world * B, out.shape[1], dtype=out.dtype).pin_memory()
+        from vitcap_b200.stream import OverlappedCaptioner
+        host_batch = {k: v.pin_memory() for k, v in host.items()}
+        host_batch["image"] = img_host
+        oc = OverlappedCaptioner(model, dev, depth=2, gather=True, with_tags=True)
 
-        def step_e2e():
-            d = {k: v.to(dev, non_blocking=True) for k, v in host_data.items()}
-            d["image"] = img_host.to(dev, non_blocking=True)
-            ids, lp = model(d)
-            rec = parallel.pack_records(ids, lp, model.engine._enc_ws["tag_idx"][:B], model.engine._enc_ws["tag_prob"][:B])
-            full = parallel.all_gather_records(rec)
-            out_host.copy_(full, non_blocking=True)
-            torch.cuda.current_stream().synchronize()        # the caller reads the captions on the host
-            return full
+        def batches(n):
+            for _ in range(n):
+                yield host_batch
 
-        step_e2e()
+        for _ in oc.run(batches(2)):                      # warm-up: staging buffers, pinned result buffers
+            pass
         sync_all()
+        oc.h2d_bytes = oc.d2h_bytes = 0
+        n_e2e = max(2, min(args.steps, 8))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n_e2e = max(1, min(args.steps, 5))
         t0 = time.time()
         e0.record()
-        for _ in range(n_e2e):
-            step_e2e()
+        n_out = 0
+        for res in oc.run(batches(n_e2e)):
+            n_out += res[0].shape[0]
         e1.record()
         sync_all()
         wall = time.time() - t0
+        assert n_out == world * B * n_e2e
         ems = max(e0.elapsed_time(e1), wall * 1e3)
         te = torch.tensor([ems], device=dev)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        h2d = img_host.numel() * 4 + sum(v.numel() * v.element_size() for v in host_data.values())
-        e2e = {"value": world * B * n_e2e / (float(te.item()) / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(out_host.numel() * out_host.element_size()), "steps": n_e2e}
+        e2e = {"value": world * B * n_e2e / (float(te.item()) / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(oc.h2d_bytes // n_e2e),
+               "d2h_bytes_per_step": int(oc.d2h_bytes // n_e2e), "steps": n_e2e,
+               "api": "vitcap_b200.stream.OverlappedCaptioner(FastImageCaptioning).run(host batches): upload of step i+1 "
+                      "overlaps captioning of step i"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
