@@ -1,0 +1,133 @@
+"""BASELINE.json configurations at their FULL sizes on the GPU, checked through size-independent properties (the CPU oracle
+cannot run 512 images): images are independent, so every image's result in the big batch must equal -- bit for bit, the
+kernels are deterministic and their per-row arithmetic does not depend on the batch size -- its result in a small batch
+(which test_e2e_gpu.py pins to the reference goldens / the oracle), plus the structural invariants of each search mode."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from vitcap_b200 import config as vcfg  # noqa: E402
+from vitcap_b200 import synth  # noqa: E402
+from vitcap_b200.model import FastImageCaptioning  # noqa: E402
+
+DEV = "cuda:0"
+_CACHE = {}
+
+
+def _model(variant, eos_bias, extra_kw, max_batch, mode="bf16", seed=0):
+    key = (variant, eos_bias, seed)
+    if key not in _CACHE:
+        _CACHE.clear()                                   # one 217 M-parameter state_dict alive at a time
+        cfg = vcfg.variant(variant)
+        _CACHE[key] = (cfg, synth.make_state_dict(cfg, seed=seed, eos_bias=eos_bias))
+    cfg, sd = _CACHE[key]
+    extra = synth.default_test_extra_input(cfg, **extra_kw)
+    m = FastImageCaptioning(cfg, test_extra_input=extra, mode=mode, max_batch=max_batch)
+    m.load_state_dict(sd)
+    return cfg, m.to(DEV)
+
+
+def _data(cfg, B, seed, lo=0, hi=None):
+    hi = B if hi is None else hi
+    d = synth.make_text_inputs(cfg, hi - lo)
+    img = synth.make_images(cfg, B, seed=seed)[lo:hi].contiguous()
+    d["image"] = img
+    return {k: v.to(DEV) for k, v in d.items()}
+
+
+def _check_caption_structure(ids, lp, bos=101, eos=102, pad=0, pad_inside_ok=False):
+    ids = ids.cpu().numpy()
+    lp = lp.cpu().numpy()
+    assert (ids[..., 0] == bos).all()
+    assert np.isfinite(lp).all() and (lp <= 1e-6).all()
+    flat = ids.reshape(-1, ids.shape[-1])
+    for row in flat:
+        w = np.nonzero(row == eos)[0]
+        assert len(w) >= 1, row                          # every caption ends with [SEP] (forced at the last slot at the latest)
+        assert (row[w[0] + 1:] == pad).all(), row        # and is PAD-filled after it
+        if not pad_inside_ok:                            # (a sampler may legitimately draw vocabulary id 0 = [PAD])
+            assert (row[1:w[0]] != pad).all(), row
+
+
+def test_config2_encoder_tags_b256():
+    """BASELINE configs[1]: ViT-B/16-384 encoder + concept head top-50, batch 256, bf16."""
+    cfg, m = _model("16_384", 0.0, {}, 256)
+    B = 256
+    data = _data(cfg, B, seed=1234)
+    lg, idx, pr, n = m.forward_tags(data["image"])
+    assert lg.shape == (B, cfg.vocab) and idx.shape == (B, 50) and pr.shape == (B, 50) and n.shape == (B,)
+    pr_c, idx_c = pr.cpu(), idx.cpu()
+    assert bool((pr_c[:, :-1] >= pr_c[:, 1:]).all())                       # sorted like torch.topk(sorted=True)
+    assert all(len(set(r.tolist())) == 50 for r in idx_c)                  # distinct vocabulary ids
+    assert torch.equal(n.cpu(), (pr_c >= 0.2).sum(1))                      # topk_len, modeling_bert.py:1432
+    # the selection is the true top-50 of the logits this very run produced
+    ref_p, ref_i = torch.sigmoid(lg).topk(50, dim=1)
+    assert torch.equal(idx_c, ref_i.cpu())
+    np.testing.assert_allclose(pr_c.numpy(), ref_p.cpu().numpy(), atol=1e-6)
+    # batch independence: images 40..47 alone give bitwise the same logits
+    lg8, idx8, _, _ = m.forward_tags(data["image"][40:48].contiguous())
+    assert torch.equal(lg8, lg[40:48]) and torch.equal(idx8, idx[40:48])
+    cap, tag = m.encode_features(data["image"][:64].contiguous())
+    assert torch.isfinite(cap).all() and torch.isfinite(tag).all()
+
+
+def test_config3_greedy_b512_batch_independent():
+    """BASELINE configs[2]: full greedy captioning, batch 512, bf16; EOS planted so early stop / PAD fill / forced EOS all occur."""
+    cfg, m = _model("16_384", 1.9, {}, 512)
+    B = 512
+    data = _data(cfg, B, seed=99)
+    ids, lp = m(data)
+    assert ids.shape == (B, 1, 20) and ids.dtype == torch.int64 and lp.shape == (B, 1)
+    _check_caption_structure(ids, lp)
+    ids2, lp2 = m(data)                                                     # CUDA-graph replay: identical
+    assert torch.equal(ids, ids2) and torch.equal(lp, lp2)
+    for lo in (0, 300, 504):
+        sub = _data(cfg, B, seed=99, lo=lo, hi=lo + 8)
+        i8, l8 = m(sub)
+        assert torch.equal(i8, ids[lo:lo + 8]), lo
+        np.testing.assert_allclose(l8.cpu().numpy(), lp[lo:lo + 8].cpu().numpy(), atol=1e-6)
+    lens = (ids[:, 0] != 0).sum(1)
+    assert int(lens.min()) < 20                                             # some captions stop early
+
+
+def test_config4_beam4_b256():
+    """BASELINE configs[3]: beam search, 4 beams, batch 256 (context K/V shared by the beams, ancestor-table reorder)."""
+    cfg, m = _model("16_384", 1.9, dict(num_beams=4, num_keep_best=2, length_penalty=0.8), 256)
+    B = 256
+    data = _data(cfg, B, seed=7)
+    ids, lp = m(data)
+    assert ids.shape == (B, 2, 20) and lp.shape == (B, 2)
+    lpc = lp.cpu()
+    filled = lpc > -1e4
+    assert bool(filled[:, 0].all())
+    assert bool((lpc[:, 0] >= lpc[:, 1]).all())                             # best hypothesis first (modeling_utils.py:1086)
+    _check_caption_structure(ids[:, :1], lp[:, :1])
+    sub = _data(cfg, B, seed=7, lo=100, hi=104)
+    i4, l4 = m(sub)
+    assert torch.equal(i4, ids[100:104])
+    np.testing.assert_allclose(l4.cpu().numpy(), lp[100:104].cpu().numpy(), atol=1e-6)
+    # the two kept hypotheses of an image are different sequences
+    idc = ids.cpu()
+    assert bool((idc[:, 0] != idc[:, 1]).any(dim=1)[filled[:, 1]].all())
+
+
+def test_config5_sampling_k5_b512_16_224():
+    """BASELINE configs[4]: SCST-style sampling, 5 samples per image, batch 512, the 16_224 variant."""
+    cfg, m = _model("16_224", 1.5, dict(do_sample=True, num_return_sequences=5), 512)
+    B, K = 512, 5
+    data = _data(cfg, B, seed=5)
+    m.sample_seed = 1234
+    m._sample_calls = 0
+    ids, lp = m(data)
+    assert ids.shape == (B * K, 1, 20) and lp.shape == (B * K, 1)
+    _check_caption_structure(ids, lp, pad_inside_ok=True)
+    per_img = ids.view(B, K, 20)
+    distinct = [len({tuple(s.tolist()) for s in per_img[b]}) for b in range(0, B, 37)]
+    assert np.mean(distinct) > 1.5                                          # the samples of an image differ
+    m._sample_calls = 0
+    ids2, lp2 = m(data)                                                     # same seed and call index: same samples
+    assert torch.equal(ids, ids2)
+    ids3, _ = m(data)                                                       # next call index: fresh noise
+    assert not torch.equal(ids, ids3)

@@ -197,7 +197,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
           if (ACT == ACT_GELU) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_erf_poly(v[j]);
+            for (int j = 0; j < 32; ++j) v[j] = gelu_erf_tanh(v[j]);
           } else if (ACT == ACT_TANH) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
@@ -237,7 +237,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             }
             if (ACT == ACT_GELU) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = gelu_erf_poly(v[j]);
+              for (int j = 0; j < 32; ++j) v[j] = gelu_erf_tanh(v[j]);
             } else if (ACT == ACT_TANH) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);

@@ -95,22 +95,6 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
       "}\n"
       ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ float tanh_approx(float x) {
-  float y;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-// erf(z) ~= tanh(z * (C0 + C1 u + C2 u^2)), u = min(z^2, 30): max |gelu error| 2.5e-5 (fit in DESIGN.md section 4)
-__device__ __forceinline__ float gelu_erf_tanh(float x) {
-  const float z = x * 0.70710678118654752440f;
-  const float u = fminf(z * z, 30.0f);
-  float p = fmaf(-1.988479253896676e-03f, u, 1.0466777301852825e-01f);
-  p = fmaf(p, u, 1.1278464660309704f);
-  const float t = tanh_approx(z * p);
-  const float hx = 0.5f * x;
-  return fmaf(hx, t, hx);
-}
-
 template <int ACT> __device__ __forceinline__ float apply_act(float v) {
   if (ACT == ACT2_GELU) return gelu_erf_tanh(v);
   if (ACT == ACT2_TANH) return tanhf(v);

@@ -309,6 +309,15 @@ class CaptionEngine:
         self._head(w.cls_head, mask_rows, R, ws["head_f"], ws["head_t"], ws["logits"])
 
     # ------------------------------------------------------------------ search drivers
+    @staticmethod
+    def _eos_tensor(ws, eos_ids):
+        """Device copy of the EOS id list, created ONCE per workspace: a captured CUDA graph keeps its raw pointer, so it must
+        outlive every replay (a per-call tensor would be freed and its block reused under the graph's feet)."""
+        key = ("eos", tuple(int(e) for e in eos_ids))
+        if key not in ws:
+            ws[key] = torch.tensor(list(key[1]), device=ws["ids"].device, dtype=torch.int32)
+        return ws[key]
+
     def _maybe_graph(self, key, fn):
         """Runs fn() eagerly once (warm-up: lazy kernel attribute setup, descriptor cache), then captures and replays it."""
         if not self.use_cuda_graph:
@@ -335,7 +344,7 @@ class CaptionEngine:
         cfg = self.cfg
         ws = self._decoder_ws(B, E, max_len)
         R = ws["R"]
-        eos = torch.tensor(list(eos_ids), device=self.dev, dtype=torch.int32)
+        eos = self._eos_tensor(ws, eos_ids)
         filt = do_sample and (top_k > 0 or top_p < 1.0)
 
         def reset():
@@ -358,7 +367,6 @@ class CaptionEngine:
             ops.greedy_finalize(ws["ids"], ws["unfinished"], ws["sum_lp"], ws["n_steps"], int(eos_ids[0]), R, ws["out_ids"],
                                 ws["out_lp"])
 
-        ws["_eos"] = eos
         self._maybe_graph(("tok", B, E, max_len, do_sample, temperature, top_k, top_p, seed, bos, pad, tuple(eos_ids), mask_id), run)
         return ws["out_ids"].view(R, 1, max_len).clone(), ws["out_lp"].view(R, 1).clone()
 
@@ -386,8 +394,7 @@ class CaptionEngine:
                 "init_scores": torch.tensor(([0.0] + [-1e9] * (nb - 1)) * B, device=self.dev, dtype=f32),
             }
         st = ws["beam"]
-        eos = torch.tensor(list(eos_ids), device=self.dev, dtype=torch.int32)
-        st["_eos"] = eos
+        eos = self._eos_tensor(ws, eos_ids)
 
         def run():
             st["ids"].zero_()
