@@ -83,6 +83,13 @@ int vc_assemble_ctx(int bf16, const float* cap, const float* tag, float* ctx_f, 
 int vc_attention(int bf16, const void* qkv, void* out, int B, int N, int heads, float scale, void* stream);
 int vc_attention_simt(int bf16, const void* qkv, void* out, int B, int N, int heads, float scale, void* stream);
 
+/* single-query attention: out[b] = softmax(q[b] K_b^T * scale) V_b with K, V taken from the packed qkv [B,N,3H] and ONE query
+ * row per image (q [B,H], pitch ldq). Used for the last block of the concept branch, of which only the CLS row is consumed
+ * (pooler, modeling_bert.py:1424; tag token of the context, modeling_bert.py:1493; Attention.forward vision_transformer.py:174-200
+ * restricted to query row 0). */
+int vc_cls_attention(int bf16, const void* q, int ldq, const void* qkv, void* out, int ldo, int B, int N, int heads, float scale,
+                     void* stream);
+
 /* concept head selection: sigmoid -> topk(K) sorted desc -> count(prob >= thresh); modeling_bert.py:1429-1432 */
 int vc_tag_topk(const float* logits, int ld, int rows, int V, int K, float thresh, int* out_idx, float* out_prob, int* out_len,
                 void* stream);

@@ -282,3 +282,18 @@ def test_tag_topk_ties_and_small_rows():
     order = sorted(range(V), key=lambda i: (-float(v0[i]), i))[:K]
     assert idx[0].tolist() == order
     assert idx[1].tolist() == list(range(K))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,N,heads", [(3, 577, 12), (2, 197, 12), (1, 17, 2), (5, 64, 1)])
+def test_cls_attention(B, N, heads, dtype):
+    """Single-query attention of the last concept-branch block: row 0 of the full attention output."""
+    H = heads * 64
+    qkv = rnd(B, N, 3 * H, seed=31, dtype=dtype)
+    ref = ref_attention(qkv, heads, 0.125)[:, 0]                     # [B, H]
+    q = qkv[:, 0, :H]                                                # strided view: pitch N*3H
+    out = torch.full((B, 2 * H), float("nan"), device=dev(), dtype=dtype)
+    ops.cls_attention(q, qkv, out[:, :H], B, N, heads, 0.125)
+    tol = 2e-5 if dtype == torch.float32 else 1e-2
+    torch.testing.assert_close(out[:, :H].float(), ref, rtol=tol, atol=tol)
+    assert bool(torch.isnan(out[:, H:]).all())                       # pitch respected

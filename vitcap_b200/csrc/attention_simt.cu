@@ -104,3 +104,126 @@ int attention_simt(int is_bf16, const void* qkv, void* out, int B, int N, int he
 }
 
 }  // namespace vc
+
+// ------------------------------------------------------------------------------------------
+// One query row per image against all N keys of the packed qkv buffer: the LAST block of the concept (tag) branch.
+// Only the CLS row of that block's output is ever consumed -- by the pooler / tag head (modeling_bert.py:1424-1425) and as
+// the tag token prepended to the visual context (modeling_bert.py:1493) -- so the block computes K, V for all rows but
+// Q, attention, proj and the MLP for row 0 only (identical mathematics for that row, 85 % of the block's FLOPs skipped).
+// HBM-bound: reads K and V of one (image, head) once; 8 lanes share a 64-dim row (16-byte loads), 4 warps split the keys.
+// ------------------------------------------------------------------------------------------
+namespace vc {
+
+template <typename T>
+__global__ void __launch_bounds__(128)
+cls_attention_kernel(const T* __restrict__ q, int ldq, const T* __restrict__ qkv, T* __restrict__ out, int ldo, int N, int H,
+                     float scale) {
+  constexpr int D = 64, U = 4;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = lane >> 3, part = lane & 7;
+  const size_t ld = 3 * (size_t)H;
+  float qf[8], o[8];
+  load8<T>(q + (size_t)b * ldq + h * D + part * 8, qf);
+#pragma unroll
+  for (int d = 0; d < 8; ++d) { qf[d] *= scale; o[d] = 0.f; }
+  float m = -1e30f, l = 0.f;
+  const T* kbase = qkv + (size_t)b * N * ld + H + h * D + part * 8;
+  const T* vbase = kbase + H;
+  for (int kb = warp * 4; kb < N; kb += 16 * U) {        // warp-uniform trip count (shuffles inside)
+    const int k0 = kb + grp;
+    float kf[U][8], vf[U][8];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int k = k0 + 16 * u;
+      if (k < N) {
+        load8<T>(kbase + (size_t)k * ld, kf[u]);
+        load8<T>(vbase + (size_t)k * ld, vf[u]);
+      } else {
+#pragma unroll
+        for (int d = 0; d < 8; ++d) { kf[u][d] = 0.f; vf[u][d] = 0.f; }
+      }
+    }
+    float s[U];
+    float mx = m;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float a = 0.f;
+#pragma unroll
+      for (int d = 0; d < 8; ++d) a = fmaf(qf[d], kf[u][d], a);
+      a += __shfl_xor_sync(0xffffffffu, a, 1);
+      a += __shfl_xor_sync(0xffffffffu, a, 2);
+      a += __shfl_xor_sync(0xffffffffu, a, 4);
+      s[u] = (k0 + 16 * u < N) ? a : -1e30f;
+      mx = fmaxf(mx, s[u]);
+    }
+    const float corr = expf(m - mx);
+    m = mx;
+    l *= corr;
+#pragma unroll
+    for (int d = 0; d < 8; ++d) o[d] *= corr;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const float p = (k0 + 16 * u < N) ? expf(s[u] - mx) : 0.f;
+      l += p;
+#pragma unroll
+      for (int d = 0; d < 8; ++d) o[d] = fmaf(p, vf[u][d], o[d]);
+    }
+  }
+  // merge the 4 lane groups of the warp, then the 4 warps
+#pragma unroll
+  for (int x = 8; x <= 16; x <<= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, x);
+    const float l2 = __shfl_xor_sync(0xffffffffu, l, x);
+    const float mx = fmaxf(m, m2);
+    const float c1 = expf(m - mx), c2 = expf(m2 - mx);
+    l = l * c1 + l2 * c2;
+#pragma unroll
+    for (int d = 0; d < 8; ++d) {
+      const float o2 = __shfl_xor_sync(0xffffffffu, o[d], x);
+      o[d] = o[d] * c1 + o2 * c2;
+    }
+    m = mx;
+  }
+  __shared__ float sm_m[4], sm_l[4], sm_o[4][D];
+  if (grp == 0) {
+    if (part == 0) { sm_m[warp] = m; sm_l[warp] = l; }
+#pragma unroll
+    for (int d = 0; d < 8; ++d) sm_o[warp][part * 8 + d] = o[d];
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    const int pt = threadIdx.x;
+    float mx = sm_m[0];
+#pragma unroll
+    for (int w = 1; w < 4; ++w) mx = fmaxf(mx, sm_m[w]);
+    float lt = 0.f, acc[8];
+#pragma unroll
+    for (int d = 0; d < 8; ++d) acc[d] = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const float c = expf(sm_m[w] - mx);
+      lt += sm_l[w] * c;
+#pragma unroll
+      for (int d = 0; d < 8; ++d) acc[d] += sm_o[w][pt * 8 + d] * c;
+    }
+    const float inv = 1.f / lt;
+#pragma unroll
+    for (int d = 0; d < 8; ++d) acc[d] *= inv;
+    store8<T>(out + (size_t)b * ldo + h * D + pt * 8, acc);
+  }
+}
+
+// q [B, heads*64] (row pitch ldq), qkv [B, N, 3*heads*64], out [B, heads*64] (row pitch ldo)
+int cls_attention(int is_bf16, const void* q, int ldq, const void* qkv, void* out, int ldo, int B, int N, int heads, float scale,
+                  cudaStream_t s) {
+  if (B <= 0 || N <= 0 || heads <= 0 || B > 65535 || (ldq % 8) || (ldo % 8)) { set_last_error("cls_attention: bad args"); return VC_ERR_BAD_ARG; }
+  const int H = heads * 64;
+  if (is_bf16)
+    cls_attention_kernel<bf16><<<dim3(heads, B), 128, 0, s>>>((const bf16*)q, ldq, (const bf16*)qkv, (bf16*)out, ldo, N, H, scale);
+  else
+    cls_attention_kernel<float><<<dim3(heads, B), 128, 0, s>>>((const float*)q, ldq, (const float*)qkv, (float*)out, ldo, N, H, scale);
+  return check_launch("cls_attention");
+}
+
+}  // namespace vc

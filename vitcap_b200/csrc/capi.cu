@@ -19,6 +19,8 @@ int gather_rows(int out_bf16, const float* in, size_t row_stride, void* out, int
 int assemble_ctx(int out_bf16, const float* cap, const float* tag, float* ctx_f, void* ctx_t, int B, int N, int H, cudaStream_t s);
 int attention_simt(int is_bf16, const void* qkv, void* out, int B, int N, int heads, float scale, cudaStream_t s);
 int attention_tc(const void* qkv, void* out, int B, int N, int heads, float scale, cudaStream_t s);
+int cls_attention(int is_bf16, const void* q, int ldq, const void* qkv, void* out, int ldo, int B, int N, int heads, float scale,
+                  cudaStream_t s);
 int tag_topk(const float* logits, int ld, int rows, int V, int K, float thresh, int* out_idx, float* out_prob, int* out_len,
              cudaStream_t s);
 int embed_ln(int out_bf16, const int* ids, int max_len, int cur_len, int mask_id, const float* word, const float* pos,
@@ -91,6 +93,10 @@ int vc_attention(int bf16, const void* qkv, void* out, int B, int N, int heads, 
 }
 int vc_attention_simt(int bf16, const void* qkv, void* out, int B, int N, int heads, float scale, void* stream) {
   VC_COUNT(1, vc::attention_simt(bf16, qkv, out, B, N, heads, scale, ST(stream)));
+}
+int vc_cls_attention(int bf16, const void* q, int ldq, const void* qkv, void* out, int ldo, int B, int N, int heads, float scale,
+                     void* stream) {
+  VC_COUNT(1, vc::cls_attention(bf16, q, ldq, qkv, out, ldo, B, N, heads, scale, ST(stream)));
 }
 int vc_tag_topk(const float* logits, int ld, int rows, int V, int K, float thresh, int* out_idx, float* out_prob, int* out_len,
                 void* stream) {

@@ -145,6 +145,11 @@ class CaptionEngine:
         ws["tag_idx"] = self._alloc(B, cfg.topk, dtype=torch.int32)
         ws["tag_prob"] = self._alloc(B, cfg.topk, dtype=f32)
         ws["tag_len"] = self._alloc(B, dtype=torch.int32)
+        # last concept-branch block, CLS row only
+        ws["q_cls"] = self._alloc(B, H)
+        ws["att_cls"] = self._alloc(B, H)
+        ws["ln_cls"] = self._alloc(B, H)
+        ws["hid_cls"] = self._alloc(B, F)
         self._enc_ws = ws
         self._dec_ws = {}
         self._graphs = {}
@@ -203,6 +208,25 @@ class CaptionEngine:
         ops.linear(h, p["fc1_w"], p["fc1_b"], hid, act=ops.ACT_GELU, M=rows)
         ops.linear(hid, p["fc2_w"], p["fc2_b"], x, resid=x, M=rows)
 
+    def _vit_block_cls_only(self, p, x, rows, B, N, ws):
+        """The same block, evaluated for the CLS row of every image only (K and V still come from all rows). Used for the last
+        block of the concept branch: its output is consumed at row 0 alone (pooler -> tag head, modeling_bert.py:1424-1425;
+        tag token of the context, modeling_bert.py:1493), so the other 576 rows of Q / attention / proj / MLP are dead work."""
+        cfg = self.cfg
+        H = cfg.hidden
+        ln, qkv = ws["ln"][:rows], ws["qkv"][:rows]
+        q_cls, att_cls, ln_cls, hid_cls = ws["q_cls"][:B], ws["att_cls"][:B], ws["ln_cls"][:B], ws["hid_cls"][:B]
+        h = self._ln(x, p["n1w"], p["n1b"], cfg.vit_ln_eps, ln, rows=rows)
+        ops.linear(h, p["qkv_w"][H:], p["qkv_b"][H:], qkv[:, H:], M=rows, ldo=3 * H)          # K | V of every row
+        h_cls = h.view(B, N * H)[:, :H]                                                        # row 0 of every image
+        ops.linear(h_cls, p["qkv_w"][:H], p["qkv_b"][:H], q_cls, M=B)
+        ops.cls_attention(q_cls, qkv, att_cls, B, N, cfg.heads, cfg.head_dim ** -0.5)
+        x_cls = x.view(B, N * H)[:, :H]                                                        # fp32 stream, row 0 of every image
+        ops.linear(att_cls, p["proj_w"], p["proj_b"], x_cls, resid=x_cls, M=B)
+        h2 = self._ln(x_cls, p["n2w"], p["n2b"], cfg.vit_ln_eps, ln_cls, rows=B)
+        ops.linear(h2, p["fc1_w"], p["fc1_b"], hid_cls, act=ops.ACT_GELU, M=B)
+        ops.linear(hid_cls, p["fc2_w"], p["fc2_b"], x_cls, resid=x_cls, M=B)
+
     # ------------------------------------------------------------------ stages
     def patch_embed(self, image):
         """image fp32 [B,3,S,S] (device) -> img_feats fp32 [B,N,H] (a view of the trunk stream buffer)."""
@@ -218,8 +242,9 @@ class CaptionEngine:
         ops.assemble_tokens(po, w.cls_token, w.pos_embed, x, B, P, H)
         return x.view(B, N, H)
 
-    def encode(self, img_feats, caption_branch=True):
-        """TIMMVitSplitEncoder.forward (modeling_bert.py:458-478): returns (caption feats, tag feats) fp32 [B,N,H]."""
+    def encode(self, img_feats, caption_branch=True, full_tag_feats=False):
+        """TIMMVitSplitEncoder.forward (modeling_bert.py:458-478): returns (caption feats, tag feats) fp32 [B,N,H]. Unless
+        ``full_tag_feats`` is set only row 0 (CLS) of the tag features is valid -- all the caption path consumes."""
         cfg, w = self.cfg, self.w
         B, N, H = img_feats.shape
         ws = self._encoder_ws(B)
@@ -236,7 +261,10 @@ class CaptionEngine:
             for i in range(split_at, cfg.enc_blocks):
                 self._vit_block(w.blocks[i], x, rows, B, N, ws)
         for j in range(cfg.split_blocks):
-            self._vit_block(w.tag_blocks[j], xt, rows, B, N, ws)
+            if j == cfg.split_blocks - 1 and not full_tag_feats:
+                self._vit_block_cls_only(w.tag_blocks[j], xt, rows, B, N, ws)
+            else:
+                self._vit_block(w.tag_blocks[j], xt, rows, B, N, ws)
         return x.view(B, N, H), xt.view(B, N, H)
 
     def _head(self, hp, a_t, rows, th_f, th_t, logits):

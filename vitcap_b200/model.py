@@ -351,7 +351,7 @@ class FastImageCaptioning(nn.Module):
         eng = self.engine
         assert image.shape[0] <= self.max_batch
         f = self._patch_embed(image)
-        cap, tag = eng.encode(f)
+        cap, tag = eng.encode(f, full_tag_feats=True)
         return cap.clone(), tag.clone()
 
 

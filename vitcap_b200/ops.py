@@ -29,6 +29,7 @@ SIGNATURES = {
     "vc_assemble_ctx": [_I, _P, _P, _P, _P, _I, _I, _I, _P],
     "vc_attention": [_I, _P, _P, _I, _I, _I, _F, _P],
     "vc_attention_simt": [_I, _P, _P, _I, _I, _I, _F, _P],
+    "vc_cls_attention": [_I, _P, _I, _P, _P, _I, _I, _I, _I, _F, _P],
     "vc_tag_topk": [_P, _I, _I, _I, _I, _F, _P, _P, _P, _P],
     "vc_embed_ln": [_I, _P, _I, _I, _I, _P, _P, _P, _P, _P, _F, _P, _P, _I, _I, _P],
     "vc_decode_attention": [_I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
@@ -176,6 +177,13 @@ def attention(qkv, out, B, N, heads, scale, impl="auto"):
         _check(lib.vc_attention_simt(_is_bf16(qkv), _ptr(qkv), _ptr(out), B, N, heads, float(scale), _stream()), "vc_attention_simt")
     else:
         _check(lib.vc_attention(_is_bf16(qkv), _ptr(qkv), _ptr(out), B, N, heads, float(scale), _stream()), "vc_attention")
+    return out
+
+
+def cls_attention(q, qkv, out, B, N, heads, scale):
+    """out[b] = softmax(q[b] K_b^T * scale) V_b: one query row per image against the packed qkv buffer."""
+    _check(load_library().vc_cls_attention(_is_bf16(qkv), _ptr(q), q.stride(0), _ptr(qkv), _ptr(out), out.stride(0), B, N, heads,
+                                           float(scale), _stream()), "vc_cls_attention")
     return out
 
 
