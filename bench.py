@@ -261,11 +261,21 @@ def main():
     if not peak:
         peak, peak_src = 1400.0, "fallback (B200_PROFILING.md: ~1.4 PFLOP/s sustained)"
     achieved = flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    # DRAM traffic of the largest GEMM launch (MLP fc1 + GELU, M = 512 x 577) from the committed ncu --set full capture
+    traffic, traffic_note = None, "no ncu capture committed"
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
+        k = next(k for k in tj if "gemm_tc2_kernel<1, 0, 0, 2>" in k)
+        traffic = tj[k]["dram_bytes"]
+        traffic_note = "dram__bytes_read+write of one fc1+GELU launch (M=295424, N=3072, K=768; algorithmic 2.27 GB), " \
+                       "profiles/r01_ncu_summary.md"
+    except Exception:
+        pass
     roofline = {
-        "kernel": "gemm_tc_kernel (tcgen05 bf16 GEMM; %d eager launches/step: ViT qkv/proj/fc1/fc2, patch embed, decoder prefill, heads)"
-                  % (len(prof) // max(1, args.steps)),
+        "kernel": "gemm_tc2_kernel / gemm_tc_kernel (tcgen05 bf16 GEMM, cta_group::2 pairs for the large shapes; %d eager "
+                  "launches/step: ViT qkv/proj/fc1/fc2, patch embed, decoder prefill, heads)" % (len(prof) // max(1, args.steps)),
         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-        "peak_source": peak_src, "traffic": None,
+        "peak_source": peak_src, "traffic": traffic, "traffic_note": traffic_note,
         "share_of_step": gemm_ms / ms if ms > 0 else None,
         "algorithmic_flops_per_step": flops / max(1, args.steps),
     }

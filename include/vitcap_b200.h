@@ -64,6 +64,10 @@ int vc_linear_tc(const void* A, int lda, const void* W, int ldw, const float* bi
 /* image fp32 [B,3,S,S] -> patch matrix [B*(S/p)^2, 3*p*p] (column order = Conv2d weight.flatten(1));
  * PatchEmbed.forward, vision_transformer.py:267-275 */
 int vc_patchify(int bf16, const float* image, void* out, int B, int img_size, int patch, void* stream);
+/* same from 8-bit pixels: image uint8 [B,S,S,3] (HWC, channel order BGR if bgr else RGB) with the tail of the reference's test
+ * transform fused in: BGR2RGB, ToTensor (x/255, HWC->CHW), Normalize(0.5, 0.5) -- uni_pipeline.py:1233-1256, transform.py:47-50 --
+ * bit-identical to the fp32 path fed with the host-transformed tensor; resize / center-crop stay on the host. */
+int vc_patchify_u8(int bf16, const uint8_t* image, void* out, int B, int img_size, int patch, int bgr, void* stream);
 /* x[b,0] = cls + pos[0]; x[b,1+i] = patch_out[b*P+i] + pos[1+i]; forward_features, vision_transformer.py:423-427 */
 int vc_assemble_tokens(const float* patch_out, const float* cls, const float* pos, float* x, int B, int P, int H, void* stream);
 

@@ -166,3 +166,42 @@ def test_overlapped_host_loop_matches_direct_forward():
         assert torch.equal(lp, rlp.cpu())
         assert tidx.shape == (4, cfg.topk) and tprob.shape == (4, cfg.topk)
     assert len({tuple(g[0].flatten().tolist()) for g in got}) > 1          # different batches, different captions
+
+
+def _host_transform_tail(u8_bgr_hwc):
+    """BGR2RGB -> ToTensor -> Normalize(0.5, 0.5) exactly as torchvision computes them (uni_pipeline.py:1233-1256)."""
+    rgb = u8_bgr_hwc[..., [2, 1, 0]]
+    t = rgb.permute(0, 3, 1, 2).contiguous().to(torch.float32).div(255)
+    mean = torch.tensor([0.5, 0.5, 0.5]).view(1, 3, 1, 1)
+    std = torch.tensor([0.5, 0.5, 0.5]).view(1, 3, 1, 1)
+    return t.sub_(mean).div_(std)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_patchify_u8_bit_identical_to_host_transform(dtype):
+    from vitcap_b200 import ops
+    B, S, p = 3, 64, 16
+    u8 = torch.randint(0, 256, (B, S, S, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(3))
+    ref_img = _host_transform_tail(u8).to(DEV)
+    a = torch.empty(B * (S // p) ** 2, 3 * p * p, device=DEV, dtype=dtype)
+    b = torch.empty_like(a)
+    ops.patchify(ref_img, a, p)
+    ops.patchify_u8(u8.to(DEV), b, p, bgr=True)
+    assert torch.equal(a, b)
+    ops.patchify_u8(u8[..., [2, 1, 0]].contiguous().to(DEV), b, p, bgr=False)
+    assert torch.equal(a, b)
+
+
+def test_uint8_images_caption_like_host_transformed_floats():
+    cfg = vcfg.tiny()
+    sd = synth.make_state_dict(cfg, seed=7, eos_bias=1.0)
+    extra = synth.default_test_extra_input(cfg)
+    m = build(cfg, sd, extra, "fp32", max_batch=4)
+    B = 6
+    u8 = torch.randint(0, 256, (B, cfg.img_size, cfg.img_size, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(5))
+    data = synth.make_text_inputs(cfg, B)
+    d_f = dict(data, image=_host_transform_tail(u8))
+    d_u = dict(data, image=u8)
+    ids_f, lp_f = m(to_dev(d_f))
+    ids_u, lp_u = m(to_dev(d_u))
+    assert torch.equal(ids_f, ids_u) and torch.equal(lp_f, lp_u)

@@ -12,6 +12,7 @@ int gemm_bf16_tc(const void* A, int lda, const void* W, int ldw, const float* bi
 int gemm_simt(int in_bf16, const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldo, int out_f32,
               int act, const float* resid, int ldr, int M, int N, int K, cudaStream_t s);
 int patchify(int out_bf16, const float* img, void* out, int B, int img_size, int patch, cudaStream_t s);
+int patchify_u8(int out_bf16, const uint8_t* img, void* out, int B, int img_size, int patch, int bgr, cudaStream_t s);
 int assemble_tokens(const float* patch_out, const float* cls, const float* pos, float* x, int B, int P, int H, cudaStream_t s);
 int layernorm(int out_bf16, const float* in, int ld_in, const float* gamma, const float* beta, float eps, void* out_t, int ld_t,
               float* out_f, int ld_f, int rows, int H, cudaStream_t s);
@@ -73,6 +74,9 @@ int vc_linear_tc(const void* A, int lda, const void* W, int ldw, const float* bi
 }
 int vc_patchify(int bf16, const float* image, void* out, int B, int img_size, int patch, void* stream) {
   VC_COUNT(1, vc::patchify(bf16, image, out, B, img_size, patch, ST(stream)));
+}
+int vc_patchify_u8(int bf16, const uint8_t* image, void* out, int B, int img_size, int patch, int bgr, void* stream) {
+  VC_COUNT(1, vc::patchify_u8(bf16, image, out, B, img_size, patch, bgr, ST(stream)));
 }
 int vc_assemble_tokens(const float* patch_out, const float* cls, const float* pos, float* x, int B, int P, int H, void* stream) {
   VC_COUNT(1, vc::assemble_tokens(patch_out, cls, pos, x, B, P, H, ST(stream)));

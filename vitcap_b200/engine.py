@@ -228,15 +228,19 @@ class CaptionEngine:
         ops.linear(hid_cls, p["fc2_w"], p["fc2_b"], x_cls, resid=x_cls, M=B)
 
     # ------------------------------------------------------------------ stages
-    def patch_embed(self, image):
-        """image fp32 [B,3,S,S] (device) -> img_feats fp32 [B,N,H] (a view of the trunk stream buffer)."""
+    def patch_embed(self, image, bgr=True):
+        """image fp32 [B,3,S,S] normalised, or uint8 [B,S,S,3] HWC pixels (ToTensor + Normalize fused on the device; ``bgr``
+        gives their channel order) -> img_feats fp32 [B,N,H] (a view of the trunk stream buffer)."""
         cfg, w = self.cfg, self.w
         B = image.shape[0]
         ws = self._encoder_ws(B)
         P, H, N = cfg.n_patches, cfg.hidden, cfg.n_tokens
         patches = ws["patches"][:B * P]
         po = ws["patch_out"][:B * P]
-        ops.patchify(image, patches, cfg.patch)
+        if image.dtype == torch.uint8:
+            ops.patchify_u8(image, patches, cfg.patch, bgr=bgr)
+        else:
+            ops.patchify(image, patches, cfg.patch)
         ops.linear(patches, w.patch_w, w.patch_b, po, M=B * P)
         x = ws["x"][:B * N]
         ops.assemble_tokens(po, w.cls_token, w.pos_embed, x, B, P, H)

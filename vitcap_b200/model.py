@@ -231,6 +231,7 @@ class FastImageCaptioning(nn.Module):
         self.max_batch = max_batch
         self.use_cuda_graph = use_cuda_graph
         self.sample_seed = sample_seed
+        self.u8_channel_order = "bgr"       # what cv2 / the reference's TSV image decoder deliver (BGR2RGB is then fused)
         self._engine = None
         self._sample_calls = 0
         self.register_load_state_dict_post_hook(lambda m, keys: m._invalidate())
@@ -259,8 +260,15 @@ class FastImageCaptioning(nn.Module):
 
     # ---- pieces called by the sub-modules ----------------------------------------------------------------------------
     def _patch_embed(self, image):
+        S = self.cfg.img_size
+        if image.dtype == torch.uint8:
+            # 8-bit pixels straight from the host pipeline (after resize / center-crop): uint8 (B, S, S, 3), HWC, channel order
+            # self.u8_channel_order; ToTensor + Normalize(0.5, 0.5) run on the device (additive to the reference contract)
+            if image.dim() != 4 or tuple(image.shape[1:]) != (S, S, 3):
+                raise ValueError("uint8 images must be (B, %d, %d, 3) HWC" % (S, S))
+            return self.engine.patch_embed(image.contiguous(), bgr=(self.u8_channel_order == "bgr"))
         image = image.to(dtype=torch.float32).contiguous()
-        if image.shape[-1] != self.cfg.img_size or image.shape[-2] != self.cfg.img_size:
+        if image.shape[-1] != S or image.shape[-2] != S:
             raise NotImplementedError(_UNSUPPORTED % "position-embedding interpolation for a different image size")
         return self.engine.patch_embed(image)
 

@@ -23,6 +23,7 @@ SIGNATURES = {
     "vc_linear_simt": [_I, _P, _I, _P, _I, _P, _P, _I, _I, _I, _P, _I, _I, _I, _I, _P],
     "vc_linear_tc": [_P, _I, _P, _I, _P, _P, _I, _I, _I, _P, _I, _I, _I, _I, _I, _P],
     "vc_patchify": [_I, _P, _P, _I, _I, _I, _P],
+    "vc_patchify_u8": [_I, _P, _P, _I, _I, _I, _I, _P],
     "vc_assemble_tokens": [_P, _P, _P, _P, _I, _I, _I, _P],
     "vc_layernorm": [_I, _P, _I, _P, _P, _F, _P, _I, _P, _I, _I, _I, _P],
     "vc_gather_rows": [_I, _P, _SZ, _P, _I, _I, _I, _P],
@@ -142,6 +143,14 @@ def patchify(image, out, patch):
     B, _, S, _ = image.shape
     assert image.dtype == torch.float32 and image.is_contiguous()
     _check(load_library().vc_patchify(_is_bf16(out), _ptr(image), _ptr(out), B, S, patch, _stream()), "vc_patchify")
+    return out
+
+
+def patchify_u8(image, out, patch, bgr=True):
+    """image uint8 [B,S,S,3] (HWC) -> normalised patch matrix (ToTensor + Normalize(0.5,0.5) fused)."""
+    B, S, S2, C = image.shape
+    assert image.dtype == torch.uint8 and image.is_contiguous() and C == 3 and S == S2
+    _check(load_library().vc_patchify_u8(_is_bf16(out), _ptr(image), _ptr(out), B, S, patch, int(bool(bgr)), _stream()), "vc_patchify_u8")
     return out
 
 
