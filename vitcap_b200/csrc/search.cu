@@ -206,35 +206,57 @@ __device__ __forceinline__ float u32_to_unit(uint32_t x) {   // (0,1), 24 bits
 //   sample : x' = x / T; tok = argmax_i(x'_i + Gumbel_i)  (== multinomial(softmax(x'))), lp = log_softmax(x')[tok]
 //   update : modeling_utils.py:855-862
 // ------------------------------------------------------------------------------------------
+// Two vectorised sweeps of the row (the second one hits L1/L2): sweep 1 = row max of x/T and the arg-max of the selection
+// key (x for greedy, x/T + Gumbel noise for sampling), sweep 2 = sum exp(x/T - max). Columns >= V are padding.
+template <bool VEC>
+__device__ __forceinline__ float4 row_load4(const float* __restrict__ row, int i4, int V) {
+  float4 v;
+  const int i = i4 * 4;
+  if (VEC && i + 3 < V) return __ldg(reinterpret_cast<const float4*>(row) + i4);
+  v.x = (i < V) ? row[i] : -INFINITY;
+  v.y = (i + 1 < V) ? row[i + 1] : -INFINITY;
+  v.z = (i + 2 < V) ? row[i + 2] : -INFINITY;
+  v.w = (i + 3 < V) ? row[i + 3] : -INFINITY;
+  return v;
+}
+
+template <bool VEC>
 __global__ void __launch_bounds__(256)
 token_step_kernel(const float* __restrict__ logits, int ld, int V, int do_sample, float inv_temp, uint64_t seed, int cur_len,
                   int max_len, int pad_id, const int* __restrict__ eos_ids, int n_eos, int* __restrict__ ids,
                   int* __restrict__ unfinished, float* __restrict__ sum_lp, int* __restrict__ n_steps) {
-  __shared__ LseSmem lse;
-  __shared__ float bv[8];
+  __shared__ float bv[8], bm[8], bs[8];
   __shared__ int bi[8];
+  __shared__ float s_max;
   const int r = blockIdx.x, tid = threadIdx.x;
   const float* row = logits + (size_t)r * ld;
-  block_lse(row, V, do_sample ? inv_temp : 1.f, lse);
-  float best = -INFINITY;
+  const float it = do_sample ? inv_temp : 1.f;
+  const int n4 = (V + 3) >> 2;
+  float best = -INFINITY, m = -INFINITY;
   int besti = 0x7fffffff;
   if (!do_sample) {
-    for (int i = tid; i < V; i += 256) {
-      const float x = row[i];
-      if (x > best) { best = x; besti = i; }
+    for (int i4 = tid; i4 < n4; i4 += 256) {
+      const float4 v = row_load4<VEC>(row, i4, V);
+      const float xs[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (xs[j] > best) { best = xs[j]; besti = i4 * 4 + j; }     // first index on ties (ascending scan per thread)
     }
+    m = best;
   } else {
     const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
-    for (int i4 = tid; i4 * 4 < V; i4 += 256) {
+    for (int i4 = tid; i4 < n4; i4 += 256) {
+      const float4 v = row_load4<VEC>(row, i4, V);
+      const float xs[4] = {v.x, v.y, v.z, v.w};
       const uint4 rnd = philox4x32_10(make_uint4((uint32_t)i4, (uint32_t)r, (uint32_t)cur_len, 0u), key);
       const uint32_t rr[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int i = i4 * 4 + j;
-        if (i < V) {
-          const float g = -logf(-logf(u32_to_unit(rr[j])));
-          const float x = row[i] * inv_temp + g;
-          if (x > best) { best = x; besti = i; }
+        if (i4 * 4 + j < V) {
+          const float xt = xs[j] * inv_temp;
+          m = fmaxf(m, xt);
+          const float x = xt + -logf(-logf(u32_to_unit(rr[j])));
+          if (x > best) { best = x; besti = i4 * 4 + j; }
         }
       }
     }
@@ -244,14 +266,36 @@ token_step_kernel(const float* __restrict__ logits, int ld, int V, int do_sample
     const float v2 = __shfl_xor_sync(0xffffffffu, best, o);
     const int i2 = __shfl_xor_sync(0xffffffffu, besti, o);
     if (v2 > best || (v2 == best && i2 < besti)) { best = v2; besti = i2; }
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   }
-  if ((tid & 31) == 0) { bv[tid >> 5] = best; bi[tid >> 5] = besti; }
+  if ((tid & 31) == 0) { bv[tid >> 5] = best; bi[tid >> 5] = besti; bm[tid >> 5] = m; }
   __syncthreads();
   if (tid == 0) {
-    for (int w = 1; w < 8; ++w)
+    for (int w = 1; w < 8; ++w) {
       if (bv[w] > best || (bv[w] == best && bi[w] < besti)) { best = bv[w]; besti = bi[w]; }
-    const float x = row[besti] * (do_sample ? inv_temp : 1.f);
-    const float lp = (x - lse.row_max) - lse.row_logsum;
+      m = fmaxf(m, bm[w]);
+    }
+    bi[0] = besti;
+    s_max = m;
+  }
+  __syncthreads();
+  const float row_max = s_max;
+  // filtered logits are -inf (modeling_utils.py:1120/1134): exp(-inf - max) == 0, they contribute nothing
+  float s = 0.f;
+  for (int i4 = tid; i4 < n4; i4 += 256) {
+    const float4 v = row_load4<VEC>(row, i4, V);
+    s += (expf(v.x * it - row_max) + expf(v.y * it - row_max)) + (expf(v.z * it - row_max) + expf(v.w * it - row_max));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((tid & 31) == 0) bs[tid >> 5] = s;
+  __syncthreads();
+  if (tid == 0) {
+    float tot = 0.f;
+    for (int w = 0; w < 8; ++w) tot += bs[w];
+    besti = bi[0];
+    const float x = row[besti] * it;
+    const float lp = (x - row_max) - logf(tot);
     const int unf = unfinished[r];
     const int tok = unf ? besti : pad_id;
     ids[(size_t)r * max_len + cur_len] = tok;
@@ -269,8 +313,13 @@ int token_step(const float* logits, int ld, int rows, int V, int do_sample, floa
   if (rows <= 0 || V <= 0 || cur_len < 1 || cur_len >= max_len || temperature <= 0.f) {
     set_last_error("token_step: bad args"); return VC_ERR_BAD_ARG;
   }
-  token_step_kernel<<<rows, 256, 0, s>>>(logits, ld, V, do_sample, 1.f / temperature, seed, cur_len, max_len, pad_id, eos_ids,
-                                         n_eos, ids, unfinished, sum_lp, n_steps);
+  const bool vec = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(logits) & 15) == 0);
+  if (vec)
+    token_step_kernel<true><<<rows, 256, 0, s>>>(logits, ld, V, do_sample, 1.f / temperature, seed, cur_len, max_len, pad_id,
+                                                 eos_ids, n_eos, ids, unfinished, sum_lp, n_steps);
+  else
+    token_step_kernel<false><<<rows, 256, 0, s>>>(logits, ld, V, do_sample, 1.f / temperature, seed, cur_len, max_len, pad_id,
+                                                  eos_ids, n_eos, ids, unfinished, sum_lp, n_steps);
   return check_launch("token_step");
 }
 
