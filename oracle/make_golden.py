@@ -38,11 +38,28 @@ CASES = {
     "g8_sample_filtered_16_224": ("16_224", {}, dict(seed=0, eos_bias=1.8), 2, 1234,
                                   dict(do_sample=True, num_return_sequences=2, temperature=0.7, top_k=50, top_p=0.9), 78),
     "g9_greedy_refinit_16_224": ("16_224", {}, dict(seed=4, style="reference"), 2, 11, {}, None),
+    # visible od/tag label region: text_b label strings per sample -> 0 / 4 / 50 visible slots
+    "g10_greedy_labels_16_224": ("16_224", {}, dict(seed=0, eos_bias=1.7), 4, 1234, {}, None,
+                                 ["", "dog cat person", " ".join(["tree"] * 60), " ".join(["sky", "grass"] * 11)]),
+    "g11_beam3_labels_16_224": ("16_224", {}, dict(seed=0, eos_bias=1.8), 3, 1234,
+                                dict(num_beams=3, num_keep_best=2, length_penalty=0.8), None,
+                                ["a man riding a wave on top of a surfboard", " ".join(["sky", "grass", "field"] * 7),
+                                 " ".join(["tree"] * 60)]),
+    # tag_bias moves topk_len[0] below 50 so that the label-embedding recipe (modeling_bert.py:1435) flips mid-caption
+    # (g12, g13) or is the raw one from the first step (g14)
+    "g12_greedy_labels_flip_16_224": ("16_224", {}, dict(seed=0, eos_bias=1.7, tag_bias=-3.176), 3, 1234, {}, None,
+                                      [" ".join(["sky", "grass"] * 11), " ".join(["tree"] * 60), "dog cat person"]),
+    "g13_beam3_labels_flip_16_224": ("16_224", {}, dict(seed=0, eos_bias=1.75, tag_bias=-3.16), 2, 1234,
+                                     dict(num_beams=3, num_keep_best=1), None,
+                                     [" ".join(["tree"] * 60), " ".join(["sky", "grass", "field"] * 7)]),
+    "g14_greedy_labels_raw_16_224": ("16_224", {}, dict(seed=0, eos_bias=1.7, tag_bias=-3.3), 3, 1234, {}, None,
+                                     [" ".join(["tree"] * 60), "", " ".join(["sky", "grass"] * 11)]),
 }
 
 
 def run_case(name):
-    variant, over, wkw, B, iseed, dec, tseed = CASES[name]
+    variant, over, wkw, B, iseed, dec, tseed = CASES[name][:7]
+    text_b = CASES[name][7] if len(CASES[name]) > 7 else None
     cfg = vcfg.variant(variant, **over)
     sd = synth.make_state_dict(cfg, **wkw)
     ref, tok = ref_loader.build_reference(variant, decoder_layer=over.get("dec_layers"))
@@ -50,9 +67,14 @@ def run_case(name):
     extra = synth.default_test_extra_input(cfg, **dec)
     ref.test_extra_input = extra
     img = synth.make_images(cfg, B, seed=iseed)
-    ti = ref_loader.reference_text_inputs(tok, B)
-    mine = synth.make_text_inputs(cfg, B)
+    ti = ref_loader.reference_text_inputs(tok, B, text_b)
+    n_label = (ti["attention_mask"][:, 0, cfg.max_seq_a:].sum(1)).tolist()
+    mine = synth.make_text_inputs(cfg, B, n_label=n_label)
     for k in ti:
+        if text_b is not None and k == "input_ids":      # label word pieces: synth uses a filler id (never reaches the output)
+            assert torch.equal(ti[k][:, :cfg.max_seq_a], mine[k][:, :cfg.max_seq_a])
+            assert torch.equal(ti[k] == 0, mine[k] == 0)
+            continue
         assert torch.equal(ti[k], mine[k]) and ti[k].dtype == mine[k].dtype, k
 
     cap = {"step_top": [], "n_calls": 0}
@@ -103,6 +125,7 @@ def run_case(name):
         "meta": np.array(json.dumps({
             "case": name, "variant": variant, "cfg_overrides": over, "weights": wkw, "batch": B,
             "image_seed": iseed, "decode": dec, "torch_seed": tseed, "torch": torch.__version__,
+            "text_b": text_b, "n_label": n_label,
             "n_model_calls": cap["n_calls"], "reference_seconds": round(dt, 1),
             "reference_threads": torch.get_num_threads(),
         })),

@@ -253,7 +253,19 @@ class FaithfulStepper:
 # cached restatement (the algorithm the kernels implement)
 # =========================================================================================
 class CachedStepper:
-    def __init__(self, model: PortModel, img_feats, num_expand, mask_token_id, keep_intermediates=False):
+    """``n_label`` (int64 [B] or None): number of visible od/tag label slots per image, i.e. the mask family
+    dataset.py:371-417 produces for a non-empty ``text_b`` (full L-L block, caption rows see L, image rows do not).
+    The label rows then join the context: rows [tag-CLS | image | L_0..L_49]; image rows never see them, label rows
+    see the image context and the first n_label[b] label rows, caption rows see all of that.
+
+    L_i comes from one of two recipes, chosen PER STEP by the reference from the first sample's tag count
+    (modeling_bert.py:1435, ``topk_len[0] + 20 <= input_ids.shape[1]`` with input length cur_len + 1 + 50):
+      'raw' (1447-1470): word embedding of the i-th predicted tag, last slot forced to [SEP];
+      'ln'  (1472-1489 -> encode_tag_to_embedding 1381-1406): the same + position 20+i + type 0 -> LayerNorm.
+    The reference recomputes everything every step, so when the recipe flips at some step every cached row that saw the
+    label rows is stale: the label rows are prefilled again and the caption rows replayed under the new recipe."""
+
+    def __init__(self, model: PortModel, img_feats, num_expand, mask_token_id, keep_intermediates=False, n_label=None):
         self.m = model
         cfg = model.cfg
         self.E = num_expand
@@ -261,24 +273,73 @@ class CachedStepper:
         cap, tag = model.split_encoder(img_feats)
         self.cap, self.tag = cap, tag
         self.last_tag = model.tag_head(tag)
-        ctx = torch.cat([tag[:, 0:1], cap], dim=1)
-        self.ctx0 = ctx
+        self.ctx_img = torch.cat([tag[:, 0:1], cap], dim=1)
+        self.n_label = None
+        self.recipe = None
+        if n_label is not None and int(n_label.max()) > 0:
+            self.n_label = n_label.clone()
+        else:
+            self._prefill(None)
+        self.n_calls = 0
+        self.n_flips = 0
+
+    def label_recipe(self, cur_len):
+        """Which label embedding the reference uses at the step whose input holds cur_len tokens + [MASK]."""
+        t0 = int(self.last_tag[3][0])
+        return "raw" if t0 + 20 <= cur_len + 1 + self.m.cfg.topk else "ln"
+
+    def _prefill(self, recipe):
+        m, cfg = self.m, self.m.cfg
+        ctx = self.ctx_img
+        add = None
+        if recipe is not None:
+            B, C = ctx.shape[0], ctx.shape[1]
+            pred_topk = self.last_tag[2].clone()
+            pred_topk[:, -1] = 102                                         # modeling_bert.py:1447 / 1477
+            lab = m.p("module.cls.predictions.decoder.weight")[pred_topk]   # cls_emb == tied word embeddings (:766)
+            if recipe == "ln":
+                pre = "module.bert.embeddings."
+                tpos = torch.arange(cfg.topk) + 20                         # encode_tag_to_embedding, :1397
+                lab = lab + m.p(pre + "position_embeddings.weight")[tpos] + m.p(pre + "token_type_embeddings.weight")[0]
+                lab = F.layer_norm(lab, (cfg.hidden,), m.p(pre + "LayerNorm.weight"), m.p(pre + "LayerNorm.bias"),
+                                   cfg.bert_ln_eps)
+            ctx = torch.cat([ctx, lab], dim=1)
+            S = ctx.shape[1]
+            vis = torch.zeros(B, S, S)
+            vis[:, :, :C] = 1.0
+            for b in range(B):
+                vis[b, C:, C:C + int(self.n_label[b])] = 1.0
+            add = ((1.0 - vis) * NEG_MASK).unsqueeze(1)
+            key_vis = torch.cat([torch.ones(B, C), (torch.arange(S - C).unsqueeze(0) < self.n_label.unsqueeze(1)).float()], 1)
+            self.key_add = (1.0 - key_vis) * NEG_MASK
+        self.recipe = recipe
         self.Kc, self.Vc = [], []
         for l in range(cfg.dec_layers):
-            ctx_out, k, v = model.bert_layer(l, ctx, ctx, None)
+            ctx_out, k, v = m.bert_layer(l, ctx, ctx, add)
             self.Kc.append(k)
             self.Vc.append(v)
             ctx = ctx_out
         self.Kt = [None] * cfg.dec_layers
         self.Vt = [None] * cfg.dec_layers
-        self.n_calls = 0
 
     def __call__(self, cur_ids, beam_idx=None):
         m, cfg = self.m, self.m.cfg
         R, L = cur_ids.shape                       # R = B * E rows
-        E = self.E
-        B = R // E
         self.n_calls += 1
+        if self.n_label is not None:
+            want = self.label_recipe(L)
+            if want != self.recipe:
+                self.n_flips += self.recipe is not None
+                self._prefill(want)
+                for s in range(1, L):              # replay the caption rows under the new label rows
+                    self._step(cur_ids[:, :s])
+                beam_idx = None                    # cur_ids already holds the re-parented histories
+        return self._step(cur_ids, beam_idx)
+
+    def _step(self, cur_ids, beam_idx=None):
+        m, cfg = self.m, self.m.cfg
+        R, L = cur_ids.shape
+        E = self.E
         if beam_idx is not None:                   # reorder caption K/V rows (modeling_utils.py:1055-1065)
             for l in range(cfg.dec_layers):
                 if self.Kt[l] is not None:
@@ -297,6 +358,10 @@ class CachedStepper:
             V = torch.cat(parts_v, dim=2)
             add = torch.zeros(1, 1, 2, K.shape[2])
             add[..., 0, -1] = NEG_MASK             # the real-token row must not see the MASK row
+            if self.recipe is not None:            # invisible label slots of the image's context
+                ka = self.key_add.repeat_interleave(E, dim=0) if E > 1 else self.key_add
+                add = add.repeat(R, 1, 1, 1)
+                add[:, 0, :, :ka.shape[1]] += ka.unsqueeze(1)
             e = m.bert_layer_from_kv(l, e, q, K, V, add)
             self.Kt[l] = k[:, :, 0:1] if self.Kt[l] is None else torch.cat([self.Kt[l], k[:, :, 0:1]], dim=2)
             self.Vt[l] = v[:, :, 0:1] if self.Vt[l] is None else torch.cat([self.Vt[l], v[:, :, 0:1]], dim=2)
@@ -457,10 +522,22 @@ def beam_search(step, batch, max_length, bos, pad, eos_ids, num_beams, vocab, le
 def _canonical(text_mask, max_seq_a):
     """True iff the 70x70 mask is the eval pipeline's: caption triangle only (dataset.py:371-390 with
     text_b == '')."""
+    n = label_counts(text_mask, max_seq_a)
+    return n is not None and int(n.max()) == 0
+
+
+def label_counts(text_mask, max_seq_a):
+    """Number of visible label slots per sample if the mask belongs to the seq2seq family of dataset.py:371-417
+    (caption triangle; full attention L-L and C-L over the first n label slots; nothing else), else None."""
     B, S, _ = text_mask.shape
-    ref = torch.zeros(S, S, dtype=text_mask.dtype)
-    ref[:max_seq_a, :max_seq_a] = torch.tril(torch.ones(max_seq_a, max_seq_a, dtype=text_mask.dtype))
-    return bool((text_mask == ref.unsqueeze(0)).all())
+    n = text_mask[:, 0, max_seq_a:].sum(dim=1).long()
+    ref = torch.zeros(B, S, S, dtype=text_mask.dtype)
+    ref[:, :max_seq_a, :max_seq_a] = torch.tril(torch.ones(max_seq_a, max_seq_a, dtype=text_mask.dtype))
+    for b in range(B):
+        e = max_seq_a + int(n[b])
+        ref[b, max_seq_a:e, max_seq_a:e] = 1
+        ref[b, :max_seq_a, max_seq_a:e] = 1
+    return n if bool((text_mask == ref).all()) else None
 
 
 def caption(model: PortModel, data, extra, algorithm="cached", sampler=None, trace=None, info=None):
@@ -482,8 +559,9 @@ def caption(model: PortModel, data, extra, algorithm="cached", sampler=None, tra
                                   extra["od_labels_start_posid"], extra["mask_token_id"],
                                   add_od_labels=extra.get("add_od_labels", True))
     else:
-        assert _canonical(data["attention_mask"], cfg.max_seq_a), "cached algorithm needs the canonical eval mask"
-        stepper = CachedStepper(model, img_feats, num_expand, extra["mask_token_id"])
+        n_label = label_counts(data["attention_mask"], cfg.max_seq_a)
+        assert n_label is not None, "cached algorithm needs a mask of the seq2seq family (dataset.py:371-417)"
+        stepper = CachedStepper(model, img_feats, num_expand, extra["mask_token_id"], n_label=n_label)
     eff = B * nret
     if nb > 1:
         out = beam_search(stepper, eff, max_length, extra["bos_token_id"], extra["pad_token_id"],

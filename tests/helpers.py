@@ -22,7 +22,7 @@ def golden_setup(meta):
     cfg = vcfg.variant(meta["variant"], **meta["cfg_overrides"])
     sd = synth.make_state_dict(cfg, **meta["weights"])
     B = meta["batch"]
-    data = synth.make_text_inputs(cfg, B)
+    data = synth.make_text_inputs(cfg, B, n_label=meta.get("n_label"))
     data["image"] = synth.make_images(cfg, B, seed=meta["image_seed"])
     extra = synth.default_test_extra_input(cfg, **meta["decode"])
     return cfg, sd, data, extra

@@ -8,7 +8,10 @@ from oracle import port
 from tests.helpers import golden_setup, load_golden
 
 CACHED_CASES = ["g1_greedy_16_384", "g3_greedy_eos_16_224", "g4_beam3_keep3_16_224", "g6_greedy_32_384",
-                "g7_greedy_dec12_16_224", "g9_greedy_refinit_16_224"]
+                "g7_greedy_dec12_16_224", "g9_greedy_refinit_16_224",
+                # visible od/tag label region: 'ln' recipe until the last step, flip at step 8,
+                # 'raw' recipe throughout
+                "g10_greedy_labels_16_224", "g12_greedy_labels_flip_16_224", "g14_greedy_labels_raw_16_224"]
 
 
 def _run(name, algorithm):
@@ -43,10 +46,21 @@ def test_cached_port_matches_reference(name):
             np.testing.assert_allclose(v.numpy(), z["step_top_val"][s], atol=5e-5)
 
 
-def test_cached_port_beam4_16_384():
-    z, meta, cfg, ids, lp, info, trace = _run("g2_beam4_16_384", "cached")
+@pytest.mark.parametrize("name", ["g2_beam4_16_384", "g11_beam3_labels_16_224", "g13_beam3_labels_flip_16_224"])
+def test_cached_port_beam(name):
+    z, meta, cfg, ids, lp, info, trace = _run(name, "cached")
     assert np.array_equal(ids.numpy(), z["ids"])
     np.testing.assert_allclose(lp.numpy(), z["logprobs"], atol=5e-5)
+
+
+def test_label_recipe_flip_points():
+    """The step at which the reference switches the label embedding depends on the FIRST sample's tag count
+    (modeling_bert.py:1435): recorded counts 50 / 39 / 15 put it at the last step, at cur_len 8, and before step 1."""
+    for name, flip in (("g10_greedy_labels_16_224", 19), ("g12_greedy_labels_flip_16_224", 8), ("g14_greedy_labels_raw_16_224", 1)):
+        z, meta = load_golden(name)
+        t0 = int(z["tag_topk_len"][0])
+        first_raw = min(L for L in range(1, 20) if t0 + 20 <= L + 1 + 50)
+        assert first_raw == max(1, t0 - 31) == flip
 
 
 @pytest.mark.parametrize("name", ["g5_sample5_16_224", "g8_sample_filtered_16_224"])
@@ -62,7 +76,7 @@ def test_sampling_semantics_with_torch_multinomial(name):
     np.testing.assert_allclose(lp.numpy(), z["logprobs"], atol=5e-5)
 
 
-@pytest.mark.parametrize("name", ["g6_greedy_32_384", "g4_beam3_keep3_16_224"])
+@pytest.mark.parametrize("name", ["g6_greedy_32_384", "g4_beam3_keep3_16_224", "g12_greedy_labels_flip_16_224"])
 def test_faithful_port_matches_reference(name):
     """The uncached restatement (what bench.py times as the CPU baseline) reproduces the reference,
     including the number of full-model calls (19 for a 20-token caption: no KV cache is live,

@@ -88,7 +88,7 @@ def state_dict_spec(cfg: VitCapConfig):
     return spec
 
 
-def make_state_dict(cfg: VitCapConfig, seed=0, style="stress", vocab_gain=1.0, eos_bias=0.0):
+def make_state_dict(cfg: VitCapConfig, seed=0, style="stress", vocab_gain=1.0, eos_bias=0.0, tag_bias=0.0):
     """Random weights in the reference layout.
 
     style="reference": the reference's own init families (zero biases, unit LayerNorm;
@@ -137,6 +137,8 @@ def make_state_dict(cfg: VitCapConfig, seed=0, style="stress", vocab_gain=1.0, e
     out["module.cls.predictions.decoder.weight"] = we   # tied (modeling_bert.py:728-730)
     if eos_bias:
         out["module.cls.predictions.bias"][SEP_ID] += eos_bias
+    if tag_bias:     # shifts every concept logit: moves topk_len (count of top-k probabilities >= 0.2, modeling_bert.py:1432)
+        out["module.bert.tag_logit.predictions.bias"] += tag_bias
     # keep the reference's key order
     return {k: out[k] for k, _, _ in state_dict_spec(cfg)}
 
@@ -148,22 +150,37 @@ def make_images(cfg: VitCapConfig, batch, seed=1234):
     return torch.from_numpy(a.reshape(batch, 3, cfg.img_size, cfg.img_size))
 
 
-def make_text_inputs(cfg: VitCapConfig, batch):
+def make_text_inputs(cfg: VitCapConfig, batch, n_label=None, label_token=2000):
     """Test-time text tensors of the reference data layer: what
-    ``CaptionTensorizer.tensorize_ab('', text_b='', real_text_a_in_test=False)`` returns
-    (dataset.py:206-417): ids [CLS, MASK x18, SEP, PAD x50], a 70x70 mask whose only
-    non-zeros are the 20x20 caption triangle, zero segment ids, all-ones masked_pos."""
+    ``CaptionTensorizer.tensorize_ab('', text_b=..., real_text_a_in_test=False)`` returns
+    (dataset.py:206-417). ``n_label`` None / 0 (text_b == ''): ids [CLS, MASK x18, SEP, PAD x50], a 70x70 mask whose
+    only non-zeros are the 20x20 caption triangle, zero segment ids, all-ones masked_pos.
+    ``n_label`` = per-sample list of visible label slots (text_b with n-1 word pieces + [SEP]): label ids in slots
+    20..20+n (their value never reaches the output: modeling_bert.py:1470 overwrites all 50 slot embeddings with the
+    predicted tags), segment id 1 there, full attention L-L and C-L (dataset.py:405-408)."""
     a, s = cfg.max_seq_a, cfg.max_seq
-    ids = torch.zeros(s, dtype=torch.long)
-    ids[0] = CLS_ID
-    ids[1:a - 1] = MASK_ID
-    ids[a - 1] = SEP_ID
-    mask = torch.zeros(s, s, dtype=torch.long)
-    mask[:a, :a] = torch.tril(torch.ones(a, a, dtype=torch.long))
+    if n_label is None:
+        n_label = [0] * batch
+    assert len(n_label) == batch and all(0 <= int(n) <= s - a and int(n) != 1 for n in n_label)
+    ids = torch.zeros(batch, s, dtype=torch.long)
+    ids[:, 0] = CLS_ID
+    ids[:, 1:a - 1] = MASK_ID
+    ids[:, a - 1] = SEP_ID
+    mask = torch.zeros(batch, s, s, dtype=torch.long)
+    mask[:, :a, :a] = torch.tril(torch.ones(a, a, dtype=torch.long))
+    typ = torch.zeros(batch, s, dtype=torch.long)
+    for b, n in enumerate(n_label):
+        n = int(n)
+        if n:
+            ids[b, a:a + n - 1] = label_token
+            ids[b, a + n - 1] = SEP_ID
+            typ[b, a:a + n] = 1
+            mask[b, a:a + n, a:a + n] = 1
+            mask[b, :a, a:a + n] = 1
     return {
-        "input_ids": ids.unsqueeze(0).repeat(batch, 1),
-        "attention_mask": mask.unsqueeze(0).repeat(batch, 1, 1),
-        "token_type_ids": torch.zeros(batch, s, dtype=torch.long),
+        "input_ids": ids,
+        "attention_mask": mask,
+        "token_type_ids": typ,
         "masked_pos": torch.ones(batch, s, dtype=torch.int32),
     }
 
