@@ -80,12 +80,30 @@ int vc_layernorm(int bf16, const float* in, int ld_in, const float* gamma, const
 int vc_gather_rows(int bf16, const float* in, size_t row_stride, void* out, int ld_out, int rows, int H, void* stream);
 /* ctx[b] = [tag_feats[b,0] ; cap_feats[b,0..N-1]] (modeling_bert.py:1493), fp32 copy + operand copy */
 int vc_assemble_ctx(int bf16, const float* cap, const float* tag, float* ctx_f, void* ctx_t, int B, int N, int H, void* stream);
+/* the same with rows_per_image >= N + 1 context rows allocated per image (the label rows below follow the N + 1 rows) */
+int vc_assemble_ctx_pitched(int bf16, const float* cap, const float* tag, float* ctx_f, void* ctx_t, int B, int N, int H,
+                            int rows_per_image, void* stream);
+/* od/tag label rows of the context, for callers whose attention mask makes the label region visible (dataset.py:405-408):
+ * row (b, i), i < K, = word[tag_i]                                  recipe_ln = 0  (modeling_bert.py:1447-1470)
+ *                    = LN(word[tag_i] + pos[pos0 + i] + type0)      recipe_ln = 1  (encode_tag_to_embedding, :1381-1406, :1472-1489)
+ * with tag_i = tag_idx[b, i] (int32 [B,K], the sorted top-K concepts) and the last slot forced to sep_id (:1447 / :1477).
+ * Written to context rows row0 .. row0 + K - 1 of image b in ctx_f (fp32) and ctx_t (operand copy). */
+int vc_label_rows(int bf16, const int* tag_idx, int K, int sep_id, int recipe_ln, int pos0, const float* word, const float* pos,
+                  const float* type0, const float* gamma, const float* beta, float eps, float* ctx_f, void* ctx_t, int B,
+                  int rows_per_image, int row0, int H, void* stream);
 
 /* softmax(Q K^T * scale) V for packed qkv [B,N,3*heads*64] -> out [B,N,heads*64]; scores stay on chip.
  * Attention.forward vision_transformer.py:174-200 (mask is all-zero, modeling_bert.py:1415) and BertSelfAttention
  * modeling_bert.py:303-340 over the context rows. bf16=1: tcgen05 flash kernel; bf16=0: CUDA-core kernel. */
 int vc_attention(int bf16, const void* qkv, void* out, int B, int N, int heads, float scale, void* stream);
 int vc_attention_simt(int bf16, const void* qkv, void* out, int B, int N, int heads, float scale, void* stream);
+/* the same under the label-region mask of the seq2seq family (dataset.py:395-408 + the image rows of
+ * tagger_caption_uni_pipeline_expanding_bertemb.py:57-85): rows below n_base (tag-CLS + image tokens) see the keys below
+ * n_base only; rows from n_base on (label rows) also see the first n_extra[b] label keys. n_extra: int32 [B], required. */
+int vc_attention_labels(int bf16, const void* qkv, void* out, int B, int N, int heads, float scale, int n_base, const int* n_extra,
+                        void* stream);
+int vc_attention_labels_simt(int bf16, const void* qkv, void* out, int B, int N, int heads, float scale, int n_base,
+                             const int* n_extra, void* stream);
 
 /* single-query attention: out[b] = softmax(q[b] K_b^T * scale) V_b with K, V taken from the packed qkv [B,N,3H] and ONE query
  * row per image (q [B,H], pitch ldq). Used for the last block of the concept branch, of which only the CLS row is consumed
@@ -116,6 +134,13 @@ int vc_decode_attention(int bf16, const void* ctx_qkv, const void* step_qkv, con
  * bf16=1 cross-checks the mma.sync kernel in tests) */
 int vc_decode_attention_simt(int bf16, const void* ctx_qkv, const void* step_qkv, const int* anc, void* out, int B, int C,
                              int heads, int E, int cur_len, float scale, void* stream);
+/* the same with rows_per_image context rows allocated per image of which only the first ctx_vis[b] (int32 [B]) are visible:
+ * the caption rows of image b see [tag-CLS | image tokens | its visible label rows] (C-L block of dataset.py:407-408) */
+int vc_decode_attention_labels(int bf16, const void* ctx_qkv, const void* step_qkv, const int* anc, void* out, int B,
+                               int rows_per_image, const int* ctx_vis, int heads, int E, int cur_len, float scale, void* stream);
+int vc_decode_attention_labels_simt(int bf16, const void* ctx_qkv, const void* step_qkv, const int* anc, void* out, int B,
+                                    int rows_per_image, const int* ctx_vis, int heads, int E, int cur_len, float scale,
+                                    void* stream);
 
 /* greedy / sampled next token + log-prob + state update for `rows` sequences, modeling_utils.py:839-862.
  * logits fp32 [rows, ld]; sampling = Gumbel-max with Philox4x32-10 noise keyed by (seed; vocab idx/4, row, cur_len). */

@@ -51,7 +51,7 @@ def test_header_symbols_are_exported_and_bound():
         assert hasattr(lib, n), n
     simple = {"vc_last_error", "vc_abi_version", "vc_launch_count", "vc_reset_launch_count"}
     assert names - simple == set(ops.SIGNATURES), (names - simple) ^ set(ops.SIGNATURES)
-    assert lib.vc_abi_version() == 1
+    assert lib.vc_abi_version() == 2
     assert isinstance(lib.vc_last_error(), bytes)
 
 
@@ -88,9 +88,27 @@ def test_unsupported_flags_raise():
             m.module(feats, **kw)
     with pytest.raises(NotImplementedError):
         m.module(feats, is_decode=False)
-    # a mask with a visible label region is refused, not silently mis-computed
+    # a mask outside the seq2seq family of the data layer is refused, not silently mis-computed
     ti = synth.make_text_inputs(cfg, 1)
-    ti["attention_mask"][:, :20, 20:] = 1
-    with pytest.raises(NotImplementedError, match="visible od/tag"):
-        m._check_canonical_mask(ti["attention_mask"], ti["input_ids"], 20)
-    m._check_canonical_mask(synth.make_text_inputs(cfg, 2)["attention_mask"], ti["input_ids"].repeat(2, 1), 20)
+    ti["attention_mask"][:, :20, 20:] = 1          # C-L visible without the L-L block
+    with pytest.raises(NotImplementedError, match="outside the seq2seq family"):
+        m._label_counts(ti["attention_mask"], ti["input_ids"], 20)
+    ti = synth.make_text_inputs(cfg, 1)
+    ti["attention_mask"][:, 5, 9] = 1              # a caption row looking ahead
+    with pytest.raises(NotImplementedError, match="outside the seq2seq family"):
+        m._label_counts(ti["attention_mask"], ti["input_ids"], 20)
+
+
+def test_label_counts_of_the_data_layer_masks():
+    """The eval mask (text_b == '') has no visible label slot; text_b with n-1 word pieces + [SEP] shows n of them
+    (dataset.py:395-408). Also through the full (70+N)^2 mask of construct_attn_mask (pipeline file lines 57-85)."""
+    cfg = vcfg.tiny()
+    m = FastImageCaptioning(cfg)
+    ti = synth.make_text_inputs(cfg, 2)
+    assert m._label_counts(ti["attention_mask"], ti["input_ids"], 20) is None
+    ti = synth.make_text_inputs(cfg, 4, n_label=[0, 4, 50, 23])
+    assert m._label_counts(ti["attention_mask"], ti["input_ids"], 20).tolist() == [0, 4, 50, 23]
+    from oracle import port
+    full = port.construct_full_mask(ti["attention_mask"], cfg.n_tokens)
+    assert m._label_counts(full, ti["input_ids"], 20).tolist() == [0, 4, 50, 23]
+    assert port.label_counts(ti["attention_mask"], 20).tolist() == [0, 4, 50, 23]

@@ -27,6 +27,7 @@ class VitCapConfig:
     bert_ln_eps: float = 1e-12    # config.json layer_norm_eps
     max_seq_a: int = 20           # caption slots (max_seq_a_length)
     max_seq: int = 70             # caption + od/tag slots (max_seq_length)
+    sep_id: int = 102             # [SEP] of bert-base-uncased: forced into the last label slot (modeling_bert.py:1447)
 
     @property
     def head_dim(self):

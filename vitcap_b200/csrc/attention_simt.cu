@@ -8,7 +8,8 @@ namespace vc {
 
 template <typename T>
 __global__ void __launch_bounds__(256)
-attention_simt_kernel(const T* __restrict__ qkv, T* __restrict__ out, int N, int H, float scale) {
+attention_simt_kernel(const T* __restrict__ qkv, T* __restrict__ out, int N, int H, float scale, int n_base,
+                      const int* __restrict__ n_extra) {
   constexpr int D = 64, QB = 32, KB = 64;
   __shared__ float Qs[QB][D];
   __shared__ float Ks[KB][D + 1];
@@ -34,6 +35,8 @@ attention_simt_kernel(const T* __restrict__ qkv, T* __restrict__ out, int N, int
   float m[4], l[4], o0[4], o1[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) { m[i] = -INFINITY; l[i] = 0.f; o0[i] = 0.f; o1[i] = 0.f; }
+  // label-region mask (n_extra != NULL): rows below n_base see the keys below n_base, later rows n_extra[b] more
+  const int lab_lim = n_extra ? n_base + n_extra[b] : N;
 
   for (int k0 = 0; k0 < N; k0 += KB) {
     __syncthreads();
@@ -61,11 +64,12 @@ attention_simt_kernel(const T* __restrict__ qkv, T* __restrict__ out, int N, int
         s0 = fmaf(qv, Ks[lane][d], s0);
         s1 = fmaf(qv, Ks[lane + 32][d], s1);
       }
-      if (k0 + lane >= N) s0 = -INFINITY;
-      if (k0 + lane + 32 >= N) s1 = -INFINITY;
+      const int lim = (n_extra && q0 + q < n_base) ? n_base : lab_lim;
+      if (k0 + lane >= lim) s0 = -INFINITY;
+      if (k0 + lane + 32 >= lim) s1 = -INFINITY;
       const float mn = fmaxf(m[qi], warp_max(fmaxf(s0, s1)));
-      const float corr = expf(m[qi] - mn);
-      const float p0 = expf(s0 - mn), p1 = expf(s1 - mn);
+      const float corr = (m[qi] == -INFINITY) ? 0.f : expf(m[qi] - mn);
+      const float p0 = (s0 == -INFINITY) ? 0.f : expf(s0 - mn), p1 = (s1 == -INFINITY) ? 0.f : expf(s1 - mn);
       l[qi] = l[qi] * corr + warp_sum(p0 + p1);
       m[qi] = mn;
       __syncwarp();
@@ -94,12 +98,15 @@ attention_simt_kernel(const T* __restrict__ qkv, T* __restrict__ out, int N, int
   }
 }
 
-int attention_simt(int is_bf16, const void* qkv, void* out, int B, int N, int heads, float scale, cudaStream_t s) {
-  if (B <= 0 || N <= 0 || heads <= 0) { set_last_error("attention_simt: bad args"); return VC_ERR_BAD_ARG; }
+int attention_simt(int is_bf16, const void* qkv, void* out, int B, int N, int heads, float scale, int n_base, const int* n_extra,
+                   cudaStream_t s) {
+  if (B <= 0 || N <= 0 || heads <= 0 || (n_extra && (n_base < 1 || n_base > N))) {
+    set_last_error("attention_simt: bad args"); return VC_ERR_BAD_ARG;
+  }
   dim3 grid((N + 31) / 32, heads, B);
   const int H = heads * 64;
-  if (is_bf16) attention_simt_kernel<bf16><<<grid, 256, 0, s>>>((const bf16*)qkv, (bf16*)out, N, H, scale);
-  else attention_simt_kernel<float><<<grid, 256, 0, s>>>((const float*)qkv, (float*)out, N, H, scale);
+  if (is_bf16) attention_simt_kernel<bf16><<<grid, 256, 0, s>>>((const bf16*)qkv, (bf16*)out, N, H, scale, n_base, n_extra);
+  else attention_simt_kernel<float><<<grid, 256, 0, s>>>((const float*)qkv, (float*)out, N, H, scale, n_base, n_extra);
   return check_launch("attention_simt");
 }
 

@@ -85,9 +85,11 @@ __device__ __forceinline__ void store_o_row(uint32_t taddr_o, float l, bf16* op,
 }
 }  // namespace
 
+// LABELS: the label-region mask variant (per-row key limits); the plain instantiation carries none of its code
+template <bool LABELS>
 __global__ void __launch_bounds__(192, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
-                    bf16* __restrict__ out, int N, int H, float scale_log2) {
+                    bf16* __restrict__ out, int N, int H, float scale_log2, int n_base, const int* __restrict__ n_extra) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_BAR);
   uint64_t* q_full = bars;           // [2] Q tile landed
@@ -248,16 +250,22 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     float pend_l = 0.f;
     int pend_tile = 0, pend_sb = 0;
     uint32_t pend_ph = 0;
+    // label-region mask (n_extra != NULL; dataset.py:405-408 restated structurally): rows below n_base see the keys below
+    // n_base only, rows from n_base on see n_extra[b] more keys. Without it every row sees all N keys.
+    const int lab_lim = LABELS ? n_base + n_extra[b] : N;
     for (int tile = 0; tile < nq; ++tile) {
       const uint32_t taddr_o = tmem_base + lane_base + COL_O;
       float m_ref = -INFINITY;                         // exponent reference (scaled log2 units); lags the true max by < 8
       float l = 0.f;
+      const int row_lim = (LABELS && tile * QT + t < n_base) ? n_base : lab_lim;
       for (int j = 0; j < nch; ++j, ++g) {
-        const int lim = N - j * KT;                    // valid keys in this chunk (>= 64 for full chunks)
+        const int lim = row_lim - j * KT;              // valid keys in this chunk for this row (>= 64 for full chunks)
         const uint32_t taddr_s = tmem_base + lane_base + COL_S + sb * KT;
         mbar_wait(&s_full[sb], sph);
         tc_fence_after();
-        if (lim >= KT) {
+        // the two paths contain warp-wide votes: with per-row limits the choice must be made per warp
+        const bool full_chunk = LABELS ? (__all_sync(0xffffffffu, lim >= KT) != 0) : (lim >= KT);
+        if (full_chunk) {
           // ------------------------------ full chunk: 64 keys ------------------------------
           uint32_t r[64];
           tmem_ld_32x32(taddr_s, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
@@ -327,7 +335,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           // ------------------------------ ragged last chunk (1 key of 64 at N = 577) ------------------------------
           // only last_kn / 16 MMA steps exist; columns in [lim, last_kn) are scores of zero-filled keys. Plain order:
           // max, (rare) rescale, exponentials, 16 columns at a time.
-          const int ng = last_kn >> 4;
+          const int ng = ((j == nch - 1) ? last_kn : KT) >> 4;      // MMA steps issued for this chunk
           float mx = -INFINITY;
           for (int gq = 0; gq < ng; ++gq) {
             uint32_t r[16];
@@ -399,8 +407,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
-int attention_tc(const void* qkv, void* out, int B, int N, int heads, float scale, cudaStream_t s) {
-  if (B <= 0 || N <= 0 || heads <= 0 || B > 65535) { set_last_error("attention_tc: bad args"); return VC_ERR_BAD_ARG; }
+int attention_tc(const void* qkv, void* out, int B, int N, int heads, float scale, int n_base, const int* n_extra, cudaStream_t s) {
+  if (B <= 0 || N <= 0 || heads <= 0 || B > 65535 || (n_extra && (n_base < 1 || n_base > N))) {
+    set_last_error("attention_tc: bad args"); return VC_ERR_BAD_ARG;
+  }
   const int H = heads * D;
   if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(out) & 15)) {
     set_last_error("attention_tc: pointers must be 16-byte aligned"); return VC_ERR_BAD_ARG;
@@ -412,14 +422,19 @@ int attention_tc(const void* qkv, void* out, int B, int N, int heads, float scal
   if (rc) return rc;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (e != cudaSuccess) { set_last_error("attention_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return VC_ERR_LAUNCH; }
     configured = true;
   }
   dim3 grid(heads, B);
   const float scale_log2 = scale * 1.4426950408889634f;
-  attention_tc_kernel<<<grid, 192, SMEM_TOTAL, s>>>(tq, tkv, reinterpret_cast<bf16*>(out), N, H, scale_log2);
+  if (n_extra)
+    attention_tc_kernel<true><<<grid, 192, SMEM_TOTAL, s>>>(tq, tkv, reinterpret_cast<bf16*>(out), N, H, scale_log2, n_base, n_extra);
+  else
+    attention_tc_kernel<false><<<grid, 192, SMEM_TOTAL, s>>>(tq, tkv, reinterpret_cast<bf16*>(out), N, H, scale_log2, 0, nullptr);
   return check_launch("attention_tc");
 }
 

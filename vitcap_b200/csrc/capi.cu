@@ -17,9 +17,14 @@ int assemble_tokens(const float* patch_out, const float* cls, const float* pos, 
 int layernorm(int out_bf16, const float* in, int ld_in, const float* gamma, const float* beta, float eps, void* out_t, int ld_t,
               float* out_f, int ld_f, int rows, int H, cudaStream_t s);
 int gather_rows(int out_bf16, const float* in, size_t row_stride, void* out, int ld_out, int rows, int H, cudaStream_t s);
-int assemble_ctx(int out_bf16, const float* cap, const float* tag, float* ctx_f, void* ctx_t, int B, int N, int H, cudaStream_t s);
-int attention_simt(int is_bf16, const void* qkv, void* out, int B, int N, int heads, float scale, cudaStream_t s);
-int attention_tc(const void* qkv, void* out, int B, int N, int heads, float scale, cudaStream_t s);
+int assemble_ctx(int out_bf16, const float* cap, const float* tag, float* ctx_f, void* ctx_t, int B, int N, int H, int Cp,
+                 cudaStream_t s);
+int label_rows(int out_bf16, const int* tag_idx, int K, int sep_id, int recipe_ln, int pos0, const float* word, const float* pos,
+               const float* type0, const float* gamma, const float* beta, float eps, float* ctx_f, void* ctx_t, int B, int Cp,
+               int row0, int H, cudaStream_t s);
+int attention_simt(int is_bf16, const void* qkv, void* out, int B, int N, int heads, float scale, int n_base, const int* n_extra,
+                   cudaStream_t s);
+int attention_tc(const void* qkv, void* out, int B, int N, int heads, float scale, int n_base, const int* n_extra, cudaStream_t s);
 int cls_attention(int is_bf16, const void* q, int ldq, const void* qkv, void* out, int ldo, int B, int N, int heads, float scale,
                   cudaStream_t s);
 int tag_topk(const float* logits, int ld, int rows, int V, int K, float thresh, int* out_idx, float* out_prob, int* out_len,
@@ -27,10 +32,10 @@ int tag_topk(const float* logits, int ld, int rows, int V, int K, float thresh, 
 int embed_ln(int out_bf16, const int* ids, int max_len, int cur_len, int mask_id, const float* word, const float* pos,
              const float* type0, const float* gamma, const float* beta, float eps, float* out_f, void* out_t, int R, int H,
              cudaStream_t s);
-int decode_attention(int is_bf16, const void* ctx_qkv, const void* step_qkv, const int* anc, void* out, int B, int C, int heads,
-                     int E, int cur_len, float scale, cudaStream_t s);
+int decode_attention(int is_bf16, const void* ctx_qkv, const void* step_qkv, const int* anc, void* out, int B, int C,
+                     const int* ctx_vis, int heads, int E, int cur_len, float scale, cudaStream_t s);
 int decode_attention_simt(int is_bf16, const void* ctx_qkv, const void* step_qkv, const int* anc, void* out, int B, int C,
-                          int heads, int E, int cur_len, float scale, cudaStream_t s);
+                          const int* ctx_vis, int heads, int E, int cur_len, float scale, cudaStream_t s);
 int token_step(const float* logits, int ld, int rows, int V, int do_sample, float temperature, uint64_t seed, int cur_len,
                int max_len, int pad_id, const int* eos_ids, int n_eos, int* ids, int* unfinished, float* sum_lp, int* n_steps,
                cudaStream_t s);
@@ -55,7 +60,7 @@ static std::atomic<long long> g_launches{0};
 extern "C" {
 
 const char* vc_last_error(void) { return vc::last_error(); }
-int vc_abi_version(void) { return 1; }
+int vc_abi_version(void) { return 2; }
 long long vc_launch_count(void) { return g_launches.load(); }
 void vc_reset_launch_count(void) { g_launches = 0; }
 
@@ -89,14 +94,35 @@ int vc_gather_rows(int bf16, const float* in, size_t row_stride, void* out, int 
   VC_COUNT(1, vc::gather_rows(bf16, in, row_stride, out, ld_out, rows, H, ST(stream)));
 }
 int vc_assemble_ctx(int bf16, const float* cap, const float* tag, float* ctx_f, void* ctx_t, int B, int N, int H, void* stream) {
-  VC_COUNT(1, vc::assemble_ctx(bf16, cap, tag, ctx_f, ctx_t, B, N, H, ST(stream)));
+  VC_COUNT(1, vc::assemble_ctx(bf16, cap, tag, ctx_f, ctx_t, B, N, H, N + 1, ST(stream)));
+}
+int vc_assemble_ctx_pitched(int bf16, const float* cap, const float* tag, float* ctx_f, void* ctx_t, int B, int N, int H,
+                            int rows_per_image, void* stream) {
+  VC_COUNT(1, vc::assemble_ctx(bf16, cap, tag, ctx_f, ctx_t, B, N, H, rows_per_image, ST(stream)));
+}
+int vc_label_rows(int bf16, const int* tag_idx, int K, int sep_id, int recipe_ln, int pos0, const float* word, const float* pos,
+                  const float* type0, const float* gamma, const float* beta, float eps, float* ctx_f, void* ctx_t, int B,
+                  int rows_per_image, int row0, int H, void* stream) {
+  VC_COUNT(1, vc::label_rows(bf16, tag_idx, K, sep_id, recipe_ln, pos0, word, pos, type0, gamma, beta, eps, ctx_f, ctx_t, B,
+                             rows_per_image, row0, H, ST(stream)));
 }
 int vc_attention(int bf16, const void* qkv, void* out, int B, int N, int heads, float scale, void* stream) {
-  if (bf16) VC_COUNT(1, vc::attention_tc(qkv, out, B, N, heads, scale, ST(stream)));
-  VC_COUNT(1, vc::attention_simt(0, qkv, out, B, N, heads, scale, ST(stream)));
+  if (bf16) VC_COUNT(1, vc::attention_tc(qkv, out, B, N, heads, scale, 0, nullptr, ST(stream)));
+  VC_COUNT(1, vc::attention_simt(0, qkv, out, B, N, heads, scale, 0, nullptr, ST(stream)));
 }
 int vc_attention_simt(int bf16, const void* qkv, void* out, int B, int N, int heads, float scale, void* stream) {
-  VC_COUNT(1, vc::attention_simt(bf16, qkv, out, B, N, heads, scale, ST(stream)));
+  VC_COUNT(1, vc::attention_simt(bf16, qkv, out, B, N, heads, scale, 0, nullptr, ST(stream)));
+}
+int vc_attention_labels(int bf16, const void* qkv, void* out, int B, int N, int heads, float scale, int n_base, const int* n_extra,
+                        void* stream) {
+  if (n_extra == nullptr) return VC_ERR_BAD_ARG;
+  if (bf16) VC_COUNT(1, vc::attention_tc(qkv, out, B, N, heads, scale, n_base, n_extra, ST(stream)));
+  VC_COUNT(1, vc::attention_simt(0, qkv, out, B, N, heads, scale, n_base, n_extra, ST(stream)));
+}
+int vc_attention_labels_simt(int bf16, const void* qkv, void* out, int B, int N, int heads, float scale, int n_base,
+                             const int* n_extra, void* stream) {
+  if (n_extra == nullptr) return VC_ERR_BAD_ARG;
+  VC_COUNT(1, vc::attention_simt(bf16, qkv, out, B, N, heads, scale, n_base, n_extra, ST(stream)));
 }
 int vc_cls_attention(int bf16, const void* q, int ldq, const void* qkv, void* out, int ldo, int B, int N, int heads, float scale,
                      void* stream) {
@@ -113,11 +139,22 @@ int vc_embed_ln(int bf16, const int* ids, int max_len, int cur_len, int mask_id,
 }
 int vc_decode_attention(int bf16, const void* ctx_qkv, const void* step_qkv, const int* anc, void* out, int B, int C, int heads,
                         int E, int cur_len, float scale, void* stream) {
-  VC_COUNT(1, vc::decode_attention(bf16, ctx_qkv, step_qkv, anc, out, B, C, heads, E, cur_len, scale, ST(stream)));
+  VC_COUNT(1, vc::decode_attention(bf16, ctx_qkv, step_qkv, anc, out, B, C, nullptr, heads, E, cur_len, scale, ST(stream)));
+}
+int vc_decode_attention_labels(int bf16, const void* ctx_qkv, const void* step_qkv, const int* anc, void* out, int B,
+                               int rows_per_image, const int* ctx_vis, int heads, int E, int cur_len, float scale, void* stream) {
+  VC_COUNT(1, vc::decode_attention(bf16, ctx_qkv, step_qkv, anc, out, B, rows_per_image, ctx_vis, heads, E, cur_len, scale,
+                                   ST(stream)));
+}
+int vc_decode_attention_labels_simt(int bf16, const void* ctx_qkv, const void* step_qkv, const int* anc, void* out, int B,
+                                    int rows_per_image, const int* ctx_vis, int heads, int E, int cur_len, float scale,
+                                    void* stream) {
+  VC_COUNT(1, vc::decode_attention_simt(bf16, ctx_qkv, step_qkv, anc, out, B, rows_per_image, ctx_vis, heads, E, cur_len, scale,
+                                        ST(stream)));
 }
 int vc_decode_attention_simt(int bf16, const void* ctx_qkv, const void* step_qkv, const int* anc, void* out, int B, int C,
                              int heads, int E, int cur_len, float scale, void* stream) {
-  VC_COUNT(1, vc::decode_attention_simt(bf16, ctx_qkv, step_qkv, anc, out, B, C, heads, E, cur_len, scale, ST(stream)));
+  VC_COUNT(1, vc::decode_attention_simt(bf16, ctx_qkv, step_qkv, anc, out, B, C, nullptr, heads, E, cur_len, scale, ST(stream)));
 }
 int vc_token_step(const float* logits, int ld, int rows, int V, int do_sample, float temperature, uint64_t seed, int cur_len,
                   int max_len, int pad_id, const int* eos_ids, int n_eos, int* ids, int* unfinished, float* sum_lp, int* n_steps,

@@ -15,11 +15,11 @@
 
 namespace vc {
 
-int decode_attention_mma(const void* ctx_qkv, const void* step_qkv, const int* anc, void* out, int B, int C, int heads, int E,
-                         int cur_len, float scale, cudaStream_t s);
+int decode_attention_mma(const void* ctx_qkv, const void* step_qkv, const int* anc, void* out, int B, int C, const int* ctx_vis,
+                         int heads, int E, int cur_len, float scale, cudaStream_t s);
 // CUDA-core variant (exact mode, fp32 storage); also instantiable for bf16 as a cross-check of the mma kernel
 int decode_attention_simt(int is_bf16, const void* ctx_qkv, const void* step_qkv, const int* anc, void* out, int B, int C,
-                          int heads, int E, int cur_len, float scale, cudaStream_t s);
+                          const int* ctx_vis, int heads, int E, int cur_len, float scale, cudaStream_t s);
 
 template <typename T> __device__ __forceinline__ float fast_exp(float x);
 template <> __device__ __forceinline__ float fast_exp<float>(float x) { return expf(x); }
@@ -32,7 +32,7 @@ template <int NQ> struct AttnState {
 template <typename T, int EG>
 __global__ void __launch_bounds__(128)
 decode_attention_kernel(const T* __restrict__ ctx_qkv, const T* __restrict__ step_qkv, const int* __restrict__ anc,
-                        T* __restrict__ out, int C, int H, int R, int E, int cur_len, float scale) {
+                        T* __restrict__ out, int Cs, const int* __restrict__ ctx_vis, int H, int R, int E, int cur_len, float scale) {
   constexpr int NQ = 2 * EG, D = 64;
   const int h = blockIdx.x;
   const int groups = (E + EG - 1) / EG;
@@ -43,6 +43,8 @@ decode_attention_kernel(const T* __restrict__ ctx_qkv, const T* __restrict__ ste
   const size_t ld = 3 * (size_t)H;
   const int step = cur_len - 1;
   const T* cur = step_qkv + (size_t)step * 2 * R * ld;
+  // context rows of an image: Cs allocated, the first C visible (label-region masks hide a per-image tail)
+  const int C = ctx_vis ? ctx_vis[b] : Cs;
 
   float q[NQ][8];
   AttnState<NQ> st;
@@ -57,7 +59,7 @@ decode_attention_kernel(const T* __restrict__ ctx_qkv, const T* __restrict__ ste
   }
 
   // ---- phase 1: context keys, shared by all rows of the image ----
-  const T* kbase = ctx_qkv + (size_t)b * C * ld + H + h * D + part * 8;
+  const T* kbase = ctx_qkv + (size_t)b * Cs * ld + H + h * D + part * 8;
   const T* vbase = kbase + H;
   constexpr int U = 4;                                   // keys in flight per lane group
   for (int kb = warp * 4; kb < C; kb += 16 * U) {          // warp-uniform trip count (shuffles inside)
@@ -206,43 +208,43 @@ decode_attention_kernel(const T* __restrict__ ctx_qkv, const T* __restrict__ ste
 }
 
 template <typename T>
-static int launch_da(const void* ctx_qkv, const void* step_qkv, const int* anc, void* out, int B, int C, int heads, int E,
-                     int cur_len, float scale, cudaStream_t s) {
+static int launch_da(const void* ctx_qkv, const void* step_qkv, const int* anc, void* out, int B, int C, const int* ctx_vis,
+                     int heads, int E, int cur_len, float scale, cudaStream_t s) {
   const int H = heads * 64, R = B * E;
   const T* c = (const T*)ctx_qkv;
   const T* q = (const T*)step_qkv;
   T* o = (T*)out;
   if (E == 1) {
-    decode_attention_kernel<T, 1><<<dim3(heads, B), 128, 0, s>>>(c, q, anc, o, C, H, R, E, cur_len, scale);
+    decode_attention_kernel<T, 1><<<dim3(heads, B), 128, 0, s>>>(c, q, anc, o, C, ctx_vis, H, R, E, cur_len, scale);
   } else if (E == 2) {
-    decode_attention_kernel<T, 2><<<dim3(heads, B), 128, 0, s>>>(c, q, anc, o, C, H, R, E, cur_len, scale);
+    decode_attention_kernel<T, 2><<<dim3(heads, B), 128, 0, s>>>(c, q, anc, o, C, ctx_vis, H, R, E, cur_len, scale);
   } else if (E == 3) {
-    decode_attention_kernel<T, 3><<<dim3(heads, B), 128, 0, s>>>(c, q, anc, o, C, H, R, E, cur_len, scale);
+    decode_attention_kernel<T, 3><<<dim3(heads, B), 128, 0, s>>>(c, q, anc, o, C, ctx_vis, H, R, E, cur_len, scale);
   } else {
     const int groups = (E + 3) / 4;
-    decode_attention_kernel<T, 4><<<dim3(heads, B * groups), 128, 0, s>>>(c, q, anc, o, C, H, R, E, cur_len, scale);
+    decode_attention_kernel<T, 4><<<dim3(heads, B * groups), 128, 0, s>>>(c, q, anc, o, C, ctx_vis, H, R, E, cur_len, scale);
   }
   return check_launch("decode_attention");
 }
 
 // ctx_qkv [B, C, 3H]; step_qkv [max_len, 2*B*E, 3H]; anc int32 [max_len, B*E] or NULL; out [2*B*E, H]
-int decode_attention(int is_bf16, const void* ctx_qkv, const void* step_qkv, const int* anc, void* out, int B, int C, int heads,
-                     int E, int cur_len, float scale, cudaStream_t s) {
+int decode_attention(int is_bf16, const void* ctx_qkv, const void* step_qkv, const int* anc, void* out, int B, int C,
+                     const int* ctx_vis, int heads, int E, int cur_len, float scale, cudaStream_t s) {
   if (B <= 0 || C <= 0 || heads <= 0 || E <= 0 || cur_len < 1 || B * ((E + 3) / 4) > 65535) {
     set_last_error("decode_attention: bad args B=%d C=%d heads=%d E=%d cur_len=%d", B, C, heads, E, cur_len);
     return VC_ERR_BAD_ARG;
   }
-  if (is_bf16) return decode_attention_mma(ctx_qkv, step_qkv, anc, out, B, C, heads, E, cur_len, scale, s);
-  return launch_da<float>(ctx_qkv, step_qkv, anc, out, B, C, heads, E, cur_len, scale, s);
+  if (is_bf16) return decode_attention_mma(ctx_qkv, step_qkv, anc, out, B, C, ctx_vis, heads, E, cur_len, scale, s);
+  return launch_da<float>(ctx_qkv, step_qkv, anc, out, B, C, ctx_vis, heads, E, cur_len, scale, s);
 }
 
 int decode_attention_simt(int is_bf16, const void* ctx_qkv, const void* step_qkv, const int* anc, void* out, int B, int C,
-                          int heads, int E, int cur_len, float scale, cudaStream_t s) {
+                          const int* ctx_vis, int heads, int E, int cur_len, float scale, cudaStream_t s) {
   if (B <= 0 || C <= 0 || heads <= 0 || E <= 0 || cur_len < 1 || B * ((E + 3) / 4) > 65535) {
     set_last_error("decode_attention_simt: bad args"); return VC_ERR_BAD_ARG;
   }
-  if (is_bf16) return launch_da<bf16>(ctx_qkv, step_qkv, anc, out, B, C, heads, E, cur_len, scale, s);
-  return launch_da<float>(ctx_qkv, step_qkv, anc, out, B, C, heads, E, cur_len, scale, s);
+  if (is_bf16) return launch_da<bf16>(ctx_qkv, step_qkv, anc, out, B, C, ctx_vis, heads, E, cur_len, scale, s);
+  return launch_da<float>(ctx_qkv, step_qkv, anc, out, B, C, ctx_vis, heads, E, cur_len, scale, s);
 }
 
 }  // namespace vc

@@ -62,7 +62,8 @@ __device__ __forceinline__ float ex2f(float x) {
 template <bool UPPER>
 __global__ void __launch_bounds__(128, 4)
 decode_attention_mma_kernel(const bf16* __restrict__ ctx_qkv, const bf16* __restrict__ step_qkv, const int* __restrict__ anc,
-                            bf16* __restrict__ out, int C, int H, int R, int E, int cur_len, float scale_log2) {
+                            bf16* __restrict__ out, int Cs, const int* __restrict__ ctx_vis, int H, int R, int E, int cur_len,
+                            float scale_log2) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint8_t cap_info[MAX_CAP];          // (sequence-in-CTA << 1) | is_mask_key, per caption key
   __shared__ float sm_m[WARPS][16], sm_l[WARPS][16];
@@ -75,13 +76,15 @@ decode_attention_mma_kernel(const bf16* __restrict__ ctx_qkv, const bf16* __rest
   const int b = blockIdx.y / groups;
   const int e0 = (blockIdx.y % groups) * MAX_SEQ;
   const int EC = min(MAX_SEQ, E - e0);           // sequences handled by this CTA
+  // context rows of an image: Cs allocated, the first C visible (label-region masks hide a per-image tail, dataset.py:405-408)
+  const int C = ctx_vis ? ctx_vis[b] : Cs;
   const size_t ld = 3 * (size_t)H;
   const int step = cur_len - 1;
   const int nk = cur_len + 1;                    // caption keys per sequence: steps 0..step-1, this token, this MASK
   const int NK = C + EC * nk;                    // virtual key axis
   const int nblocks = (NK + KB - 1) / KB;
   const bf16* cur = step_qkv + (size_t)step * 2 * R * ld;
-  const bf16* ctx_k = ctx_qkv + (size_t)b * C * ld + H + h * 64;     // K of context key 0 (V is H elements further)
+  const bf16* ctx_k = ctx_qkv + (size_t)b * Cs * ld + H + h * 64;    // K of context key 0 (V is H elements further)
 
   for (int i = threadIdx.x; i < EC * nk; i += 128) {
     const int e = i / nk, j = i - e * nk;
@@ -296,8 +299,8 @@ decode_attention_mma_kernel(const bf16* __restrict__ ctx_qkv, const bf16* __rest
 }
 
 // ctx_qkv [B, C, 3H]; step_qkv [max_len, 2*B*E, 3H]; anc int32 [max_len, B*E] or NULL; out [2*B*E, H]; all bf16
-int decode_attention_mma(const void* ctx_qkv, const void* step_qkv, const int* anc, void* out, int B, int C, int heads, int E,
-                         int cur_len, float scale, cudaStream_t s) {
+int decode_attention_mma(const void* ctx_qkv, const void* step_qkv, const int* anc, void* out, int B, int C, const int* ctx_vis,
+                         int heads, int E, int cur_len, float scale, cudaStream_t s) {
   const int groups = (E + MAX_SEQ - 1) / MAX_SEQ;
   if (B <= 0 || C <= 0 || heads <= 0 || E <= 0 || cur_len < 1 || cur_len + 1 > 64 || (size_t)B * groups > 65535) {
     set_last_error("decode_attention: bad args B=%d C=%d heads=%d E=%d cur_len=%d", B, C, heads, E, cur_len);
@@ -314,11 +317,11 @@ int decode_attention_mma(const void* ctx_qkv, const void* step_qkv, const int* a
   const float scale_log2 = scale * 1.4426950408889634f;
   const dim3 grid(heads, B * groups);
   if (E > 4)
-    decode_attention_mma_kernel<true><<<grid, 128, SMEM_BYTES, s>>>((const bf16*)ctx_qkv, (const bf16*)step_qkv, anc, (bf16*)out, C, H,
-                                                                   R, E, cur_len, scale_log2);
+    decode_attention_mma_kernel<true><<<grid, 128, SMEM_BYTES, s>>>((const bf16*)ctx_qkv, (const bf16*)step_qkv, anc, (bf16*)out, C,
+                                                                   ctx_vis, H, R, E, cur_len, scale_log2);
   else
-    decode_attention_mma_kernel<false><<<grid, 128, SMEM_BYTES, s>>>((const bf16*)ctx_qkv, (const bf16*)step_qkv, anc, (bf16*)out, C, H,
-                                                                    R, E, cur_len, scale_log2);
+    decode_attention_mma_kernel<false><<<grid, 128, SMEM_BYTES, s>>>((const bf16*)ctx_qkv, (const bf16*)step_qkv, anc, (bf16*)out, C,
+                                                                    ctx_vis, H, R, E, cur_len, scale_log2);
   return check_launch("decode_attention_mma");
 }
 

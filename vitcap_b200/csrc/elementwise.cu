@@ -215,7 +215,7 @@ int gather_rows(int out_bf16, const float* in, size_t row_stride, void* out, int
 // ------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void assemble_ctx_kernel(const float* __restrict__ cap, const float* __restrict__ tag, float* __restrict__ ctx_f,
-                                    T* __restrict__ ctx_t, int B, int N, int H) {
+                                    T* __restrict__ ctx_t, int B, int N, int H, int Cp) {
   const int hv = H / 8;
   const size_t total = (size_t)B * (N + 1) * hv;
   for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
@@ -226,18 +226,20 @@ __global__ void assemble_ctx_kernel(const float* __restrict__ cap, const float* 
     const float* src = (t == 0) ? tag + (b * N) * H + c : cap + (b * N + t - 1) * H + c;
     float f[8];
     load8<float>(src, f);
-    store8<float>(ctx_f + row * H + c, f);
-    if (sizeof(T) == 2) store8<T>(ctx_t + row * H + c, f);
+    const size_t orow = b * Cp + t;                // Cp >= N + 1 context rows are allocated per image
+    store8<float>(ctx_f + orow * H + c, f);
+    if (sizeof(T) == 2) store8<T>(ctx_t + orow * H + c, f);
   }
 }
 
-int assemble_ctx(int out_bf16, const float* cap, const float* tag, float* ctx_f, void* ctx_t, int B, int N, int H, cudaStream_t s) {
-  if (H % 8) { set_last_error("assemble_ctx: H %% 8"); return VC_ERR_BAD_ARG; }
+int assemble_ctx(int out_bf16, const float* cap, const float* tag, float* ctx_f, void* ctx_t, int B, int N, int H, int Cp,
+                 cudaStream_t s) {
+  if (H % 8 || Cp < N + 1) { set_last_error("assemble_ctx: H %% 8, rows per image >= N + 1"); return VC_ERR_BAD_ARG; }
   const size_t total = (size_t)B * (N + 1) * (H / 8);
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  if (out_bf16) assemble_ctx_kernel<bf16><<<blocks, 256, 0, s>>>(cap, tag, ctx_f, (bf16*)ctx_t, B, N, H);
-  else assemble_ctx_kernel<float><<<blocks, 256, 0, s>>>(cap, tag, ctx_f, (float*)ctx_t, B, N, H);
+  if (out_bf16) assemble_ctx_kernel<bf16><<<blocks, 256, 0, s>>>(cap, tag, ctx_f, (bf16*)ctx_t, B, N, H, Cp);
+  else assemble_ctx_kernel<float><<<blocks, 256, 0, s>>>(cap, tag, ctx_f, (float*)ctx_t, B, N, H, Cp);
   return check_launch("assemble_ctx");
 }
 
@@ -303,6 +305,81 @@ int embed_ln(int out_bf16, const int* ids, int max_len, int cur_len, int mask_id
   if (out_bf16) embed_ln_kernel<bf16><<<blocks, 256, 0, s>>>(ids, max_len, cur_len, mask_id, word, pos, type0, gamma, beta, eps, out_f, (bf16*)out_t, R, H);
   else embed_ln_kernel<float><<<blocks, 256, 0, s>>>(ids, max_len, cur_len, mask_id, word, pos, type0, gamma, beta, eps, out_f, (float*)out_t, R, H);
   return check_launch("embed_ln");
+}
+
+// ------------------------------------------------------------------------------------------
+// label_rows: the od/tag label rows of the context when the caller's mask makes them visible.
+//   row (b, i) = E_word[tag_i]                                   recipe 0 ('raw', modeling_bert.py:1447-1470)
+//              = LN(E_word[tag_i] + E_pos[pos0 + i] + E_type[0])  recipe 1 ('ln', encode_tag_to_embedding :1381-1406)
+// with tag_i = i-th predicted concept of image b and the last slot forced to [SEP] (:1447 / :1477). Written as the fp32
+// residual copy and the T operand copy to context rows row0 .. row0 + K - 1 of image b (Cp rows per image). Warp per row.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+label_rows_kernel(const int* __restrict__ tag_idx, int K, int sep_id, int recipe_ln, int pos0, const float* __restrict__ word,
+                  const float* __restrict__ pos, const float* __restrict__ type0, const float* __restrict__ gamma,
+                  const float* __restrict__ beta, float eps, float* __restrict__ ctx_f, T* __restrict__ ctx_t, int B, int Cp,
+                  int row0, int H) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= B * K) return;
+  const int b = warp / K, i = warp - b * K;
+  const int tok = (i == K - 1) ? sep_id : tag_idx[(size_t)b * K + i];
+  const size_t orow = (size_t)b * Cp + row0 + i;
+  const int nv = H / 128;
+  float4 v[8];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (j < nv) {
+      const int c = (j * 32 + lane) * 4;
+      v[j] = __ldg(reinterpret_cast<const float4*>(word + (size_t)tok * H + c));
+      if (recipe_ln) {
+        const float4 p = __ldg(reinterpret_cast<const float4*>(pos + (size_t)(pos0 + i) * H + c));
+        const float4 t = __ldg(reinterpret_cast<const float4*>(type0 + c));
+        v[j] = make_float4(v[j].x + p.x + t.x, v[j].y + p.y + t.y, v[j].z + p.z + t.z, v[j].w + p.w + t.w);
+      }
+      s += v[j].x + v[j].y + v[j].z + v[j].w;
+    }
+  float mean = 0.f, rstd = 1.f;
+  if (recipe_ln) {
+    mean = warp_sum(s) / (float)H;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (j < nv) {
+        const float a = v[j].x - mean, bb = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+        q += a * a + bb * bb + c * c + d * d;
+      }
+    rstd = rsqrtf(warp_sum(q) / (float)H + eps);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (j < nv) {
+      const int c = (j * 32 + lane) * 4;
+      float4 o = v[j];
+      if (recipe_ln) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+        const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c));
+        o = make_float4((v[j].x - mean) * rstd * g.x + be.x, (v[j].y - mean) * rstd * g.y + be.y,
+                        (v[j].z - mean) * rstd * g.z + be.z, (v[j].w - mean) * rstd * g.w + be.w);
+      }
+      *reinterpret_cast<float4*>(ctx_f + orow * H + c) = o;
+      if (sizeof(T) == 2) {
+        const uint2 pk = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+        *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ctx_t) + orow * H + c) = pk;
+      }
+    }
+}
+
+int label_rows(int out_bf16, const int* tag_idx, int K, int sep_id, int recipe_ln, int pos0, const float* word, const float* pos,
+               const float* type0, const float* gamma, const float* beta, float eps, float* ctx_f, void* ctx_t, int B, int Cp,
+               int row0, int H, cudaStream_t s) {
+  if (H % 128 || H > 1024 || K < 1 || B < 1 || row0 + K > Cp) { set_last_error("label_rows: bad args"); return VC_ERR_BAD_ARG; }
+  const int blocks = (B * K + 7) / 8;
+  if (out_bf16) label_rows_kernel<bf16><<<blocks, 256, 0, s>>>(tag_idx, K, sep_id, recipe_ln, pos0, word, pos, type0, gamma, beta, eps, ctx_f, (bf16*)ctx_t, B, Cp, row0, H);
+  else label_rows_kernel<float><<<blocks, 256, 0, s>>>(tag_idx, K, sep_id, recipe_ln, pos0, word, pos, type0, gamma, beta, eps, ctx_f, (float*)ctx_t, B, Cp, row0, H);
+  return check_launch("label_rows");
 }
 
 }  // namespace vc

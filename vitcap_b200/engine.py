@@ -115,14 +115,19 @@ class CaptionEngine:
     def _alloc(self, *shape, dtype=None):
         return torch.empty(*shape, device=self.dev, dtype=dtype or self.T)
 
-    def _encoder_ws(self, B):
+    def _encoder_ws(self, B, ctx_rows=None):
+        """ctx_rows: context rows per image (C = tag-CLS + image tokens; C + topk when the label rows are visible)."""
         ws = self._enc_ws
-        if ws is not None and ws["B"] >= B:
-            return ws
         cfg = self.cfg
-        N, C, H, F, L = cfg.n_tokens, cfg.n_ctx, cfg.hidden, cfg.inter, cfg.dec_layers
+        ctx_rows = cfg.n_ctx if ctx_rows is None else ctx_rows
+        if ws is not None and ws["B"] >= B and ws["ctx_cap"] >= B * ctx_rows:
+            return ws
+        if ws is not None:                      # grow, never shrink (a captured graph keeps raw pointers)
+            B = max(B, ws["B"])
+            ctx_rows = max(ctx_rows, -(-ws["ctx_cap"] // B))
+        N, C, H, F, L = cfg.n_tokens, ctx_rows, cfg.hidden, cfg.inter, cfg.dec_layers
         f32 = torch.float32
-        ws = {"B": B}
+        ws = {"B": B, "ctx_cap": B * ctx_rows}
         ws["patches"] = self._alloc(B * cfg.n_patches, cfg.patch_dim)
         ws["patch_out"] = self._alloc(B * cfg.n_patches, H, dtype=f32)
         ws["x"] = self._alloc(B * N, H, dtype=f32)
@@ -145,6 +150,8 @@ class CaptionEngine:
         ws["tag_idx"] = self._alloc(B, cfg.topk, dtype=torch.int32)
         ws["tag_prob"] = self._alloc(B, cfg.topk, dtype=f32)
         ws["tag_len"] = self._alloc(B, dtype=torch.int32)
+        ws["n_label"] = torch.zeros(B, device=self.dev, dtype=torch.int32)
+        ws["ctx_vis"] = torch.zeros(B, device=self.dev, dtype=torch.int32)
         # last concept-branch block, CLS row only
         ws["q_cls"] = self._alloc(B, H)
         ws["att_cls"] = self._alloc(B, H)
@@ -181,9 +188,14 @@ class CaptionEngine:
         ws["n_steps"] = torch.zeros(R, device=self.dev, dtype=i32)
         ws["out_ids"] = torch.zeros(R, max_len, device=self.dev, dtype=torch.int64)
         ws["out_lp"] = torch.zeros(R, device=self.dev, dtype=f32)
+        ws["ident_rows"] = torch.arange(R, device=self.dev, dtype=i32)
         self._dec_ws = {key: ws}          # keep one decode workspace alive at a time
         self._graphs = {}
         return ws
+
+    def reserve(self, B, label_rows=False):
+        """Sizes the image-side workspace before a batch starts (growing it later would drop the encoder outputs)."""
+        return self._encoder_ws(B, self.cfg.n_ctx + (self.cfg.topk if label_rows else 0))
 
     # ------------------------------------------------------------------ building blocks
     def _ln(self, x, g, b, eps, out_t, out_f=None, rows=None):
@@ -291,16 +303,33 @@ class CaptionEngine:
         ops.tag_topk(logits, cfg.vocab, cfg.topk, cfg.tag_thresh, ws["tag_idx"], ws["tag_prob"], ws["tag_len"], rows=B)
         return logits[:, :cfg.vocab], ws["tag_idx"][:B], ws["tag_prob"][:B], ws["tag_len"][:B]
 
-    def prefill(self, B):
+    def set_labels(self, B, n_label):
+        """Per-image count of visible od/tag label slots (int tensor [B]) for the label-region path; the device copies live in
+        the workspace so that captured graphs see the current values."""
+        cfg = self.cfg
+        ws = self._encoder_ws(B, cfg.n_ctx + cfg.topk)
+        ws["n_label"][:B].copy_(n_label.to(device=self.dev, dtype=torch.int32))
+        ws["ctx_vis"][:B].copy_(ws["n_label"][:B] + cfg.n_ctx)
+
+    def prefill(self, B, label_recipe=None):
         """Context rows [tag-CLS | caption feats] through the decoder once; per-layer q|k|v stay in ctx_qkv (KV cache).
         BertLayer, modeling_bert.py:303-437, bidirectional over the context (image rows only see image columns,
-        pipeline file lines 57-85)."""
+        pipeline file lines 57-85).
+        label_recipe 'raw' / 'ln' (after set_labels): the topk od/tag label rows follow the C context rows of every image
+        (modeling_bert.py:1447-1489); they see the context and the visible labels, the context rows do not see them."""
         cfg, w = self.cfg, self.w
-        ws = self._encoder_ws(B)
         N, C, H = cfg.n_tokens, cfg.n_ctx, cfg.hidden
-        rows = B * C
+        Cp = C if label_recipe is None else C + cfg.topk
+        ws = self._encoder_ws(B, Cp)
+        rows = B * Cp
         ctx_f, ctx_t = ws["ctx_f"][:rows], ws["ctx_t"][:rows]
-        ops.assemble_ctx(ws["x"], ws["xt"], ctx_f, ctx_t, B, N, H)
+        ops.assemble_ctx(ws["x"], ws["xt"], ctx_f, ctx_t, B, N, H, rows_per_image=Cp)
+        n_extra = None
+        if label_recipe is not None:
+            assert label_recipe in ("raw", "ln")
+            n_extra = ws["n_label"]
+            ops.label_rows(ws["tag_idx"], cfg.sep_id, label_recipe == "ln", cfg.max_seq_a, w.word, w.pos, w.type0, w.emb_ln_w,
+                           w.emb_ln_b, cfg.bert_ln_eps, ctx_f, ctx_t, B, Cp, C)
         att, hid, tmp, a_f, ln = ws["att"][:rows], ws["hid"][:rows], ws["tmp_f"][:rows], ws["a_f"][:rows], ws["ln"][:rows]
         for l, p in enumerate(w.dec):
             qkv = ws["ctx_qkv"][l][:rows]
@@ -310,26 +339,28 @@ class CaptionEngine:
                 ops.linear(ctx_t, p["qkv_w"][H:], p["qkv_b"][H:], qkv[:, H:], M=rows, ldo=3 * H)
                 break
             ops.linear(ctx_t, p["qkv_w"], p["qkv_b"], qkv, M=rows)
-            ops.attention(qkv, att, B, C, cfg.heads, 1.0 / math.sqrt(cfg.head_dim), impl=self.attn_impl)
+            ops.attention(qkv, att, B, Cp, cfg.heads, 1.0 / math.sqrt(cfg.head_dim), impl=self.attn_impl, n_base=C, n_extra=n_extra)
             ops.linear(att, p["o_w"], p["o_b"], tmp, resid=ctx_f, M=rows)
             a_t = self._ln(tmp, p["ln1_w"], p["ln1_b"], cfg.bert_ln_eps, ln, out_f=a_f, rows=rows)
             ops.linear(a_t, p["i_w"], p["i_b"], hid, act=ops.ACT_GELU, M=rows)
             ops.linear(hid, p["f_w"], p["f_b"], tmp, resid=a_f, M=rows)
             self._ln(tmp, p["ln2_w"], p["ln2_b"], cfg.bert_ln_eps, ctx_t, out_f=ctx_f, rows=rows)
 
-    def _decode_layers(self, ws, B, E, cur_len, anc, mask_id):
-        """One decode step up to the vocabulary logits of the MASK rows."""
+    def _decode_layers(self, ws, B, E, cur_len, anc, mask_id, labels=False, head=True):
+        """One decode step up to the vocabulary logits of the MASK rows. labels: the context holds C + topk rows per image of
+        which ctx_vis[b] are visible. head=False stops after the decoder layers (caption-row replay after a recipe flip)."""
         cfg, w = self.cfg, self.w
         R, H = ws["R"], cfg.hidden
-        C = cfg.n_ctx
+        C = cfg.n_ctx + (cfg.topk if labels else 0)
         enc = self._enc_ws
+        ctx_vis = enc["ctx_vis"] if labels else None
         e_f, e_t = ws["e_f"], ws["e_t"]
         ops.embed_ln(ws["ids"], cur_len, mask_id, w.word, w.pos, w.type0, w.emb_ln_w, w.emb_ln_b, cfg.bert_ln_eps, e_f, e_t, R)
         scale = 1.0 / math.sqrt(cfg.head_dim)
         for l, p in enumerate(w.dec):
             sq = ws["step_qkv"][l]
             ops.linear(e_t, p["qkv_w"], p["qkv_b"], sq[cur_len - 1], M=2 * R)
-            ops.decode_attention(enc["ctx_qkv"][l], sq, anc, ws["att"], B, C, cfg.heads, E, cur_len, scale)
+            ops.decode_attention(enc["ctx_qkv"][l], sq, anc, ws["att"], B, C, cfg.heads, E, cur_len, scale, ctx_vis=ctx_vis)
             ops.linear(ws["att"], p["o_w"], p["o_b"], ws["tmp"], resid=e_f, M=2 * R)
             a_t = self._ln(ws["tmp"], p["ln1_w"], p["ln1_b"], cfg.bert_ln_eps, ws["a_t"], out_f=ws["a_f"], rows=2 * R)
             ops.linear(a_t, p["i_w"], p["i_b"], ws["hid"], act=ops.ACT_GELU, M=2 * R)
@@ -337,8 +368,19 @@ class CaptionEngine:
             self._ln(ws["tmp"], p["ln2_w"], p["ln2_b"], cfg.bert_ln_eps, e_t, out_f=e_f, rows=2 * R)
         # vocabulary head on the MASK rows only (rows 1::2); the reference runs it over all T text rows
         # (modeling_bert.py:809-810) and keeps one
-        mask_rows = e_t[1::2]
-        self._head(w.cls_head, mask_rows, R, ws["head_f"], ws["head_t"], ws["logits"])
+        if head:
+            mask_rows = e_t[1::2]
+            self._head(w.cls_head, mask_rows, R, ws["head_f"], ws["head_t"], ws["logits"])
+
+    def _flip_labels(self, ws, B, E, cur_len, mask_id, anc_table=None):
+        """The reference switches the label embedding to the 'raw' recipe at this step (modeling_bert.py:1435) and, having no
+        cache, recomputes every row under it: prefill the context again and replay the caption rows of steps 1..cur_len-1
+        (each sequence's own token history is in ws['ids']; beams were re-parented there, so the replay is row-local)."""
+        self.prefill(B, label_recipe="raw")
+        for s in range(1, cur_len):
+            self._decode_layers(ws, B, E, s, None, mask_id, labels=True, head=False)
+        if anc_table is not None and cur_len > 1:
+            anc_table[:cur_len - 1].copy_(ws["ident_rows"].unsqueeze(0).expand(cur_len - 1, -1))
 
     # ------------------------------------------------------------------ search drivers
     @staticmethod
@@ -370,9 +412,11 @@ class CaptionEngine:
         self.stats["graph_replays"] = self.stats.get("graph_replays", 0) + 1
 
     def greedy_or_sample(self, B, E, max_len, bos, pad, eos_ids, mask_id, do_sample=False, temperature=1.0, top_k=0,
-                         top_p=1.0, seed=0):
+                         top_p=1.0, seed=0, label_flip=None):
         """_generate_no_beam_search (modeling_utils.py:768-886) for R = B*E sequences; returns (ids int64 [R,1,max_len],
-        logprob fp32 [R,1])."""
+        logprob fp32 [R,1]). label_flip: None = no visible label region; else the first cur_len decoded under the 'raw' label
+        recipe (the context must have been prefilled with 'ln' if label_flip > 1, else with 'raw')."""
+        labels = label_flip is not None
         cfg = self.cfg
         ws = self._decoder_ws(B, E, max_len)
         R = ws["R"]
@@ -389,7 +433,9 @@ class CaptionEngine:
         def run():
             reset()
             for cur_len in range(1, max_len):
-                self._decode_layers(ws, B, E, cur_len, None, mask_id)
+                if labels and cur_len == label_flip and cur_len > 1:
+                    self._flip_labels(ws, B, E, cur_len, mask_id)
+                self._decode_layers(ws, B, E, cur_len, None, mask_id, labels=labels)
                 t = temperature
                 if filt:
                     ops.filter_logits(ws["logits"], cfg.vocab, R, 1.0 / temperature, top_k, top_p)
@@ -399,12 +445,14 @@ class CaptionEngine:
             ops.greedy_finalize(ws["ids"], ws["unfinished"], ws["sum_lp"], ws["n_steps"], int(eos_ids[0]), R, ws["out_ids"],
                                 ws["out_lp"])
 
-        self._maybe_graph(("tok", B, E, max_len, do_sample, temperature, top_k, top_p, seed, bos, pad, tuple(eos_ids), mask_id), run)
+        self._maybe_graph(("tok", B, E, max_len, do_sample, temperature, top_k, top_p, seed, bos, pad, tuple(eos_ids), mask_id,
+                           label_flip), run)
         return ws["out_ids"].view(R, 1, max_len).clone(), ws["out_lp"].view(R, 1).clone()
 
-    def beam_search(self, B, nb, max_len, bos, pad, eos_ids, mask_id, length_penalty=1.0, keep=1):
+    def beam_search(self, B, nb, max_len, bos, pad, eos_ids, mask_id, length_penalty=1.0, keep=1, label_flip=None):
         """_generate_beam_search (modeling_utils.py:888-1100), do_sample=False. Returns (ids int64 [B,keep,max_len],
-        logprob fp32 [B,keep])."""
+        logprob fp32 [B,keep]). label_flip as in greedy_or_sample."""
+        labels = label_flip is not None
         cfg = self.cfg
         ws = self._decoder_ws(B, nb, max_len)
         R, K = ws["R"], 2 * nb
@@ -437,11 +485,13 @@ class CaptionEngine:
             st["hyp_count"].zero_()
             st["worst"].fill_(1e9)
             for cur_len in range(1, max_len):
-                self._decode_layers(ws, B, nb, cur_len, st["anc"], mask_id)
+                if labels and cur_len == label_flip and cur_len > 1:
+                    self._flip_labels(ws, B, nb, cur_len, mask_id, anc_table=st["anc"])
+                self._decode_layers(ws, B, nb, cur_len, st["anc"], mask_id, labels=labels)
                 ops.beam_row_topk(ws["logits"], cfg.vocab, R, K, st["cand_val"], st["cand_idx"], st["row_max"], st["row_logsum"])
                 ops.beam_advance(st, st["cand_val"], st["cand_idx"], st["row_max"], st["row_logsum"], B, nb, cfg.vocab, cur_len,
                                  keep, length_penalty, pad, eos)
             ops.beam_finalize(st, B, keep, pad, int(eos_ids[0]), st["out_ids"], st["out_lp"])
 
-        self._maybe_graph(("beam", B, nb, max_len, keep, float(length_penalty), bos, pad, tuple(eos_ids), mask_id), run)
+        self._maybe_graph(("beam", B, nb, max_len, keep, float(length_penalty), bos, pad, tuple(eos_ids), mask_id, label_flip), run)
         return st["out_ids"].clone(), st["out_lp"].clone()

@@ -205,8 +205,10 @@ class FastViTCAP(nn.Module):
         max_length = int(max_length)
         if max_length > cfg.max_seq or max_length < 2:
             raise ValueError("max_length must be in [2, %d]" % cfg.max_seq)
-        owner._check_canonical_mask(attention_mask, input_ids, max_length)
-        return owner._generate(img_feats, max_length=max_length, do_sample=bool(do_sample), num_beams=num_beams,
+        n_label = owner._label_counts(attention_mask, input_ids, max_length)
+        if n_label is not None and not add_od_labels:
+            raise NotImplementedError(_UNSUPPORTED % "a visible label region with add_od_labels=False (the reference fails there)")
+        return owner._generate(img_feats, n_label=n_label, max_length=max_length, do_sample=bool(do_sample), num_beams=num_beams,
                                temperature=float(1.0 if temperature is None else temperature),
                                top_k=int(top_k or 0), top_p=float(1.0 if top_p is None else top_p),
                                bos=int(bos_token_id), pad=int(pad_token_id), eos_ids=[int(e) for e in eos_token_ids],
@@ -234,6 +236,7 @@ class FastImageCaptioning(nn.Module):
         self.u8_channel_order = "bgr"       # what cv2 / the reference's TSV image decoder deliver (BGR2RGB is then fused)
         self._engine = None
         self._sample_calls = 0
+        self._label_flip_hold = None        # None: decide per generate() call; False: forward() in progress, not decided yet
         self.register_load_state_dict_post_hook(lambda m, keys: m._invalidate())
         self.eval()
 
@@ -272,32 +275,46 @@ class FastImageCaptioning(nn.Module):
             raise NotImplementedError(_UNSUPPORTED % "position-embedding interpolation for a different image size")
         return self.engine.patch_embed(image)
 
-    def _check_canonical_mask(self, attention_mask, input_ids, max_length):
-        """The eval pipeline always passes the 70x70 mask whose only non-zeros are the caption triangle
-        (dataset.py:371-390 with text_b == ''), i.e. the 50 od/tag slots are attended by no row.
-        The kernels encode exactly that structure; anything else is refused instead of silently diverging."""
+    def _label_counts(self, attention_mask, input_ids, max_length):
+        """Validates the text attention mask and returns the number of visible od/tag label slots per sample (int64 [B]), or
+        None when there is none. Accepted: the seq2seq family of the reference data layer (dataset.py:395-408): the caption
+        triangle; for the first n label slots full attention L-L and C-L; nothing else. n == 0 everywhere is what the eval
+        pipeline passes (text_b == ''). The kernels encode exactly that structure; any other mask is refused
+        instead of silently diverging."""
         if attention_mask is None:
-            return
+            return None
         cfg = self.cfg
         m = attention_mask
         if m.dim() != 3 or m.shape[1] != m.shape[2]:
             raise NotImplementedError(_UNSUPPORTED % "attention_mask that is not (B, S, S)")
         S = m.shape[1]
-        n_img = cfg.n_tokens
-        if S == input_ids.shape[1] + n_img:          # full mask built by construct_attn_mask: check its text block
-            m = m[:, :input_ids.shape[1], :input_ids.shape[1]]
-            S = m.shape[1]
+        T = input_ids.shape[1]
+        if S == T + cfg.n_tokens:                    # full mask built by construct_attn_mask: check its text block
+            m = m[:, :T, :T]
+            S = T
         a = max_length
-        ref = torch.zeros(S, S, device=m.device, dtype=m.dtype)
-        ref[:a, :a] = torch.tril(torch.ones(a, a, device=m.device, dtype=m.dtype))
-        if not bool((m == ref.unsqueeze(0)).all()):
-            raise NotImplementedError(_UNSUPPORTED % "a text attention mask with a visible od/tag label region")
+        n = (m[:, 0, a:] != 0).sum(dim=1)
+        ar = torch.arange(S, device=m.device)
+        in_c = (ar < a)
+        in_l = (ar.unsqueeze(0) >= a) & (ar.unsqueeze(0) < a + n.unsqueeze(1))            # (B, S) visible label slots
+        tri = torch.tril(torch.ones(S, S, device=m.device, dtype=torch.bool)) & in_c.unsqueeze(0) & in_c.unsqueeze(1)
+        ref = tri.unsqueeze(0) | ((in_c.view(1, S, 1) | in_l.unsqueeze(2)) & in_l.unsqueeze(1))
+        if not bool(((m != 0) == ref).all()):
+            raise NotImplementedError(_UNSUPPORTED % "a text attention mask outside the seq2seq family of dataset.py:395-408")
+        if not bool((n > 0).any()):
+            return None
+        if T - a != cfg.topk:
+            # modeling_bert.py:1470/1489 writes the topk tag embeddings over the LAST topk input slots
+            raise NotImplementedError(_UNSUPPORTED % "a label region whose length differs from config.topk")
+        return n
 
     def _generate(self, img_feats, max_length, do_sample, num_beams, temperature, top_k, top_p, bos, pad, eos_ids, mask_id,
-                  length_penalty, nret, keep, seed):
+                  length_penalty, nret, keep, seed, n_label=None):
         eng = self.engine
         B = img_feats.shape[0]
         outs_i, outs_l = [], []
+        hold = self._label_flip_hold           # an int once forward() has decided it for a caller batch fed in several chunks
+        flip = None if (hold is None or hold is False) else hold
         if do_sample:
             if seed is None:
                 seed = self.sample_seed + self._sample_calls * 0x9E3779B97F4A7C15
@@ -305,14 +322,29 @@ class FastImageCaptioning(nn.Module):
         for s in range(0, B, self.max_batch):
             chunk = img_feats[s:s + self.max_batch]
             b = chunk.shape[0]
+            if n_label is not None:
+                eng.reserve(b, label_rows=True)    # before encode(): growing the workspace later would drop its outputs
             eng.encode(chunk)
-            eng.tag_head(b)
-            eng.prefill(b)
+            _, _, _, tag_len = eng.tag_head(b)
+            if n_label is None:
+                eng.prefill(b)
+            else:
+                # The reference picks the label-embedding recipe per step from the FIRST sample's tag count
+                # (modeling_bert.py:1435: topk_len[0] + 20 <= cur_len + 1 + label slots -> 'raw', else 'ln'); one host read,
+                # where the reference itself synchronises. `flip` = first cur_len decoded under 'raw'.
+                if flip is None:
+                    flip = max(1, int(tag_len[0].item()) + 20 - 1 - self.cfg.topk)
+                    if self._label_flip_hold is False:
+                        self._label_flip_hold = flip
+                eng.set_labels(b, n_label[s:s + b])
+                eng.prefill(b, label_recipe="raw" if flip <= 1 else "ln")
             if num_beams > 1:
-                ids, lp = eng.beam_search(b, num_beams, max_length, bos, pad, eos_ids, mask_id, length_penalty, keep)
+                ids, lp = eng.beam_search(b, num_beams, max_length, bos, pad, eos_ids, mask_id, length_penalty, keep,
+                                          label_flip=flip if n_label is not None else None)
             else:
                 ids, lp = eng.greedy_or_sample(b, nret, max_length, bos, pad, eos_ids, mask_id, do_sample, temperature, top_k,
-                                               top_p, seed=(seed + s) if do_sample else 0)
+                                               top_p, seed=(seed + s) if do_sample else 0,
+                                               label_flip=flip if n_label is not None else None)
             outs_i.append(ids)
             outs_l.append(lp)
         return torch.cat(outs_i, 0), torch.cat(outs_l, 0)
@@ -329,14 +361,18 @@ class FastImageCaptioning(nn.Module):
         B = image.shape[0]
         extra = dict(self.test_extra_input)
         ids_all, lp_all = [], []
-        for s in range(0, B, self.max_batch):      # the image stream buffer holds max_batch images
-            sub = {k: (v[s:s + self.max_batch] if torch.is_tensor(v) and v.shape[:1] == (B,) else v) for k, v in data.items()}
-            sub["img_feats"] = self.image_encoder({"image": image[s:s + self.max_batch]})
-            sub["gen_tag_ratio"] = 1
-            sub.update(extra)
-            ids, lp = self.module(**sub)
-            ids_all.append(ids)
-            lp_all.append(lp)
+        self._label_flip_hold = False              # the label recipe follows the first sample of the WHOLE batch (see _generate)
+        try:
+            for s in range(0, B, self.max_batch):      # the image stream buffer holds max_batch images
+                sub = {k: (v[s:s + self.max_batch] if torch.is_tensor(v) and v.shape[:1] == (B,) else v) for k, v in data.items()}
+                sub["img_feats"] = self.image_encoder({"image": image[s:s + self.max_batch]})
+                sub["gen_tag_ratio"] = 1
+                sub.update(extra)
+                ids, lp = self.module(**sub)
+                ids_all.append(ids)
+                lp_all.append(lp)
+        finally:
+            self._label_flip_hold = None
         return torch.cat(ids_all, 0), torch.cat(lp_all, 0)
 
     @torch.no_grad()

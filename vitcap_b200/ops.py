@@ -28,7 +28,13 @@ SIGNATURES = {
     "vc_layernorm": [_I, _P, _I, _P, _P, _F, _P, _I, _P, _I, _I, _I, _P],
     "vc_gather_rows": [_I, _P, _SZ, _P, _I, _I, _I, _P],
     "vc_assemble_ctx": [_I, _P, _P, _P, _P, _I, _I, _I, _P],
+    "vc_assemble_ctx_pitched": [_I, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "vc_label_rows": [_I, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _F, _P, _P, _I, _I, _I, _I, _P],
     "vc_attention": [_I, _P, _P, _I, _I, _I, _F, _P],
+    "vc_attention_labels": [_I, _P, _P, _I, _I, _I, _F, _I, _P, _P],
+    "vc_attention_labels_simt": [_I, _P, _P, _I, _I, _I, _F, _I, _P, _P],
+    "vc_decode_attention_labels": [_I, _P, _P, _P, _P, _I, _I, _P, _I, _I, _I, _F, _P],
+    "vc_decode_attention_labels_simt": [_I, _P, _P, _P, _P, _I, _I, _P, _I, _I, _I, _F, _P],
     "vc_attention_simt": [_I, _P, _P, _I, _I, _I, _F, _P],
     "vc_cls_attention": [_I, _P, _I, _P, _P, _I, _I, _I, _I, _F, _P],
     "vc_tag_topk": [_P, _I, _I, _I, _I, _F, _P, _P, _P, _P],
@@ -175,13 +181,34 @@ def gather_rows(x, row_stride, out, rows, H):
     return out
 
 
-def assemble_ctx(cap, tag, ctx_f, ctx_t, B, N, H):
-    _check(load_library().vc_assemble_ctx(_is_bf16(ctx_t), _ptr(cap), _ptr(tag), _ptr(ctx_f), _ptr(ctx_t), B, N, H, _stream()),
-           "vc_assemble_ctx")
+def assemble_ctx(cap, tag, ctx_f, ctx_t, B, N, H, rows_per_image=None):
+    if rows_per_image is None or rows_per_image == N + 1:
+        _check(load_library().vc_assemble_ctx(_is_bf16(ctx_t), _ptr(cap), _ptr(tag), _ptr(ctx_f), _ptr(ctx_t), B, N, H, _stream()),
+               "vc_assemble_ctx")
+    else:
+        _check(load_library().vc_assemble_ctx_pitched(_is_bf16(ctx_t), _ptr(cap), _ptr(tag), _ptr(ctx_f), _ptr(ctx_t), B, N, H,
+                                                      rows_per_image, _stream()), "vc_assemble_ctx_pitched")
 
 
-def attention(qkv, out, B, N, heads, scale, impl="auto"):
+def label_rows(tag_idx, sep_id, recipe_ln, pos0, word, pos, type0, gamma, beta, eps, ctx_f, ctx_t, B, rows_per_image, row0):
+    """Label rows of the context (see vc_label_rows): tag_idx int32 [B,K]; recipe_ln False = raw word embedding,
+    True = word + position(pos0 + i) + type 0 -> LayerNorm."""
+    K, H = tag_idx.shape[1], word.shape[1]
+    assert tag_idx.dtype == torch.int32 and tag_idx.is_contiguous()
+    _check(load_library().vc_label_rows(_is_bf16(ctx_t), _ptr(tag_idx), K, int(sep_id), int(bool(recipe_ln)), int(pos0), _ptr(word),
+                                        _ptr(pos), _ptr(type0), _ptr(gamma), _ptr(beta), float(eps), _ptr(ctx_f), _ptr(ctx_t), B,
+                                        rows_per_image, row0, H, _stream()), "vc_label_rows")
+
+
+def attention(qkv, out, B, N, heads, scale, impl="auto", n_base=0, n_extra=None):
+    """n_extra (int32 [B]) selects the label-region mask: rows < n_base see keys < n_base, later rows n_extra[b] more."""
     lib = load_library()
+    if n_extra is not None:
+        assert n_extra.dtype == torch.int32 and n_extra.numel() >= B
+        fn = lib.vc_attention_labels_simt if impl == "simt" else lib.vc_attention_labels
+        _check(fn(_is_bf16(qkv), _ptr(qkv), _ptr(out), B, N, heads, float(scale), int(n_base), _ptr(n_extra), _stream()),
+               "vc_attention_labels")
+        return out
     if impl == "simt":
         _check(lib.vc_attention_simt(_is_bf16(qkv), _ptr(qkv), _ptr(out), B, N, heads, float(scale), _stream()), "vc_attention_simt")
     else:
@@ -209,7 +236,14 @@ def embed_ln(ids, cur_len, mask_id, word, pos, type0, gamma, beta, eps, out_f, o
                                       _stream()), "vc_embed_ln")
 
 
-def decode_attention(ctx_qkv, step_qkv, anc, out, B, C, heads, E, cur_len, scale, impl="auto"):
+def decode_attention(ctx_qkv, step_qkv, anc, out, B, C, heads, E, cur_len, scale, impl="auto", ctx_vis=None):
+    """ctx_vis (int32 [B]): C context rows are allocated per image, only the first ctx_vis[b] are visible."""
+    if ctx_vis is not None:
+        assert ctx_vis.dtype == torch.int32 and ctx_vis.numel() >= B
+        fn = load_library().vc_decode_attention_labels_simt if impl == "simt" else load_library().vc_decode_attention_labels
+        _check(fn(_is_bf16(ctx_qkv), _ptr(ctx_qkv), _ptr(step_qkv), _ptr(anc), _ptr(out), B, C, _ptr(ctx_vis), heads, E, cur_len,
+                  float(scale), _stream()), "vc_decode_attention_labels")
+        return
     fn = load_library().vc_decode_attention_simt if impl == "simt" else load_library().vc_decode_attention
     _check(fn(_is_bf16(ctx_qkv), _ptr(ctx_qkv), _ptr(step_qkv), _ptr(anc), _ptr(out), B, C, heads, E, cur_len, float(scale),
               _stream()), "vc_decode_attention")
