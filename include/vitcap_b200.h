@@ -68,6 +68,20 @@ int vc_patchify(int bf16, const float* image, void* out, int B, int img_size, in
  * transform fused in: BGR2RGB, ToTensor (x/255, HWC->CHW), Normalize(0.5, 0.5) -- uni_pipeline.py:1233-1256, transform.py:47-50 --
  * bit-identical to the fp32 path fed with the host-transformed tensor; resize / center-crop stay on the host. */
 int vc_patchify_u8(int bf16, const uint8_t* image, void* out, int B, int img_size, int patch, int bgr, void* stream);
+/* Head of the same test transform on the device, for a ragged batch of decoded 8-bit images (HWC, 3 channels, order kept):
+ * Resize(resize_to, BICUBIC) of the shorter edge + CenterCrop(crop) -- uni_pipeline.py:1246-1250 (crop_pct 1.0 in the shipped
+ * yaml => resize_to == crop). Bit-identical to torchvision's output geometry and Pillow's 8-bit ImagingResample (the two
+ * third-party libraries the reference calls there): double-precision Keys-cubic windows -> 22-bit fixed point, horizontal pass
+ * into an 8-bit intermediate, vertical pass, saturating shift. Only the cropped window is computed.
+ *   vc_resize_crop_plan  (HOST function, no device work): hw = host int32 [B][2] (height, width). Returns the widest window
+ *                        `kmax`, the tallest image `max_rows` and tmp_off host int64 [B+1] (byte offsets of each image's
+ *                        intermediate rows; tmp_off[B] = bytes of `tmp`). Fails if an image would resize below the crop.
+ *   vc_resize_crop_u8    src = packed source pixels, src_off device int64 [B] byte offsets, hw device int32 [B][2],
+ *                        coef = workspace int32 [B][2][kmax+2][crop], tmp = workspace of tmp_off[B] bytes (4-byte aligned),
+ *                        tmp_off device int64 [B], out uint8 [B, crop, crop, 3] (feeds vc_patchify_u8). crop % 4 == 0. */
+int vc_resize_crop_plan(const int* hw, int B, int resize_to, int crop, int* kmax, long long* tmp_off, int* max_rows);
+int vc_resize_crop_u8(const uint8_t* src, const long long* src_off, const int* hw, int B, int resize_to, int crop, int kmax,
+                      int max_rows, int* coef, uint8_t* tmp, const long long* tmp_off, uint8_t* out, void* stream);
 /* x[b,0] = cls + pos[0]; x[b,1+i] = patch_out[b*P+i] + pos[1+i]; forward_features, vision_transformer.py:423-427 */
 int vc_assemble_tokens(const float* patch_out, const float* cls, const float* pos, float* x, int B, int P, int H, void* stream);
 

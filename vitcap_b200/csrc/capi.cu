@@ -13,6 +13,9 @@ int gemm_simt(int in_bf16, const void* A, int lda, const void* W, int ldw, const
               int act, const float* resid, int ldr, int M, int N, int K, cudaStream_t s);
 int patchify(int out_bf16, const float* img, void* out, int B, int img_size, int patch, cudaStream_t s);
 int patchify_u8(int out_bf16, const uint8_t* img, void* out, int B, int img_size, int patch, int bgr, cudaStream_t s);
+int resize_crop_plan(const int* hw, int B, int resize_to, int S, int* kmax, long long* tmp_off, int* max_rows);
+int resize_crop_u8(const uint8_t* src, const long long* src_off, const int* hw, int B, int resize_to, int S, int kmax, int max_rows,
+                   int* coef, uint8_t* tmp, const long long* tmp_off, uint8_t* out, cudaStream_t s);
 int assemble_tokens(const float* patch_out, const float* cls, const float* pos, float* x, int B, int P, int H, cudaStream_t s);
 int layernorm(int out_bf16, const float* in, int ld_in, const float* gamma, const float* beta, float eps, void* out_t, int ld_t,
               float* out_f, int ld_f, int rows, int H, cudaStream_t s);
@@ -82,6 +85,13 @@ int vc_patchify(int bf16, const float* image, void* out, int B, int img_size, in
 }
 int vc_patchify_u8(int bf16, const uint8_t* image, void* out, int B, int img_size, int patch, int bgr, void* stream) {
   VC_COUNT(1, vc::patchify_u8(bf16, image, out, B, img_size, patch, bgr, ST(stream)));
+}
+int vc_resize_crop_plan(const int* hw, int B, int resize_to, int crop, int* kmax, long long* tmp_off, int* max_rows) {
+  return vc::resize_crop_plan(hw, B, resize_to, crop, kmax, tmp_off, max_rows);
+}
+int vc_resize_crop_u8(const uint8_t* src, const long long* src_off, const int* hw, int B, int resize_to, int crop, int kmax,
+                      int max_rows, int* coef, uint8_t* tmp, const long long* tmp_off, uint8_t* out, void* stream) {
+  VC_COUNT(3, vc::resize_crop_u8(src, src_off, hw, B, resize_to, crop, kmax, max_rows, coef, tmp, tmp_off, out, ST(stream)));
 }
 int vc_assemble_tokens(const float* patch_out, const float* cls, const float* pos, float* x, int B, int P, int H, void* stream) {
   VC_COUNT(1, vc::assemble_tokens(patch_out, cls, pos, x, B, P, H, ST(stream)));

@@ -24,6 +24,8 @@ SIGNATURES = {
     "vc_linear_tc": [_P, _I, _P, _I, _P, _P, _I, _I, _I, _P, _I, _I, _I, _I, _I, _P],
     "vc_patchify": [_I, _P, _P, _I, _I, _I, _P],
     "vc_patchify_u8": [_I, _P, _P, _I, _I, _I, _I, _P],
+    "vc_resize_crop_plan": [_P, _I, _I, _I, _P, _P, _P],
+    "vc_resize_crop_u8": [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P],
     "vc_assemble_tokens": [_P, _P, _P, _P, _I, _I, _I, _P],
     "vc_layernorm": [_I, _P, _I, _P, _P, _F, _P, _I, _P, _I, _I, _I, _P],
     "vc_gather_rows": [_I, _P, _SZ, _P, _I, _I, _I, _P],
@@ -157,6 +159,30 @@ def patchify_u8(image, out, patch, bgr=True):
     B, S, S2, C = image.shape
     assert image.dtype == torch.uint8 and image.is_contiguous() and C == 3 and S == S2
     _check(load_library().vc_patchify_u8(_is_bf16(out), _ptr(image), _ptr(out), B, S, patch, int(bool(bgr)), _stream()), "vc_patchify_u8")
+    return out
+
+
+def resize_crop_plan(hw, resize_to, crop):
+    """Host-side planning for resize_crop_u8. hw: int32 CPU tensor [B,2] (height, width).
+    Returns (kmax, max_rows, tmp_off int64 CPU tensor [B+1])."""
+    assert hw.dtype == torch.int32 and not hw.is_cuda and hw.is_contiguous() and hw.dim() == 2 and hw.shape[1] == 2
+    B = hw.shape[0]
+    kmax, max_rows = _c.c_int(0), _c.c_int(0)
+    tmp_off = torch.empty(B + 1, dtype=torch.int64)
+    _check(load_library().vc_resize_crop_plan(hw.data_ptr(), B, resize_to, crop, _c.addressof(kmax), tmp_off.data_ptr(),
+                                              _c.addressof(max_rows)), "vc_resize_crop_plan")
+    return kmax.value, max_rows.value, tmp_off
+
+
+def resize_crop_u8(src, src_off, hw, resize_to, crop, kmax, max_rows, coef, tmp, tmp_off, out):
+    """Ragged batch of uint8 HWC images (packed in ``src``) -> uint8 [B,crop,crop,3]: Resize(resize_to, BICUBIC) +
+    CenterCrop(crop), bit-identical to torchvision + Pillow. All tensors on the device; see include/vitcap_b200.h."""
+    B = hw.shape[0]
+    assert src.dtype == torch.uint8 and out.dtype == torch.uint8 and out.is_contiguous() and tuple(out.shape) == (B, crop, crop, 3)
+    assert src_off.dtype == torch.int64 and tmp_off.dtype == torch.int64 and hw.dtype == torch.int32 and coef.dtype == torch.int32
+    assert coef.numel() >= B * 2 * (kmax + 2) * crop
+    _check(load_library().vc_resize_crop_u8(_ptr(src), _ptr(src_off), _ptr(hw), B, resize_to, crop, kmax, max_rows, _ptr(coef),
+                                            _ptr(tmp), _ptr(tmp_off), _ptr(out), _stream()), "vc_resize_crop_u8")
     return out
 
 
