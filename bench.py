@@ -38,15 +38,28 @@ def parse():
     ap.add_argument("--dec-layers", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--cpu-sample-images", type=int, default=2)
+    ap.add_argument("--cpu-sample-images", type=int, default=4)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --batch images on EVERY GPU (the contract's default); strong: --batch images in total, "
+                         "split over the GPUs (SURVEY.md section 8d asks for both)")
     return ap.parse_args()
 
 
+def per_gpu_batch(args):
+    world = max(1, int(os.environ.get("WORLD_SIZE", str(max(1, args.gpus)))))
+    if args.scaling == "strong":
+        if args.batch % world:
+            raise SystemExit("bench.py: --scaling strong needs --batch divisible by the number of GPUs")
+        return args.batch // world
+    return args.batch
+
+
 def workload_config(args, cfg):
+    b = per_gpu_batch(args)
     return {
         "workload": "BASELINE.json configs[2]: full ViTCAP greedy captioning, ViT-B/16-%d, %d-layer decoder, max_len 20, "
-                    "batch %d per GPU, data-parallel" % (cfg.img_size, cfg.dec_layers, args.batch),
-        "variant": args.variant, "batch_per_gpu": args.batch, "global_batch": args.batch * max(1, args.gpus),
+                    "batch %d per GPU, data-parallel" % (cfg.img_size, cfg.dec_layers, b),
+        "variant": args.variant, "batch_per_gpu": b, "global_batch": b * max(1, args.gpus),
         "max_length": 20, "num_beams": 1, "decoder_layers": cfg.dec_layers, "parallelism": "dp%d" % max(1, args.gpus),
         "weights": "random-init (synth.make_state_dict seed 0, reference layout)",
         "l2": "inputs larger than L2 (906 MB of images and >10 GB of activations per step vs 126 MB L2)",
@@ -123,6 +136,52 @@ def cpu_baseline(cfg, sd, n_images, extra):
                       "19 full-model calls), %.1f s" % (n_images, cfg.img_size, dt)}, ids
 
 
+def decode_roofline(torch, ops, cfg, B, dev, peaks):
+    """Algorithmic bytes (K+V rows a step must read, context rows counted once per image) / measured
+    duration of decode_attention_mma_kernel at the middle decode step, against the measured copy bandwidth."""
+    H, heads, C, L = cfg.hidden, cfg.heads, cfg.n_ctx, cfg.dec_layers
+    cur_len = 10
+    ctx = [torch.randn(B, C, 3 * H, device=dev).to(torch.bfloat16) for _ in range(L)]
+    stepq = [torch.randn(20, 2 * B, 3 * H, device=dev).to(torch.bfloat16) for _ in range(L)]
+    out = torch.empty(2 * B, H, device=dev, dtype=torch.bfloat16)
+
+    def run():
+        for l in range(L):
+            ops.decode_attention(ctx[l], stepq[l], None, out, B, C, heads, 1, cur_len, cfg.head_dim ** -0.5)
+
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iters = 10
+    e0.record()
+    for _ in range(iters):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / (iters * L)
+    byt = B * (C + cur_len + 1) * 2 * H * 2
+    peak = peaks.get("hbm_gbs")
+    src = "MEASURED_PEAKS.json hbm_gbs (copy bandwidth, read+write)"
+    if not peak:
+        peak, src = 6500.0, "fallback (B200_PROFILING.md: ~6.5 TB/s measured copy)"
+    ach = byt / (ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
+        traffic = next(v["dram_bytes"] for k, v in tj.items() if "decode_attention_mma_kernel" in k)
+    except Exception:
+        pass
+    return {"kernel": "decode_attention_mma_kernel (2 query rows per sequence over 578 context + %d caption keys, bf16 K/V, "
+                      "%d launches per decode step, 19 steps per batch)" % (cur_len + 1, L),
+            "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": src,
+            "algorithmic_bytes_per_launch": byt, "us_per_launch": ms * 1e3, "traffic": traffic,
+            "traffic_note": "dram__bytes_read+write of one launch at B=512 from the committed ncu --set full capture "
+                            "(profiles/r01_ncu_summary.md)",
+            "how": "eager launches after the timed region (the decode loop itself is one CUDA graph): one launch per decoder "
+                   "layer over distinct %0.2f GB caches, CUDA events, %d iterations" % (byt / 1e9, iters)}
+
+
 def run_reference_arm(args):
     import torch
     rank = int(os.environ.get("RANK", "0"))
@@ -196,7 +255,7 @@ def main():
     cfg = vcfg.variant(args.variant, dec_layers=args.dec_layers)
     sd = synth.make_state_dict(cfg, seed=0)
     extra = synth.default_test_extra_input(cfg)
-    B = args.batch
+    B = per_gpu_batch(args)
     model = FastImageCaptioning(cfg, test_extra_input=extra, mode=args.mode, max_batch=B)
     model.load_state_dict(sd)
     model = model.to(dev)
@@ -280,6 +339,14 @@ def main():
         "algorithmic_flops_per_step": flops / max(1, args.steps),
     }
 
+    # ---- second roofline object: the HBM-bound kernel of the decode steps (single-token attention over the KV cache). It runs
+    # inside the CUDA graph of the decode loop, where events cannot bracket it, so the same launches (one per decoder layer,
+    # distinct caches of the bench's own size: 3.6 GB, far beyond L2) are timed eagerly right after the timed region.
+    roofline_decode = None
+    if args.mode == "bf16" and rank == 0:
+        roofline_decode = decode_roofline(torch, ops, cfg, B, dev, peaks)
+    sync_all()
+
     # ---- e2e: the same steps through the public host loop (vitcap_b200.stream.OverlappedCaptioner, the drop-in for the
     # reference's predict_iter) with HOST buffers: every step uploads its own 512 images from pinned memory and reads its
     # result records back; the upload of step i+1 overlaps the captioning of step i (double-buffered device staging)
@@ -320,9 +387,9 @@ def main():
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "bf16" if args.mode == "bf16" else "f32", "data": "synthetic", "config": workload_config(args, cfg),
-        "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": roofline, "roofline_decode": roofline_decode, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cb, _ = cpu_baseline(cfg, sd, args.cpu_sample_images, extra)

@@ -19,7 +19,9 @@
 //            tcgen05.ld S_g, row max (FMNMX3, two chains), lazy rescale of O (the exponent reference only moves when the
 //            max grew by > 2^8), P = exp2(.) with packed FFMA2 / FADD2 arithmetic around the MUFU, tcgen05.st P_g;
 //            per tile epilogue O / l -> bf16 -> global while the MMAs of the next tile already run.
-// The MUFU (exp2) pipe is the bound of this d=64 attention: 16 exp/clk/SM.
+// The MUFU (exp2) pipe is the nominal bound of this d=64 attention (16 exp2/clk/SM = 0.61 ms at B = 512); measured 0.99 ms
+// with the pipe 62 % busy. Moving 1/8, 1/4 or 3/8 of the exponentials to an FMA-pipe cubic (the FlashAttention-4 trick)
+// was measured SLOWER (0.99 -> 1.01 / 1.06 / 1.07 ms): the softmax warps are issue/latency bound, not MUFU bound.
 #include "common.cuh"
 
 #include <type_traits>
@@ -263,6 +265,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         const uint32_t taddr_s = tmem_base + lane_base + COL_S + sb * KT;
         mbar_wait(&s_full[sb], sph);
         tc_fence_after();
+        if (tile * QT + quad * 32 >= N) {
+          // every row of this warp lies past the last query (N = 577: rows 608..639 of the last tile): its S rows are exact
+          // zeros of the zero-filled Q rows, which read as P = 0 where the PV MMA looks; nothing to compute, keep in step
+          tc_fence_before();
+          mbar_arrive(&p_full[sb]);
+        } else {
         // the two paths contain warp-wide votes: with per-row limits the choice must be made per warp
         const bool full_chunk = LABELS ? (__all_sync(0xffffffffu, lim >= KT) != 0) : (lim >= KT);
         if (full_chunk) {
@@ -382,6 +390,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&p_full[sb]);
+        }
         if (pend && j == 0) {
           // epilogue of the previous tile, after this tile's first chunk has been handed to the tensor core
           mbar_wait(&pv_done[pend_sb], pend_ph);
@@ -407,6 +416,21 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
+template <bool LABELS>
+static int launch_attention(dim3 grid, const CUtensorMap& tq, const CUtensorMap& tkv, bf16* out, int N, int H, float scale_log2,
+                            int n_base, const int* n_extra, cudaStream_t s) {
+  auto kern = attention_tc_kernel<LABELS>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (e != cudaSuccess) { set_last_error("attention_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return VC_ERR_LAUNCH; }
+    configured = true;
+  }
+  kern<<<grid, 192, SMEM_TOTAL, s>>>(tq, tkv, out, N, H, scale_log2, n_base, n_extra);
+  return check_launch("attention_tc");
+}
+
 int attention_tc(const void* qkv, void* out, int B, int N, int heads, float scale, int n_base, const int* n_extra, cudaStream_t s) {
   if (B <= 0 || N <= 0 || heads <= 0 || B > 65535 || (n_extra && (n_base < 1 || n_base > N))) {
     set_last_error("attention_tc: bad args"); return VC_ERR_BAD_ARG;
@@ -420,22 +444,11 @@ int attention_tc(const void* qkv, void* out, int B, int N, int heads, float scal
   if (rc) return rc;
   rc = get_tmap_3d_bf16(&tkv, qkv, (uint64_t)B, (uint64_t)N, (uint64_t)3 * H, (uint64_t)3 * H, (uint64_t)N * 3 * H, KT, 64);
   if (rc) return rc;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    if (e != cudaSuccess) { set_last_error("attention_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return VC_ERR_LAUNCH; }
-    configured = true;
-  }
   dim3 grid(heads, B);
   const float scale_log2 = scale * 1.4426950408889634f;
-  if (n_extra)
-    attention_tc_kernel<true><<<grid, 192, SMEM_TOTAL, s>>>(tq, tkv, reinterpret_cast<bf16*>(out), N, H, scale_log2, n_base, n_extra);
-  else
-    attention_tc_kernel<false><<<grid, 192, SMEM_TOTAL, s>>>(tq, tkv, reinterpret_cast<bf16*>(out), N, H, scale_log2, 0, nullptr);
-  return check_launch("attention_tc");
+  bf16* o = reinterpret_cast<bf16*>(out);
+  if (n_extra) return launch_attention<true>(grid, tq, tkv, o, N, H, scale_log2, n_base, n_extra, s);
+  return launch_attention<false>(grid, tq, tkv, o, N, H, scale_log2, 0, nullptr, s);
 }
 
 }  // namespace vc
