@@ -198,6 +198,11 @@ __device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
   return r;
 }
+__device__ __forceinline__ uint64_t mul_f32x2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
 
 // GELU of the bf16 tensor-core epilogues: x/2 * (1 + erf(x / sqrt 2)) with erf(z) ~= tanh(z * (C0 + C1 u + C2 u^2)),
 // u = min(z^2, 30): a minimax fit (max |gelu error| 2.5e-5 before the MUFU.TANH error of 2^-11 relative), 10 issue slots
@@ -215,6 +220,23 @@ __device__ __forceinline__ float gelu_erf_tanh(float x) {
   const float t = tanh_approx(z * p);
   const float hx = 0.5f * x;
   return fmaf(hx, t, hx);
+}
+// the same arithmetic on a register pair with packed FMUL2 / FFMA2 (same roundings, element for element): 7 packed issue
+// slots + 2 FMNMX + 2 MUFU per pair instead of 20
+__device__ __forceinline__ void gelu_erf_tanh_x2(float& a, float& b) {
+  const uint64_t x = pack_f32x2(a, b);
+  const uint64_t z = mul_f32x2(x, pack_f32x2(0.70710678118654752440f, 0.70710678118654752440f));
+  float u0, u1;
+  unpack_f32x2(mul_f32x2(z, z), u0, u1);
+  const uint64_t u = pack_f32x2(fminf(u0, 30.0f), fminf(u1, 30.0f));
+  uint64_t p = fma_f32x2(pack_f32x2(-1.988479253896676e-03f, -1.988479253896676e-03f), u,
+                         pack_f32x2(1.0466777301852825e-01f, 1.0466777301852825e-01f));
+  p = fma_f32x2(p, u, pack_f32x2(1.1278464660309704f, 1.1278464660309704f));
+  float q0, q1;
+  unpack_f32x2(mul_f32x2(z, p), q0, q1);
+  const uint64_t t = pack_f32x2(tanh_approx(q0), tanh_approx(q1));
+  const uint64_t hx = mul_f32x2(x, pack_f32x2(0.5f, 0.5f));
+  unpack_f32x2(fma_f32x2(hx, t, hx), a, b);
 }
 
 

@@ -262,15 +262,21 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
                 const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + cb + j));
-                v[j] += bb.x; v[j + 1] += bb.y; v[j + 2] += bb.z; v[j + 3] += bb.w;
+                unpack_f32x2(add_f32x2(pack_f32x2(v[j], v[j + 1]), pack_f32x2(bb.x, bb.y)), v[j], v[j + 1]);
+                unpack_f32x2(add_f32x2(pack_f32x2(v[j + 2], v[j + 3]), pack_f32x2(bb.z, bb.w)), v[j + 2], v[j + 3]);
               }
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] += (cb + j < N) ? __ldg(bias + cb + j) : 0.f;
             }
           }
+          if (ACT == ACT2_GELU) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = apply_act<ACT>(v[j]);
+            for (int j = 0; j < 32; j += 2) gelu_erf_tanh_x2(v[j], v[j + 1]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = apply_act<ACT>(v[j]);
+          }
           if (OUT_F32) {
             if (RESID) {
               mbar_wait(&gres[b], (g / C::NBUF_G) & 1);
