@@ -157,10 +157,12 @@ int vc_decode_attention_labels_simt(int bf16, const void* ctx_qkv, const void* s
                                     void* stream);
 
 /* greedy / sampled next token + log-prob + state update for `rows` sequences, modeling_utils.py:839-862.
- * logits fp32 [rows, ld]; sampling = Gumbel-max with Philox4x32-10 noise keyed by (seed; vocab idx/4, row, cur_len). */
-int vc_token_step(const float* logits, int ld, int rows, int V, int do_sample, float temperature, uint64_t seed, int cur_len,
-                  int max_len, int pad_id, const int* eos_ids, int n_eos, int* ids, int* unfinished, float* sum_lp, int* n_steps,
-                  void* stream);
+ * logits fp32 [rows, ld]; sampling = Gumbel-max with Philox4x32-10 noise keyed by (seed; vocab idx/4, row, cur_len).
+ * seed_dev: NULL, or a device pointer to the 64-bit seed, read when the kernel RUNS (it then replaces `seed`): a decode loop
+ * captured once in a CUDA graph draws fresh noise on every replay after the caller rewrites that word. */
+int vc_token_step(const float* logits, int ld, int rows, int V, int do_sample, float temperature, uint64_t seed,
+                  const uint64_t* seed_dev, int cur_len, int max_len, int pad_id, const int* eos_ids, int n_eos, int* ids,
+                  int* unfinished, float* sum_lp, int* n_steps, void* stream);
 /* modeling_utils.py:869-886: force EOS, mean log-prob, int64 ids [R,max_len] */
 int vc_greedy_finalize(const int* ids, const int* unfinished, const float* sum_lp, const int* n_steps, int eos0, int max_len, int R,
                        long long* out_ids, float* out_lp, void* stream);

@@ -160,8 +160,14 @@ class _TableLogits:
         return self._dev[key][self.index(ids)]
 
 
-def _greedy_kernels(tl, R, max_len, bos, pad, eos_ids, do_sample=False, temperature=1.0, top_k=0, top_p=1.0, seed=0):
+def _greedy_kernels(tl, R, max_len, bos, pad, eos_ids, do_sample=False, temperature=1.0, top_k=0, top_p=1.0, seed=0,
+                    seed_on_device=False):
     V = tl.V
+    seed_dev = None
+    if seed_on_device:                      # the seed word is read by the kernel; the scalar argument is then ignored
+        s64 = seed & 0xFFFFFFFFFFFFFFFF
+        seed_dev = torch.tensor([s64 - (1 << 64) if s64 >= (1 << 63) else s64], dtype=torch.int64, device=DEV)
+        seed = 12345
     ldl = (V + 63) // 64 * 64
     ids = torch.zeros(R, max_len, dtype=torch.int32, device=DEV)
     ids[:, 0] = bos
@@ -176,7 +182,7 @@ def _greedy_kernels(tl, R, max_len, bos, pad, eos_ids, do_sample=False, temperat
         if do_sample and (top_k > 0 or top_p < 1.0):
             ops.filter_logits(logits, V, R, 1.0 / temperature, top_k, top_p)
             t = 1.0
-        ops.token_step(logits, V, R, do_sample, t, seed, cur_len, pad, eos, ids, unf, sum_lp, n_steps)
+        ops.token_step(logits, V, R, do_sample, t, seed, cur_len, pad, eos, ids, unf, sum_lp, n_steps, seed_dev=seed_dev)
     out_ids = torch.zeros(R, max_len, dtype=torch.int64, device=DEV)
     out_lp = torch.zeros(R, device=DEV)
     ops.greedy_finalize(ids, unf, sum_lp, n_steps, eos_ids[0], R, out_ids, out_lp)
@@ -191,6 +197,17 @@ def test_greedy_kernels_vs_oracle_loop(V, R):
     assert torch.equal(ids, rids[:, 0])
     np.testing.assert_allclose(lp.numpy(), rlp[:, 0].numpy(), atol=1e-5)
     assert (ids == 0).any() and (ids[:, -1] == 102).any()      # both early EOS (PAD fill) and forced EOS occur
+
+
+def test_sampling_seed_from_device_memory_equals_scalar_seed():
+    """vc_token_step with seed_dev (what a captured decode loop uses) draws the same noise as the scalar seed."""
+    tl = _RowTable(_TableLogits(3000, seed=5, eos_boost=6.0), 1)
+    for seed in (7, 0x9E3779B97F4A7C15, (1 << 64) - 3):
+        a = _greedy_kernels(tl, 32, 20, 101, 0, [102], do_sample=True, seed=seed)
+        b = _greedy_kernels(tl, 32, 20, 101, 0, [102], do_sample=True, seed=seed, seed_on_device=True)
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    c = _greedy_kernels(tl, 32, 20, 101, 0, [102], do_sample=True, seed=8, seed_on_device=True)
+    assert not torch.equal(a[0], c[0])
 
 
 class _RowTable:

@@ -205,3 +205,36 @@ def test_uint8_images_caption_like_host_transformed_floats():
     ids_f, lp_f = m(to_dev(d_f))
     ids_u, lp_u = m(to_dev(d_u))
     assert torch.equal(ids_f, ids_u) and torch.equal(lp_f, lp_u)
+
+
+def test_alternating_search_modes_keep_their_workspaces_and_graphs():
+    """SCST runs a greedy pass and a sampling pass per batch (legacy pipeline lines 447-462): the engine keeps both decode
+    workspaces (and their captured graphs) alive instead of re-allocating and re-capturing on every switch."""
+    cfg = vcfg.tiny()
+    sd = synth.make_state_dict(cfg, seed=7, eos_bias=1.0)
+    B = 3
+    data = synth.make_text_inputs(cfg, B)
+    data["image"] = synth.make_images(cfg, B, seed=9)
+    m = build(cfg, sd, synth.default_test_extra_input(cfg), "fp32", max_batch=4)
+    greedy = synth.default_test_extra_input(cfg)
+    sample = synth.default_test_extra_input(cfg, do_sample=True, num_return_sequences=5)
+    m.sample_seed = 11
+    outs = {"g": [], "s": []}
+    for rnd in range(3):
+        m.test_extra_input = greedy
+        outs["g"].append(m(to_dev(data)))
+        m.test_extra_input = sample
+        if rnd == 2:
+            m._sample_calls = 0                  # round 2 repeats the seed of round 0; round 1 draws with the next seed
+        outs["s"].append(m(to_dev(data)))
+    eng = m.engine
+    assert len(eng._dec_ws) == 2
+    # one captured loop per mode: the sampling seed lives in device memory, not in the graph
+    assert all(len(ws["graphs"]) == 1 for ws in eng._dec_ws.values())
+    # round 0 = eager + capture for each mode, rounds 1-2 = replays only
+    assert eng.stats.get("graph_replays", 0) == 4
+    for ids, lp in outs["g"][1:]:
+        assert torch.equal(ids, outs["g"][0][0]) and torch.equal(lp, outs["g"][0][1])
+    assert torch.equal(outs["s"][2][0], outs["s"][0][0]) and torch.equal(outs["s"][2][1], outs["s"][0][1])
+    assert not torch.equal(outs["s"][1][0], outs["s"][0][0])
+    assert tuple(outs["s"][0][0].shape) == (B * 5, 1, cfg.max_seq_a)

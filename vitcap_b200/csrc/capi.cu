@@ -39,9 +39,9 @@ int decode_attention(int is_bf16, const void* ctx_qkv, const void* step_qkv, con
                      const int* ctx_vis, int heads, int E, int cur_len, float scale, cudaStream_t s);
 int decode_attention_simt(int is_bf16, const void* ctx_qkv, const void* step_qkv, const int* anc, void* out, int B, int C,
                           const int* ctx_vis, int heads, int E, int cur_len, float scale, cudaStream_t s);
-int token_step(const float* logits, int ld, int rows, int V, int do_sample, float temperature, uint64_t seed, int cur_len,
-               int max_len, int pad_id, const int* eos_ids, int n_eos, int* ids, int* unfinished, float* sum_lp, int* n_steps,
-               cudaStream_t s);
+int token_step(const float* logits, int ld, int rows, int V, int do_sample, float temperature, uint64_t seed,
+               const uint64_t* seed_dev, int cur_len, int max_len, int pad_id, const int* eos_ids, int n_eos, int* ids,
+               int* unfinished, float* sum_lp, int* n_steps, cudaStream_t s);
 int greedy_finalize(const int* ids, const int* unfinished, const float* sum_lp, const int* n_steps, int eos0, int max_len, int R,
                     long long* out_ids, float* out_lp, cudaStream_t s);
 int beam_row_topk(const float* logits, int ld, int rows, int V, int K, float* cand_val, int* cand_idx, float* row_max,
@@ -63,7 +63,7 @@ static std::atomic<long long> g_launches{0};
 extern "C" {
 
 const char* vc_last_error(void) { return vc::last_error(); }
-int vc_abi_version(void) { return 2; }
+int vc_abi_version(void) { return 3; }
 long long vc_launch_count(void) { return g_launches.load(); }
 void vc_reset_launch_count(void) { g_launches = 0; }
 
@@ -166,11 +166,11 @@ int vc_decode_attention_simt(int bf16, const void* ctx_qkv, const void* step_qkv
                              int heads, int E, int cur_len, float scale, void* stream) {
   VC_COUNT(1, vc::decode_attention_simt(bf16, ctx_qkv, step_qkv, anc, out, B, C, nullptr, heads, E, cur_len, scale, ST(stream)));
 }
-int vc_token_step(const float* logits, int ld, int rows, int V, int do_sample, float temperature, uint64_t seed, int cur_len,
-                  int max_len, int pad_id, const int* eos_ids, int n_eos, int* ids, int* unfinished, float* sum_lp, int* n_steps,
-                  void* stream) {
-  VC_COUNT(1, vc::token_step(logits, ld, rows, V, do_sample, temperature, seed, cur_len, max_len, pad_id, eos_ids, n_eos, ids,
-                             unfinished, sum_lp, n_steps, ST(stream)));
+int vc_token_step(const float* logits, int ld, int rows, int V, int do_sample, float temperature, uint64_t seed,
+                  const uint64_t* seed_dev, int cur_len, int max_len, int pad_id, const int* eos_ids, int n_eos, int* ids,
+                  int* unfinished, float* sum_lp, int* n_steps, void* stream) {
+  VC_COUNT(1, vc::token_step(logits, ld, rows, V, do_sample, temperature, seed, seed_dev, cur_len, max_len, pad_id, eos_ids, n_eos,
+                             ids, unfinished, sum_lp, n_steps, ST(stream)));
 }
 int vc_greedy_finalize(const int* ids, const int* unfinished, const float* sum_lp, const int* n_steps, int eos0, int max_len, int R,
                        long long* out_ids, float* out_lp, void* stream) {

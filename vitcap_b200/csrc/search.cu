@@ -222,8 +222,8 @@ __device__ __forceinline__ float4 row_load4(const float* __restrict__ row, int i
 
 template <bool VEC>
 __global__ void __launch_bounds__(256)
-token_step_kernel(const float* __restrict__ logits, int ld, int V, int do_sample, float inv_temp, uint64_t seed, int cur_len,
-                  int max_len, int pad_id, const int* __restrict__ eos_ids, int n_eos, int* __restrict__ ids,
+token_step_kernel(const float* __restrict__ logits, int ld, int V, int do_sample, float inv_temp, uint64_t seed,
+                  const uint64_t* __restrict__ seed_dev, int cur_len, int max_len, int pad_id, const int* __restrict__ eos_ids, int n_eos, int* __restrict__ ids,
                   int* __restrict__ unfinished, float* __restrict__ sum_lp, int* __restrict__ n_steps) {
   __shared__ float bv[8], bm[8], bs[8];
   __shared__ int bi[8];
@@ -244,6 +244,7 @@ token_step_kernel(const float* __restrict__ logits, int ld, int V, int do_sample
     }
     m = best;
   } else {
+    if (seed_dev != nullptr) seed = __ldg(seed_dev);
     const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
     for (int i4 = tid; i4 < n4; i4 += 256) {
       const float4 v = row_load4<VEC>(row, i4, V);
@@ -307,19 +308,19 @@ token_step_kernel(const float* __restrict__ logits, int ld, int V, int do_sample
   }
 }
 
-int token_step(const float* logits, int ld, int rows, int V, int do_sample, float temperature, uint64_t seed, int cur_len,
-               int max_len, int pad_id, const int* eos_ids, int n_eos, int* ids, int* unfinished, float* sum_lp, int* n_steps,
-               cudaStream_t s) {
+int token_step(const float* logits, int ld, int rows, int V, int do_sample, float temperature, uint64_t seed,
+               const uint64_t* seed_dev, int cur_len, int max_len, int pad_id, const int* eos_ids, int n_eos, int* ids,
+               int* unfinished, float* sum_lp, int* n_steps, cudaStream_t s) {
   if (rows <= 0 || V <= 0 || cur_len < 1 || cur_len >= max_len || temperature <= 0.f) {
     set_last_error("token_step: bad args"); return VC_ERR_BAD_ARG;
   }
   const bool vec = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(logits) & 15) == 0);
   if (vec)
-    token_step_kernel<true><<<rows, 256, 0, s>>>(logits, ld, V, do_sample, 1.f / temperature, seed, cur_len, max_len, pad_id,
-                                                 eos_ids, n_eos, ids, unfinished, sum_lp, n_steps);
+    token_step_kernel<true><<<rows, 256, 0, s>>>(logits, ld, V, do_sample, 1.f / temperature, seed, seed_dev, cur_len, max_len,
+                                                 pad_id, eos_ids, n_eos, ids, unfinished, sum_lp, n_steps);
   else
-    token_step_kernel<false><<<rows, 256, 0, s>>>(logits, ld, V, do_sample, 1.f / temperature, seed, cur_len, max_len, pad_id,
-                                                  eos_ids, n_eos, ids, unfinished, sum_lp, n_steps);
+    token_step_kernel<false><<<rows, 256, 0, s>>>(logits, ld, V, do_sample, 1.f / temperature, seed, seed_dev, cur_len, max_len,
+                                                  pad_id, eos_ids, n_eos, ids, unfinished, sum_lp, n_steps);
   return check_launch("token_step");
 }
 

@@ -18,6 +18,7 @@ HBM layout (T = bf16 in fast mode, fp32 in exact mode; all row-major, rows = tok
     logits       fp32 [R, ldl]       vocabulary logits of the MASK rows (ldl = vocab rounded up to 64)
 """
 import math
+from collections import OrderedDict
 
 import torch
 
@@ -106,8 +107,8 @@ class CaptionEngine:
         self.use_cuda_graph = use_cuda_graph
         self.ldl = _round_up(cfg.vocab, 64)
         self._enc_ws = None
-        self._dec_ws = {}
-        self._graphs = {}
+        self._dec_ws = OrderedDict()           # (B, E, max_len) -> decode workspace with its captured graphs, LRU
+        self.max_decode_workspaces = 3         # e.g. SCST alternates a greedy (E = 1) and a sampling (E = 5) pass per batch
         self.attn_impl = "auto"
         self.stats = {}
 
@@ -158,13 +159,13 @@ class CaptionEngine:
         ws["ln_cls"] = self._alloc(B, H)
         ws["hid_cls"] = self._alloc(B, F)
         self._enc_ws = ws
-        self._dec_ws = {}
-        self._graphs = {}
+        self._dec_ws.clear()                   # captured graphs hold raw pointers into the old image-side workspace
         return ws
 
     def _decoder_ws(self, B, E, max_len):
         key = (B, E, max_len)
         if key in self._dec_ws:
+            self._dec_ws.move_to_end(key)
             return self._dec_ws[key]
         cfg = self.cfg
         H, F, L = cfg.hidden, cfg.inter, cfg.dec_layers
@@ -189,8 +190,11 @@ class CaptionEngine:
         ws["out_ids"] = torch.zeros(R, max_len, device=self.dev, dtype=torch.int64)
         ws["out_lp"] = torch.zeros(R, device=self.dev, dtype=f32)
         ws["ident_rows"] = torch.arange(R, device=self.dev, dtype=i32)
-        self._dec_ws = {key: ws}          # keep one decode workspace alive at a time
-        self._graphs = {}
+        ws["seed"] = torch.zeros(1, device=self.dev, dtype=torch.int64)     # sampling seed, rewritten before every replay
+        ws["graphs"] = {}                  # captured decode loops over THIS workspace; they die with it
+        self._dec_ws[key] = ws
+        while len(self._dec_ws) > self.max_decode_workspaces:
+            self._dec_ws.popitem(last=False)
         return ws
 
     def reserve(self, B, label_rows=False):
@@ -392,12 +396,13 @@ class CaptionEngine:
             ws[key] = torch.tensor(list(key[1]), device=ws["ids"].device, dtype=torch.int32)
         return ws[key]
 
-    def _maybe_graph(self, key, fn):
+    def _maybe_graph(self, ws, key, fn):
         """Runs fn() eagerly once (warm-up: lazy kernel attribute setup, descriptor cache), then captures and replays it."""
         if not self.use_cuda_graph:
             fn()
             return
-        g = self._graphs.get(key)
+        graphs = ws["graphs"]
+        g = graphs.get(key)
         if g is None:
             fn()                                         # warm-up / first execution is the real one
             torch.cuda.current_stream().synchronize()
@@ -406,7 +411,7 @@ class CaptionEngine:
             with torch.cuda.graph(g):
                 fn()
             self.stats["graph_kernels"] = ops.launch_count() - before
-            self._graphs[key] = g
+            graphs[key] = g
             return "captured_after_eager"
         g.replay()
         self.stats["graph_replays"] = self.stats.get("graph_replays", 0) + 1
@@ -440,12 +445,16 @@ class CaptionEngine:
                 if filt:
                     ops.filter_logits(ws["logits"], cfg.vocab, R, 1.0 / temperature, top_k, top_p)
                     t = 1.0
-                ops.token_step(ws["logits"], cfg.vocab, R, do_sample, t, seed, cur_len, pad, eos, ws["ids"], ws["unfinished"],
-                               ws["sum_lp"], ws["n_steps"])
+                ops.token_step(ws["logits"], cfg.vocab, R, do_sample, t, 0, cur_len, pad, eos, ws["ids"], ws["unfinished"],
+                               ws["sum_lp"], ws["n_steps"], seed_dev=ws["seed"] if do_sample else None)
             ops.greedy_finalize(ws["ids"], ws["unfinished"], ws["sum_lp"], ws["n_steps"], int(eos_ids[0]), R, ws["out_ids"],
                                 ws["out_lp"])
 
-        self._maybe_graph(("tok", B, E, max_len, do_sample, temperature, top_k, top_p, seed, bos, pad, tuple(eos_ids), mask_id,
+        if do_sample:
+            # the seed lives in device memory, outside the captured loop: one graph serves every call
+            s64 = int(seed) & 0xFFFFFFFFFFFFFFFF
+            ws["seed"].fill_(s64 - (1 << 64) if s64 >= (1 << 63) else s64)
+        self._maybe_graph(ws, ("tok", B, E, max_len, do_sample, temperature, top_k, top_p, bos, pad, tuple(eos_ids), mask_id,
                            label_flip), run)
         return ws["out_ids"].view(R, 1, max_len).clone(), ws["out_lp"].view(R, 1).clone()
 
@@ -493,5 +502,5 @@ class CaptionEngine:
                                  keep, length_penalty, pad, eos)
             ops.beam_finalize(st, B, keep, pad, int(eos_ids[0]), st["out_ids"], st["out_lp"])
 
-        self._maybe_graph(("beam", B, nb, max_len, keep, float(length_penalty), bos, pad, tuple(eos_ids), mask_id, label_flip), run)
+        self._maybe_graph(ws, ("beam", B, nb, max_len, keep, float(length_penalty), bos, pad, tuple(eos_ids), mask_id, label_flip), run)
         return st["out_ids"].clone(), st["out_lp"].clone()

@@ -43,7 +43,7 @@ SIGNATURES = {
     "vc_embed_ln": [_I, _P, _I, _I, _I, _P, _P, _P, _P, _P, _F, _P, _P, _I, _I, _P],
     "vc_decode_attention": [_I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
     "vc_decode_attention_simt": [_I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
-    "vc_token_step": [_P, _I, _I, _I, _I, _F, _U64, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P],
+    "vc_token_step": [_P, _I, _I, _I, _I, _F, _U64, _P, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P],
     "vc_greedy_finalize": [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P],
     "vc_beam_row_topk": [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P],
     "vc_beam_advance": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _D, _I, _P, _I, _P],
@@ -275,9 +275,12 @@ def decode_attention(ctx_qkv, step_qkv, anc, out, B, C, heads, E, cur_len, scale
               _stream()), "vc_decode_attention")
 
 
-def token_step(logits, V, rows, do_sample, temperature, seed, cur_len, pad_id, eos_ids, ids, unfinished, sum_lp, n_steps):
+def token_step(logits, V, rows, do_sample, temperature, seed, cur_len, pad_id, eos_ids, ids, unfinished, sum_lp, n_steps,
+               seed_dev=None):
+    """seed_dev: optional int64 CUDA tensor [1] holding the seed (read at run time; see include/vitcap_b200.h)."""
+    assert seed_dev is None or (seed_dev.dtype == torch.int64 and seed_dev.numel() == 1)
     _check(load_library().vc_token_step(_ptr(logits), logits.stride(0), rows, V, int(do_sample), float(temperature),
-                                        int(seed) & 0xFFFFFFFFFFFFFFFF, cur_len, ids.shape[1], pad_id, _ptr(eos_ids),
+                                        int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(seed_dev), cur_len, ids.shape[1], pad_id, _ptr(eos_ids),
                                         eos_ids.numel(), _ptr(ids), _ptr(unfinished), _ptr(sum_lp), _ptr(n_steps), _stream()),
            "vc_token_step")
 
