@@ -268,7 +268,7 @@ def main():
 
     def step_device():
         ids, lp = model(data_dev)
-        rec = parallel.pack_records(ids, lp, model.engine._enc_ws["tag_idx"][:B], model.engine._enc_ws["tag_prob"][:B])
+        rec = parallel.pack_records(ids, lp, *model.last_tags)
         return parallel.all_gather_records(rec)
 
     def sync_all():

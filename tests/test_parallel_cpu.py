@@ -33,14 +33,20 @@ def test_pack_unpack_roundtrip():
 
 
 class _FakeCaptioner:
-    """ids encode the image content so that ordering mistakes are visible."""
+    """ids encode the image content so that ordering mistakes are visible. ``per_image`` > 1 mimics num_return_sequences."""
+
+    def __init__(self, per_image=1):
+        self.per_image = per_image
+        self.last_tags = None
 
     def __call__(self, data):
         img = data["image"]
         B = img.shape[0]
         tag = img.view(B, -1)[:, 0].long()
-        ids = tag.view(B, 1, 1).repeat(1, 1, 20)
-        lp = -tag.float().view(B, 1)
+        self.last_tags = ((tag.view(B, 1) * 10 + torch.arange(3)).to(torch.int32), tag.float().view(B, 1).repeat(1, 3) / 64)
+        tag = tag.repeat_interleave(self.per_image)
+        ids = tag.view(-1, 1, 1).repeat(1, 1, 20)
+        lp = -tag.float().view(-1, 1)
         return ids, lp
 
 
@@ -52,6 +58,13 @@ def _worker(rank, world, port, n_items, q):
         image = torch.arange(n_items).float().view(n_items, 1, 1, 1).repeat(1, 3, 2, 2)
         dp = parallel.DataParallelCaptioner(_FakeCaptioner())
         ids, lp = dp({"image": image, "key": list(range(n_items))})
+        # the same with the concept top-k riding along and two returned sequences per image
+        dp2 = parallel.DataParallelCaptioner(_FakeCaptioner(per_image=2), with_tags=True)
+        ids2, lp2, tidx, tprob = dp2({"image": image, "key": list(range(n_items))})
+        want = torch.arange(n_items).repeat_interleave(2)
+        assert ids2[:, 0, 0].tolist() == want.tolist() and tuple(ids2.shape) == (2 * n_items, 1, 20)
+        assert torch.equal(tidx, want.view(-1, 1) * 10 + torch.arange(3)) and tidx.dtype == torch.int64
+        assert torch.equal(tprob, want.float().view(-1, 1).repeat(1, 3) / 64)
         q.put((rank, ids[:, 0, 0].tolist(), lp[:, 0].tolist()))
     finally:
         dist.destroy_process_group()

@@ -235,8 +235,10 @@ class FastImageCaptioning(nn.Module):
         self.sample_seed = sample_seed
         self.u8_channel_order = "bgr"       # what cv2 / the reference's TSV image decoder deliver (BGR2RGB is then fused)
         self._engine = None
+        self.last_tags = None               # (topk idx int32 (B,K), prob fp32 (B,K)) of the most recent forward(), device tensors
         self._sample_calls = 0
         self._label_flip_hold = None        # None: decide per generate() call; False: forward() in progress, not decided yet
+        self._tag_parts = None              # list while forward() runs: per-chunk concept top-k collected by _generate
         self.register_load_state_dict_post_hook(lambda m, keys: m._invalidate())
         self.eval()
 
@@ -313,6 +315,7 @@ class FastImageCaptioning(nn.Module):
         eng = self.engine
         B = img_feats.shape[0]
         outs_i, outs_l = [], []
+        tags = self._tag_parts
         hold = self._label_flip_hold           # an int once forward() has decided it for a caller batch fed in several chunks
         flip = None if (hold is None or hold is False) else hold
         if do_sample:
@@ -325,7 +328,9 @@ class FastImageCaptioning(nn.Module):
             if n_label is not None:
                 eng.reserve(b, label_rows=True)    # before encode(): growing the workspace later would drop its outputs
             eng.encode(chunk)
-            _, _, _, tag_len = eng.tag_head(b)
+            _, tag_idx, tag_prob, tag_len = eng.tag_head(b)
+            if tags is not None:               # the concept head's top-k of this chunk (the workspace is reused by the next)
+                tags.append((tag_idx.clone(), tag_prob.clone()))
             if n_label is None:
                 eng.prefill(b)
             else:
@@ -362,6 +367,7 @@ class FastImageCaptioning(nn.Module):
         extra = dict(self.test_extra_input)
         ids_all, lp_all = [], []
         self._label_flip_hold = False              # the label recipe follows the first sample of the WHOLE batch (see _generate)
+        self._tag_parts = []
         try:
             for s in range(0, B, self.max_batch):      # the image stream buffer holds max_batch images
                 sub = {k: (v[s:s + self.max_batch] if torch.is_tensor(v) and v.shape[:1] == (B,) else v) for k, v in data.items()}
@@ -373,6 +379,8 @@ class FastImageCaptioning(nn.Module):
                 lp_all.append(lp)
         finally:
             self._label_flip_hold = None
+            parts, self._tag_parts = self._tag_parts, None
+        self.last_tags = (torch.cat([p[0] for p in parts], 0), torch.cat([p[1] for p in parts], 0)) if parts else None
         return torch.cat(ids_all, 0), torch.cat(lp_all, 0)
 
     @torch.no_grad()

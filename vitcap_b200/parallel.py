@@ -66,7 +66,8 @@ def gather_in_dataset_order(rec, n_items, group=None):
 
 
 class DataParallelCaptioner:
-    """Runs a FastImageCaptioning replica on this rank's shard and returns the gathered results of the whole batch."""
+    """Runs a FastImageCaptioning replica on this rank's shard and returns the gathered results of the whole batch:
+    (ids, logprobs), plus (tag_idx, tag_prob) of the concept head when ``with_tags`` is set."""
 
     def __init__(self, model, group=None, with_tags=False):
         self.model = model
@@ -85,6 +86,12 @@ class DataParallelCaptioner:
             sub["key"] = [data["key"][i] for i in idx]
         ids, lp = self.model(sub)
         keep, max_len = ids.shape[1], ids.shape[2]
-        rec = pack_records(ids, lp)
-        full = gather_in_dataset_order(rec, n * (ids.shape[0] // len(idx)), self.group)
-        return unpack_records(full, keep, max_len)
+        per_image = ids.shape[0] // len(idx)             # num_return_sequences rows per image
+        tags = getattr(self.model, "last_tags", None) if self.with_tags else None
+        if tags is not None:
+            # one record row per returned sequence: repeat the image's concept top-k for each of its sequences
+            rec = pack_records(ids, lp, tags[0].repeat_interleave(per_image, 0), tags[1].repeat_interleave(per_image, 0))
+        else:
+            rec = pack_records(ids, lp)
+        full = gather_in_dataset_order(rec, n * per_image, self.group)
+        return unpack_records(full, keep, max_len, tags[0].shape[1] if tags is not None else None)

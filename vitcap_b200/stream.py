@@ -55,11 +55,13 @@ class OverlappedCaptioner:
         cur = torch.cuda.current_stream(self.device)
         cur.wait_event(ready)
         ids, lp = self.model(dev_batch)
-        B = ids.shape[0]
         keep, max_len = ids.shape[1], ids.shape[2]
-        eng = self.model.engine
         if self.with_tags:
-            rec = parallel.pack_records(ids, lp, eng._enc_ws["tag_idx"][:B], eng._enc_ws["tag_prob"][:B])
+            tag_idx, tag_prob = self.model.last_tags
+            per_image = ids.shape[0] // tag_idx.shape[0]          # num_return_sequences rows per image
+            if per_image > 1:
+                tag_idx, tag_prob = tag_idx.repeat_interleave(per_image, 0), tag_prob.repeat_interleave(per_image, 0)
+            rec = parallel.pack_records(ids, lp, tag_idx, tag_prob)
         else:
             rec = parallel.pack_records(ids, lp)
         full = parallel.all_gather_records(rec) if self.gather else rec
