@@ -39,6 +39,15 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-sample-images", type=int, default=4)
+    ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
+                    help="--impl reference only. cpu (the contract's reference arm): the reference algorithm on the host cores. "
+                         "cuda: the same oracle port executed by stock PyTorch library kernels (cuBLAS / ATen) on cuda:0 -- the "
+                         "'library-kernel comparator' of BASELINE.md section 4 item 5; its line says impl = reference-on-gpu")
+    ap.add_argument("--ref-dtype", default="f32", choices=["f32", "bf16"], help="with --ref-device cuda: fp32 (TF32 off) or "
+                    "torch.autocast(bfloat16)")
+    ap.add_argument("--ref-algorithm", default="faithful", choices=["faithful", "cached"],
+                    help="with --ref-device cuda: the algorithm as shipped (no KV cache) or the cached re-formulation")
+    ap.add_argument("--ref-batch", type=int, default=32, help="with --ref-device cuda: images per step")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --batch images on EVERY GPU (the contract's default); strong: --batch images in total, "
                          "split over the GPUs (SURVEY.md section 8d asks for both)")
@@ -182,11 +191,62 @@ def decode_roofline(torch, ops, cfg, B, dev, peaks):
                    "layer over distinct %0.2f GB caches, CUDA events, %d iterations" % (byt / 1e9, iters)}
 
 
+def run_reference_on_gpu(args):
+    """the reference's modules through stock PyTorch on one B200. /root/reference does not exist
+    on the GPU box, so the thing executed is oracle/port.py (pinned to the reference's outputs by tests/golden) with every
+    tensor on cuda:0: ATen / cuBLAS kernels, no kernel of this repo. A comparator line, never the product and never the
+    contract's reference arm."""
+    import contextlib
+    import torch
+    from vitcap_b200 import config as vcfg
+    from vitcap_b200 import synth
+    from oracle import port
+    cfg = vcfg.variant(args.variant, dec_layers=args.dec_layers)
+    sd = synth.make_state_dict(cfg, seed=0)
+    extra = synth.default_test_extra_input(cfg)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    B = args.ref_batch
+    data = {k: v.to("cuda:0") for k, v in synth.make_text_inputs(cfg, B).items()}
+    data["image"] = synth.make_images(cfg, B, seed=1234).to("cuda:0")
+    pm = port.PortModel(cfg, {k: v.to("cuda:0") for k, v in sd.items()})
+    torch.set_default_device("cuda:0")          # the port creates its masks / position ids with bare factory calls
+    ctx = (lambda: torch.autocast("cuda", dtype=torch.bfloat16)) if args.ref_dtype == "bf16" else contextlib.nullcontext
+
+    def step():
+        with torch.no_grad(), ctx():
+            return port.caption(pm, data, extra, algorithm=args.ref_algorithm)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    wl = workload_config(args, cfg)
+    wl.update(batch_per_gpu=B, global_batch=B,
+              workload="library-kernel comparator: oracle/port.py '%s' algorithm (%s) executed by stock PyTorch on cuda:0, "
+                       "%s, batch %d, ViT-B/16-%d, %d-layer decoder, greedy 20 tokens"
+                       % (args.ref_algorithm, "the reference as shipped: every decode step re-runs the whole model"
+                          if args.ref_algorithm == "faithful" else "trunk once, K/V cached, two rows per step",
+                          "fp32, TF32 off" if args.ref_dtype == "f32" else "torch.autocast(bfloat16)", B, cfg.img_size,
+                          cfg.dec_layers))
+    print(json.dumps({"impl": "reference-on-gpu", "metric": METRIC, "value": B / ms * 1e3, "unit": UNIT, "n_gpus": 1,
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                      "dtype": args.ref_dtype, "data": "synthetic", "config": wl, "gpu_launches": 0}), flush=True)
+
+
 def run_reference_arm(args):
     import torch
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.ref_device == "cuda":
+        return run_reference_on_gpu(args)
     from vitcap_b200 import config as vcfg
     from vitcap_b200 import synth
     from oracle import port
