@@ -211,15 +211,21 @@ class CaptionEngine:
         ops.layernorm(x, g, b, eps, out_t=out_t, out_f=out_f, rows=rows)
         return out_t
 
-    def _vit_block(self, p, x, rows, B, N, ws):
-        """Pre-LN ViT block on the fp32 stream x (in place). vision_transformer.py:233-250."""
+    def _vit_block(self, p, x, rows, B, N, ws, out=None):
+        """Pre-LN ViT block on the fp32 stream x (in place). vision_transformer.py:233-250.
+        out: another stream buffer that receives the block's result while x stays untouched (the fork of the split encoder:
+        the first concept block reads the shared trunk's output and starts its own stream without a copy)."""
         cfg = self.cfg
         H = cfg.hidden
         ln, qkv, att, hid = ws["ln"][:rows], ws["qkv"][:rows], ws["att"][:rows], ws["hid"][:rows]
         h = self._ln(x, p["n1w"], p["n1b"], cfg.vit_ln_eps, ln, rows=rows)
         ops.linear(h, p["qkv_w"], p["qkv_b"], qkv, M=rows)
         ops.attention(qkv, att, B, N, cfg.heads, cfg.head_dim ** -0.5, impl=self.attn_impl)
-        ops.linear(att, p["proj_w"], p["proj_b"], x, resid=x, M=rows)
+        if out is not None:
+            ops.linear(att, p["proj_w"], p["proj_b"], out, resid=x, M=rows)
+            x = out
+        else:
+            ops.linear(att, p["proj_w"], p["proj_b"], x, resid=x, M=rows)
         h = self._ln(x, p["n2w"], p["n2b"], cfg.vit_ln_eps, ln, rows=rows)
         ops.linear(h, p["fc1_w"], p["fc1_b"], hid, act=ops.ACT_GELU, M=rows)
         ops.linear(hid, p["fc2_w"], p["fc2_b"], x, resid=x, M=rows)
@@ -276,15 +282,25 @@ class CaptionEngine:
         split_at = cfg.enc_blocks - cfg.split_blocks
         for i in range(split_at):
             self._vit_block(w.blocks[i], x, rows, B, N, ws)
-        xt.copy_(x)                                    # fork: both branches start from the block-8 input
+        # fork: both branches start from the block-8 input (modeling_bert.py:464-474). The concept branch runs first; its first
+        # block reads x and writes xt, so the 0.9 GB stream is never copied
+        forked = False
+        for j in range(cfg.split_blocks):
+            if j == cfg.split_blocks - 1 and not full_tag_feats:
+                if not forked:
+                    xt.copy_(x)
+                    forked = True
+                self._vit_block_cls_only(w.tag_blocks[j], xt, rows, B, N, ws)
+            elif not forked:
+                self._vit_block(w.tag_blocks[j], x, rows, B, N, ws, out=xt)
+                forked = True
+            else:
+                self._vit_block(w.tag_blocks[j], xt, rows, B, N, ws)
+        if not forked:
+            xt.copy_(x)
         if caption_branch:
             for i in range(split_at, cfg.enc_blocks):
                 self._vit_block(w.blocks[i], x, rows, B, N, ws)
-        for j in range(cfg.split_blocks):
-            if j == cfg.split_blocks - 1 and not full_tag_feats:
-                self._vit_block_cls_only(w.tag_blocks[j], xt, rows, B, N, ws)
-            else:
-                self._vit_block(w.tag_blocks[j], xt, rows, B, N, ws)
         return x.view(B, N, H), xt.view(B, N, H)
 
     def _head(self, hp, a_t, rows, th_f, th_t, logits):
