@@ -39,6 +39,12 @@ int vc_abi_version(void);
 /* number of kernels launched through this library since the last vc_reset_launch_count() (bench.py gpu_launches) */
 long long vc_launch_count(void);
 void vc_reset_launch_count(void);
+/* programmatic dependent launch between consecutive kernels of this library (griddepcontrol: launch latency and prologue of
+ * kernel i+1 hide under kernel i; every kernel waits for its predecessor's completion before touching global memory).
+ * mode 0 = never, 1 = launches captured into a CUDA graph only (default: the decode loop), 2 = every launch; environment
+ * VITCAP_PDL presets it; takes effect for launches (and graph captures) made afterwards. */
+void vc_set_pdl(int mode);
+int vc_get_pdl(void);
 
 /* out[M,N] = act(A[M,K] * W[N,K]^T + bias[N]) (+ resid[M,N]);  replaces torch.nn.functional.linear behind
  *   vision_transformer.py:152-158 (Mlp fc1/fc2), :169-201 (Attention qkv/proj), :267-275 (PatchEmbed conv as GEMM),
@@ -50,7 +56,9 @@ void vc_reset_launch_count(void);
  * out_f32: output element type (1 = fp32, 0 = bf16 in fast mode / fp32 in exact mode is selected by the caller).
  * bias may be NULL; resid (fp32, pitch ldr) may be NULL and may alias out when out_f32 = 1.
  * bf16=1 stores tiles with TMA, which clips at 16-byte granularity: if N * sizeof(out element) is not a multiple of 16,
- * the pad columns up to the next 16-byte boundary of each row (< ldo) are overwritten. */
+ * the pad columns up to the next 16-byte boundary of each row (< ldo) are overwritten.
+ * bf16=1 treats W as a weight: its first tiles are fetched before the kernel waits for its predecessor in the stream, so with
+ * programmatic dependent launch active (vc_set_pdl) W must not be written by the kernel launched immediately before. */
 int vc_linear(int bf16, const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldo, int out_f32,
               int act, const float* resid, int ldr, int M, int N, int K, void* stream);
 /* same contract, forcing the CUDA-core kernel for bf16 operands (cross-check of the tensor-core kernel in tests) */

@@ -238,3 +238,68 @@ def test_alternating_search_modes_keep_their_workspaces_and_graphs():
     assert torch.equal(outs["s"][2][0], outs["s"][0][0]) and torch.equal(outs["s"][2][1], outs["s"][0][1])
     assert not torch.equal(outs["s"][1][0], outs["s"][0][0])
     assert tuple(outs["s"][0][0].shape) == (B * 5, 1, cfg.max_seq_a)
+
+
+@pytest.mark.parametrize("mode", ["bf16", "fp32"])
+def test_programmatic_dependent_launch_does_not_change_results(mode):
+    """Every kernel of the path is launched with programmatic stream serialization and waits (griddepcontrol.wait) for its
+    predecessor before touching global memory: greedy, beam and sampling results -- eager first call and CUDA-graph replays --
+    must be bit-identical with the attribute off (ordinary stream order)."""
+    from vitcap_b200 import ops
+    cfg = vcfg.tiny()
+    sd = synth.make_state_dict(cfg, seed=3, eos_bias=1.0)
+    B = 5
+    data = synth.make_text_inputs(cfg, B)
+    data["image"] = synth.make_images(cfg, B, seed=4)
+    runs = {}
+    default = ops.get_pdl()
+    assert default == 1
+    try:
+        for pdl in (2, 1, 0):
+            ops.set_pdl(pdl)
+            outs = []
+            for kw in ({}, dict(num_beams=3, num_keep_best=2), dict(do_sample=True, num_return_sequences=4)):
+                m = build(cfg, sd, synth.default_test_extra_input(cfg, **kw), mode, max_batch=8)
+                m.sample_seed = 5
+                for rep in range(3):                   # eager + capture, then two replays
+                    m._sample_calls = 0
+                    ids, lp = m(to_dev(data))
+                    outs.append((ids.cpu(), lp.cpu()))
+                lg, idx, pr, n = m.forward_tags(data["image"].to(DEV))
+                outs.append((idx.cpu(), lg.cpu()))
+            runs[pdl] = outs
+    finally:
+        ops.set_pdl(default)
+    assert len(runs[0]) == len(runs[1]) == len(runs[2]) == 12
+    for k in (1, 2):
+        for (a0, a1), (b0, b1) in zip(runs[k], runs[0]):
+            assert torch.equal(a0, b0) and torch.equal(a1, b1)
+
+
+@pytest.mark.parametrize("kw", [{}, dict(num_beams=3, num_keep_best=2)])
+def test_whole_forward_graph_matches_eager_path(kw):
+    """graph_forward=True (small-batch serving): the whole forward of a batch shape is captured once and replayed with new
+    images copied into its input buffer; ids, log-probs and the concept top-k must equal the eager path's bit for bit, for
+    every new image batch, and a different batch size gets its own graph."""
+    cfg = vcfg.tiny()
+    sd = synth.make_state_dict(cfg, seed=3, eos_bias=1.0)
+    extra = synth.default_test_extra_input(cfg, **kw)
+    ref = build(cfg, sd, extra, "bf16", max_batch=8)
+    fast = build(cfg, sd, extra, "bf16", max_batch=8, graph_forward=True)
+    for rnd, (B, seed) in enumerate([(2, 1), (2, 2), (2, 3), (5, 4), (2, 5), (5, 6)]):
+        data = synth.make_text_inputs(cfg, B)
+        data["image"] = synth.make_images(cfg, B, seed=seed)
+        d = to_dev(data)
+        i0, l0 = ref(d)
+        t0 = ref.last_tags
+        i1, l1 = fast(d)
+        t1 = fast.last_tags
+        assert torch.equal(i0, i1) and torch.equal(l0, l1), rnd
+        assert torch.equal(t0[0], t1[0]) and torch.equal(t0[1], t1[1]), rnd
+    eng = fast.engine
+    assert len(eng.forward_graphs) == 2                       # one per batch shape
+    assert eng.stats.get("forward_graph_replays", 0) == 4     # first call of each shape is eager (+ capture)
+    # sampling and label-region calls fall back to the eager path
+    fast.test_extra_input = synth.default_test_extra_input(cfg, do_sample=True)
+    fast(d)
+    assert eng.stats.get("forward_graph_replays", 0) == 4

@@ -121,6 +121,33 @@ def stage_probe(B, variant="16_384"):
     return t
 
 
+def pdl_probe(B, variant="16_384"):
+    """A/B of programmatic dependent launch (ops.set_pdl) in one process, alternating, same model and inputs."""
+    cfg = vcfg.variant(variant)
+    sd = synth.make_state_dict(cfg, seed=0)
+    m = FastImageCaptioning(cfg, mode="bf16", max_batch=B)
+    m.load_state_dict(sd)
+    m = m.to(dev)
+    eng = m.engine
+    data = {k: v.to(dev) for k, v in synth.make_text_inputs(cfg, B).items()}
+    data["image"] = synth.make_images(cfg, B, seed=1).to(dev)
+    for rnd in range(2):
+        for pdl in (2, 1, 0):
+            ops.set_pdl(pdl)
+            eng._dec_ws.clear()                      # captured decode loops keep the setting they were captured with
+            m(data)
+            m(data)
+            torch.cuda.synchronize()
+            f = eng.patch_embed(data["image"])
+            t_enc = timeit(lambda: eng.encode(f), iters=3, warm=1)
+            t_pre = timeit(lambda: eng.prefill(B), iters=3, warm=1)
+            t_dec = timeit(lambda: eng.greedy_or_sample(B, 1, 20, 101, 0, [102], 103), iters=5, warm=1)
+            t_all = timeit(lambda: m(data), iters=5, warm=1)
+            print("pdl=%d round %d: encode %.2f  prefill %.2f  decode(graph) %.2f  full forward %.2f ms  (%.1f images/s)"
+                  % (pdl, rnd, t_enc, t_pre, t_dec, t_all, B / t_all * 1e3), flush=True)
+    ops.set_pdl(1)
+
+
 if __name__ == "__main__":
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 512
     what = sys.argv[2] if len(sys.argv) > 2 else "all"
@@ -135,3 +162,5 @@ if __name__ == "__main__":
         decode_attn_probe(min(B, 256), E=4)
     if what in ("all", "stage"):
         stage_probe(B)
+    if what == "pdl":
+        pdl_probe(B)

@@ -129,6 +129,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();                        // programmatic dependent launch: global memory from here on
 
   if (warp == 0) {
     // ===================== TMA loader (one elected thread): never on the MMA critical path =====================
@@ -427,7 +429,7 @@ static int launch_attention(dim3 grid, const CUtensorMap& tq, const CUtensorMap&
     if (e != cudaSuccess) { set_last_error("attention_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return VC_ERR_LAUNCH; }
     configured = true;
   }
-  kern<<<grid, 192, SMEM_TOTAL, s>>>(tq, tkv, out, N, H, scale_log2, n_base, n_extra);
+  launch_pdl(kern, grid, dim3(192), SMEM_TOTAL, s, tq, tkv, out, N, H, scale_log2, n_base, n_extra);
   return check_launch("attention_tc");
 }
 

@@ -63,9 +63,11 @@ static std::atomic<long long> g_launches{0};
 extern "C" {
 
 const char* vc_last_error(void) { return vc::last_error(); }
-int vc_abi_version(void) { return 3; }
+int vc_abi_version(void) { return 4; }
 long long vc_launch_count(void) { return g_launches.load(); }
 void vc_reset_launch_count(void) { g_launches = 0; }
+void vc_set_pdl(int mode) { vc::set_pdl_mode(mode); }
+int vc_get_pdl(void) { return vc::pdl_mode(); }
 
 int vc_linear(int bf16, const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldo, int out_f32, int act,
               const float* resid, int ldr, int M, int N, int K, void* stream) {

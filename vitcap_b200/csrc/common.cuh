@@ -23,6 +23,45 @@ void set_last_error(const char* fmt, ...);
 int check_launch(const char* what);
 
 // ------------------------------------------------------------------------------------------
+// programmatic dependent launch (PDL): a kernel launched through launch_pdl() may be scheduled while its predecessor in the
+// stream is still running (as soon as every CTA of the predecessor executed pdl_launch_dependents() or exited); it must
+// execute pdl_wait() -- which returns once the predecessor has COMPLETED and its writes are visible -- before its first
+// access to global memory. Launch latency and the prologue (barrier init, TMEM allocation, descriptor prefetch) of kernel
+// i+1 then hide under kernel i, which matters for the 19-step decode loop (33 short kernels per step inside one CUDA graph).
+// Both instructions are no-ops in a kernel launched the ordinary way.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// Policy (runtime.cu; environment VITCAP_PDL or vc_set_pdl): 0 = never, 1 = only for launches that are being captured into a
+// CUDA graph (the decode loop: measured 19.1 -> 18.3 ms per 19 steps at B = 512), 2 = every launch. Default 1: on the long
+// eager kernels of the encoder the early-resident, waiting CTAs of the next kernel cost more than the hidden launch latency
+// (measured: encoder 81.3 -> 84.0 ms with mode 2).
+int pdl_mode();
+void set_pdl_mode(int mode);
+
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  const int mode = pdl_mode();
+  bool on = (mode == 2);
+  if (mode == 1) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    on = (cudaStreamIsCapturing(stream, &st) == cudaSuccess && st == cudaStreamCaptureStatusActive);
+  }
+  cfg.numAttrs = on ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);          // errors are picked up by check_launch()
+}
+
+// ------------------------------------------------------------------------------------------
 // small device utilities
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -154,6 +193,11 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+// warm L2 with a tile (no shared-memory destination, no completion tracking)
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* m, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
   asm volatile(

@@ -77,6 +77,8 @@ decode_attention_mma_kernel(const bf16* __restrict__ ctx_qkv, const bf16* __rest
   const int e0 = (blockIdx.y % groups) * MAX_SEQ;
   const int EC = min(MAX_SEQ, E - e0);           // sequences handled by this CTA
   // context rows of an image: Cs allocated, the first C visible (label-region masks hide a per-image tail, dataset.py:405-408)
+  pdl_launch_dependents();
+  pdl_wait();                                    // programmatic dependent launch: global memory from here on
   const int C = ctx_vis ? ctx_vis[b] : Cs;
   const size_t ld = 3 * (size_t)H;
   const int step = cur_len - 1;
@@ -317,11 +319,11 @@ int decode_attention_mma(const void* ctx_qkv, const void* step_qkv, const int* a
   const float scale_log2 = scale * 1.4426950408889634f;
   const dim3 grid(heads, B * groups);
   if (E > 4)
-    decode_attention_mma_kernel<true><<<grid, 128, SMEM_BYTES, s>>>((const bf16*)ctx_qkv, (const bf16*)step_qkv, anc, (bf16*)out, C,
-                                                                   ctx_vis, H, R, E, cur_len, scale_log2);
+    launch_pdl(decode_attention_mma_kernel<true>, grid, dim3(128), SMEM_BYTES, s, (const bf16*)ctx_qkv, (const bf16*)step_qkv, anc,
+               (bf16*)out, C, ctx_vis, H, R, E, cur_len, scale_log2);
   else
-    decode_attention_mma_kernel<false><<<grid, 128, SMEM_BYTES, s>>>((const bf16*)ctx_qkv, (const bf16*)step_qkv, anc, (bf16*)out, C,
-                                                                    ctx_vis, H, R, E, cur_len, scale_log2);
+    launch_pdl(decode_attention_mma_kernel<false>, grid, dim3(128), SMEM_BYTES, s, (const bf16*)ctx_qkv, (const bf16*)step_qkv, anc,
+               (bf16*)out, C, ctx_vis, H, R, E, cur_len, scale_log2);
   return check_launch("decode_attention_mma");
 }
 

@@ -129,6 +129,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ in, int ld_in, const float* __restrict__ gamma, const float* __restrict__ beta,
                  float eps, T* __restrict__ out_t, int ld_t, float* __restrict__ out_f, int ld_f, int rows, int H) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
@@ -178,8 +180,8 @@ int layernorm(int out_bf16, const float* in, int ld_in, const float* gamma, cons
     return VC_ERR_BAD_ARG;
   }
   const int blocks = (rows + 7) / 8;
-  if (out_bf16) layernorm_kernel<bf16><<<blocks, 256, 0, s>>>(in, ld_in, gamma, beta, eps, (bf16*)out_t, ld_t, out_f, ld_f, rows, H);
-  else layernorm_kernel<float><<<blocks, 256, 0, s>>>(in, ld_in, gamma, beta, eps, (float*)out_t, ld_t, out_f, ld_f, rows, H);
+  if (out_bf16) launch_pdl(layernorm_kernel<bf16>, dim3(blocks), dim3(256), 0, s, in, ld_in, gamma, beta, eps, (bf16*)out_t, ld_t, out_f, ld_f, rows, H);
+  else launch_pdl(layernorm_kernel<float>, dim3(blocks), dim3(256), 0, s, in, ld_in, gamma, beta, eps, (float*)out_t, ld_t, out_f, ld_f, rows, H);
   return check_launch("layernorm");
 }
 
@@ -253,6 +255,8 @@ __global__ void __launch_bounds__(256)
 embed_ln_kernel(const int* __restrict__ ids, int max_len, int cur_len, int mask_id, const float* __restrict__ word,
                 const float* __restrict__ pos, const float* __restrict__ type0, const float* __restrict__ gamma,
                 const float* __restrict__ beta, float eps, float* __restrict__ out_f, T* __restrict__ out_t, int R, int H) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= 2 * R) return;
@@ -302,8 +306,8 @@ int embed_ln(int out_bf16, const int* ids, int max_len, int cur_len, int mask_id
              cudaStream_t s) {
   if (H % 128 || H > 1024 || cur_len < 1 || cur_len >= max_len) { set_last_error("embed_ln: bad args"); return VC_ERR_BAD_ARG; }
   const int blocks = (2 * R + 7) / 8;
-  if (out_bf16) embed_ln_kernel<bf16><<<blocks, 256, 0, s>>>(ids, max_len, cur_len, mask_id, word, pos, type0, gamma, beta, eps, out_f, (bf16*)out_t, R, H);
-  else embed_ln_kernel<float><<<blocks, 256, 0, s>>>(ids, max_len, cur_len, mask_id, word, pos, type0, gamma, beta, eps, out_f, (float*)out_t, R, H);
+  if (out_bf16) launch_pdl(embed_ln_kernel<bf16>, dim3(blocks), dim3(256), 0, s, ids, max_len, cur_len, mask_id, word, pos, type0, gamma, beta, eps, out_f, (bf16*)out_t, R, H);
+  else launch_pdl(embed_ln_kernel<float>, dim3(blocks), dim3(256), 0, s, ids, max_len, cur_len, mask_id, word, pos, type0, gamma, beta, eps, out_f, (float*)out_t, R, H);
   return check_launch("embed_ln");
 }
 

@@ -23,7 +23,9 @@ template <int BN, bool OUT_F32, bool RESID> struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;           // 16 KB
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int NBUF = RESID ? 4 : 2;            // epilogue staging tiles (128 rows x 128 B)
+  // epilogue staging tiles (128 rows x 128 B); the residual tile of chunk g + NBUF - 2 is prefetched by TMA while chunk g is
+  // processed (8 tiles with a 128-wide N tile were measured slower for the K = 768 residual GEMM: 0.51 vs 0.43 ms)
+  static constexpr int NBUF = RESID ? 4 : 2;
   static constexpr int EPI_BYTES = 16384;
   static constexpr int BUDGET = 227 * 1024 - 1024 /*align slack*/ - 512 /*barriers*/ - NBUF * EPI_BYTES;
   static constexpr int STAGES_MAX = BUDGET / STAGE_BYTES;
@@ -79,22 +81,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();      // the next kernel's prologue may start; it blocks in its own pdl_wait() until this grid is done
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
+      // W is a weight matrix: never written by the preceding kernel, so its tiles of this CTA's first output tile are
+      // requested BEFORE the dependency wait (the first STAGES k-blocks into their pipeline stages, the rest into L2) and
+      // travel while the predecessor is still running; the activations follow after the wait.
+      int pre = 0;
+      if ((int)blockIdx.x < num_tiles) {
+        const int n0 = ((int)blockIdx.x % n_tiles) * BN;
+        pre = num_kb < C::STAGES ? num_kb : C::STAGES;
+        for (int kb = 0; kb < pre; ++kb) {
+          mbar_arrive_expect_tx(&full_bar[kb], C::STAGE_BYTES);
+          tma_load_2d(smem + kb * C::STAGE_BYTES + C::A_BYTES, &tmap_b, &full_bar[kb], kb * C::BK, n0);
+        }
+        for (int kb = pre; kb < num_kb; ++kb) tma_prefetch_l2_2d(&tmap_b, kb * C::BK, n0);
+      }
+      pdl_wait();
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m0 = (tile / n_tiles) * C::BM;
         const int n0 = (tile % n_tiles) * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + C::A_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
-          tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * C::BK, m0);
-          tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * C::BK, n0);
+          if (pre > 0) {                      // stage armed and its W half already in flight (fresh barriers: nothing to wait for)
+            --pre;
+            tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * C::BK, m0);
+          } else {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+            tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * C::BK, m0);
+            tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * C::BK, n0);
+          }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -102,6 +124,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
+      pdl_wait();
       constexpr uint32_t idesc = make_idesc_bf16(C::BM, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -142,6 +165,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // residual prefetch cursor (leader only): chunk index pf_g, its tile and chunk-in-tile
     uint32_t pf_g = 0;
     int pf_tile = blockIdx.x, pf_c = 0;
+    pdl_wait();                               // programmatic dependent launch: global memory (residual, bias, output) from here on
     auto prefetch_resid = [&]() {
       if (pf_tile >= num_tiles) return;
       const int pm0 = (pf_tile / n_tiles) * C::BM;
@@ -289,7 +313,7 @@ static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const CUtens
   }
   const int tiles = ((M + C::BM - 1) / C::BM) * ((N + BN - 1) / BN);
   int grid = tiles < sm_count() ? tiles : sm_count();
-  kern<<<grid, 192, C::SMEM_BYTES, stream>>>(ta, tb, to, tr, bias, M, N, K);
+  launch_pdl(kern, dim3(grid), dim3(192), C::SMEM_BYTES, stream, ta, tb, to, tr, bias, M, N, K);
   return check_launch("gemm_tc");
 }
 

@@ -151,6 +151,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   cluster_sync_all();                                   // barriers of both CTAs initialised, TMEM allocated in both
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();                                           // programmatic dependent launch: global memory from here on
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs: own A rows, own half of the W tile) =====================
@@ -337,7 +339,7 @@ static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
   const int tiles = ((M + 2 * C::BM - 1) / (2 * C::BM)) * ((N + C::BN - 1) / C::BN);
   int clusters = sm_count() / 2;
   if (tiles < clusters) clusters = tiles;
-  kern<<<2 * clusters, C::THREADS, C::SMEM_BYTES, stream>>>(ta, tb, to, tr, bias, M, N, K);
+  launch_pdl(kern, dim3(2 * clusters), dim3(C::THREADS), C::SMEM_BYTES, stream, ta, tb, to, tr, bias, M, N, K);
   return check_launch("gemm_tc2");
 }
 

@@ -5,6 +5,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <unordered_map>
@@ -29,6 +30,16 @@ int check_launch(const char* what) {
   }
   return VC_OK;
 }
+
+static int g_pdl = -1;
+int pdl_mode() {
+  if (g_pdl < 0) {
+    const char* e = getenv("VITCAP_PDL");
+    g_pdl = (e != nullptr && e[0] >= '0' && e[0] <= '2') ? (e[0] - '0') : 1;
+  }
+  return g_pdl;
+}
+void set_pdl_mode(int mode) { g_pdl = mode < 0 ? 0 : (mode > 2 ? 2 : mode); }
 
 int sm_count() {
   static int n = 0;

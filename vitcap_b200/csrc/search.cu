@@ -228,6 +228,8 @@ token_step_kernel(const float* __restrict__ logits, int ld, int V, int do_sample
   __shared__ float bv[8], bm[8], bs[8];
   __shared__ int bi[8];
   __shared__ float s_max;
+  pdl_launch_dependents();
+  pdl_wait();                   // programmatic dependent launch: global memory from here on
   const int r = blockIdx.x, tid = threadIdx.x;
   const float* row = logits + (size_t)r * ld;
   const float it = do_sample ? inv_temp : 1.f;
@@ -316,11 +318,11 @@ int token_step(const float* logits, int ld, int rows, int V, int do_sample, floa
   }
   const bool vec = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(logits) & 15) == 0);
   if (vec)
-    token_step_kernel<true><<<rows, 256, 0, s>>>(logits, ld, V, do_sample, 1.f / temperature, seed, seed_dev, cur_len, max_len,
-                                                 pad_id, eos_ids, n_eos, ids, unfinished, sum_lp, n_steps);
+    launch_pdl(token_step_kernel<true>, dim3(rows), dim3(256), 0, s, logits, ld, V, do_sample, 1.f / temperature, seed, seed_dev,
+               cur_len, max_len, pad_id, eos_ids, n_eos, ids, unfinished, sum_lp, n_steps);
   else
-    token_step_kernel<false><<<rows, 256, 0, s>>>(logits, ld, V, do_sample, 1.f / temperature, seed, seed_dev, cur_len, max_len,
-                                                  pad_id, eos_ids, n_eos, ids, unfinished, sum_lp, n_steps);
+    launch_pdl(token_step_kernel<false>, dim3(rows), dim3(256), 0, s, logits, ld, V, do_sample, 1.f / temperature, seed, seed_dev,
+               cur_len, max_len, pad_id, eos_ids, n_eos, ids, unfinished, sum_lp, n_steps);
   return check_launch("token_step");
 }
 
@@ -355,6 +357,8 @@ beam_row_topk_kernel(const float* __restrict__ logits, int ld, int V, int K, flo
   __shared__ LseSmem lse;
   __shared__ float vals[64];
   __shared__ int idxs[64];
+  pdl_launch_dependents();
+  pdl_wait();                   // programmatic dependent launch: global memory from here on
   const float* row = logits + (size_t)blockIdx.x * ld;
   block_lse(row, V, 1.f, lse);
   block_topk(row, V, K, sm, vals, idxs);
@@ -368,7 +372,7 @@ beam_row_topk_kernel(const float* __restrict__ logits, int ld, int V, int K, flo
 int beam_row_topk(const float* logits, int ld, int rows, int V, int K, float* cand_val, int* cand_idx, float* row_max,
                   float* row_logsum, cudaStream_t s) {
   if (K < 1 || K > 64 || K > V) { set_last_error("beam_row_topk: need K <= 64"); return VC_ERR_BAD_ARG; }
-  beam_row_topk_kernel<<<rows, 256, 0, s>>>(logits, ld, V, K, cand_val, cand_idx, row_max, row_logsum);
+  launch_pdl(beam_row_topk_kernel, dim3(rows), dim3(256), 0, s, logits, ld, V, K, cand_val, cand_idx, row_max, row_logsum);
   return check_launch("beam_row_topk");
 }
 
@@ -396,6 +400,8 @@ __global__ void beam_advance_kernel(BeamState st, const float* __restrict__ cand
                                     const float* __restrict__ row_max, const float* __restrict__ row_logsum, int B, int nb, int V,
                                     int cur_len, int max_len, int keep, double length_penalty, int pad_id,
                                     const int* __restrict__ eos_ids, int n_eos) {
+  pdl_launch_dependents();
+  pdl_wait();                   // programmatic dependent launch: global memory from here on
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const int R = B * nb, K = 2 * nb, step = cur_len - 1;
@@ -513,8 +519,8 @@ int beam_advance(int* ids, float* beam_scores, int* done, int* anc, double* hyp_
     return VC_ERR_BAD_ARG;
   }
   BeamState st = {ids, beam_scores, done, anc, hyp_score, hyp_len, hyp_ids, hyp_count, worst};
-  beam_advance_kernel<<<(B + 31) / 32, 32, 0, s>>>(st, cand_val, cand_idx, row_max, row_logsum, B, nb, V, cur_len, max_len, keep,
-                                                   length_penalty, pad_id, eos_ids, n_eos);
+  launch_pdl(beam_advance_kernel, dim3((B + 31) / 32), dim3(32), 0, s, st, cand_val, cand_idx, row_max, row_logsum, B, nb, V, cur_len,
+             max_len, keep, length_penalty, pad_id, eos_ids, n_eos);
   return check_launch("beam_advance");
 }
 
@@ -582,6 +588,8 @@ filter_logits_kernel(float* __restrict__ logits, int ld, int V, float inv_temp, 
   __shared__ TopkSmem sm;
   __shared__ LseSmem lse;
   __shared__ float red[8];
+  pdl_launch_dependents();
+  pdl_wait();                   // programmatic dependent launch: global memory from here on
   float* row = logits + (size_t)blockIdx.x * ld;
   const int tid = threadIdx.x;
   if (inv_temp != 1.f) {
@@ -647,7 +655,7 @@ int filter_logits(float* logits, int ld, int rows, int V, float inv_temperature,
                   cudaStream_t s) {
   if (min_tokens_to_keep != 1) { set_last_error("filter_logits: min_tokens_to_keep must be 1 (beam sampling unsupported)"); return VC_ERR_UNSUPPORTED; }
   if (rows <= 0 || V <= 0 || top_k < 0 || !(top_p > 0.f)) { set_last_error("filter_logits: bad args"); return VC_ERR_BAD_ARG; }
-  filter_logits_kernel<<<rows, 256, 0, s>>>(logits, ld, V, inv_temperature, top_k, top_p);
+  launch_pdl(filter_logits_kernel, dim3(rows), dim3(256), 0, s, logits, ld, V, inv_temperature, top_k, top_p);
   return check_launch("filter_logits");
 }
 

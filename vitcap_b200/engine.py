@@ -111,6 +111,8 @@ class CaptionEngine:
         self.max_decode_workspaces = 3         # e.g. SCST alternates a greedy (E = 1) and a sampling (E = 5) pass per batch
         self.attn_impl = "auto"
         self.stats = {}
+        self.forward_graphs = {}               # whole-forward CUDA graphs of the small-batch latency path (model.py); they hold
+        self.inline_graphs = False             # raw workspace pointers. inline_graphs: an outer capture is running
 
     # ------------------------------------------------------------------ workspaces
     def _alloc(self, *shape, dtype=None):
@@ -160,6 +162,7 @@ class CaptionEngine:
         ws["hid_cls"] = self._alloc(B, F)
         self._enc_ws = ws
         self._dec_ws.clear()                   # captured graphs hold raw pointers into the old image-side workspace
+        self.forward_graphs.clear()
         return ws
 
     def _decoder_ws(self, B, E, max_len):
@@ -414,7 +417,7 @@ class CaptionEngine:
 
     def _maybe_graph(self, ws, key, fn):
         """Runs fn() eagerly once (warm-up: lazy kernel attribute setup, descriptor cache), then captures and replays it."""
-        if not self.use_cuda_graph:
+        if not self.use_cuda_graph or self.inline_graphs:
             fn()
             return
         graphs = ws["graphs"]

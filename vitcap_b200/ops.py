@@ -78,6 +78,9 @@ def load_library(path=None):
     lib.vc_abi_version.restype = _I
     lib.vc_launch_count.restype = _LL
     lib.vc_reset_launch_count.restype = None
+    lib.vc_set_pdl.restype = None
+    lib.vc_set_pdl.argtypes = [_I]
+    lib.vc_get_pdl.restype = _I
     if path is None:
         _lib = lib
     return lib
@@ -106,6 +109,16 @@ def launch_count():
 
 def reset_launch_count():
     load_library().vc_reset_launch_count()
+
+
+def set_pdl(mode):
+    """Programmatic dependent launch between consecutive kernels: 0 never, 1 (default) launches captured into a CUDA graph
+    only, 2 every launch. Graphs captured earlier keep the setting they were captured with."""
+    load_library().vc_set_pdl(int(mode))
+
+
+def get_pdl():
+    return int(load_library().vc_get_pdl())
 
 
 def _is_bf16(t):
