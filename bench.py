@@ -308,9 +308,12 @@ def main():
         raise SystemExit("bench.py: no CUDA device (the caption path has no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_cores = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+        # one process per GPU: keep the process and its pinned image buffers on the GPU's own socket
+        numa_cores = parallel.bind_to_gpu_numa(local_rank)
 
     cfg = vcfg.variant(args.variant, dec_layers=args.dec_layers)
     sd = synth.make_state_dict(cfg, seed=0)
@@ -425,7 +428,9 @@ def main():
             pass
         sync_all()
         oc.h2d_bytes = oc.d2h_bytes = 0
-        n_e2e = max(2, min(args.steps, 8))
+        # the first upload of a run cannot overlap anything (pipeline fill: 0.9 GB over PCIe = 3 % of a 5-step run): time at
+        # least 10 steps so that the figure is the steady state a long evaluation sees, fill included
+        n_e2e = max(10, min(args.steps, 20))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.time()
         e0.record()
@@ -445,12 +450,47 @@ def main():
                "api": "vitcap_b200.stream.OverlappedCaptioner(FastImageCaptioning).run(host batches): upload of step i+1 "
                       "overlaps captioning of step i"}
 
+    # ---- the same host loop fed with 8-bit pixels (an additive input format: uint8 HWC after
+    # resize / crop; ToTensor + Normalize + BGR2RGB run inside patch extraction on the device): a quarter of the upload
+    e2e_u8 = None
+    if e2e is not None:
+        u8 = ((img_host * 0.5 + 0.5).clamp_(0, 1) * 255.0).round_().to(torch.uint8).permute(0, 2, 3, 1).contiguous().pin_memory()
+        host_batch_u8 = dict(host_batch, image=u8)
+
+        def batches_u8(n):
+            for _ in range(n):
+                yield host_batch_u8
+
+        for _ in oc.run(batches_u8(2)):
+            pass
+        sync_all()
+        oc.h2d_bytes = oc.d2h_bytes = 0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        e0.record()
+        n_out = 0
+        for res in oc.run(batches_u8(n_e2e)):
+            n_out += res[0].shape[0]
+        e1.record()
+        sync_all()
+        wall = time.time() - t0
+        ems = max(e0.elapsed_time(e1), wall * 1e3)
+        te = torch.tensor([ems], device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_u8 = {"value": world * B * n_e2e / (float(te.item()) / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(oc.h2d_bytes // n_e2e),
+                  "d2h_bytes_per_step": int(oc.d2h_bytes // n_e2e), "steps": n_e2e,
+                  "api": "the same loop with uint8 HWC images (8-bit pixels; ToTensor/Normalize/BGR2RGB fused into patch extraction)"}
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "bf16" if args.mode == "bf16" else "f32", "data": "synthetic", "config": workload_config(args, cfg),
-        "roofline": roofline, "roofline_decode": roofline_decode, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": roofline, "roofline_decode": roofline_decode, "e2e": e2e, "e2e_u8": e2e_u8, "gpu_launches": int(launches), "clocks": clocks,
     }
+    if world > 1:
+        line["config"]["host_binding"] = ("rank bound to the %d CPU cores NVML reports as local to its GPU" % len(numa_cores)
+                                          if numa_cores else "none (NVML affinity unavailable)")
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cb, _ = cpu_baseline(cfg, sd, args.cpu_sample_images, extra)
         line["cpu_baseline"] = cb

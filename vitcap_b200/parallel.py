@@ -13,6 +13,37 @@ import torch
 import torch.distributed as dist
 
 
+def bind_to_gpu_numa(device_index):
+    """Pins this process (and the pinned host buffers it allocates afterwards) to the CPU cores NVML reports as local to GPU
+    ``device_index``: with one process per GPU on a two-socket host, uploads of 0.9 GB per batch otherwise cross the
+    inter-socket link for half of the ranks. Returns the core list, or None when NVML / the affinity call is unavailable
+    (nothing is changed then). Call it before allocating pinned memory; undo with os.sched_setaffinity(0, previous)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = device_index
+        if vis:
+            ent = vis.split(",")[device_index].strip()
+            if ent.isdigit():
+                phys = int(ent)
+            else:
+                return None
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cores = [w * 64 + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cores = sorted(set(cores) & set(allowed))
+        if not cores:
+            return None
+        os.sched_setaffinity(0, cores)
+        return cores
+    except Exception:
+        return None
+
+
 def shard_indices(n_items, world_size, rank):
     """Indices of the reference's non-shuffled DistributedSampler for ``rank`` (samplers.py:127-146)."""
     num_samples = int(math.ceil(n_items * 1.0 / world_size))

@@ -77,20 +77,22 @@ class OverlappedCaptioner:
         return o, done, keep, max_len
 
     def run(self, host_batches):
-        pending = deque()
+        """Software pipeline of depth ``self.depth``: batch i is uploaded AND its kernels are queued as soon as the host hands
+        it over; the host then waits for the oldest batch in flight. The ~170 eager launches of batch i+1 (a few ms of host
+        time) are issued while batch i is still running, so the GPU never waits for the host between batches."""
+        inflight = deque()
         i = 0
         for hb in host_batches:
             slot = i % self.depth
             i += 1
+            if len(inflight) == self.depth:              # the slot's staging and result buffers are about to be reused
+                yield self._finish(*inflight.popleft())
             dev_batch, ready = self._upload(slot, hb)
-            pending.append((slot, dev_batch, ready))
-            if len(pending) == self.depth:
-                yield self._finish(*pending.popleft())
-        while pending:
-            yield self._finish(*pending.popleft())
+            inflight.append(self._caption(slot, dev_batch, ready))
+        while inflight:
+            yield self._finish(*inflight.popleft())
 
-    def _finish(self, slot, dev_batch, ready):
-        o, done, keep, max_len = self._caption(slot, dev_batch, ready)
+    def _finish(self, o, done, keep, max_len):
         done.synchronize()                               # the caller reads the captions on the host
         topk = self.model.cfg.topk if self.with_tags else None
         return parallel.unpack_records(o.clone(), keep, max_len, topk)
