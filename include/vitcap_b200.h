@@ -69,6 +69,18 @@ int vc_linear_simt(int in_bf16, const void* A, int lda, const void* W, int ldw, 
 int vc_linear_tc(const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldo, int out_f32, int act,
                  const float* resid, int ldr, int M, int N, int K, int tile_n, void* stream);
 
+/* LayerNorm folded around two GEMMs of a pre-LN block (Block.forward, vision_transformer.py:233-250: x + mlp(norm2(x)) followed
+ * by the next block's attn(norm1(x))): a stand-alone LayerNorm pass re-reads the 0.9 GB fp32 stream.
+ * vc_linear_ln_emit = vc_linear(bf16, fp32 out, residual) that ALSO stores xb = bf16(out) [M,N] and
+ *   stats[M, ceil(N/256), 2] = per-256-column partial (sum, sum of squares) of every fp32 output row.   N % 64 == 0.
+ * vc_linear_ln_fold: out(bf16)[M,N] = act(LayerNorm(x)[M,K] * W[N,K]^T + b) evaluated from the raw copy A = xb and those
+ *   statistics (st_tiles partials per row):  rstd * (xb * Wf^T - mean * colsum) + bias_f  with  Wf = bf16(gamma o W),
+ *   colsum[n] = sum_k Wf[n,k] (fp32), bias_f = b + W beta, prepared by the caller.  act: VC_ACT_NONE / VC_ACT_GELU. */
+int vc_linear_ln_emit(const void* A, int lda, const void* W, int ldw, const float* bias, float* out, int ldo, const float* resid,
+                      int ldr, void* xb, int ldxb, float* stats, int M, int N, int K, void* stream);
+int vc_linear_ln_fold(const void* A, int lda, const void* Wf, int ldw, const float* bias_f, const float* colsum, const float* stats,
+                      int st_tiles, float ln_eps, void* out, int ldo, int act, int M, int N, int K, void* stream);
+
 /* image fp32 [B,3,S,S] -> patch matrix [B*(S/p)^2, 3*p*p] (column order = Conv2d weight.flatten(1));
  * PatchEmbed.forward, vision_transformer.py:267-275 */
 int vc_patchify(int bf16, const float* image, void* out, int B, int img_size, int patch, void* stream);

@@ -297,3 +297,50 @@ def test_cls_attention(B, N, heads, dtype):
     tol = 2e-5 if dtype == torch.float32 else 1e-2
     torch.testing.assert_close(out[:, :H].float(), ref, rtol=tol, atol=tol)
     assert bool(torch.isnan(out[:, H:]).all())                       # pitch respected
+
+
+@pytest.mark.parametrize("M", [577 * 3, 20000, 4111])
+@pytest.mark.parametrize("act", [ops.ACT_NONE, ops.ACT_GELU])
+@pytest.mark.parametrize("row_mean", [0.0, 3.0])
+def test_linear_ln_emit_and_fold(M, act, row_mean):
+    """Folded LayerNorm (vc_linear_ln_emit / vc_linear_ln_fold): the producer GEMM's fp32 result is bit-identical to the plain
+    residual GEMM, its bf16 copy is the rounded result, its statistics are the fp32 row sums; the consumer GEMM on the raw copy
+    reproduces act(LayerNorm(x) W^T + b) as closely as the two-kernel path (LayerNorm kernel + plain GEMM) does."""
+    K1, H, N2 = 3072, 768, 2304
+    a, w, b = rnd(M, K1, seed=5, dtype=torch.bfloat16), rnd(H, K1, seed=6, scale=0.03, dtype=torch.bfloat16), rnd(H, seed=7)
+    x = rnd(M, H, seed=8) + row_mean
+    plain = torch.empty(M, H, device=dev())
+    ops.linear(a, w, b, plain, resid=x, impl="tc", tile_n=512)
+    out = x.clone()                                              # in place, as the residual stream is updated
+    xb = torch.zeros(M, H, device=dev(), dtype=torch.bfloat16)
+    stats = torch.zeros(M, 3, 2, device=dev())
+    ops.linear_ln_emit(a, w, b, out, out, xb, stats)
+    assert torch.equal(out, plain)
+    assert torch.equal(xb, out.to(torch.bfloat16))
+    s = stats.sum(1)
+    torch.testing.assert_close(s[:, 0], out.double().sum(1).float(), rtol=1e-5, atol=1e-3)
+    torch.testing.assert_close(s[:, 1], (out.double() ** 2).sum(1).float(), rtol=1e-5, atol=1e-3)
+    # consumer
+    eps = 1e-6
+    gamma, beta = 1.0 + 0.1 * rnd(H, seed=11), 0.05 * rnd(H, seed=12)
+    w2, b2 = rnd(N2, H, seed=13, scale=0.03), rnd(N2, seed=14)
+    wf = (w2 * gamma).to(torch.bfloat16)
+    colsum = wf.float().sum(1).contiguous()
+    bias_f = (b2 + w2 @ beta).contiguous()
+    got = torch.empty(M, N2, device=dev(), dtype=torch.bfloat16)
+    ops.linear_ln_fold(xb, wf, bias_f, colsum, stats, 3, eps, got, act=act)
+    ln_ref = torch.nn.functional.layer_norm(out.double(), (H,), gamma.double(), beta.double(), eps)
+    ref = ln_ref @ w2.double().t() + b2.double()
+    if act == ops.ACT_GELU:
+        ref = torch.nn.functional.gelu(ref)
+    ref = ref.float()
+    # the two-kernel path it replaces
+    ln_t = torch.empty(M, H, device=dev(), dtype=torch.bfloat16)
+    ops.layernorm(out, gamma, beta, eps, out_t=ln_t)
+    two = torch.empty(M, N2, device=dev(), dtype=torch.bfloat16)
+    ops.linear(ln_t, w2.to(torch.bfloat16), b2, two, act=act, impl="tc", tile_n=512)
+    e_fold = float((got.float() - ref).norm() / ref.norm())
+    e_two = float((two.float() - ref).norm() / ref.norm())
+    print("folded LN rel err %.3g, LayerNorm kernel + GEMM rel err %.3g" % (e_fold, e_two))
+    assert e_fold < 6e-3 and e_fold < 1.5 * e_two + 1e-4
+    torch.testing.assert_close(got.float(), ref, rtol=3e-2, atol=3e-2)

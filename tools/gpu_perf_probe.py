@@ -121,6 +121,53 @@ def stage_probe(B, variant="16_384"):
     return t
 
 
+def fold_probe(B):
+    """Folded LayerNorm: producer (fc2 + residual, emitting the bf16 copy and statistics) and consumer (qkv from the raw copy)
+    against the plain GEMMs and the LayerNorm kernel they replace. Long loops (steady state under the power cap)."""
+    M, H = B * 577, 768
+    hid = torch.randn(M, 3072, device=dev).to(torch.bfloat16)
+    w2 = (torch.randn(H, 3072, device=dev) * 0.02).to(torch.bfloat16)
+    b2 = torch.randn(H, device=dev)
+    x = torch.randn(M, H, device=dev)
+    xb = torch.empty(M, H, device=dev, dtype=torch.bfloat16)
+    stats = torch.empty(M, 3, 2, device=dev)
+    wq = (torch.randn(2304, H, device=dev) * 0.02).to(torch.bfloat16)
+    bq, cq = torch.randn(2304, device=dev), torch.randn(2304, device=dev)
+    qkv = torch.empty(M, 2304, device=dev, dtype=torch.bfloat16)
+    ln = torch.empty(M, H, device=dev, dtype=torch.bfloat16)
+    g, b = torch.randn(H, device=dev), torch.randn(H, device=dev)
+    for name, fn in [("fc2+res plain", lambda: ops.linear(hid, w2, b2, x, resid=x)),
+                     ("fc2+res emit", lambda: ops.linear_ln_emit(hid, w2, b2, x, x, xb, stats)),
+                     ("layernorm", lambda: ops.layernorm(x, g, b, 1e-6, out_t=ln)),
+                     ("qkv plain", lambda: ops.linear(ln, wq, bq, qkv)),
+                     ("qkv fold", lambda: ops.linear_ln_fold(xb, wq, bq, cq, stats, 3, 1e-6, qkv))]:
+        x.normal_()
+        ms_burst = timeit(fn, iters=5, warm=2)
+        ms = timeit(fn, iters=400, warm=20)
+        print("%-16s burst %.3f ms   steady %.3f ms" % (name, ms_burst, ms), flush=True)
+
+
+def fold_ab_probe(B, variant="16_384"):
+    """A/B of the folded norm1 (engine.ln_fold) in one process, alternating, steady state (20 forwards per sample)."""
+    cfg = vcfg.variant(variant)
+    sd = synth.make_state_dict(cfg, seed=0)
+    m = FastImageCaptioning(cfg, mode="bf16", max_batch=B)
+    m.load_state_dict(sd)
+    m = m.to(dev)
+    eng = m.engine
+    data = {k: v.to(dev) for k, v in synth.make_text_inputs(cfg, B).items()}
+    data["image"] = synth.make_images(cfg, B, seed=1).to(dev)
+    for rnd in range(3):
+        for fold in (True, False):
+            eng.ln_fold = fold
+            f = eng.patch_embed(data["image"])
+            t_enc = timeit(lambda: eng.encode(f), iters=20, warm=3)
+            t_all = timeit(lambda: m(data), iters=20, warm=3)
+            print("ln_fold=%d round %d: encode %.2f ms  full forward %.2f ms  (%.1f images/s)" % (fold, rnd, t_enc, t_all, B / t_all * 1e3),
+                  flush=True)
+    eng.ln_fold = True
+
+
 def pdl_probe(B, variant="16_384"):
     """A/B of programmatic dependent launch (ops.set_pdl) in one process, alternating, same model and inputs."""
     cfg = vcfg.variant(variant)
@@ -164,3 +211,7 @@ if __name__ == "__main__":
         stage_probe(B)
     if what == "pdl":
         pdl_probe(B)
+    if what == "fold":
+        fold_probe(B)
+    if what == "foldab":
+        fold_ab_probe(B)

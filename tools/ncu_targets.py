@@ -31,6 +31,19 @@ if what == "attn":
         ops.attention(qkv, out, B, 577, 12, 0.125)
 elif what == "gemm_qkv":
     gemm(2304, 768, 0, False, False)
+elif what in ("gemm_qkv_fold", "gemm_fc2_emit"):
+    hid = torch.randn(M, 3072, device=dev).to(torch.bfloat16)
+    w2 = (torch.randn(768, 3072, device=dev) * 0.02).to(torch.bfloat16)
+    b2 = torch.randn(768, device=dev)
+    x = torch.randn(M, 768, device=dev)
+    xb = torch.empty(M, 768, device=dev, dtype=torch.bfloat16)
+    stats = torch.empty(M, 3, 2, device=dev)
+    wq = (torch.randn(2304, 768, device=dev) * 0.02).to(torch.bfloat16)
+    bq, cq = torch.randn(2304, device=dev), torch.randn(2304, device=dev)
+    qkv = torch.empty(M, 2304, device=dev, dtype=torch.bfloat16)
+    for _ in range(reps):
+        ops.linear_ln_emit(hid, w2, b2, x, x, xb, stats)
+        ops.linear_ln_fold(xb, wq, bq, cq, stats, 3, 1e-6, qkv)
 elif what == "gemm_proj":
     gemm(768, 768, 0, True, True)
 elif what == "gemm_fc1":

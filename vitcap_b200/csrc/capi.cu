@@ -7,6 +7,11 @@
 
 namespace vc {
 const char* last_error();
+int gemm_bf16_tc2_ln_emit(const void* A, int lda, const void* W, int ldw, const float* bias, float* out, int ldo, const float* resid,
+                          int ldr, void* xb, int ldxb, float* stats, int M, int N, int K, cudaStream_t stream);
+int gemm_bf16_tc2_ln_fold(const void* A, int lda, const void* Wf, int ldw, const float* bias_f, const float* colsum,
+                          const float* stats, int st_tiles, float ln_eps, void* out, int ldo, int act, int M, int N, int K,
+                          cudaStream_t stream);
 int gemm_bf16_tc(const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldo, int out_f32, int act,
                  const float* resid, int ldr, int M, int N, int K, int force_bn, cudaStream_t stream);
 int gemm_simt(int in_bf16, const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldo, int out_f32,
@@ -73,6 +78,14 @@ int vc_linear(int bf16, const void* A, int lda, const void* W, int ldw, const fl
               const float* resid, int ldr, int M, int N, int K, void* stream) {
   if (bf16) VC_COUNT(1, vc::gemm_bf16_tc(A, lda, W, ldw, bias, out, ldo, out_f32, act, resid, ldr, M, N, K, 0, ST(stream)));
   VC_COUNT(1, vc::gemm_simt(0, A, lda, W, ldw, bias, out, ldo, 1, act, resid, ldr, M, N, K, ST(stream)));
+}
+int vc_linear_ln_emit(const void* A, int lda, const void* W, int ldw, const float* bias, float* out, int ldo, const float* resid,
+                      int ldr, void* xb, int ldxb, float* stats, int M, int N, int K, void* stream) {
+  VC_COUNT(1, vc::gemm_bf16_tc2_ln_emit(A, lda, W, ldw, bias, out, ldo, resid, ldr, xb, ldxb, stats, M, N, K, ST(stream)));
+}
+int vc_linear_ln_fold(const void* A, int lda, const void* Wf, int ldw, const float* bias_f, const float* colsum, const float* stats,
+                      int st_tiles, float ln_eps, void* out, int ldo, int act, int M, int N, int K, void* stream) {
+  VC_COUNT(1, vc::gemm_bf16_tc2_ln_fold(A, lda, Wf, ldw, bias_f, colsum, stats, st_tiles, ln_eps, out, ldo, act, M, N, K, ST(stream)));
 }
 int vc_linear_simt(int in_bf16, const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldo, int out_f32,
                    int act, const float* resid, int ldr, int M, int N, int K, void* stream) {

@@ -15,6 +15,14 @@
 //     (the erf-GELU epilogue was issue/latency bound with a single warp per scheduler)
 //   * GELU is x/2 * (1 + tanh(z * (c0 + c1 z^2 + c2 z^4))), z = x / sqrt(2): a minimax fit of erf(z) by one MUFU.TANH
 //     (|gelu error| < 3e-5 + tanh.approx error, far below the bf16 output resolution), 10 issue slots instead of 17.
+//   * LayerNorm folded around the GEMM (LN = 1 / 2). Under the board's power cap every GB of HBM traffic costs ~0.11 ms
+//     whether or not it overlaps tensor work (tools/power_probe.py), and a stand-alone LayerNorm pass is 1.36 GB. So the
+//     residual GEMM that PRODUCES a stream row (LN = 1, "emit") also stores a bf16 copy of the row and its partial
+//     (sum, sum of squares) per 256-column tile, and the GEMM that CONSUMES the normalised row (LN = 2, "fold") multiplies the
+//     RAW bf16 row by gamma-scaled weights and applies the normalisation in its epilogue:
+//         LN(x) W^T + b  =  rstd * (x (gamma o W)^T  -  mean * colsum(gamma o W))  +  (b + W beta)
+//     (bf16 rounding is relative, so rounding x before instead of after the affine map gives the same error bound as long as
+//     |mean| is not much larger than the row's standard deviation; the statistics are fp32 over the fp32 row).
 #include "common.cuh"
 
 namespace vc {
@@ -22,10 +30,11 @@ namespace vc {
 namespace {
 
 enum { ACT2_NONE = 0, ACT2_GELU = 1, ACT2_TANH = 2 };
+enum { LN_NONE = 0, LN_EMIT = 1, LN_FOLD = 2 };
 
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;    // clears the CTA-rank bit of a shared::cluster address -> rank 0 of the pair
 
-template <bool OUT_F32, bool RESID, int G> struct Gemm2Cfg {
+template <bool OUT_F32, bool RESID, int G, int LN = 0> struct Gemm2Cfg {
   static constexpr int BM = 128;                        // rows per CTA (256 per pair)
   static constexpr int BN = 256;                        // columns per pair tile; each CTA stages 128 rows of W
   static constexpr int BK = 64;
@@ -35,15 +44,19 @@ template <bool OUT_F32, bool RESID, int G> struct Gemm2Cfg {
   static constexpr int EPI_BYTES = 16384;               // staging tile: 128 rows x 128 B
   static constexpr int NBUF_G = (G == 2) ? 2 : (RESID ? 4 : 2);     // staging tiles per epilogue group
   static constexpr int NBUF = NBUF_G * G;
-  static constexpr int BUDGET = 227 * 1024 - 1024 - 512 - NBUF * EPI_BYTES;
+  static constexpr int XB_BUFS = 0;                     // (the emitted bf16 row copy goes to global memory straight from registers:
+                                                        //  staging it would cost the fifth pipeline stage of the K = 3072 GEMM)
+  static constexpr int BUDGET = 227 * 1024 - 1024 - 512 - (NBUF + XB_BUFS) * EPI_BYTES;
   static constexpr int STAGES_MAX = BUDGET / STAGE_BYTES;
   static constexpr int STAGES = STAGES_MAX > 8 ? 8 : STAGES_MAX;
   static constexpr int TMEM_COLS = 512;                 // two accumulator stages of 256 columns
   static constexpr int CW = OUT_F32 ? 32 : 64;          // output columns per staging tile
   static constexpr int NCH = BN / CW;
   static constexpr int THREADS = 64 + 128 * G;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NBUF * EPI_BYTES + 1024 + 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + (NBUF + XB_BUFS) * EPI_BYTES + 1024 + 512;
   static_assert(!(RESID && G == 2), "the residual epilogue runs with one group (4 staging tiles)");
+  static_assert(LN != 1 || (OUT_F32 && RESID && G == 1), "emit: fp32 residual epilogue");
+  static_assert(LN != 2 || (!OUT_F32 && !RESID), "fold: bf16 output");
   static_assert(STAGES >= 4, "pipeline too shallow");
 };
 
@@ -103,12 +116,25 @@ template <int ACT> __device__ __forceinline__ float apply_act(float v) {
 
 }  // namespace
 
-template <int ACT, bool OUT_F32, bool RESID, int G>
+// LN = 1: xb = bf16 [M, N] copy of the output row (pitch ldxb), stats = float [M, n_tiles, 2] partial (sum, sum of squares)
+// LN = 2: stats = the producer's partials [M, st_tiles, 2] of the K-wide input row, colsum = float [N] row sums of W (bf16
+//         values, fp32 sum), inv_k = 1 / K, ln_eps; bias already holds b + W beta
+struct LnArgs {
+  bf16* xb;
+  int ldxb;
+  float* stats;
+  const float* colsum;
+  float ln_eps;
+  float inv_k;
+  int st_tiles;
+};
+
+template <int ACT, bool OUT_F32, bool RESID, int G, int LN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 128 * G, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                 const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
-                const float* __restrict__ bias, int M, int N, int K) {
-  using C = Gemm2Cfg<OUT_F32, RESID, G>;
+                const float* __restrict__ bias, LnArgs ln, int M, int N, int K) {
+  using C = Gemm2Cfg<OUT_F32, RESID, G, LN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* epi = smem + C::STAGES * C::STAGE_BYTES;
@@ -230,9 +256,31 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     if (RESID && leader) {
       for (int i = 0; i < C::NBUF_G - 2; ++i) prefetch_resid();
     }
+    float nx_s = 0.f, nx_q = 0.f;
+    auto load_row_stats = [&](int row, float& s, float& q) {
+      s = 0.f;
+      q = 0.f;
+      if (row < M) {
+        const float2* sp = reinterpret_cast<const float2*>(ln.stats) + (size_t)row * ln.st_tiles;
+        for (int i = 0; i < ln.st_tiles; ++i) { const float2 pq = __ldg(sp + i); s += pq.x; q += pq.y; }
+      }
+    };
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       const int m0 = (tile / n_tiles) * (2 * C::BM) + (int)rank * C::BM;
       const int n0 = (tile % n_tiles) * C::BN;
+      // LN = 2: mean / rstd of this thread's input row from the producer's partial sums. The sums of the NEXT tile's row are
+      // requested here and consumed one tile later, so their latency never sits in front of the accumulator read
+      float ln_rstd = 0.f, ln_nm = 0.f;
+      if (LN == LN_FOLD) {
+        if (tile == cluster_id) load_row_stats(m0 + t, nx_s, nx_q);
+        const float mean = nx_s * ln.inv_k;
+        const float var = fmaxf(fmaf(nx_q, ln.inv_k, -mean * mean), 0.f);
+        ln_rstd = (m0 + t < M) ? rsqrtf(var + ln.ln_eps) : 0.f;
+        ln_nm = -mean * ln_rstd;
+        const int nt = tile + num_clusters;
+        if (nt < num_tiles) load_row_stats((nt / n_tiles) * (2 * C::BM) + (int)rank * C::BM + t, nx_s, nx_q);
+      }
+      float st_s = 0.f, st_q = 0.f;                      // LN = 1: this row's partial statistics over the tile's columns
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
 #pragma unroll 1
@@ -259,7 +307,21 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
           const int cb = col0 + hh * 32;
-          if (bias != nullptr) {
+          if (LN == LN_FOLD) {
+            // v = rstd * acc + (nm * colsum + bias'),  nm = -mean * rstd   (N % 4 == 0 is checked by the launcher)
+            const uint64_t r2 = pack_f32x2(ln_rstd, ln_rstd), n2 = pack_f32x2(ln_nm, ln_nm);
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (full || cb + j < N) {
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + cb + j));
+                const float4 cc = __ldg(reinterpret_cast<const float4*>(ln.colsum + cb + j));
+                unpack_f32x2(fma_f32x2(r2, pack_f32x2(v[j], v[j + 1]), fma_f32x2(n2, pack_f32x2(cc.x, cc.y), pack_f32x2(bb.x, bb.y))),
+                             v[j], v[j + 1]);
+                unpack_f32x2(fma_f32x2(r2, pack_f32x2(v[j + 2], v[j + 3]), fma_f32x2(n2, pack_f32x2(cc.z, cc.w), pack_f32x2(bb.z, bb.w))),
+                             v[j + 2], v[j + 3]);
+              }
+            }
+          } else if (bias != nullptr) {
             if (full) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
@@ -291,6 +353,24 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               *reinterpret_cast<float4*>(myrow + ((j ^ sw) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            if (LN == LN_EMIT) {
+              // statistics of the fp32 row (columns >= N hold zeros: TMA zero-fills the operand tiles and the residual tile,
+              // and bias is not added there) and the bf16 copy: two 32-column chunks fill one 64-column staging tile
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float xv = (full || cb + j < N) ? v[j] : 0.f;
+                st_s += xv;
+                st_q = fmaf(xv, xv, st_q);
+              }
+              // 64 contiguous bytes of this thread's row; the K = 3072 tile leaves the epilogue ample time for the 4 stores
+              if (m0 + t < M) {
+                uint4* xp = reinterpret_cast<uint4*>(ln.xb + (size_t)(m0 + t) * ln.ldxb + cb);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  xp[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                     pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+              }
+            }
           } else {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -309,6 +389,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         }
         ++g;
       }
+      if (LN == LN_EMIT && m0 + t < M) {
+        const int nt = tile % n_tiles;
+        reinterpret_cast<float2*>(ln.stats)[(size_t)(m0 + t) * n_tiles + nt] = make_float2(st_s, st_q);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tmem_empty[as]);
@@ -325,11 +409,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 // ------------------------------------------------------------------------------------------
 // host launcher
 // ------------------------------------------------------------------------------------------
-template <int ACT, bool OUT_F32, bool RESID, int G>
+template <int ACT, bool OUT_F32, bool RESID, int G, int LN = 0>
 static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr, const float* bias,
-                   int M, int N, int K, cudaStream_t stream) {
-  using C = Gemm2Cfg<OUT_F32, RESID, G>;
-  auto kern = gemm_tc2_kernel<ACT, OUT_F32, RESID, G>;
+                   int M, int N, int K, cudaStream_t stream, LnArgs ln = LnArgs()) {
+  using C = Gemm2Cfg<OUT_F32, RESID, G, LN>;
+  auto kern = gemm_tc2_kernel<ACT, OUT_F32, RESID, G, LN>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
@@ -339,7 +423,7 @@ static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
   const int tiles = ((M + 2 * C::BM - 1) / (2 * C::BM)) * ((N + C::BN - 1) / C::BN);
   int clusters = sm_count() / 2;
   if (tiles < clusters) clusters = tiles;
-  launch_pdl(kern, dim3(2 * clusters), dim3(C::THREADS), C::SMEM_BYTES, stream, ta, tb, to, tr, bias, M, N, K);
+  launch_pdl(kern, dim3(2 * clusters), dim3(C::THREADS), C::SMEM_BYTES, stream, ta, tb, to, tr, bias, ln, M, N, K);
   return check_launch("gemm_tc2");
 }
 
@@ -377,6 +461,73 @@ int gemm_bf16_tc2(const void* A, int lda, const void* W, int ldw, const float* b
     case ACT2_TANH: return launch2_act<ACT2_TANH>(ta, tb, to, tr, bias, out_f32, resid != nullptr, M, N, K, stream);
   }
   set_last_error("gemm_tc2: unknown activation %d", act);
+  return VC_ERR_BAD_ARG;
+}
+
+// out (fp32) = A W^T + bias + resid, plus xb = bf16(out) and stats[M, ceil(N/256), 2] = per-256-column partial (sum, sum of
+// squares) of every output row: the producer half of the folded LayerNorm
+int gemm_bf16_tc2_ln_emit(const void* A, int lda, const void* W, int ldw, const float* bias, float* out, int ldo, const float* resid,
+                          int ldr, void* xb, int ldxb, float* stats, int M, int N, int K, cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0 || (K % 64) != 0 || (N % 64) != 0 || resid == nullptr || xb == nullptr || stats == nullptr) {
+    set_last_error("gemm_tc2_ln_emit: need K %% 64 == 0, N %% 64 == 0, a residual, xb and stats (N=%d K=%d)", N, K);
+    return VC_ERR_BAD_ARG;
+  }
+  if ((lda % 8) || (ldw % 8) || (ldo % 4) || (ldr % 4) || (ldxb % 8) || (reinterpret_cast<uintptr_t>(A) & 15) ||
+      (reinterpret_cast<uintptr_t>(W) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(resid) & 15) ||
+      (reinterpret_cast<uintptr_t>(xb) & 15) || (reinterpret_cast<uintptr_t>(bias) & 15) || (reinterpret_cast<uintptr_t>(stats) & 7)) {
+    set_last_error("gemm_tc2_ln_emit: pointers must be 16-byte aligned and row pitches multiples of 16 bytes");
+    return VC_ERR_BAD_ARG;
+  }
+  CUtensorMap ta, tb, to, tr;
+  int rc = get_tmap_2d_bf16(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 128, 64);
+  if (rc) return rc;
+  rc = get_tmap_2d_bf16(&tb, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, 128, 64);
+  if (rc) return rc;
+  rc = get_tmap_2d_f32(&to, out, (uint64_t)M, (uint64_t)N, (uint64_t)ldo, 128, 32);
+  if (rc) return rc;
+  rc = get_tmap_2d_f32(&tr, resid, (uint64_t)M, (uint64_t)N, (uint64_t)ldr, 128, 32);
+  if (rc) return rc;
+  LnArgs ln = LnArgs();
+  ln.xb = static_cast<bf16*>(xb);
+  ln.ldxb = ldxb;
+  ln.stats = stats;
+  return launch2<ACT2_NONE, true, true, 1, LN_EMIT>(ta, tb, to, tr, bias, M, N, K, stream, ln);
+}
+
+// out (bf16) = act(LN(x) W^T + b) computed from the RAW bf16 row copy A = xb and the producer's statistics:
+// Wf = bf16(gamma o W), colsum[n] = sum_k float(Wf[n, k]), bias_f = b + W beta (all prepared by the host)
+int gemm_bf16_tc2_ln_fold(const void* A, int lda, const void* Wf, int ldw, const float* bias_f, const float* colsum,
+                          const float* stats, int st_tiles, float ln_eps, void* out, int ldo, int act, int M, int N, int K,
+                          cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0 || (K % 64) != 0 || (N % 4) != 0 || bias_f == nullptr || colsum == nullptr || stats == nullptr ||
+      st_tiles < 1) {
+    set_last_error("gemm_tc2_ln_fold: need K %% 64 == 0, N %% 4 == 0, bias, colsum and stats (N=%d K=%d)", N, K);
+    return VC_ERR_BAD_ARG;
+  }
+  if ((lda % 8) || (ldw % 8) || (ldo % 8) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(Wf) & 15) ||
+      (reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(bias_f) & 15) ||
+      (reinterpret_cast<uintptr_t>(colsum) & 15) || (reinterpret_cast<uintptr_t>(stats) & 7)) {
+    set_last_error("gemm_tc2_ln_fold: pointers must be 16-byte aligned and row pitches multiples of 16 bytes");
+    return VC_ERR_BAD_ARG;
+  }
+  CUtensorMap ta, tb, to;
+  int rc = get_tmap_2d_bf16(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 128, 64);
+  if (rc) return rc;
+  rc = get_tmap_2d_bf16(&tb, Wf, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, 128, 64);
+  if (rc) return rc;
+  rc = get_tmap_2d_bf16(&to, out, (uint64_t)M, (uint64_t)N, (uint64_t)ldo, 128, 64);
+  if (rc) return rc;
+  LnArgs ln = LnArgs();
+  ln.stats = const_cast<float*>(stats);
+  ln.colsum = colsum;
+  ln.ln_eps = ln_eps;
+  ln.inv_k = 1.0f / (float)K;
+  ln.st_tiles = st_tiles;
+  switch (act) {
+    case ACT2_NONE: return launch2<ACT2_NONE, false, false, 2, LN_FOLD>(ta, tb, to, to, bias_f, M, N, K, stream, ln);
+    case ACT2_GELU: return launch2<ACT2_GELU, false, false, 2, LN_FOLD>(ta, tb, to, to, bias_f, M, N, K, stream, ln);
+  }
+  set_last_error("gemm_tc2_ln_fold: unsupported activation %d", act);
   return VC_ERR_BAD_ARG;
 }
 

@@ -52,8 +52,15 @@ class PackedWeights:
         self.cls_token = Fp(ie + "cls_token").reshape(H).contiguous()
         self.pos_embed = Fp(ie + "pos_embed").reshape(cfg.n_tokens, H).contiguous()
 
+        def folded(w_key, b_key, g_key, beta_key):
+            """LayerNorm folded into the consuming Linear (vc_linear_ln_fold): Wf = bf16(gamma o W), colsum = fp32 row sums of
+            the ROUNDED Wf (so that mean * colsum cancels what the tensor cores accumulate), bias_f = b + W beta."""
+            w32, b32, g32, be32 = Fp(w_key), Fp(b_key), Fp(g_key), Fp(beta_key)
+            wf = (w32 * g32.unsqueeze(0)).to(torch.bfloat16).contiguous()
+            return wf, wf.float().sum(1).contiguous(), (b32 + w32 @ be32).contiguous()
+
         def block(prefix):
-            return {
+            d = {
                 "n1w": Fp(prefix + "norm1.weight"), "n1b": Fp(prefix + "norm1.bias"),
                 "qkv_w": W(prefix + "attn.qkv.weight"), "qkv_b": Fp(prefix + "attn.qkv.bias"),
                 "proj_w": W(prefix + "attn.proj.weight"), "proj_b": Fp(prefix + "attn.proj.bias"),
@@ -61,6 +68,10 @@ class PackedWeights:
                 "fc1_w": W(prefix + "mlp.fc1.weight"), "fc1_b": Fp(prefix + "mlp.fc1.bias"),
                 "fc2_w": W(prefix + "mlp.fc2.weight"), "fc2_b": Fp(prefix + "mlp.fc2.bias"),
             }
+            if mode == "bf16":
+                d["qkv_wf"], d["qkv_cf"], d["qkv_bf"] = folded(prefix + "attn.qkv.weight", prefix + "attn.qkv.bias",
+                                                               prefix + "norm1.weight", prefix + "norm1.bias")
+            return d
         self.blocks = [block("module.bert.encoder.blocks.%d." % i) for i in range(cfg.enc_blocks)]
         self.tag_blocks = [block("module.bert.encoder.tag_blocks.%d." % i) for i in range(cfg.split_blocks)]
 
@@ -111,6 +122,9 @@ class CaptionEngine:
         self.max_decode_workspaces = 3         # e.g. SCST alternates a greedy (E = 1) and a sampling (E = 5) pass per batch
         self.attn_impl = "auto"
         self.stats = {}
+        # norm1 of a ViT block folded into the fc2 GEMM before it (statistics + bf16 row copy) and the qkv GEMM after it
+        # (gemm_tc2.cu, LN = 1 / 2): one 1.36 GB LayerNorm pass less per block. Fast mode only
+        self.ln_fold = (self.mode == "bf16")
         self.forward_graphs = {}               # whole-forward CUDA graphs of the small-batch latency path (model.py); they hold
         self.inline_graphs = False             # raw workspace pointers. inline_graphs: an outer capture is running
 
@@ -160,6 +174,11 @@ class CaptionEngine:
         ws["att_cls"] = self._alloc(B, H)
         ws["ln_cls"] = self._alloc(B, H)
         ws["hid_cls"] = self._alloc(B, F)
+        if self.ln_fold:
+            # raw bf16 copy + per-256-column (sum, sum of squares) of the caption / concept stream, written by the fc2 GEMM
+            st = (H + 255) // 256
+            ws["fold_x"] = (self._alloc(B * N, H), self._alloc(B * N, st, 2, dtype=f32), st)
+            ws["fold_t"] = (self._alloc(B * N, H), self._alloc(B * N, st, 2, dtype=f32), st)
         self._enc_ws = ws
         self._dec_ws.clear()                   # captured graphs hold raw pointers into the old image-side workspace
         self.forward_graphs.clear()
@@ -214,15 +233,20 @@ class CaptionEngine:
         ops.layernorm(x, g, b, eps, out_t=out_t, out_f=out_f, rows=rows)
         return out_t
 
-    def _vit_block(self, p, x, rows, B, N, ws, out=None):
+    def _vit_block(self, p, x, rows, B, N, ws, out=None, pre=None, emit=None):
         """Pre-LN ViT block on the fp32 stream x (in place). vision_transformer.py:233-250.
         out: another stream buffer that receives the block's result while x stays untouched (the fork of the split encoder:
-        the first concept block reads the shared trunk's output and starts its own stream without a copy)."""
+        the first concept block reads the shared trunk's output and starts its own stream without a copy).
+        pre: (bf16 copy, statistics, tiles) of x left by the GEMM that produced it -> norm1 is folded into the qkv GEMM.
+        emit: the same triple to be filled for the block's RESULT by its fc2 GEMM (for the next block's norm1)."""
         cfg = self.cfg
         H = cfg.hidden
         ln, qkv, att, hid = ws["ln"][:rows], ws["qkv"][:rows], ws["att"][:rows], ws["hid"][:rows]
-        h = self._ln(x, p["n1w"], p["n1b"], cfg.vit_ln_eps, ln, rows=rows)
-        ops.linear(h, p["qkv_w"], p["qkv_b"], qkv, M=rows)
+        if pre is not None:
+            ops.linear_ln_fold(pre[0][:rows], p["qkv_wf"], p["qkv_bf"], p["qkv_cf"], pre[1], pre[2], cfg.vit_ln_eps, qkv, M=rows)
+        else:
+            h = self._ln(x, p["n1w"], p["n1b"], cfg.vit_ln_eps, ln, rows=rows)
+            ops.linear(h, p["qkv_w"], p["qkv_b"], qkv, M=rows)
         ops.attention(qkv, att, B, N, cfg.heads, cfg.head_dim ** -0.5, impl=self.attn_impl)
         if out is not None:
             ops.linear(att, p["proj_w"], p["proj_b"], out, resid=x, M=rows)
@@ -231,7 +255,10 @@ class CaptionEngine:
             ops.linear(att, p["proj_w"], p["proj_b"], x, resid=x, M=rows)
         h = self._ln(x, p["n2w"], p["n2b"], cfg.vit_ln_eps, ln, rows=rows)
         ops.linear(h, p["fc1_w"], p["fc1_b"], hid, act=ops.ACT_GELU, M=rows)
-        ops.linear(hid, p["fc2_w"], p["fc2_b"], x, resid=x, M=rows)
+        if emit is not None:
+            ops.linear_ln_emit(hid, p["fc2_w"], p["fc2_b"], x, x, emit[0][:rows], emit[1], M=rows)
+        else:
+            ops.linear(hid, p["fc2_w"], p["fc2_b"], x, resid=x, M=rows)
 
     def _vit_block_cls_only(self, p, x, rows, B, N, ws):
         """The same block, evaluated for the CLS row of every image only (K and V still come from all rows). Used for the last
@@ -283,28 +310,54 @@ class CaptionEngine:
             x.copy_(img_feats.reshape(rows, H))
         xt = ws["xt"][:rows]
         split_at = cfg.enc_blocks - cfg.split_blocks
+        # folded norm1: a block's fc2 GEMM leaves the bf16 copy + statistics of its result for the NEXT block's qkv GEMM
+        # (fold_x: trunk / caption stream, fold_t: concept stream). Not for the very first block (its input comes from the
+        # patch embedding) nor for the CLS-only last concept block (it normalises with the LayerNorm kernel)
+        fx = ws["fold_x"] if self.ln_fold else None
+        ft = ws["fold_t"] if self.ln_fold else None
+        n_cap = cfg.enc_blocks - split_at if caption_branch else 0
+        cls_only_last = not full_tag_feats
+        n_tag_fold = cfg.split_blocks - (1 if cls_only_last else 0)     # concept blocks that run as full blocks
+        pre = None
         for i in range(split_at):
-            self._vit_block(w.blocks[i], x, rows, B, N, ws)
+            last_trunk = (i == split_at - 1)
+            wanted = (not last_trunk) or n_cap > 0 or n_tag_fold > 0
+            self._vit_block(w.blocks[i], x, rows, B, N, ws, pre=pre, emit=fx if wanted else None)
+            pre = fx if wanted else None
+        pre_trunk = pre
         # fork: both branches start from the block-8 input (modeling_bert.py:464-474). The concept branch runs first; its first
         # block reads x and writes xt, so the 0.9 GB stream is never copied
         forked = False
+        pre_t = pre_trunk
         for j in range(cfg.split_blocks):
-            if j == cfg.split_blocks - 1 and not full_tag_feats:
+            if j == cfg.split_blocks - 1 and cls_only_last:
                 if not forked:
                     xt.copy_(x)
                     forked = True
                 self._vit_block_cls_only(w.tag_blocks[j], xt, rows, B, N, ws)
-            elif not forked:
-                self._vit_block(w.tag_blocks[j], x, rows, B, N, ws, out=xt)
+                continue
+            nxt_full = (j + 1 < n_tag_fold)                              # the next concept block consumes the folded form
+            emit_t = ft if (self.ln_fold and nxt_full) else None
+            if not forked:
+                # reads the trunk's stream x (and its copy/statistics), writes the concept stream xt out of place
+                self._vit_block_fork(w.tag_blocks[j], x, xt, rows, B, N, ws, pre=pre_t, emit=emit_t)
                 forked = True
             else:
-                self._vit_block(w.tag_blocks[j], xt, rows, B, N, ws)
+                self._vit_block(w.tag_blocks[j], xt, rows, B, N, ws, pre=pre_t, emit=emit_t)
+            pre_t = emit_t
         if not forked:
             xt.copy_(x)
         if caption_branch:
+            pre = pre_trunk
             for i in range(split_at, cfg.enc_blocks):
-                self._vit_block(w.blocks[i], x, rows, B, N, ws)
+                emit = fx if (self.ln_fold and i + 1 < cfg.enc_blocks) else None
+                self._vit_block(w.blocks[i], x, rows, B, N, ws, pre=pre, emit=emit)
+                pre = emit
         return x.view(B, N, H), xt.view(B, N, H)
+
+    def _vit_block_fork(self, p, x, xt, rows, B, N, ws, pre=None, emit=None):
+        """First block of the concept branch: input = the shared trunk's stream x (left untouched), result -> xt."""
+        self._vit_block(p, x, rows, B, N, ws, out=xt, pre=pre, emit=emit)
 
     def _head(self, hp, a_t, rows, th_f, th_t, logits):
         """BertLMPredictionHead (modeling_bert.py:540-563): dense + gelu -> LN(1e-12) -> tied/untied decoder + bias."""

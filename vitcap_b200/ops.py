@@ -22,6 +22,8 @@ SIGNATURES = {
     "vc_linear": [_I, _P, _I, _P, _I, _P, _P, _I, _I, _I, _P, _I, _I, _I, _I, _P],
     "vc_linear_simt": [_I, _P, _I, _P, _I, _P, _P, _I, _I, _I, _P, _I, _I, _I, _I, _P],
     "vc_linear_tc": [_P, _I, _P, _I, _P, _P, _I, _I, _I, _P, _I, _I, _I, _I, _I, _P],
+    "vc_linear_ln_emit": [_P, _I, _P, _I, _P, _P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _P],
+    "vc_linear_ln_fold": [_P, _I, _P, _I, _P, _P, _P, _I, _F, _P, _I, _I, _I, _I, _I, _P],
     "vc_patchify": [_I, _P, _P, _I, _I, _I, _P],
     "vc_patchify_u8": [_I, _P, _P, _I, _I, _I, _I, _P],
     "vc_resize_crop_plan": [_P, _I, _I, _I, _P, _P, _P],
@@ -157,6 +159,46 @@ def linear(a, w, bias, out, act=ACT_NONE, resid=None, M=None, lda=None, ldo=None
             prof.append((2.0 * M * N * K, e0, e1))
         else:
             _check(lib.vc_linear(_is_bf16(a), *args, _stream()), "vc_linear")
+    return out
+
+
+def _profiled(flops, call):
+    prof = GEMM_PROFILE
+    if prof is not None and not torch.cuda.is_current_stream_capturing():
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        call()
+        e1.record()
+        prof.append((flops, e0, e1))
+    else:
+        call()
+
+
+def linear_ln_emit(a, w, bias, out, resid, xb, stats, M=None):
+    """out (fp32) = a @ w^T + bias + resid, plus xb = bf16(out) and stats [M, ceil(N/256), 2] = partial (sum, sum of squares) per
+    256-column tile of every output row (the producer half of the folded LayerNorm, vc_linear_ln_emit)."""
+    lib = load_library()
+    N, K = w.shape
+    M = a.shape[0] if M is None else M
+    assert a.dtype == w.dtype == xb.dtype == torch.bfloat16 and out.dtype == resid.dtype == stats.dtype == torch.float32
+    assert stats.is_contiguous() and stats.numel() >= M * ((N + 255) // 256) * 2
+    _profiled(2.0 * M * N * K, lambda: _check(lib.vc_linear_ln_emit(
+        _ptr(a), a.stride(0), _ptr(w), w.stride(0), _ptr(bias), _ptr(out), out.stride(0), _ptr(resid), resid.stride(0), _ptr(xb),
+        xb.stride(0), _ptr(stats), M, N, K, _stream()), "vc_linear_ln_emit"))
+    return out
+
+
+def linear_ln_fold(xb, wf, bias_f, colsum, stats, st_tiles, eps, out, act=ACT_NONE, M=None, ldo=None):
+    """out (bf16) = act(LayerNorm(x) @ w^T + b) from the raw bf16 row copy xb and the producer's statistics (vc_linear_ln_fold):
+    wf = bf16(gamma o w), colsum = fp32 row sums of wf, bias_f = b + w beta."""
+    lib = load_library()
+    N, K = wf.shape
+    M = xb.shape[0] if M is None else M
+    ldo = out.stride(0) if ldo is None else ldo
+    assert xb.dtype == wf.dtype == out.dtype == torch.bfloat16 and bias_f.dtype == colsum.dtype == stats.dtype == torch.float32
+    _profiled(2.0 * M * N * K, lambda: _check(lib.vc_linear_ln_fold(
+        _ptr(xb), xb.stride(0), _ptr(wf), wf.stride(0), _ptr(bias_f), _ptr(colsum), _ptr(stats), st_tiles, float(eps), _ptr(out), ldo,
+        act, M, N, K, _stream()), "vc_linear_ln_fold"))
     return out
 
 
