@@ -81,6 +81,10 @@ def main():
             out.normal_()
         fl = 2.0 * M * N * K
         run("ours   " + name, lambda: ops.linear(a, w, b, out, act=act, resid=out if resid else None), fl, smi)
+        if name == "proj+res":
+            for tn in (256, 512):
+                run("ours   proj+res tile_n=%d" % tn,
+                    lambda: ops.linear(a, w, b, out, act=act, resid=out, impl="tc", tile_n=tn), fl, smi)
         ob = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
         run("cublas " + name.split()[0] + " (plain bf16)", lambda: torch.matmul(a, w.t(), out=ob), fl, smi)
         del a, w, out, ob
