@@ -2,6 +2,8 @@
 cannot run 512 images): images are independent, so every image's result in the big batch must equal -- bit for bit, the
 kernels are deterministic and their per-row arithmetic does not depend on the batch size -- its result in a small batch
 (which test_e2e_gpu.py pins to the reference goldens / the oracle), plus the structural invariants of each search mode."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -153,22 +155,25 @@ def _oracle_on_gpu(cfg, sd, data, extra):
     return ids, lp, trace
 
 
-@pytest.mark.parametrize("vocab_gain,min_agree,max_gap", [(1.0, 0.98, 1.5e-2), (4.0, 0.97, 6e-2)])
+@pytest.mark.parametrize("vocab_gain,min_agree,max_gap", [(1.0, 0.975, 1.5e-2), (4.0, 0.96, 6e-2)])
 def test_bf16_mode_token_agreement_fullsize_vs_oracle(vocab_gain, min_agree, max_gap):
     """North-star criterion for the fast mode: >= 99 % greedy-token agreement with the fp32 reference algorithm. Full-size
-    ViT-B/16-384 model, 48 images, oracle = oracle/port.py (cached, fp32) run by torch on the same GPU. Agreement is counted
+    ViT-B/16-384 model, 192 images, oracle = oracle/port.py (cached, fp32) run by torch on the same GPU. Agreement is counted
     over the tokens produced under an identical prefix (every token of a row up to and including its first divergence: the
     teacher-forced condition); every divergence must sit on a reference near-tie (top-1/top-2 logit gap < max_gap).
-    vocab_gain 1 = the bench's own weights (synth seed 0; median top-2 gap 0.08). Measured on B200:
-    811/819 tokens = 99.0 %, 8 of 48 rows diverge, all at reference gaps <= 4.1e-3. vocab_gain 4 scales logits AND their
-    bf16 error by 4 (measured 98.2 %, gaps <= 3e-2): the flip rate is set by relative precision, not by peakiness. The asserted
-    floors leave room for one or two more near-tie flips on other boards; the measured values are printed."""
+    vocab_gain 1 = the bench's own weights (synth seed 0; median top-2 gap 0.08). Measured on B200 over 256
+    images: 98.4-98.6 % (4026/4091 .. 4106/4165 tokens; 59-65 of 256 rows diverge, all at reference gaps <= 1e-2; the first 48
+    images alone give 98.9-99.0 %). The 99 % of the north star is NOT reached with random-init weights: bf16 operands leave the
+    logits with ~0.9 % relative error (0.005 absolute at their 0.55 standard deviation) and 1.5 % of this model's argmax decisions
+    have a top-2 gap below that. The folded LayerNorms do not move the figure (98.58 / 98.54 / 98.41 % for none / norm1 / both,
+    one standard error = 0.18 %). vocab_gain 4 scales logits AND their error by 4 (97.7-98.2 %, gaps <= 3e-2): the flip rate is
+    set by relative precision, not by peakiness. The asserted floors leave room for sampling noise; measured values are printed."""
     cfg = vcfg.variant("16_384")
     sd = synth.make_state_dict(cfg, seed=0, vocab_gain=vocab_gain, eos_bias=1.0)
     extra = synth.default_test_extra_input(cfg)
-    B = 48
+    B = int(os.environ.get("VITCAP_AGREE_B", "192"))     # (environment override for A/B measurements of numerics changes)
     data = _data(cfg, B, seed=321)
-    m = FastImageCaptioning(cfg, test_extra_input=extra, mode="bf16", max_batch=B)
+    m = FastImageCaptioning(cfg, test_extra_input=extra, mode="bf16", max_batch=min(B, 128))
     m.load_state_dict(sd)
     m = m.to(DEV)
     ids, lp = m(data)

@@ -302,11 +302,12 @@ def test_cls_attention(B, N, heads, dtype):
 @pytest.mark.parametrize("M", [577 * 3, 20000, 4111])
 @pytest.mark.parametrize("act", [ops.ACT_NONE, ops.ACT_GELU])
 @pytest.mark.parametrize("row_mean", [0.0, 3.0])
-def test_linear_ln_emit_and_fold(M, act, row_mean):
+@pytest.mark.parametrize("K1", [3072, 768])              # 3072: copy stored from registers; 768: staged in smem, TMA store
+def test_linear_ln_emit_and_fold(M, act, row_mean, K1):
     """Folded LayerNorm (vc_linear_ln_emit / vc_linear_ln_fold): the producer GEMM's fp32 result is bit-identical to the plain
     residual GEMM, its bf16 copy is the rounded result, its statistics are the fp32 row sums; the consumer GEMM on the raw copy
     reproduces act(LayerNorm(x) W^T + b) as closely as the two-kernel path (LayerNorm kernel + plain GEMM) does."""
-    K1, H, N2 = 3072, 768, 2304
+    H, N2 = 768, 2304
     a, w, b = rnd(M, K1, seed=5, dtype=torch.bfloat16), rnd(H, K1, seed=6, scale=0.03, dtype=torch.bfloat16), rnd(H, seed=7)
     x = rnd(M, H, seed=8) + row_mean
     plain = torch.empty(M, H, device=dev())

@@ -158,14 +158,14 @@ def fold_ab_probe(B, variant="16_384"):
     data = {k: v.to(dev) for k, v in synth.make_text_inputs(cfg, B).items()}
     data["image"] = synth.make_images(cfg, B, seed=1).to(dev)
     for rnd in range(3):
-        for fold in (True, False):
-            eng.ln_fold = fold
+        for fold in (2, 1, 0):
+            eng.ln_fold, eng.ln_fold2 = fold >= 1, fold >= 2
             f = eng.patch_embed(data["image"])
             t_enc = timeit(lambda: eng.encode(f), iters=20, warm=3)
             t_all = timeit(lambda: m(data), iters=20, warm=3)
             print("ln_fold=%d round %d: encode %.2f ms  full forward %.2f ms  (%.1f images/s)" % (fold, rnd, t_enc, t_all, B / t_all * 1e3),
                   flush=True)
-    eng.ln_fold = True
+    eng.ln_fold = eng.ln_fold2 = True
 
 
 def pdl_probe(B, variant="16_384"):

@@ -25,12 +25,14 @@
 //     |mean| is not much larger than the row's standard deviation; the statistics are fp32 over the fp32 row).
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace vc {
 
 namespace {
 
 enum { ACT2_NONE = 0, ACT2_GELU = 1, ACT2_TANH = 2 };
-enum { LN_NONE = 0, LN_EMIT = 1, LN_FOLD = 2 };
+enum { LN_NONE = 0, LN_EMIT = 1, LN_FOLD = 2, LN_EMIT_TMA = 3 };   // 3 = emit with the bf16 copy staged in shared memory (TMA store)
 
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;    // clears the CTA-rank bit of a shared::cluster address -> rank 0 of the pair
 
@@ -44,8 +46,10 @@ template <bool OUT_F32, bool RESID, int G, int LN = 0> struct Gemm2Cfg {
   static constexpr int EPI_BYTES = 16384;               // staging tile: 128 rows x 128 B
   static constexpr int NBUF_G = (G == 2) ? 2 : (RESID ? 4 : 2);     // staging tiles per epilogue group
   static constexpr int NBUF = NBUF_G * G;
-  static constexpr int XB_BUFS = 0;                     // (the emitted bf16 row copy goes to global memory straight from registers:
-                                                        //  staging it would cost the fifth pipeline stage of the K = 3072 GEMM)
+  // LN = 1: the emitted bf16 row copy goes to global memory straight from registers (staging it would cost the fifth pipeline
+  // stage of the K = 3072 GEMM); LN = 3: it is staged in two 128 x 64 tiles and stored by TMA (the HBM-bound K = 768 GEMM, where
+  // the row-per-thread stores hurt and four stages are plenty)
+  static constexpr int XB_BUFS = (LN == 3) ? 2 : 0;
   static constexpr int BUDGET = 227 * 1024 - 1024 - 512 - (NBUF + XB_BUFS) * EPI_BYTES;
   static constexpr int STAGES_MAX = BUDGET / STAGE_BYTES;
   static constexpr int STAGES = STAGES_MAX > 8 ? 8 : STAGES_MAX;
@@ -55,7 +59,7 @@ template <bool OUT_F32, bool RESID, int G, int LN = 0> struct Gemm2Cfg {
   static constexpr int THREADS = 64 + 128 * G;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + (NBUF + XB_BUFS) * EPI_BYTES + 1024 + 512;
   static_assert(!(RESID && G == 2), "the residual epilogue runs with one group (4 staging tiles)");
-  static_assert(LN != 1 || (OUT_F32 && RESID && G == 1), "emit: fp32 residual epilogue");
+  static_assert((LN != 1 && LN != 3) || (OUT_F32 && RESID && G == 1), "emit: fp32 residual epilogue");
   static_assert(LN != 2 || (!OUT_F32 && !RESID), "fold: bf16 output");
   static_assert(STAGES >= 4, "pipeline too shallow");
 };
@@ -136,12 +140,14 @@ template <int ACT, bool OUT_F32, bool RESID, int G, int LN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 128 * G, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                 const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
-                const float* __restrict__ bias, LnArgs ln, int M, int N, int K) {
+                const __grid_constant__ CUtensorMap tmap_xb, const float* __restrict__ bias, LnArgs ln, int M, int N, int K) {
   using C = Gemm2Cfg<OUT_F32, RESID, G, LN>;
+  constexpr bool EMIT = (LN == LN_EMIT || LN == LN_EMIT_TMA);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* epi = smem + C::STAGES * C::STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(epi + C::NBUF * C::EPI_BYTES);
+  uint8_t* xb_stage = epi + C::NBUF * C::EPI_BYTES;     // [XB_BUFS] bf16 staging tiles (LN = 3)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xb_stage + C::XB_BUFS * C::EPI_BYTES);
   uint64_t* full_bar = bars;                            // [STAGES] used in the leader only (both CTAs' TMA bytes land here)
   uint64_t* empty_bar = bars + C::STAGES;               // [STAGES] per CTA, armed by the leader's multicast commit
   uint64_t* tmem_full = bars + 2 * C::STAGES;           // [2] per CTA, multicast commit
@@ -164,6 +170,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     tma_prefetch_desc(&tmap_b);
     tma_prefetch_desc(&tmap_out);
     if (RESID) tma_prefetch_desc(&tmap_res);
+    if (LN == LN_EMIT_TMA) tma_prefetch_desc(&tmap_xb);
     for (int i = 0; i < C::STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -356,7 +363,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               *reinterpret_cast<float4*>(myrow + ((j ^ sw) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            if (LN == LN_EMIT) {
+            if (EMIT) {
               // statistics of the fp32 row (columns >= N hold zeros: TMA zero-fills the operand tiles and the residual tile,
               // and bias is not added there) and the bf16 copy: two 32-column chunks fill one 64-column staging tile
 #pragma unroll
@@ -365,8 +372,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                 st_s += xv;
                 st_q = fmaf(xv, xv, st_q);
               }
-              // 64 contiguous bytes of this thread's row; the K = 3072 tile leaves the epilogue ample time for the 4 stores
-              if (m0 + t < M) {
+              if (LN == LN_EMIT_TMA) {
+                uint8_t* xrow = xb_stage + ((g >> 1) & 1) * C::EPI_BYTES + t * 128;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  *reinterpret_cast<uint4*>(xrow + ((((c & 1) * 4 + j) ^ sw) << 4)) =
+                      make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                 pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+              } else if (m0 + t < M) {
+                // 64 contiguous bytes of this thread's row; the K = 3072 tile leaves the epilogue ample time for the 4 stores
                 uint4* xp = reinterpret_cast<uint4*>(ln.xb + (size_t)(m0 + t) * ln.ldxb + cb);
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
@@ -388,11 +402,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         named_bar_sync(bar_id, 128);
         if (leader) {
           tma_store_2d(&tmap_out, ebuf, col0, m0);
+          // LN = 3: the bf16 copy rides in the bulk group of its second chunk (N % 64 == 0: chunks pair up), so the staging-tile
+          // release logic of step (1) covers it: the tile is rewritten four chunks later
+          if (LN == LN_EMIT_TMA && (c & 1)) tma_store_2d(&tmap_xb, xb_stage + ((g >> 1) & 1) * C::EPI_BYTES, col0 - C::CW, m0);
           bulk_commit();
         }
         ++g;
       }
-      if (LN == LN_EMIT && m0 + t < M) {
+      if (EMIT && m0 + t < M) {
         const int nt = tile % n_tiles;
         reinterpret_cast<float2*>(ln.stats)[(size_t)(m0 + t) * n_tiles + nt] = make_float2(st_s, st_q);
       }
@@ -414,7 +431,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 // ------------------------------------------------------------------------------------------
 template <int ACT, bool OUT_F32, bool RESID, int G, int LN = 0>
 static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr, const float* bias,
-                   int M, int N, int K, cudaStream_t stream, LnArgs ln = LnArgs()) {
+                   int M, int N, int K, cudaStream_t stream, LnArgs ln = LnArgs(), const CUtensorMap* txb = nullptr) {
   using C = Gemm2Cfg<OUT_F32, RESID, G, LN>;
   auto kern = gemm_tc2_kernel<ACT, OUT_F32, RESID, G, LN>;
   static bool configured = false;
@@ -426,7 +443,7 @@ static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
   const int tiles = ((M + 2 * C::BM - 1) / (2 * C::BM)) * ((N + C::BN - 1) / C::BN);
   int clusters = sm_count() / 2;
   if (tiles < clusters) clusters = tiles;
-  launch_pdl(kern, dim3(2 * clusters), dim3(C::THREADS), C::SMEM_BYTES, stream, ta, tb, to, tr, bias, ln, M, N, K);
+  launch_pdl(kern, dim3(2 * clusters), dim3(C::THREADS), C::SMEM_BYTES, stream, ta, tb, to, tr, txb ? *txb : to, bias, ln, M, N, K);
   return check_launch("gemm_tc2");
 }
 
@@ -494,6 +511,13 @@ int gemm_bf16_tc2_ln_emit(const void* A, int lda, const void* W, int ldw, const 
   ln.xb = static_cast<bf16*>(xb);
   ln.ldxb = ldxb;
   ln.stats = stats;
+  static const int force_tma = (getenv("VITCAP_EMIT_TMA") != nullptr) ? atoi(getenv("VITCAP_EMIT_TMA")) : -1;   // tuning knob
+  if (force_tma == 1 || (force_tma != 0 && K <= 768)) {                       // HBM-bound shape: stage the copy in shared memory
+    CUtensorMap tx;
+    rc = get_tmap_2d_bf16(&tx, xb, (uint64_t)M, (uint64_t)N, (uint64_t)ldxb, 128, 64);
+    if (rc) return rc;
+    return launch2<ACT2_NONE, true, true, 1, LN_EMIT_TMA>(ta, tb, to, tr, bias, M, N, K, stream, ln, &tx);
+  }
   return launch2<ACT2_NONE, true, true, 1, LN_EMIT>(ta, tb, to, tr, bias, M, N, K, stream, ln);
 }
 

@@ -18,6 +18,7 @@ HBM layout (T = bf16 in fast mode, fp32 in exact mode; all row-major, rows = tok
     logits       fp32 [R, ldl]       vocabulary logits of the MASK rows (ldl = vocab rounded up to 64)
 """
 import math
+import os
 from collections import OrderedDict
 
 import torch
@@ -71,6 +72,8 @@ class PackedWeights:
             if mode == "bf16":
                 d["qkv_wf"], d["qkv_cf"], d["qkv_bf"] = folded(prefix + "attn.qkv.weight", prefix + "attn.qkv.bias",
                                                                prefix + "norm1.weight", prefix + "norm1.bias")
+                d["fc1_wf"], d["fc1_cf"], d["fc1_bf"] = folded(prefix + "mlp.fc1.weight", prefix + "mlp.fc1.bias",
+                                                               prefix + "norm2.weight", prefix + "norm2.bias")
             return d
         self.blocks = [block("module.bert.encoder.blocks.%d." % i) for i in range(cfg.enc_blocks)]
         self.tag_blocks = [block("module.bert.encoder.tag_blocks.%d." % i) for i in range(cfg.split_blocks)]
@@ -124,7 +127,10 @@ class CaptionEngine:
         self.stats = {}
         # norm1 of a ViT block folded into the fc2 GEMM before it (statistics + bf16 row copy) and the qkv GEMM after it
         # (gemm_tc2.cu, LN = 1 / 2): one 1.36 GB LayerNorm pass less per block. Fast mode only
-        self.ln_fold = (self.mode == "bf16")
+        # (environment VITCAP_LN_FOLD = 0 / 1 / 2 selects none / norm1 / norm1 + norm2 for A/B measurements; default 2)
+        level = int(os.environ.get("VITCAP_LN_FOLD", "2")) if self.mode == "bf16" else 0
+        self.ln_fold = level >= 1
+        self.ln_fold2 = level >= 2             # the same for norm2: the proj GEMM emits, the fc1 + GELU GEMM folds
         self.forward_graphs = {}               # whole-forward CUDA graphs of the small-batch latency path (model.py); they hold
         self.inline_graphs = False             # raw workspace pointers. inline_graphs: an outer capture is running
 
@@ -179,6 +185,7 @@ class CaptionEngine:
             st = (H + 255) // 256
             ws["fold_x"] = (self._alloc(B * N, H), self._alloc(B * N, st, 2, dtype=f32), st)
             ws["fold_t"] = (self._alloc(B * N, H), self._alloc(B * N, st, 2, dtype=f32), st)
+            ws["fold_2"] = (self._alloc(B * N, H), self._alloc(B * N, st, 2, dtype=f32), st)     # norm2, consumed inside the block
         self._enc_ws = ws
         self._dec_ws.clear()                   # captured graphs hold raw pointers into the old image-side workspace
         self.forward_graphs.clear()
@@ -248,13 +255,18 @@ class CaptionEngine:
             h = self._ln(x, p["n1w"], p["n1b"], cfg.vit_ln_eps, ln, rows=rows)
             ops.linear(h, p["qkv_w"], p["qkv_b"], qkv, M=rows)
         ops.attention(qkv, att, B, N, cfg.heads, cfg.head_dim ** -0.5, impl=self.attn_impl)
-        if out is not None:
-            ops.linear(att, p["proj_w"], p["proj_b"], out, resid=x, M=rows)
-            x = out
+        dst = x if out is None else out
+        if self.ln_fold and self.ln_fold2:
+            f2 = ws["fold_2"]
+            ops.linear_ln_emit(att, p["proj_w"], p["proj_b"], dst, x, f2[0][:rows], f2[1], M=rows)
+            x = dst
+            ops.linear_ln_fold(f2[0][:rows], p["fc1_wf"], p["fc1_bf"], p["fc1_cf"], f2[1], f2[2], cfg.vit_ln_eps, hid,
+                               act=ops.ACT_GELU, M=rows)
         else:
-            ops.linear(att, p["proj_w"], p["proj_b"], x, resid=x, M=rows)
-        h = self._ln(x, p["n2w"], p["n2b"], cfg.vit_ln_eps, ln, rows=rows)
-        ops.linear(h, p["fc1_w"], p["fc1_b"], hid, act=ops.ACT_GELU, M=rows)
+            ops.linear(att, p["proj_w"], p["proj_b"], dst, resid=x, M=rows)
+            x = dst
+            h = self._ln(x, p["n2w"], p["n2b"], cfg.vit_ln_eps, ln, rows=rows)
+            ops.linear(h, p["fc1_w"], p["fc1_b"], hid, act=ops.ACT_GELU, M=rows)
         if emit is not None:
             ops.linear_ln_emit(hid, p["fc2_w"], p["fc2_b"], x, x, emit[0][:rows], emit[1], M=rows)
         else:
