@@ -103,15 +103,16 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
                ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
 // arrive on the barrier at this offset in CTA rank 0 of the pair (local arrive when executed by rank 0).
-// .relaxed: the barrier only tells the MMA thread that this warp's tcgen05.ld reads of the accumulator stage have completed
-// (tcgen05.wait::ld + tcgen05.fence::before_thread_sync precede it); no generic-proxy data is published through it. With
-// .release.cluster every epilogue warp paid MEMBAR.ALL.CTA + ERRBAR per tile (ncu: 25 % of the kernel's stall samples).
+// Default semantics (release at CTA scope, the form CUTLASS's ClusterBarrier::arrive uses): the barrier only tells the MMA thread
+// that this warp's tcgen05.ld reads of the accumulator stage have completed (tcgen05.wait::ld + tcgen05.fence::before_thread_sync
+// precede it); no generic-proxy data is published through it. Spelled .release.cluster, every epilogue warp paid
+// MEMBAR.ALL.CTA + MEMBAR.ALL.GPU + ERRBAR per tile (ncu: 25 % of the kernel's stall samples); this form is one SYNCS.ARRIVE.
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
   asm volatile(
       "{\n"
       ".reg .b32 ra;\n"
       "mapa.shared::cluster.u32 ra, %0, 0;\n"
-      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n"
       "}\n"
       ::"r"(smem_u32(bar)) : "memory");
 }
