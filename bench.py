@@ -36,6 +36,8 @@ def parse():
     ap.add_argument("--variant", default="16_384")
     ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--dec-layers", type=int, default=4)
+    ap.add_argument("--decode-precision", default=None, choices=["bf16", "bf16x3"],
+                    help="operands of the decode-step MLP / vocabulary-head GEMMs (default: the model's, bf16x3)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-sample-images", type=int, default=4)
@@ -71,6 +73,7 @@ def workload_config(args, cfg):
         "variant": args.variant, "batch_per_gpu": b, "global_batch": b * max(1, args.gpus),
         "max_length": 20, "num_beams": 1, "decoder_layers": cfg.dec_layers, "parallelism": "dp%d" % max(1, args.gpus),
         "weights": "random-init (synth.make_state_dict seed 0, reference layout)",
+        "decode_precision": getattr(args, "decode_precision", None) or "bf16x3",
         "l2": "inputs larger than L2 (906 MB of images and >10 GB of activations per step vs 126 MB L2)",
     }
 
@@ -319,7 +322,8 @@ def main():
     sd = synth.make_state_dict(cfg, seed=0)
     extra = synth.default_test_extra_input(cfg)
     B = per_gpu_batch(args)
-    model = FastImageCaptioning(cfg, test_extra_input=extra, mode=args.mode, max_batch=B)
+    model = FastImageCaptioning(cfg, test_extra_input=extra, mode=args.mode, max_batch=B, decode_precision=args.decode_precision)
+    args.decode_precision = model.decode_precision
     model.load_state_dict(sd)
     model = model.to(dev)
     host = synth.make_text_inputs(cfg, B)

@@ -107,9 +107,20 @@ int vc_assemble_tokens(const float* patch_out, const float* cls, const float* po
 
 /* LayerNorm over the last dim of fp32 rows (nn.LayerNorm eps 1e-6 in ViT blocks, vision_transformer.py:218/229/352;
  * eps 1e-12 in BERT layers/heads, modeling_bert.py:219/350/412/538). out_t: operand copy (bf16 or fp32), may be NULL;
- * out_f: fp32 copy, may be NULL. */
+ * out_f: fp32 copy, may be NULL.
+ * bf16 = 2 (VC_OPERAND_BF16X3): out_t is the split-bf16 operand [hi | lo | hi], 3H columns (ld_t >= 3H), hi = bf16(y),
+ * lo = bf16(y - hi). Multiplied on the tensor cores against the weight laid out as [w_hi | w_hi | w_lo] (K' = 3K) it gives
+ * y_hi w_hi + y_lo w_hi + y_hi w_lo with fp32 accumulation: ~2^-16 relative operand error instead of bf16's 2^-9, the
+ * precision the decode-step Linear layers of the fast mode need for the reference's argmax decisions
+ * (modeling_utils.py:815-822). The first H columns are the plain bf16 copy. */
+#define VC_OPERAND_F32 0
+#define VC_OPERAND_BF16 1
+#define VC_OPERAND_BF16X3 2
 int vc_layernorm(int bf16, const float* in, int ld_in, const float* gamma, const float* beta, float eps, void* out_t, int ld_t,
                  float* out_f, int ld_f, int rows, int H, void* stream);
+/* fp32 rows [rows, K] (pitch ld_in) -> the same split-bf16 operand [rows, 3K] (pitch ld_out >= 3K); K % 8 == 0.
+ * Used for the GELU output of BertIntermediate (modeling_bert.py:395-407) on its way into BertOutput.dense. */
+int vc_split_bf16x3(const float* in, int ld_in, void* out, int ld_out, int rows, int K, void* stream);
 /* out[r,:] = cast(in[r*row_stride : +H]) -- e.g. hidden_states[:, 0] of BertPooler (modeling_bert.py:524) */
 int vc_gather_rows(int bf16, const float* in, size_t row_stride, void* out, int ld_out, int rows, int H, void* stream);
 /* ctx[b] = [tag_feats[b,0] ; cap_feats[b,0..N-1]] (modeling_bert.py:1493), fp32 copy + operand copy */

@@ -155,8 +155,9 @@ def _oracle_on_gpu(cfg, sd, data, extra):
     return ids, lp, trace
 
 
-@pytest.mark.parametrize("vocab_gain,min_agree,max_gap", [(1.0, 0.975, 2.5e-2), (4.0, 0.96, 1e-1)])
-def test_bf16_mode_token_agreement_fullsize_vs_oracle(vocab_gain, min_agree, max_gap):
+@pytest.mark.parametrize("precision,vocab_gain,min_agree,max_gap", [("bf16x3", 1.0, 0.99, 2.5e-2), ("bf16", 1.0, 0.975, 2.5e-2),
+                                                                    ("bf16x3", 4.0, 0.98, 1e-1), ("bf16", 4.0, 0.96, 1e-1)])
+def test_bf16_mode_token_agreement_fullsize_vs_oracle(precision, vocab_gain, min_agree, max_gap):
     """North-star criterion for the fast mode: >= 99 % greedy-token agreement with the fp32 reference algorithm. Full-size
     ViT-B/16-384 model, 192 images, oracle = oracle/port.py (cached, fp32) run by torch on the same GPU. Agreement is counted
     over the tokens produced under an identical prefix (every token of a row up to and including its first divergence: the
@@ -174,7 +175,7 @@ def test_bf16_mode_token_agreement_fullsize_vs_oracle(vocab_gain, min_agree, max
     extra = synth.default_test_extra_input(cfg)
     B = int(os.environ.get("VITCAP_AGREE_B", "192"))     # (environment override for A/B measurements of numerics changes)
     data = _data(cfg, B, seed=321)
-    m = FastImageCaptioning(cfg, test_extra_input=extra, mode="bf16", max_batch=min(B, 128))
+    m = FastImageCaptioning(cfg, test_extra_input=extra, mode="bf16", max_batch=min(B, 128), decode_precision=precision)
     m.load_state_dict(sd)
     m = m.to(DEV)
     ids, lp = m(data)
@@ -203,9 +204,9 @@ def test_bf16_mode_token_agreement_fullsize_vs_oracle(vocab_gain, min_agree, max
         agree += t - 1
         diverged += 1
     frac = agree / same_prefix_tokens
-    print("bf16 vs fp32 oracle, vocab_gain %.0f: %d/%d same-prefix tokens agree (%.4f), %d/%d rows diverge, largest excused "
+    print("%s decode vs fp32 oracle, vocab_gain %.0f: %d/%d same-prefix tokens agree (%.4f), %d/%d rows diverge, largest excused "
           "gap %.3g; gap-aware: %d of the decisions are reference near-ties (gap < %.3g), the other %d agree 100 %%"
-          % (vocab_gain, agree, same_prefix_tokens, frac, diverged, B, worst_gap, near_ties, max_gap, same_prefix_tokens - near_ties))
+          % (precision, vocab_gain, agree, same_prefix_tokens, frac, diverged, B, worst_gap, near_ties, max_gap, same_prefix_tokens - near_ties))
     assert frac >= min_agree
     if diverged == 0:
         np.testing.assert_allclose(lp.cpu().numpy(), ref_lp.cpu().numpy(), atol=3e-2)

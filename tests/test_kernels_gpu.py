@@ -345,3 +345,68 @@ def test_linear_ln_emit_and_fold(M, act, row_mean, K1):
     print("folded LN rel err %.3g, LayerNorm kernel + GEMM rel err %.3g" % (e_fold, e_two))
     assert e_fold < 6e-3 and e_fold < 1.5 * e_two + 1e-4
     torch.testing.assert_close(got.float(), ref, rtol=3e-2, atol=3e-2)
+
+
+# ---- split-bf16 operands of the decode-step GEMMs (include/vitcap_b200.h, VC_OPERAND_BF16X3) ---------------------------------
+def _split_ref(y):
+    hi = y.to(torch.bfloat16)
+    lo = (y - hi.float()).to(torch.bfloat16)
+    return torch.cat([hi, lo, hi], dim=-1)
+
+
+@pytest.mark.parametrize("rows,K", [(1, 8), (1024, 3072), (77, 768)])
+def test_split_bf16x3_bit_exact(rows, K):
+    x = rnd(rows, K + 8, seed=5, scale=3.0)[:, :K]                # pitched input view
+    out = torch.zeros(rows, 3 * K + 16, device=dev(), dtype=torch.bfloat16)
+    ops.split_bf16x3(x, out[:, :3 * K])
+    assert torch.equal(out[:, :3 * K].view(torch.int16), _split_ref(x).view(torch.int16))
+    assert int(out[:, 3 * K:].abs().sum()) == 0                   # nothing written past the operand
+
+
+def test_split_bf16x3_refuses_narrow_output():
+    x = rnd(4, 64, seed=1)
+    out = torch.zeros(4, 128, device=dev(), dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError):
+        ops._check(ops.load_library().vc_split_bf16x3(ops._ptr(x), 64, ops._ptr(out), 128, 4, 64, ops._stream()), "vc_split_bf16x3")
+
+
+def test_layernorm_x3_is_the_split_of_the_fp32_output():
+    rows, H = 1000, 768
+    x, g, b = rnd(rows, H, seed=1, scale=2.0), rnd(H, seed=2), rnd(H, seed=3)
+    o_t = torch.zeros(2 * rows, 3 * H, device=dev(), dtype=torch.bfloat16)[1::2]     # strided rows, as the MASK rows are
+    o_f = torch.zeros(rows, H, device=dev())
+    ops.layernorm(x, g, b, 1e-12, out_t=o_t, out_f=o_f, x3=True)
+    torch.testing.assert_close(o_f, F.layer_norm(x, (H,), g, b, 1e-12), rtol=1e-5, atol=1e-5)
+    assert torch.equal(o_t.contiguous().view(torch.int16), _split_ref(o_f).view(torch.int16))
+    # the first H columns are what the plain bf16 flavour writes
+    o_b = torch.zeros(rows, H, device=dev(), dtype=torch.bfloat16)
+    ops.layernorm(x, g, b, 1e-12, out_t=o_b)
+    assert torch.equal(o_t[:, :H].contiguous().view(torch.int16), o_b.view(torch.int16))
+
+
+@pytest.mark.parametrize("M,N,K,act,resid", [(1024, 3072, 768, ops.ACT_GELU, False), (1024, 768, 3072, ops.ACT_NONE, True),
+                                             (512, 30522, 768, ops.ACT_NONE, False), (100, 768, 768, ops.ACT_GELU, False)])
+def test_linear_bf16x3_reaches_fp32_operand_precision(M, N, K, act, resid):
+    """Three tensor-core products on [hi | lo | hi] x [w_hi | w_hi | w_lo]: error against the fp64 product of the UNROUNDED
+    operands must be ~fp32-accumulation sized (< 2e-5 of the output scale), two orders below the plain bf16 GEMM's."""
+    a, w, b = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=0.05), rnd(N, seed=3)
+    r = rnd(M, N, seed=4) if resid else None
+    a3 = torch.zeros(M, 3 * K, device=dev(), dtype=torch.bfloat16)
+    ops.split_bf16x3(a, a3)
+    w3 = ops.split_weight_bf16x3(w)
+    assert w3.shape == (N, 3 * K)
+    ldo = (N + 63) // 64 * 64
+    out = torch.zeros(M, ldo, device=dev())
+    ops.linear(a3, w3, b, out[:, :N], act=act, resid=r, ldo=ldo)
+    y = a.double() @ w.double().t() + b.double()
+    if act == ops.ACT_GELU:
+        y = y * 0.5 * (1 + torch.erf(y / math.sqrt(2)))
+    if resid:
+        y = y + r.double()
+    scale = float(y.abs().max())
+    err3 = float((out[:, :N].double() - y).abs().max()) / scale
+    out1 = torch.zeros(M, ldo, device=dev())
+    ops.linear(a.to(torch.bfloat16), w.to(torch.bfloat16), b, out1[:, :N], act=act, resid=r, ldo=ldo)
+    err1 = float((out1[:, :N].double() - y).abs().max()) / scale
+    print("bf16x3 max error / scale %.3g, plain bf16 %.3g" % (err3, err1))
+    assert err3 < 2e-5 and err3 < err1 / 50

@@ -24,6 +24,7 @@ int resize_crop_u8(const uint8_t* src, const long long* src_off, const int* hw, 
 int assemble_tokens(const float* patch_out, const float* cls, const float* pos, float* x, int B, int P, int H, cudaStream_t s);
 int layernorm(int out_bf16, const float* in, int ld_in, const float* gamma, const float* beta, float eps, void* out_t, int ld_t,
               float* out_f, int ld_f, int rows, int H, cudaStream_t s);
+int split_bf16x3(const float* in, int ld_in, void* out, int ld_out, int rows, int K, cudaStream_t s);
 int gather_rows(int out_bf16, const float* in, size_t row_stride, void* out, int ld_out, int rows, int H, cudaStream_t s);
 int assemble_ctx(int out_bf16, const float* cap, const float* tag, float* ctx_f, void* ctx_t, int B, int N, int H, int Cp,
                  cudaStream_t s);
@@ -68,7 +69,7 @@ static std::atomic<long long> g_launches{0};
 extern "C" {
 
 const char* vc_last_error(void) { return vc::last_error(); }
-int vc_abi_version(void) { return 4; }
+int vc_abi_version(void) { return 5; }
 long long vc_launch_count(void) { return g_launches.load(); }
 void vc_reset_launch_count(void) { g_launches = 0; }
 void vc_set_pdl(int mode) { vc::set_pdl_mode(mode); }
@@ -114,6 +115,9 @@ int vc_assemble_tokens(const float* patch_out, const float* cls, const float* po
 int vc_layernorm(int bf16, const float* in, int ld_in, const float* gamma, const float* beta, float eps, void* out_t, int ld_t,
                  float* out_f, int ld_f, int rows, int H, void* stream) {
   VC_COUNT(1, vc::layernorm(bf16, in, ld_in, gamma, beta, eps, out_t, ld_t, out_f, ld_f, rows, H, ST(stream)));
+}
+int vc_split_bf16x3(const float* in, int ld_in, void* out, int ld_out, int rows, int K, void* stream) {
+  VC_COUNT(1, vc::split_bf16x3(in, ld_in, out, ld_out, rows, K, ST(stream)));
 }
 int vc_gather_rows(int bf16, const float* in, size_t row_stride, void* out, int ld_out, int rows, int H, void* stream) {
   VC_COUNT(1, vc::gather_rows(bf16, in, row_stride, out, ld_out, rows, H, ST(stream)));

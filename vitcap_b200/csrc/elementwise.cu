@@ -124,8 +124,17 @@ int assemble_tokens(const float* patch_out, const float* cls, const float* pos, 
 // LayerNorm over the last dim (H % 128 == 0, H <= 1024); fp32 in; one warp per row.
 // out_t: T copy (GEMM operand), out_f: optional fp32 copy (residual stream of the post-LN decoder).
 // Two-pass mean/variance in registers (matches torch's fp32 LayerNorm to ~1 ulp).
+// X3: out_t is the split-bf16 operand [hi | lo | hi] (3H columns, hi = bf16(y), lo = bf16(y - hi)) of the three-product
+// tensor-core GEMM against [w_hi | w_hi | w_lo]; its first H columns are the plain bf16 copy.
 // ------------------------------------------------------------------------------------------
-template <typename T>
+__device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  hi = pack_bf16x2(a, b);
+  float ha, hb;
+  unpack_bf16x2(hi, ha, hb);
+  lo = pack_bf16x2(a - ha, b - hb);
+}
+
+template <typename T, bool X3 = false>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ in, int ld_in, const float* __restrict__ gamma, const float* __restrict__ beta,
                  float eps, T* __restrict__ out_t, int ld_t, float* __restrict__ out_f, int ld_f, int rows, int H) {
@@ -165,6 +174,14 @@ layernorm_kernel(const float* __restrict__ in, int ld_in, const float* __restric
       if (out_t) {
         if (sizeof(T) == 4) {
           *reinterpret_cast<float4*>(reinterpret_cast<float*>(out_t) + (size_t)warp * ld_t + c) = o;
+        } else if (X3) {
+          uint2 hi, lo;
+          split_bf16x2(o.x, o.y, hi.x, lo.x);
+          split_bf16x2(o.z, o.w, hi.y, lo.y);
+          bf16* op = reinterpret_cast<bf16*>(out_t) + (size_t)warp * ld_t + c;
+          *reinterpret_cast<uint2*>(op) = hi;
+          *reinterpret_cast<uint2*>(op + H) = lo;
+          *reinterpret_cast<uint2*>(op + 2 * H) = hi;
         } else {
           uint2 pk = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
           *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(out_t) + (size_t)warp * ld_t + c) = pk;
@@ -180,9 +197,48 @@ int layernorm(int out_bf16, const float* in, int ld_in, const float* gamma, cons
     return VC_ERR_BAD_ARG;
   }
   const int blocks = (rows + 7) / 8;
-  if (out_bf16) launch_pdl(layernorm_kernel<bf16>, dim3(blocks), dim3(256), 0, s, in, ld_in, gamma, beta, eps, (bf16*)out_t, ld_t, out_f, ld_f, rows, H);
+  if (out_bf16 == 2) {
+    if (!out_t || ld_t < 3 * H) { set_last_error("layernorm: the split-bf16 operand needs ld_t >= 3 H"); return VC_ERR_BAD_ARG; }
+    launch_pdl(layernorm_kernel<bf16, true>, dim3(blocks), dim3(256), 0, s, in, ld_in, gamma, beta, eps, (bf16*)out_t, ld_t, out_f, ld_f, rows, H);
+  } else if (out_bf16) launch_pdl(layernorm_kernel<bf16>, dim3(blocks), dim3(256), 0, s, in, ld_in, gamma, beta, eps, (bf16*)out_t, ld_t, out_f, ld_f, rows, H);
   else launch_pdl(layernorm_kernel<float>, dim3(blocks), dim3(256), 0, s, in, ld_in, gamma, beta, eps, (float*)out_t, ld_t, out_f, ld_f, rows, H);
   return check_launch("layernorm");
+}
+
+// ------------------------------------------------------------------------------------------
+// split_bf16x3: fp32 rows [rows, K] -> split-bf16 operand [rows, 3K] = [hi | lo | hi] (see layernorm_kernel, X3).
+// One thread per 8 consecutive elements: 32 B in, 3 x 16 B out.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+split_bf16x3_kernel(const float* __restrict__ in, int ld_in, bf16* __restrict__ out, int ld_out, int rows, int K) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int per_row = K >> 3;
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long)rows * per_row) return;
+  const int r = (int)(t / per_row), c = (int)(t % per_row) * 8;
+  float f[8];
+  load8<float>(in + (size_t)r * ld_in + c, f);
+  uint4 hi, lo;
+  split_bf16x2(f[0], f[1], hi.x, lo.x);
+  split_bf16x2(f[2], f[3], hi.y, lo.y);
+  split_bf16x2(f[4], f[5], hi.z, lo.z);
+  split_bf16x2(f[6], f[7], hi.w, lo.w);
+  bf16* op = out + (size_t)r * ld_out + c;
+  *reinterpret_cast<uint4*>(op) = hi;
+  *reinterpret_cast<uint4*>(op + K) = lo;
+  *reinterpret_cast<uint4*>(op + 2 * K) = hi;
+}
+
+int split_bf16x3(const float* in, int ld_in, void* out, int ld_out, int rows, int K, cudaStream_t s) {
+  if (rows <= 0 || K <= 0 || (K % 8) || (ld_in % 4) || (ld_out % 8) || ld_out < 3 * K ||
+      (reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 15)) {
+    set_last_error("split_bf16x3: need K %% 8 == 0, ld_out >= 3 K, 16-byte aligned rows (K=%d)", K);
+    return VC_ERR_BAD_ARG;
+  }
+  const long n = (long)rows * (K >> 3);
+  launch_pdl(split_bf16x3_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, in, ld_in, (bf16*)out, ld_out, rows, K);
+  return check_launch("split_bf16x3");
 }
 
 // ------------------------------------------------------------------------------------------

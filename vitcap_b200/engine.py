@@ -34,9 +34,11 @@ def _round_up(a, b):
 class PackedWeights:
     """Weights re-laid for the kernels from a reference-layout state_dict (fp32 masters stay in the nn.Module)."""
 
-    def __init__(self, cfg: VitCapConfig, sd, mode, device):
+    def __init__(self, cfg: VitCapConfig, sd, mode, device, decode_x3=False):
         self.cfg = cfg
         self.mode = mode
+        # split-bf16 copies [w_hi | w_hi | w_lo] of the decode-step MLP and vocabulary-head weights (see _decode_layers)
+        self.decode_x3 = bool(decode_x3) and mode == "bf16"
         wt = torch.bfloat16 if mode == "bf16" else torch.float32
         self.wt = wt
 
@@ -88,6 +90,9 @@ class PackedWeights:
             }
         self.tag_head = head("module.bert.tag_logit.predictions.")
         self.cls_head = head("module.cls.predictions.")
+        if self.decode_x3:
+            self.cls_head["t_w3"] = ops.split_weight_bf16x3(Fp("module.cls.predictions.transform.dense.weight"))
+            self.cls_head["dec_w3"] = ops.split_weight_bf16x3(Fp("module.cls.predictions.decoder.weight"))
 
         e = "module.bert.embeddings."
         self.word = Fp(e + "word_embeddings.weight")
@@ -109,6 +114,9 @@ class PackedWeights:
                 "f_w": W(p + "output.dense.weight"), "f_b": Fp(p + "output.dense.bias"),
                 "ln2_w": Fp(p + "output.LayerNorm.weight"), "ln2_b": Fp(p + "output.LayerNorm.bias"),
             })
+            if self.decode_x3:
+                self.dec[-1]["i_w3"] = ops.split_weight_bf16x3(Fp(p + "intermediate.dense.weight"))
+                self.dec[-1]["f_w3"] = ops.split_weight_bf16x3(Fp(p + "output.dense.weight"))
 
 
 class CaptionEngine:
@@ -131,6 +139,8 @@ class CaptionEngine:
         level = int(os.environ.get("VITCAP_LN_FOLD", "2")) if self.mode == "bf16" else 0
         self.ln_fold = level >= 1
         self.ln_fold2 = level >= 2             # the same for norm2: the proj GEMM emits, the fc1 + GELU GEMM folds
+        # decode-step MLP and vocabulary head on split-bf16 operands (three tensor-core products, ~fp32 operand precision)
+        self.decode_x3 = weights.decode_x3
         self.forward_graphs = {}               # whole-forward CUDA graphs of the small-batch latency path (model.py); they hold
         self.inline_graphs = False             # raw workspace pointers. inline_graphs: an outer capture is running
 
@@ -212,6 +222,12 @@ class CaptionEngine:
         ws["head_f"] = self._alloc(R, H, dtype=f32)
         ws["head_t"] = ws["head_f"] if self.T == f32 else self._alloc(R, H)
         ws["logits"] = self._alloc(R, self.ldl, dtype=f32)
+        if self.decode_x3:
+            ws["a_t3"] = self._alloc(2 * R, 3 * H)          # LayerNorm 1 output, [hi | lo | hi]
+            ws["hid_f"] = self._alloc(2 * R, F, dtype=f32)  # GELU output in fp32 ...
+            ws["hid3"] = self._alloc(2 * R, 3 * F)          # ... and split
+            ws["e_t3"] = self._alloc(2 * R, 3 * H)          # last layer's LayerNorm 2 output (feeds the head)
+            ws["head_t3"] = self._alloc(R, 3 * H)
         ws["ids"] = torch.zeros(R, max_len, device=self.dev, dtype=i32)
         ws["unfinished"] = torch.ones(R, device=self.dev, dtype=i32)
         ws["sum_lp"] = torch.zeros(R, device=self.dev, dtype=f32)
@@ -445,18 +461,40 @@ class CaptionEngine:
         e_f, e_t = ws["e_f"], ws["e_t"]
         ops.embed_ln(ws["ids"], cur_len, mask_id, w.word, w.pos, w.type0, w.emb_ln_w, w.emb_ln_b, cfg.bert_ln_eps, e_f, e_t, R)
         scale = 1.0 / math.sqrt(cfg.head_dim)
+        x3 = self.decode_x3
+        n_layers = len(w.dec)
         for l, p in enumerate(w.dec):
             sq = ws["step_qkv"][l]
             ops.linear(e_t, p["qkv_w"], p["qkv_b"], sq[cur_len - 1], M=2 * R)
             ops.decode_attention(enc["ctx_qkv"][l], sq, anc, ws["att"], B, C, cfg.heads, E, cur_len, scale, ctx_vis=ctx_vis)
             ops.linear(ws["att"], p["o_w"], p["o_b"], ws["tmp"], resid=e_f, M=2 * R)
+            if x3:
+                # BertIntermediate / BertOutput (modeling_bert.py:395-419) on split-bf16 operands: the operand rounding of
+                # these two layers and of the vocabulary head is what flips near-tie argmax decisions against the fp32
+                # reference; the attention projections stay plain bf16
+                ops.layernorm(ws["tmp"], p["ln1_w"], p["ln1_b"], cfg.bert_ln_eps, out_t=ws["a_t3"], out_f=ws["a_f"], rows=2 * R,
+                              x3=True)
+                ops.linear(ws["a_t3"], p["i_w3"], p["i_b"], ws["hid_f"], act=ops.ACT_GELU, M=2 * R)
+                ops.split_bf16x3(ws["hid_f"], ws["hid3"], rows=2 * R)
+                ops.linear(ws["hid3"], p["f_w3"], p["f_b"], ws["tmp"], resid=ws["a_f"], M=2 * R)
+                if head and l == n_layers - 1:
+                    ops.layernorm(ws["tmp"], p["ln2_w"], p["ln2_b"], cfg.bert_ln_eps, out_t=ws["e_t3"], out_f=e_f, rows=2 * R,
+                                  x3=True)
+                else:
+                    self._ln(ws["tmp"], p["ln2_w"], p["ln2_b"], cfg.bert_ln_eps, e_t, out_f=e_f, rows=2 * R)
+                continue
             a_t = self._ln(ws["tmp"], p["ln1_w"], p["ln1_b"], cfg.bert_ln_eps, ws["a_t"], out_f=ws["a_f"], rows=2 * R)
             ops.linear(a_t, p["i_w"], p["i_b"], ws["hid"], act=ops.ACT_GELU, M=2 * R)
             ops.linear(ws["hid"], p["f_w"], p["f_b"], ws["tmp"], resid=ws["a_f"], M=2 * R)
             self._ln(ws["tmp"], p["ln2_w"], p["ln2_b"], cfg.bert_ln_eps, e_t, out_f=e_f, rows=2 * R)
         # vocabulary head on the MASK rows only (rows 1::2); the reference runs it over all T text rows
         # (modeling_bert.py:809-810) and keeps one
-        if head:
+        if head and x3:
+            hp = w.cls_head
+            ops.linear(ws["e_t3"][1::2], hp["t_w3"], hp["t_b"], ws["head_f"], act=ops.ACT_GELU, M=R)
+            ops.layernorm(ws["head_f"], hp["ln_w"], hp["ln_b"], cfg.bert_ln_eps, out_t=ws["head_t3"], rows=R, x3=True)
+            ops.linear(ws["head_t3"], hp["dec_w3"], hp["bias"], ws["logits"][:, :cfg.vocab], M=R, ldo=ws["logits"].stride(0))
+        elif head:
             mask_rows = e_t[1::2]
             self._head(w.cls_head, mask_rows, R, ws["head_f"], ws["head_t"], ws["logits"])
 

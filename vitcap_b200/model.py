@@ -7,6 +7,8 @@ with ``data`` = {'image', 'input_ids', 'attention_mask', 'token_type_ids', 'mask
 of ``test_extra_input``. Same parameter names, so ``state_dict`` / ``Checkpointer.load`` work unchanged.
 All compute runs in the sm_100a kernels of libvitcap_b200.so; this file only holds parameters and orchestration.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -221,11 +223,18 @@ class FastImageCaptioning(nn.Module):
     accumulation; 'fp32' = exact mode on CUDA cores (token ids / tag indices match the fp32 reference)."""
 
     def __init__(self, cfg: VitCapConfig, test_extra_input=None, mode="bf16", tokenizer=None, max_batch=64,
-                 use_cuda_graph=True, sample_seed=0, graph_forward=False):
+                 use_cuda_graph=True, sample_seed=0, graph_forward=False, decode_precision=None):
         super().__init__()
         assert mode in ("bf16", "fp32")
         self.cfg = cfg
         self.mode = mode
+        # fast mode only: 'bf16x3' = the decode-step MLP and vocabulary-head GEMMs run on split-bf16 operands (three
+        # tensor-core products per GEMM, ~fp32 operand precision: the token ids then agree with the fp32 reference on > 99 %
+        # of the steps), 'bf16' = plain bf16 operands everywhere. Default from VITCAP_DECODE_PRECISION, else 'bf16x3'.
+        if decode_precision is None:
+            decode_precision = os.environ.get("VITCAP_DECODE_PRECISION", "bf16x3")
+        assert decode_precision in ("bf16", "bf16x3")
+        self.decode_precision = decode_precision if mode == "bf16" else "fp32"
         self.module = FastViTCAP(cfg, self)
         self.image_encoder = FastImageEncoder(cfg, self)
         self.test_extra_input = dict(test_extra_input) if test_extra_input is not None else synth.default_test_extra_input(cfg)
@@ -257,7 +266,7 @@ class FastImageCaptioning(nn.Module):
         if dev.type != "cuda":
             raise RuntimeError("vitcap_b200 runs on a CUDA device only (no CPU path): move the module with .cuda() first")
         sd = self.state_dict()
-        w = PackedWeights(self.cfg, sd, self.mode, dev)
+        w = PackedWeights(self.cfg, sd, self.mode, dev, decode_x3=self.decode_precision == "bf16x3")
         self._engine = CaptionEngine(self.cfg, w, dev, use_cuda_graph=self.use_cuda_graph)
         return self
 

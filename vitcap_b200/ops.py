@@ -30,6 +30,7 @@ SIGNATURES = {
     "vc_resize_crop_u8": [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P],
     "vc_assemble_tokens": [_P, _P, _P, _P, _I, _I, _I, _P],
     "vc_layernorm": [_I, _P, _I, _P, _P, _F, _P, _I, _P, _I, _I, _I, _P],
+    "vc_split_bf16x3": [_P, _I, _P, _I, _I, _I, _P],
     "vc_gather_rows": [_I, _P, _SZ, _P, _I, _I, _I, _P],
     "vc_assemble_ctx": [_I, _P, _P, _P, _P, _I, _I, _I, _P],
     "vc_assemble_ctx_pitched": [_I, _P, _P, _P, _P, _I, _I, _I, _I, _P],
@@ -247,13 +248,32 @@ def assemble_tokens(patch_out, cls, pos, x, B, P, H):
     return x
 
 
-def layernorm(x, gamma, beta, eps, out_t=None, out_f=None, rows=None):
+def layernorm(x, gamma, beta, eps, out_t=None, out_f=None, rows=None, x3=False):
+    """x3: out_t (bf16, >= 3H columns) receives the split operand [hi | lo | hi] (include/vitcap_b200.h, VC_OPERAND_BF16X3)."""
     rows = x.shape[0] if rows is None else rows
     H = x.shape[-1]
     bf = _is_bf16(out_t) if out_t is not None else 0
+    if x3:
+        assert bf and out_t.shape[-1] >= 3 * H
+        bf = 2
     _check(load_library().vc_layernorm(bf, _ptr(x), x.stride(0), _ptr(gamma), _ptr(beta), float(eps), _ptr(out_t),
                                        out_t.stride(0) if out_t is not None else 0, _ptr(out_f),
                                        out_f.stride(0) if out_f is not None else 0, rows, H, _stream()), "vc_layernorm")
+
+
+def split_bf16x3(x, out, rows=None):
+    """fp32 [rows, K] -> bf16 [rows, 3K] = [hi | lo | hi]."""
+    rows = x.shape[0] if rows is None else rows
+    K = x.shape[-1]
+    assert x.dtype == torch.float32 and out.dtype == torch.bfloat16 and out.shape[-1] >= 3 * K
+    _check(load_library().vc_split_bf16x3(_ptr(x), x.stride(0), _ptr(out), out.stride(0), rows, K, _stream()), "vc_split_bf16x3")
+
+
+def split_weight_bf16x3(w32):
+    """Host-side (torch) layout of a Linear weight for the three-product GEMM: [w_hi | w_hi | w_lo] along K."""
+    hi = w32.to(torch.bfloat16)
+    lo = (w32.float() - hi.float()).to(torch.bfloat16)
+    return torch.cat([hi, hi, lo], dim=1).contiguous()
 
 
 def gather_rows(x, row_stride, out, rows, H):
