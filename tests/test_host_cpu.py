@@ -112,3 +112,18 @@ def test_label_counts_of_the_data_layer_masks():
     full = port.construct_full_mask(ti["attention_mask"], cfg.n_tokens)
     assert m._label_counts(full, ti["input_ids"], 20).tolist() == [0, 4, 50, 23]
     assert port.label_counts(ti["attention_mask"], 20).tolist() == [0, 4, 50, 23]
+
+
+def test_split_weight_bf16x3_layout_and_precision():
+    """Host-side weight layout of the three-product decode GEMMs: [w_hi | w_hi | w_lo]; hi + lo restores the fp32 weight to
+    ~2^-16 relative (the kernel-side operand split is checked on the GPU, tests/test_kernels_gpu.py)."""
+    import torch
+    from vitcap_b200 import ops
+    w = torch.randn(37, 64, generator=torch.Generator().manual_seed(3)) * 0.02
+    w3 = ops.split_weight_bf16x3(w)
+    assert w3.shape == (37, 192) and w3.dtype == torch.bfloat16 and w3.is_contiguous()
+    hi, hi2, lo = w3[:, :64], w3[:, 64:128], w3[:, 128:]
+    assert torch.equal(hi, w.to(torch.bfloat16)) and torch.equal(hi, hi2)
+    rel = ((hi.float() + lo.float()) - w).abs().max() / w.abs().max()
+    assert float(rel) < 2.0 ** -15
+    assert float((hi.float() - w).abs().max() / w.abs().max()) > 2.0 ** -11          # what plain bf16 leaves

@@ -1,6 +1,8 @@
-"""Experiment (not a test: pytest does not collect this file): how much of the bf16 fast mode's token disagreement with the fp32
+"""Experiment (measurement script, not a test): how much of the bf16 fast mode's token disagreement with the fp32
 oracle comes from the DECODE-step GEMM operands? The encoder, the prefill and the decode attention stay bf16; the decode-step
-Linear layers and the vocabulary head run on the fp32 CUDA-core kernel with fp32 weights.   python tests/exp_precise_decode.py [B]"""
+Linear layers and the vocabulary head run on the fp32 CUDA-core kernel with fp32 weights.   python tools/exp/precise_decode.py [B]
+Result (256 images, profiles/r01_precise_decode_exp_s9.log): fc1 + fc2 + head + vocab in fp32 -> 99.5 %; that became the
+split-bf16 decode path (engine._decode_layers, decode_precision="bf16x3")."""
 import math
 import os
 import sys
@@ -8,7 +10,7 @@ import sys
 import numpy as np
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from tests.test_fullsize_gpu import DEV, _data, _oracle_on_gpu  # noqa: E402
 from vitcap_b200 import config as vcfg  # noqa: E402
 from vitcap_b200 import ops, synth  # noqa: E402
@@ -40,7 +42,7 @@ def main():
     extra = synth.default_test_extra_input(cfg)
     data = _data(cfg, B, seed=321)
     ref_ids, _, _ = _oracle_on_gpu(cfg, sd, data, extra)
-    m = FastImageCaptioning(cfg, test_extra_input=extra, mode="bf16", max_batch=128, use_cuda_graph=False)
+    m = FastImageCaptioning(cfg, test_extra_input=extra, mode="bf16", max_batch=128, use_cuda_graph=False, decode_precision="bf16")
     m.load_state_dict(sd)
     m = m.to(DEV)
     ids, _ = m(data)
@@ -52,10 +54,11 @@ def main():
     f32 = torch.float32
 
     PRECISE = set()
+    LAYER = [-1]                       # decoder layer being evaluated ("fc1@3" selects one layer's GEMM)
 
     def lin(name, a_f, a_t, p32, p16, wk, bk, out, **kw):
         """fp32 CUDA-core GEMM when `name` is in PRECISE, else the bf16 tensor-core GEMM on the bf16 copy of the operand."""
-        if name in PRECISE:
+        if name in PRECISE or "%s@%d" % (name, LAYER[0]) in PRECISE:
             ops.linear(a_f, p32[wk], p32[bk], out, **kw)
         else:
             ops.linear(a_t if a_t is not None else a_f.to(torch.bfloat16), p16[wk], p16[bk], out, **kw)
@@ -70,6 +73,7 @@ def main():
         hid_f = torch.empty(2 * R, cfg.inter, device=DEV, dtype=f32)
         for l, (p, q) in enumerate(zip(w32.dec, w.dec)):
             sq = ws["step_qkv"][l]
+            LAYER[0] = l
             lin("qkv", e_f, e_t, p, q, "qkv_w", "qkv_b", qkv_f)
             sq[cur_len - 1].copy_(qkv_f)                                   # the caption-row K/V cache stays bf16
             ops.decode_attention(eng._enc_ws["ctx_qkv"][l], sq, anc, ws["att"], Bc, cfg.n_ctx, cfg.heads, E, cur_len, scale)
@@ -78,6 +82,7 @@ def main():
             lin("fc1", ws["a_f"], ws["a_t"], p, q, "i_w", "i_b", hid_f, act=ops.ACT_GELU)
             lin("fc2", hid_f, None, p, q, "f_w", "f_b", ws["tmp"], resid=ws["a_f"])
             ops.layernorm(ws["tmp"], p["ln2_w"], p["ln2_b"], cfg.bert_ln_eps, out_t=e_t, out_f=e_f, rows=2 * R)
+        LAYER[0] = -1
         if head:
             hp, hq = w32.cls_head, w.cls_head
             rows_f = e_f[1::2].contiguous()
@@ -88,8 +93,13 @@ def main():
             lin("vocab", th2, ws["head_t"], hp, hq, "dec_w", "bias", ws["logits"][:, :cfg.vocab], ldo=ws["logits"].stride(0))
 
     eng._decode_layers = decode_layers
-    for sel in (["qkv", "o", "fc1", "fc2", "head_t", "vocab"], [], ["head_t", "vocab"], ["vocab"], ["fc1", "fc2"], ["qkv", "o"],
-                ["fc1", "fc2", "head_t", "vocab"], ["qkv", "o", "fc1", "fc2"]):
+    sels = (["qkv", "o", "fc1", "fc2", "head_t", "vocab"], [], ["head_t", "vocab"], ["vocab"], ["fc1", "fc2"], ["qkv", "o"],
+            ["fc1", "fc2", "head_t", "vocab"], ["qkv", "o", "fc1", "fc2"])
+    if len(sys.argv) > 2 and sys.argv[2] == "layers":
+        hv = ["head_t", "vocab"]
+        sels = (hv + ["fc1", "fc2"], hv + ["fc1@3", "fc2@3"], hv + ["fc1@2", "fc2@2", "fc1@3", "fc2@3"], hv + ["fc2"], hv + ["fc1"],
+                ["vocab", "fc1", "fc2"], hv + ["fc1@0", "fc2@0"], hv + ["fc2@2", "fc2@3"])
+    for sel in sels:
         PRECISE.clear()
         PRECISE.update(sel)
         ids2, _ = m(data)

@@ -195,6 +195,43 @@ def pdl_probe(B, variant="16_384"):
     ops.set_pdl(1)
 
 
+def x3_probe(B):
+    """Decode-step GEMMs at their shapes (2B or B rows): plain bf16 against the split-bf16 three-product form (K' = 3K), per
+    tile width. Eight weight copies are rotated so that no launch finds its weights in L2 (as inside a decode step, where
+    3.7 GB of K/V pass between two uses of a weight)."""
+    R = B
+    flush = torch.empty(256 << 20, device=dev, dtype=torch.uint8)
+    for (name, M, N, K, act, resid) in [("fc1+gelu", 2 * R, 3072, 768, 1, False), ("fc2+res", 2 * R, 768, 3072, 0, True),
+                                        ("vocab", R, 30522, 768, 0, False), ("head_t", R, 768, 768, 1, False)]:
+        for kk, tag in ((K, "bf16"), (3 * K, "bf16x3")):
+            a = torch.randn(M, kk, device=dev).to(torch.bfloat16)
+            ncopy = 2 if N > 10000 else 8
+            ws = [(torch.randn(N, kk, device=dev) * 0.02).to(torch.bfloat16) for _ in range(ncopy)]
+            b = torch.randn(N, device=dev)
+            ldo = (N + 63) // 64 * 64
+            out = torch.empty(M, ldo, device=dev)
+            r = torch.randn(M, ldo, device=dev) if resid else None
+            for tile in (0, 64, 128, 256, 512):
+                if tile == 512 and N < 256:
+                    continue
+                i = [0]
+
+                def fn():
+                    i[0] += 1
+                    ops.linear(a, ws[i[0] % ncopy], b, out[:, :N], act=act, resid=r[:, :N] if resid else None, ldo=ldo,
+                               impl="tc" if tile else "auto", tile_n=tile)
+                try:
+                    ms = timeit(fn, iters=16, warm=4)
+                except RuntimeError as e:
+                    print("x3probe %-9s %-7s tile %3d: %s" % (name, tag, tile, str(e)[:60]))
+                    continue
+                print("x3probe %-9s %-7s M=%d N=%d K=%d tile %3d: %7.1f us  %6.1f TFLOP/s" %
+                      (name, tag, M, N, kk, tile, ms * 1e3, 2.0 * M * N * kk / ms / 1e9), flush=True)
+    x = torch.randn(2 * R, 3072, device=dev)
+    o = torch.empty(2 * R, 3 * 3072, device=dev, dtype=torch.bfloat16)
+    print("x3probe split_bf16x3 [%d, 3072]: %.1f us" % (2 * R, timeit(lambda: ops.split_bf16x3(x, o), iters=20, warm=3) * 1e3))
+
+
 if __name__ == "__main__":
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 512
     what = sys.argv[2] if len(sys.argv) > 2 else "all"
@@ -209,6 +246,8 @@ if __name__ == "__main__":
         decode_attn_probe(min(B, 256), E=4)
     if what in ("all", "stage"):
         stage_probe(B)
+    if what == "x3":
+        x3_probe(B)
     if what == "pdl":
         pdl_probe(B)
     if what == "fold":

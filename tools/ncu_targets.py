@@ -1,5 +1,5 @@
 """Launches single hot kernels at the bench shapes (B=512) for `ncu --set full -k regex:...` captures.
-usage: python tools/ncu_targets.py [attn|gemm_qkv|gemm_proj|gemm_fc1|gemm_fc2|dattn|ln] [reps]"""
+usage: python tools/ncu_targets.py [attn|gemm_qkv|gemm_proj|gemm_fc1|gemm_fc2|x3_fc1|x3_fc2|x3_vocab|dattn|ln] [reps]"""
 import os
 import sys
 
@@ -50,6 +50,17 @@ elif what == "gemm_fc1":
     gemm(3072, 768, 1, False, False)
 elif what == "gemm_fc2":
     gemm(768, 3072, 0, True, True)
+elif what in ("x3_fc1", "x3_fc2", "x3_vocab"):
+    # decode-step GEMMs on split-bf16 operands (K' = 3K): rows = 2B (token + MASK row per sequence) or B (MASK rows)
+    Mx, N, K, act, resid = {"x3_fc1": (2 * B, 3072, 768, 1, False), "x3_fc2": (2 * B, 768, 3072, 0, True),
+                            "x3_vocab": (B, 30522, 768, 0, False)}[what]
+    a = torch.randn(Mx, 3 * K, device=dev).to(torch.bfloat16)
+    w = (torch.randn(N, 3 * K, device=dev) * 0.02).to(torch.bfloat16)
+    b = torch.randn(N, device=dev)
+    ldo = (N + 63) // 64 * 64
+    out = torch.randn(Mx, ldo, device=dev)
+    for _ in range(reps):
+        ops.linear(a, w, b, out[:, :N], act=act, resid=out[:, :N] if resid else None, ldo=ldo)
 elif what == "dattn":
     ctx = torch.randn(B, 578, 2304, device=dev).to(torch.bfloat16)
     sq = torch.randn(20, 2 * B, 2304, device=dev).to(torch.bfloat16)

@@ -474,7 +474,10 @@ class CaptionEngine:
                 # reference; the attention projections stay plain bf16
                 ops.layernorm(ws["tmp"], p["ln1_w"], p["ln1_b"], cfg.bert_ln_eps, out_t=ws["a_t3"], out_f=ws["a_f"], rows=2 * R,
                               x3=True)
-                ops.linear(ws["a_t3"], p["i_w3"], p["i_b"], ws["hid_f"], act=ops.ACT_GELU, M=2 * R)
+                # (K' = 2304: the CTA-pair kernel's 256 x 256 tiles halve the operand bytes each SM pulls from L2 per flop;
+                # 23.4 us against 31.9 us on the heuristic's 128-wide tiles at 1024 rows, profiles/r01_x3probe_s10.log)
+                ops.linear(ws["a_t3"], p["i_w3"], p["i_b"], ws["hid_f"], act=ops.ACT_GELU, M=2 * R,
+                           impl="tc" if R >= 512 else "auto", tile_n=512 if R >= 512 else 0)
                 ops.split_bf16x3(ws["hid_f"], ws["hid3"], rows=2 * R)
                 ops.linear(ws["hid3"], p["f_w3"], p["f_b"], ws["tmp"], resid=ws["a_f"], M=2 * R)
                 if head and l == n_layers - 1:
