@@ -121,6 +121,12 @@ int vc_layernorm(int bf16, const float* in, int ld_in, const float* gamma, const
 /* fp32 rows [rows, K] (pitch ld_in) -> the same split-bf16 operand [rows, 3K] (pitch ld_out >= 3K); K % 8 == 0.
  * Used for the GELU output of BertIntermediate (modeling_bert.py:395-407) on its way into BertOutput.dense. */
 int vc_split_bf16x3(const float* in, int ld_in, void* out, int ld_out, int rows, int K, void* stream);
+/* out(fp32)[M,N] = A W^T + bias + resid for split operands A3 = [a_hi | a_lo | a_hi] [M, K3], W3 = [w_hi | w_hi | w_lo] [N, K3]
+ * (K3 = 3K, K % 64 == 0): the same three products as vc_linear(A3, W3, K3) up to fp32 summation order, but the four distinct
+ * tiles of a k-block are loaded once and multiplied three ways, 2/3 of the operand bytes per SM. BertOutput.dense of a decode
+ * step (modeling_bert.py:409-419: K = 3072, N = 768), whose launch is bound by the L2 -> SM feed of its 96 CTAs. */
+int vc_linear_x3(const void* A3, int lda, const void* W3, int ldw, const float* bias, float* out, int ldo, const float* resid,
+                 int ldr, int M, int N, int K3, void* stream);
 /* out[r,:] = cast(in[r*row_stride : +H]) -- e.g. hidden_states[:, 0] of BertPooler (modeling_bert.py:524) */
 int vc_gather_rows(int bf16, const float* in, size_t row_stride, void* out, int ld_out, int rows, int H, void* stream);
 /* ctx[b] = [tag_feats[b,0] ; cap_feats[b,0..N-1]] (modeling_bert.py:1493), fp32 copy + operand copy */

@@ -12,6 +12,8 @@ int gemm_bf16_tc2_ln_emit(const void* A, int lda, const void* W, int ldw, const 
 int gemm_bf16_tc2_ln_fold(const void* A, int lda, const void* Wf, int ldw, const float* bias_f, const float* colsum,
                           const float* stats, int st_tiles, float ln_eps, void* out, int ldo, int act, int M, int N, int K,
                           cudaStream_t stream);
+int gemm_bf16_tc_x3(const void* A, int lda, const void* W, int ldw, const float* bias, float* out, int ldo, const float* resid,
+                    int ldr, int M, int N, int K3, cudaStream_t stream);
 int gemm_bf16_tc(const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldo, int out_f32, int act,
                  const float* resid, int ldr, int M, int N, int K, int force_bn, cudaStream_t stream);
 int gemm_simt(int in_bf16, const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldo, int out_f32,
@@ -115,6 +117,10 @@ int vc_assemble_tokens(const float* patch_out, const float* cls, const float* po
 int vc_layernorm(int bf16, const float* in, int ld_in, const float* gamma, const float* beta, float eps, void* out_t, int ld_t,
                  float* out_f, int ld_f, int rows, int H, void* stream) {
   VC_COUNT(1, vc::layernorm(bf16, in, ld_in, gamma, beta, eps, out_t, ld_t, out_f, ld_f, rows, H, ST(stream)));
+}
+int vc_linear_x3(const void* A3, int lda, const void* W3, int ldw, const float* bias, float* out, int ldo, const float* resid,
+                 int ldr, int M, int N, int K3, void* stream) {
+  VC_COUNT(1, vc::gemm_bf16_tc_x3(A3, lda, W3, ldw, bias, out, ldo, resid, ldr, M, N, K3, ST(stream)));
 }
 int vc_split_bf16x3(const float* in, int ld_in, void* out, int ld_out, int rows, int K, void* stream) {
   VC_COUNT(1, vc::split_bf16x3(in, ld_in, out, ld_out, rows, K, ST(stream)));

@@ -17,12 +17,16 @@ namespace vc {
 
 enum { ACT_NONE = 0, ACT_GELU = 1, ACT_TANH = 2 };
 
-template <int BN, bool OUT_F32, bool RESID> struct GemmCfg {
+// X3: split-bf16 operands A = [a_hi | a_lo | a_hi], W = [w_hi | w_hi | w_lo] (K = 3 Kt). Instead of walking the concatenated K, a
+// stage holds the four distinct tiles (a_hi, w_hi, a_lo, w_lo) of one Kt block and the three products are issued from them:
+// 2/3 of the bytes each SM pulls from L2 (the long-K decode GEMMs are bound by exactly that).
+template <int BN, bool OUT_F32, bool RESID, bool X3 = false> struct GemmCfg {
   static constexpr int BM = 128;
   static constexpr int BK = 64;                         // 64 bf16 = one 128-byte swizzle row
   static constexpr int A_BYTES = BM * BK * 2;           // 16 KB
   static constexpr int B_BYTES = BN * BK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int HALF_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGE_BYTES = (X3 ? 2 : 1) * HALF_BYTES;
   // epilogue staging tiles (128 rows x 128 B); the residual tile of chunk g + NBUF - 2 is prefetched by TMA while chunk g is
   // processed (8 tiles with a 128-wide N tile were measured slower for the K = 768 residual GEMM: 0.51 vs 0.43 ms)
   static constexpr int NBUF = RESID ? 4 : 2;
@@ -36,12 +40,12 @@ template <int BN, bool OUT_F32, bool RESID> struct GemmCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NBUF * EPI_BYTES + 1024 + 512;
 };
 
-template <int BN, int ACT, bool OUT_F32, bool RESID>
+template <int BN, int ACT, bool OUT_F32, bool RESID, bool X3 = false>
 __global__ void __launch_bounds__(192, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
                const float* __restrict__ bias, int M, int N, int K) {
-  using C = GemmCfg<BN, OUT_F32, RESID>;
+  using C = GemmCfg<BN, OUT_F32, RESID, X3>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* epi = smem + C::STAGES * C::STAGE_BYTES;
@@ -58,7 +62,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int m_tiles = (M + C::BM - 1) / C::BM;
   const int n_tiles = (N + BN - 1) / BN;
   const int num_tiles = m_tiles * n_tiles;
-  const int num_kb = K / C::BK;
+  const int Kt = X3 ? K / 3 : K;            // X3: columns [0,Kt) = hi, [Kt,2Kt) = a_lo / w_hi, [2Kt,3Kt) = a_hi / w_lo
+  const int num_kb = Kt / C::BK;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -96,8 +101,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int kb = 0; kb < pre; ++kb) {
           mbar_arrive_expect_tx(&full_bar[kb], C::STAGE_BYTES);
           tma_load_2d(smem + kb * C::STAGE_BYTES + C::A_BYTES, &tmap_b, &full_bar[kb], kb * C::BK, n0);
+          if (X3) tma_load_2d(smem + kb * C::STAGE_BYTES + C::HALF_BYTES + C::A_BYTES, &tmap_b, &full_bar[kb], 2 * Kt + kb * C::BK, n0);
         }
-        for (int kb = pre; kb < num_kb; ++kb) tma_prefetch_l2_2d(&tmap_b, kb * C::BK, n0);
+        for (int kb = pre; kb < num_kb; ++kb) {
+          tma_prefetch_l2_2d(&tmap_b, kb * C::BK, n0);
+          if (X3) tma_prefetch_l2_2d(&tmap_b, 2 * Kt + kb * C::BK, n0);
+        }
       }
       pdl_wait();
       int stage = 0;
@@ -111,11 +120,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           if (pre > 0) {                      // stage armed and its W half already in flight (fresh barriers: nothing to wait for)
             --pre;
             tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * C::BK, m0);
+            if (X3) tma_load_2d(sa + C::HALF_BYTES, &tmap_a, &full_bar[stage], Kt + kb * C::BK, m0);
           } else {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
             tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * C::BK, m0);
             tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * C::BK, n0);
+            if (X3) {
+              tma_load_2d(sa + C::HALF_BYTES, &tmap_a, &full_bar[stage], Kt + kb * C::BK, m0);
+              tma_load_2d(sb + C::HALF_BYTES, &tmap_b, &full_bar[stage], 2 * Kt + kb * C::BK, n0);
+            }
           }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -145,6 +159,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           for (int k = 0; k < C::BK / 16; ++k) {
             // advance 16 bf16 (32 B) along K inside the swizzle atom: +2 in the (addr >> 4) field
             umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          }
+          if (X3) {
+            const uint64_t adesc_lo = make_smem_desc_sw128(sa + C::HALF_BYTES, 16, 1024);
+            const uint64_t bdesc_lo = make_smem_desc_sw128(sb + C::HALF_BYTES, 16, 1024);
+#pragma unroll
+            for (int k = 0; k < C::BK / 16; ++k) umma_f16(d_tmem, adesc_lo + 2 * k, bdesc + 2 * k, idesc, true);     // a_lo w_hi
+#pragma unroll
+            for (int k = 0; k < C::BK / 16; ++k) umma_f16(d_tmem, adesc + 2 * k, bdesc_lo + 2 * k, idesc, true);     // a_hi w_lo
           }
           umma_commit(&empty_bar[stage]);     // frees the smem stage once these MMAs retire
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
@@ -315,6 +337,44 @@ static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const CUtens
   int grid = tiles < sm_count() ? tiles : sm_count();
   launch_pdl(kern, dim3(grid), dim3(192), C::SMEM_BYTES, stream, ta, tb, to, tr, bias, M, N, K);
   return check_launch("gemm_tc");
+}
+
+// split-bf16 operands, the four distinct tiles loaded once per k-block (fc2 of a decode step: fp32 output + residual)
+int gemm_bf16_tc_x3(const void* A, int lda, const void* W, int ldw, const float* bias, float* out, int ldo, const float* resid,
+                    int ldr, int M, int N, int K3, cudaStream_t stream) {
+  constexpr int BN = 64;
+  using C = GemmCfg<BN, true, true, true>;
+  static_assert(C::STAGES >= 3, "not enough shared memory for a 3-stage pipeline");
+  if (M <= 0 || N <= 0 || K3 <= 0 || (K3 % 192) != 0 || resid == nullptr) {
+    set_last_error("gemm_tc_x3: need K3 %% 192 == 0 and a residual (K3=%d)", K3);
+    return VC_ERR_BAD_ARG;
+  }
+  if ((lda % 8) || (ldw % 8) || (ldo % 4) || (ldr % 4) || (reinterpret_cast<uintptr_t>(A) & 15) ||
+      (reinterpret_cast<uintptr_t>(W) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) ||
+      (reinterpret_cast<uintptr_t>(resid) & 15) || (reinterpret_cast<uintptr_t>(bias) & 15)) {
+    set_last_error("gemm_tc_x3: pointers must be 16-byte aligned and row pitches multiples of 16 bytes");
+    return VC_ERR_BAD_ARG;
+  }
+  CUtensorMap ta, tb, to, tr;
+  int rc = get_tmap_2d_bf16(&ta, A, (uint64_t)M, (uint64_t)K3, (uint64_t)lda, 128, 64);
+  if (rc) return rc;
+  rc = get_tmap_2d_bf16(&tb, W, (uint64_t)N, (uint64_t)K3, (uint64_t)ldw, (uint32_t)BN, 64);
+  if (rc) return rc;
+  rc = get_tmap_2d_f32(&to, out, (uint64_t)M, (uint64_t)N, (uint64_t)ldo, 128, 32);
+  if (rc) return rc;
+  rc = get_tmap_2d_f32(&tr, resid, (uint64_t)M, (uint64_t)N, (uint64_t)ldr, 128, 32);
+  if (rc) return rc;
+  auto kern = gemm_tc_kernel<BN, ACT_NONE, true, true, true>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) { set_last_error("gemm_tc_x3: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return VC_ERR_LAUNCH; }
+    configured = true;
+  }
+  const int tiles = ((M + C::BM - 1) / C::BM) * ((N + BN - 1) / BN);
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  launch_pdl(kern, dim3(grid), dim3(192), C::SMEM_BYTES, stream, ta, tb, to, tr, bias, M, N, K3);
+  return check_launch("gemm_tc_x3");
 }
 
 template <int BN, int ACT>

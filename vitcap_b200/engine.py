@@ -141,6 +141,9 @@ class CaptionEngine:
         self.ln_fold2 = level >= 2             # the same for norm2: the proj GEMM emits, the fc1 + GELU GEMM folds
         # decode-step MLP and vocabulary head on split-bf16 operands (three tensor-core products, ~fp32 operand precision)
         self.decode_x3 = weights.decode_x3
+        # fc2 of a decode step through vc_linear_x3 (distinct tiles loaded once) instead of the K-concatenated plain GEMM
+        # (VITCAP_X3_DEDUP=0 for A/B measurements)
+        self.x3_dedup = os.environ.get("VITCAP_X3_DEDUP", "1") != "0"
         self.forward_graphs = {}               # whole-forward CUDA graphs of the small-batch latency path (model.py); they hold
         self.inline_graphs = False             # raw workspace pointers. inline_graphs: an outer capture is running
 
@@ -479,7 +482,10 @@ class CaptionEngine:
                 ops.linear(ws["a_t3"], p["i_w3"], p["i_b"], ws["hid_f"], act=ops.ACT_GELU, M=2 * R,
                            impl="tc" if R >= 512 else "auto", tile_n=512 if R >= 512 else 0)
                 ops.split_bf16x3(ws["hid_f"], ws["hid3"], rows=2 * R)
-                ops.linear(ws["hid3"], p["f_w3"], p["f_b"], ws["tmp"], resid=ws["a_f"], M=2 * R)
+                if self.x3_dedup:
+                    ops.linear_x3(ws["hid3"], p["f_w3"], p["f_b"], ws["tmp"], ws["a_f"], M=2 * R)
+                else:
+                    ops.linear(ws["hid3"], p["f_w3"], p["f_b"], ws["tmp"], resid=ws["a_f"], M=2 * R)
                 if head and l == n_layers - 1:
                     ops.layernorm(ws["tmp"], p["ln2_w"], p["ln2_b"], cfg.bert_ln_eps, out_t=ws["e_t3"], out_f=e_f, rows=2 * R,
                                   x3=True)

@@ -31,6 +31,7 @@ SIGNATURES = {
     "vc_assemble_tokens": [_P, _P, _P, _P, _I, _I, _I, _P],
     "vc_layernorm": [_I, _P, _I, _P, _P, _F, _P, _I, _P, _I, _I, _I, _P],
     "vc_split_bf16x3": [_P, _I, _P, _I, _I, _I, _P],
+    "vc_linear_x3": [_P, _I, _P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _P],
     "vc_gather_rows": [_I, _P, _SZ, _P, _I, _I, _I, _P],
     "vc_assemble_ctx": [_I, _P, _P, _P, _P, _I, _I, _I, _P],
     "vc_assemble_ctx_pitched": [_I, _P, _P, _P, _P, _I, _I, _I, _I, _P],
@@ -267,6 +268,18 @@ def split_bf16x3(x, out, rows=None):
     K = x.shape[-1]
     assert x.dtype == torch.float32 and out.dtype == torch.bfloat16 and out.shape[-1] >= 3 * K
     _check(load_library().vc_split_bf16x3(_ptr(x), x.stride(0), _ptr(out), out.stride(0), rows, K, _stream()), "vc_split_bf16x3")
+
+
+def linear_x3(a3, w3, bias, out, resid, M=None):
+    """out(fp32) = a w^T + bias + resid on split operands a3 = [hi | lo | hi], w3 = [w_hi | w_hi | w_lo]: same result as
+    linear(a3, w3, ...) up to fp32 summation order, each distinct tile loaded once (vc_linear_x3)."""
+    M = a3.shape[0] if M is None else M
+    N, K3 = w3.shape
+    assert a3.dtype == torch.bfloat16 and w3.dtype == torch.bfloat16 and out.dtype == torch.float32 and resid.dtype == torch.float32
+    assert a3.shape[-1] == K3 and a3.stride(-1) == 1 and w3.stride(-1) == 1 and out.stride(-1) == 1 and resid.stride(-1) == 1
+    _check(load_library().vc_linear_x3(_ptr(a3), a3.stride(0), _ptr(w3), w3.stride(0), _ptr(bias), _ptr(out), out.stride(0),
+                                       _ptr(resid), resid.stride(0), M, N, K3, _stream()), "vc_linear_x3")
+    return out
 
 
 def split_weight_bf16x3(w32):
