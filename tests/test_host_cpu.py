@@ -127,3 +127,23 @@ def test_split_weight_bf16x3_layout_and_precision():
     rel = ((hi.float() + lo.float()) - w).abs().max() / w.abs().max()
     assert float(rel) < 2.0 ** -15
     assert float((hi.float() - w).abs().max() / w.abs().max()) > 2.0 ** -11          # what plain bf16 leaves
+
+
+def test_three_product_split_bf16_arithmetic_spec():
+    """Executable statement of what the decode-step split-bf16 GEMMs compute, in plain torch on the CPU:
+    with a = hi + lo and w = w_hi + w_lo (each part a bf16 number), hi w_hi + lo w_hi + hi w_lo accumulated in fp32 misses only
+    the lo w_lo term (2^-18 relative) -- two orders closer to the fp32 product than the plain bf16 GEMM. The GPU kernels are
+    pinned to the same figures in tests/test_kernels_gpu.py."""
+    import torch
+    from vitcap_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    a, w = torch.randn(64, 768, generator=g), torch.randn(96, 768, generator=g) * 0.05
+    hi = a.to(torch.bfloat16)
+    lo = (a - hi.float()).to(torch.bfloat16)
+    a3 = torch.cat([hi, lo, hi], 1).float()
+    w3 = ops.split_weight_bf16x3(w).float()
+    ref = a.double() @ w.double().t()
+    scale = float(ref.abs().max())
+    err3 = float((a3 @ w3.t() - ref).abs().max()) / scale
+    err1 = float((hi.float() @ w.to(torch.bfloat16).float().t() - ref).abs().max()) / scale
+    assert err3 < 1e-5 and err1 > 5e-4 and err3 < err1 / 100
