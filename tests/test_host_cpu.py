@@ -147,3 +147,20 @@ def test_three_product_split_bf16_arithmetic_spec():
     err3 = float((a3 @ w3.t() - ref).abs().max()) / scale
     err1 = float((hi.float() @ w.to(torch.bfloat16).float().t() - ref).abs().max()) / scale
     assert err3 < 1e-5 and err1 > 5e-4 and err3 < err1 / 100
+
+
+def test_decode_precision_option(monkeypatch):
+    """decode_precision: 'bf16x3' by default in the fast mode, overridable by argument or VITCAP_DECODE_PRECISION; the exact mode
+    ignores it; anything else is refused at construction."""
+    from vitcap_b200 import config as vcfg
+    from vitcap_b200.model import FastImageCaptioning
+    cfg = vcfg.tiny()
+    monkeypatch.delenv("VITCAP_DECODE_PRECISION", raising=False)
+    assert FastImageCaptioning(cfg).decode_precision == "bf16x3"
+    assert FastImageCaptioning(cfg, decode_precision="bf16").decode_precision == "bf16"
+    assert FastImageCaptioning(cfg, mode="fp32", decode_precision="bf16x3").decode_precision == "fp32"
+    monkeypatch.setenv("VITCAP_DECODE_PRECISION", "bf16")
+    assert FastImageCaptioning(cfg).decode_precision == "bf16"
+    assert FastImageCaptioning(cfg, decode_precision="bf16x3").decode_precision == "bf16x3"
+    with pytest.raises(AssertionError):
+        FastImageCaptioning(cfg, decode_precision="fp8")
