@@ -40,7 +40,8 @@ def parse():
                     help="operands of the decode-step MLP / vocabulary-head GEMMs (default: the model's, bf16x3)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--cpu-sample-images", type=int, default=4)
+    ap.add_argument("--cpu-sample-images", type=int, default=8, help="cpu_baseline leg: BASELINE.json configs[0] is B = 8")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra keys (12-layer decoder, EOS-planted step)")
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
                     help="--impl reference only. cpu (the contract's reference arm): the reference algorithm on the host cores. "
                          "cuda: the same oracle port executed by stock PyTorch library kernels (cuBLAS / ATen) on cuda:0 -- the "
@@ -70,12 +71,29 @@ def workload_config(args, cfg):
     return {
         "workload": "BASELINE.json configs[2]: full ViTCAP greedy captioning, ViT-B/16-%d, %d-layer decoder, max_len 20, "
                     "batch %d per GPU, data-parallel" % (cfg.img_size, cfg.dec_layers, b),
-        "variant": args.variant, "batch_per_gpu": b, "global_batch": b * max(1, args.gpus),
+        "variant": args.variant, "batch_per_gpu": b, "global_batch": b * max(1, args.gpus), "batch_per_step": b * max(1, args.gpus),
         "max_length": 20, "num_beams": 1, "decoder_layers": cfg.dec_layers, "parallelism": "dp%d" % max(1, args.gpus),
         "weights": "random-init (synth.make_state_dict seed 0, reference layout)",
         "decode_precision": getattr(args, "decode_precision", None) or "bf16x3",
         "l2": "inputs larger than L2 (906 MB of images and >10 GB of activations per step vs 126 MB L2)",
     }
+
+
+def algorithmic_flops_per_image(cfg, max_len=20):
+    """BASELINE.md section 3 / SURVEY.md section 8(d): FLOPs of the cached algorithm per image (187.95 G for ViT-B/16-384 with the
+    4-layer decoder): every block in full, although the path skips the dead rows of the last concept block."""
+    N, C, H, F, V, L = cfg.n_tokens, cfg.n_ctx, cfg.hidden, cfg.inter, cfg.vocab, cfg.dec_layers
+
+    def block(n):
+        return 2 * n * H * 3 * H + 4 * n * n * H + 2 * n * H * H + 4 * n * H * F
+    patch = 2 * cfg.n_patches * cfg.patch_dim * H
+    enc = (cfg.enc_blocks + cfg.split_blocks) * block(N)
+    tag = 2 * H * H * 2 + 2 * H * V
+    prefill = L * block(C)
+    steps = 0
+    for cl in range(1, max_len):
+        steps += L * (2 * (2 * H * 3 * H + 2 * H * H + 4 * H * F) + 4 * 2 * (C + cl + 1) * H) + 2 * H * H + 2 * H * V
+    return patch + enc + tag + prefill + steps
 
 
 # ------------------------------------------------------------------------------------------------ clocks sampling
@@ -130,13 +148,20 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------ CPU baseline
 def cpu_baseline(cfg, sd, n_images, extra):
     """The reference's algorithm as shipped (every decode step re-runs the ViT trunk, the tag head and the whole decoder;
-    oracle/port.py 'faithful', pinned against the reference's own outputs in tests/golden) on the host cores."""
+    oracle/port.py 'faithful', pinned against the reference's own outputs in tests/golden) on the host cores, as BASELINE.md
+    section 4 prescribes: all host threads, one untimed B = 1 warm-up, one timed run of B = n_images (configs[0]: 8)."""
     import torch
     from oracle import port
     from vitcap_b200 import synth
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     pm = port.PortModel(cfg, sd)
+    warm = synth.make_text_inputs(cfg, 1)
+    warm["image"] = synth.make_images(cfg, 1, seed=1233)
+    t0 = time.time()
+    with torch.no_grad():
+        port.caption(pm, warm, extra, algorithm="faithful")
+    t_warm = time.time() - t0
     data = synth.make_text_inputs(cfg, n_images)
     data["image"] = synth.make_images(cfg, n_images, seed=1234)
     t0 = time.time()
@@ -144,11 +169,12 @@ def cpu_baseline(cfg, sd, n_images, extra):
         ids, lp = port.caption(pm, data, extra, algorithm="faithful")
     dt = time.time() - t0
     return {"value": n_images / dt, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": "%d image(s) of the same workload (ViT-B/16-%d, 20-token greedy, fp32, reference algorithm without KV cache: "
-                      "19 full-model calls), %.1f s" % (n_images, cfg.img_size, dt)}, ids
+            "sample": "BASELINE.json configs[0]: one batch of %d image(s) of the same workload (ViT-B/16-%d, 20-token greedy, fp32, "
+                      "reference algorithm without KV cache: 19 full-model calls), %.1f s, after one untimed B=1 warm-up (%.1f s)"
+                      % (n_images, cfg.img_size, dt, t_warm)}, ids
 
 
-def decode_roofline(torch, ops, cfg, B, dev, peaks):
+def decode_roofline(torch, ops, cfg, B, dev, peaks, model=None, extra=None):
     """Algorithmic bytes (K+V rows a step must read, context rows counted once per image) / measured
     duration of decode_attention_mma_kernel at the middle decode step, against the measured copy bandwidth."""
     H, heads, C, L = cfg.hidden, cfg.heads, cfg.n_ctx, cfg.dec_layers
@@ -184,8 +210,36 @@ def decode_roofline(torch, ops, cfg, B, dev, peaks):
         traffic = next(v["dram_bytes"] for k, v in tj.items() if "decode_attention_mma_kernel" in k)
     except Exception:
         pass
+    # the WHOLE decode loop (19 steps, one CUDA graph: attention + the small GEMMs / LayerNorms / search kernels around it)
+    # against its HBM floor: SURVEY.md section 8(d) bytes = K+V of the visible keys per layer and step + one pass over the
+    # decoder / vocabulary-head weights (bf16) per step
+    loop = None
+    if model is not None:
+        eng = model.engine
+        max_len = int(extra["max_length"])
+        call = lambda: eng.greedy_or_sample(B, 1, max_len, int(extra["bos_token_id"]), int(extra["pad_token_id"]),   # noqa: E731
+                                            [int(e) for e in extra["eos_token_ids"]], int(extra["mask_token_id"]))
+        for _ in range(2):
+            call()
+        torch.cuda.synchronize()
+        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0.record()
+        for _ in range(5):
+            call()
+        l1.record()
+        torch.cuda.synchronize()
+        loop_ms = l0.elapsed_time(l1) / 5
+        F = cfg.inter
+        w_bytes = L * (3 * H * H + H * H + 2 * H * F) * 2 + (H * H + cfg.vocab * H) * 2
+        kv_bytes = sum(L * B * (C + cl + 1) * 2 * H * 2 for cl in range(1, max_len))
+        floor_ms = (kv_bytes + (max_len - 1) * w_bytes) / (peak * 1e9) * 1e3
+        loop = {"ms": loop_ms, "floor_ms": floor_ms, "frac": floor_ms / loop_ms, "steps": max_len - 1,
+                "kernels": eng.stats.get("graph_kernels"), "lanes": eng.decode_lanes,
+                "algorithmic_bytes": kv_bytes + (max_len - 1) * w_bytes,
+                "how": "%d-step greedy decode loop replayed 5 times as its CUDA graph right after the timed region (context K/V of "
+                       "the last batch), CUDA events; floor = algorithmic bytes / copy bandwidth" % (max_len - 1)}
     return {"kernel": "decode_attention_mma_kernel (2 query rows per sequence over 578 context + %d caption keys, bf16 K/V, "
-                      "%d launches per decode step, 19 steps per batch)" % (cur_len + 1, L),
+                      "%d launches per decode step, 19 steps per batch)" % (cur_len + 1, L), "loop": loop,
             "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": src,
             "algorithmic_bytes_per_launch": byt, "us_per_launch": ms * 1e3, "traffic": traffic,
             "traffic_note": "dram__bytes_read+write of one launch at B=512 from the committed ncu --set full capture "
@@ -259,33 +313,41 @@ def run_reference_arm(args):
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     pm = port.PortModel(cfg, sd)
-    per_step = 1
-    data = synth.make_text_inputs(cfg, per_step)
-    data["image"] = synth.make_images(cfg, per_step, seed=1234)
-    times = []
-    budget = 240.0
-    t_start = time.time()
-    done_steps = 0
-    for i in range(args.warmup + args.steps):
+
+    def run(n, seed):
+        data = synth.make_text_inputs(cfg, n)
+        data["image"] = synth.make_images(cfg, n, seed=seed)
         t0 = time.time()
         with torch.no_grad():
             port.caption(pm, data, extra, algorithm="faithful")
-        dt = time.time() - t0
-        if i >= args.warmup:
-            times.append(dt)
-            done_steps += 1
-        # keep the whole arm within a few minutes on slow hosts: stop early but never before one timed step
-        if time.time() - t_start > budget and done_steps >= 1:
-            break
+        return time.time() - t0
+
+    # Warm-up: W untimed B = 1 captions ("one untimed B=1 warm-up"); their median also sizes the timed
+    # steps: EXACTLY --steps steps are timed, each one batch of `per_step` images, per_step = the largest batch <= 8
+    # (BASELINE.json configs[0]) for which the whole arm still ends within ~4 minutes on this host.
+    warm = [run(1, 1000 + i) for i in range(max(1, args.warmup))]
+    t_img = statistics.median(warm)
+    budget = 240.0
+    per_step = int(budget / (max(1, args.steps) * t_img * 1.25))
+    per_step = max(1, min(8, per_step))
+    times = [run(per_step, 1234 + i) for i in range(args.steps)]
     total = sum(times)
     value = per_step * len(times) / total
-    sample = "%d timed step(s) of %d image(s) each, reference algorithm (no KV cache, 19 full-model calls per caption), fp32, " \
-             "%d host threads" % (len(times), per_step, threads)
+    rates = sorted(per_step / t for t in times)
+    spread = {"min": rates[0], "median": statistics.median(rates), "max": rates[-1], "unit": UNIT, "timed_steps": len(times)}
+    sample = "%d timed step(s) of %d image(s) each (BASELINE.json configs[0] is B=8; the per-step batch is the largest <= 8 that " \
+             "keeps %d steps within ~4 min at this host's %.2f s per B=1 caption), reference algorithm (no KV cache, 19 full-model " \
+             "calls per caption), fp32, %d host threads; per-step rate min/median/max %.3f/%.3f/%.3f images/s" \
+             % (len(times), per_step, args.steps, t_img, threads, spread["min"], spread["median"], spread["max"])
+    wl = workload_config(args, cfg)
+    wl["batch_per_step"] = per_step
+    wl["reference_sample"] = "the reference arm captions %d image(s) per step, not %d: a bounded sample of the workload" \
+                             % (per_step, wl["global_batch"])
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, cfg),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": wl,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample, "spread": spread},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -333,10 +395,21 @@ def main():
     img_dev = img_host.to(dev)
     data_dev = dict(text_dev, image=img_dev)
 
+    # the path's one exchange step (gather of the caption records) runs on a side stream: the compute stream of a rank never
+    # waits for the other ranks inside the timed region, only the side streams meet (vitcap_b200/parallel.py SideStreamGather)
+    side_gather = parallel.SideStreamGather(dev)
+    last_gather = [None]
+
     def step_device():
         ids, lp = model(data_dev)
         rec = parallel.pack_records(ids, lp, *model.last_tags)
-        return parallel.all_gather_records(rec)
+        full, done = side_gather(rec)
+        last_gather[0] = done
+        return full
+
+    def join_gather():
+        if last_gather[0] is not None:
+            torch.cuda.current_stream().wait_event(last_gather[0])
 
     def sync_all():
         torch.cuda.synchronize()
@@ -360,6 +433,7 @@ def main():
     ev0.record()
     for _ in range(args.steps):
         out = step_device()
+    join_gather()                                         # the timed region ends when the last batch's records are gathered
     ev1.record()
     sync_all()
     ops.GEMM_PROFILE = None
@@ -411,7 +485,7 @@ def main():
     # distinct caches of the bench's own size: 3.6 GB, far beyond L2) are timed eagerly right after the timed region.
     roofline_decode = None
     if args.mode == "bf16" and rank == 0:
-        roofline_decode = decode_roofline(torch, ops, cfg, B, dev, peaks)
+        roofline_decode = decode_roofline(torch, ops, cfg, B, dev, peaks, model=model, extra=extra)
     sync_all()
 
     # ---- e2e: the same steps through the public host loop (vitcap_b200.stream.OverlappedCaptioner, the drop-in for the
@@ -486,11 +560,42 @@ def main():
                   "d2h_bytes_per_step": int(oc.d2h_bytes // n_e2e), "steps": n_e2e,
                   "api": "the same loop with uint8 HWC images (8-bit pixels; ToTensor/Normalize/BGR2RGB fused into patch extraction)"}
 
+    # ---- extra keys: the whole step against the tensor roofline, and the BASELINE.json wording of the decoder (12 layers)
+    extras = {}
+    fl_img = algorithmic_flops_per_image(cfg)
+    step_tflops = fl_img * B * world * args.steps / (ms_max * 1e-3) / 1e12 / world
+    extras["whole_step_frac"] = {"algorithmic_gflop_per_image": fl_img / 1e9, "achieved_tflops_per_gpu": step_tflops, "peak": peak,
+                                 "frac": step_tflops / peak if peak else None,
+                                 "note": "SURVEY.md section 8(d) FLOPs of the whole step (HBM-bound decode loop included) / step "
+                                         "time, against the sustained bf16 matmul peak"}
+    if not args.no_extras and world == 1 and args.mode == "bf16" and cfg.dec_layers != 12:
+        del out
+        cfg12 = vcfg.variant(args.variant, dec_layers=12)
+        m12 = FastImageCaptioning(cfg12, test_extra_input=extra, mode=args.mode, max_batch=B, decode_precision=args.decode_precision)
+        m12.load_state_dict(synth.make_state_dict(cfg12, seed=0))
+        m12 = m12.to(dev)
+        for _ in range(3):
+            m12(data_dev)
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(5):
+            m12(data_dev)
+        a1.record()
+        torch.cuda.synchronize()
+        ms12 = a0.elapsed_time(a1) / 5
+        extras["dec12"] = {"value": B / ms12 * 1e3, "unit": UNIT, "ms_per_step": ms12, "steps": 5, "warmup": 3,
+                           "note": "the same step with a 12-layer decoder (BASELINE.json's wording; the shipped model builds 4, "
+                                   "modeling_bert.py:1342-1346), device-resident inputs, decode_precision %s" % args.decode_precision}
+        del m12
+        torch.cuda.empty_cache()
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "bf16" if args.mode == "bf16" else "f32", "data": "synthetic", "config": workload_config(args, cfg),
         "roofline": roofline, "roofline_decode": roofline_decode, "e2e": e2e, "e2e_u8": e2e_u8, "gpu_launches": int(launches), "clocks": clocks,
+        "extra": extras,
     }
     if world > 1:
         line["config"]["host_binding"] = ("rank bound to the %d CPU cores NVML reports as local to its GPU" % len(numa_cores)

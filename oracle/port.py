@@ -132,7 +132,8 @@ class PortModel:
         out = self.bert_layer_from_kv(idx, hq, q, k, v, add_mask)
         return out, k, v
 
-    def bert_layer_from_kv(self, idx, hq, q, k, v, add_mask):
+    def bert_layer_from_kv(self, idx, hq, q, k, v, add_mask, step=False):
+        """step: True when called for the two rows of a decode step (only the quantised subclass cares)."""
         cfg = self.cfg
         p = "module.bert.decoder.layer.%d." % idx
         B, Sq, C = hq.shape
@@ -159,6 +160,227 @@ class PortModel:
         return (heads(F.linear(h, self.p(p + "attention.self.query.weight"), self.p(p + "attention.self.query.bias"))),
                 heads(F.linear(h, self.p(p + "attention.self.key.weight"), self.p(p + "attention.self.key.bias"))),
                 heads(F.linear(h, self.p(p + "attention.self.value.weight"), self.p(p + "attention.self.value.bias"))))
+
+
+# =========================================================================================
+# quantisation-matched restatement of the fast (bf16) mode
+# =========================================================================================
+def q_bf16(x):
+    """Round to bf16 (nearest even) and return as fp32: one kernel rounding point."""
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+def split_bf16(x):
+    """x ~ hi + lo with hi = bf16(x), lo = bf16(x - hi): the split operand of the decode-step GEMMs (engine.py, bf16x3)."""
+    hi = q_bf16(x)
+    return hi, q_bf16(x - hi)
+
+
+def gelu_fast(x):
+    """The GELU of the tensor-core epilogues (common.cuh gelu_erf_tanh): x/2 (1 + tanh(z (c0 + c1 u + c2 u^2))), z = x/sqrt 2,
+    u = min(z^2, 30); evaluated here with an exact tanh (the kernels use MUFU.TANH, 2^-11 relative)."""
+    z = x * 0.70710678118654752440
+    u = torch.clamp(z * z, max=30.0)
+    p = (-1.988479253896676e-03 * u + 1.0466777301852825e-01) * u + 1.1278464660309704
+    hx = 0.5 * x
+    return hx * torch.tanh(z * p) + hx
+
+
+class QuantPortModel(PortModel):
+    """Executable spec of the fast mode's ARITHMETIC: the fp32 algorithm of PortModel with every operand rounded to bf16 exactly
+    where the CUDA kernels round (vitcap_b200/engine.py), fp32 accumulation everywhere else. The difference between the CUDA
+    path and THIS model is kernel error (summation order, MUFU approximations, rounding flips); the difference between this
+    model and PortModel is the operand quantisation the north star allows the bf16 mode. Rounding points:
+
+      patch embed      patches and conv weight bf16, fp32 out (engine.patch_embed)
+      ViT block        qkv / attention output / GELU(fc1) stored bf16; the residual stream stays fp32. norm1 / norm2 are either
+                       the LayerNorm kernel (h = bf16(LN(x)), W bf16) or FOLDED into the consuming GEMM (gemm_tc2.cu LN = 2):
+                       rstd (bf16(x) bf16(gamma o W)^T - mean colsum) + (b + W beta), colsum over the rounded weight
+      attention        S = Q K^T fp32, P = exp(S - max) rounded to bf16 for the P V product, row sum from the unrounded P
+      decoder prefill  post-LN BertLayer: LayerNorm kernel output bf16 (operand) + fp32 (residual), qkv / attention / GELU bf16
+      decode step      the same; with decode_x3 the MLP and the vocabulary head run on split operands (hi + lo, three products)
+      heads            dense + fast GELU fp32 -> LayerNorm -> bf16 (tag head) or split (vocabulary head) -> decoder GEMM
+
+    ln_fold: 0 = LayerNorm kernel everywhere, 1 = norm1 folded, 2 = norm1 and norm2 folded (the engine's default).
+    cls_only_last: the last concept block is evaluated for the CLS row only with LayerNorm-kernel roundings and an fp32 softmax
+    (engine._vit_block_cls_only); False = a full folded block (engine.encode(full_tag_feats=True))."""
+
+    def __init__(self, cfg, state_dict, ln_fold=2, decode_x3=True, cls_only_last=True):
+        super().__init__(cfg, state_dict, dtype=torch.float32)
+        self.ln_fold = ln_fold
+        self.decode_x3 = decode_x3
+        self.cls_only_last = cls_only_last
+        self._wq = {}
+
+    def wq(self, key):
+        if key not in self._wq:
+            self._wq[key] = q_bf16(self.sd[key])
+        return self._wq[key]
+
+    # ---- building blocks ----------------------------------------------------------------
+    def lin(self, h_q, wkey, bkey):
+        """bf16 operands (h_q already rounded), fp32 accumulate + fp32 bias."""
+        return F.linear(h_q, self.wq(wkey), self.sd[bkey] if bkey else None)
+
+    def lin_x3(self, a, wkey, bkey):
+        """Three-product split-bf16 GEMM (gemm_tc.cu X3 / the K-concatenated form): a_hi w_hi + a_lo w_hi + a_hi w_lo."""
+        key = ("x3", wkey)
+        if key not in self._wq:
+            self._wq[key] = split_bf16(self.sd[wkey])
+        w_hi, w_lo = self._wq[key]
+        a_hi, a_lo = split_bf16(a)
+        out = F.linear(a_hi, w_hi) + F.linear(a_lo, w_hi) + F.linear(a_hi, w_lo)
+        return out + self.sd[bkey] if bkey else out
+
+    def lin_ln(self, x, gkey, bekey, eps, wkey, bkey):
+        """LayerNorm kernel (two-pass fp32 statistics, bf16 output) followed by a bf16 GEMM."""
+        h = q_bf16(F.layer_norm(x, (x.shape[-1],), self.sd[gkey], self.sd[bekey], eps))
+        return self.lin(h, wkey, bkey), h
+
+    def lin_fold(self, x, gkey, bekey, eps, wkey, bkey):
+        """Folded LayerNorm (gemm_tc2.cu LN = 1/3 producer + LN = 2 consumer; weights packed in engine.PackedWeights.folded)."""
+        key = ("fold", wkey)
+        if key not in self._wq:
+            w, g, be = self.sd[wkey], self.sd[gkey], self.sd[bekey]
+            wf = q_bf16(w * g.unsqueeze(0))
+            self._wq[key] = (wf, wf.sum(1), self.sd[bkey] + w @ be)
+        wf, colsum, bias_f = self._wq[key]
+        K = x.shape[-1]
+        mean = x.sum(-1, keepdim=True) / K
+        var = torch.clamp((x * x).sum(-1, keepdim=True) / K - mean * mean, min=0.0)     # one-pass, as the GEMM epilogue
+        rstd = torch.rsqrt(var + eps)
+        acc = F.linear(q_bf16(x), wf)
+        return rstd * acc + ((-mean * rstd) * colsum + bias_f)
+
+    @staticmethod
+    def attend(q, k, v, scale, add_mask=None, round_p=True):
+        """q, k, v fp32 tensors holding bf16 values, (B, H, S, d). Returns the bf16-rounded attention output (B, Sq, H d)."""
+        # exp2 domain with an INTEGER exponent reference, as the kernels (attention_tc.cu, decode_attention_mma.cu): bf16
+        # rounding commutes with powers of two, so bf16(P) is the same whichever integer reference (lazy, per chunk, per warp)
+        # a kernel happened to use
+        s = torch.matmul(q, k.transpose(-1, -2)) * (scale * 1.4426950408889634)
+        if add_mask is not None:
+            s = s + add_mask
+        p = torch.exp2(s - torch.ceil(s.max(dim=-1, keepdim=True).values))
+        l = p.sum(dim=-1, keepdim=True)
+        o = torch.matmul(q_bf16(p) if round_p else p, v) / l
+        B, H, Sq, d = o.shape
+        return q_bf16(o.permute(0, 2, 1, 3).reshape(B, Sq, H * d))
+
+    # ---- image side ---------------------------------------------------------------------
+    def patch_embed(self, image):
+        cfg = self.cfg
+        w = self.wq("image_encoder.module.patch_embed.proj.weight")
+        b = self.p("image_encoder.module.patch_embed.proj.bias")
+        x = F.conv2d(q_bf16(image), w, b, stride=cfg.patch).flatten(2).transpose(1, 2)
+        cls = self.p("image_encoder.module.cls_token").expand(x.shape[0], -1, -1)
+        return torch.cat([cls, x], dim=1) + self.p("image_encoder.module.pos_embed")
+
+    def vit_block(self, x, prefix, fold1=False, fold2=False):
+        cfg = self.cfg
+        B, N, C = x.shape
+        H, d = cfg.heads, cfg.head_dim
+        eps = cfg.vit_ln_eps
+        n1 = (prefix + "norm1.weight", prefix + "norm1.bias", eps, prefix + "attn.qkv.weight", prefix + "attn.qkv.bias")
+        qkv = self.lin_fold(x, *n1) if fold1 else self.lin_ln(x, *n1)[0]
+        qkv = q_bf16(qkv).reshape(B, N, 3, H, d).permute(2, 0, 3, 1, 4)
+        o = self.attend(qkv[0], qkv[1], qkv[2], d ** -0.5)
+        x = x + self.lin(o, prefix + "attn.proj.weight", prefix + "attn.proj.bias")
+        n2 = (prefix + "norm2.weight", prefix + "norm2.bias", eps, prefix + "mlp.fc1.weight", prefix + "mlp.fc1.bias")
+        h = self.lin_fold(x, *n2) if fold2 else self.lin_ln(x, *n2)[0]
+        h = q_bf16(gelu_fast(h))
+        return x + self.lin(h, prefix + "mlp.fc2.weight", prefix + "mlp.fc2.bias")
+
+    def vit_block_cls_only(self, x, prefix):
+        """engine._vit_block_cls_only: K | V of every row, everything else for row 0; returns x with row 0 replaced."""
+        cfg = self.cfg
+        B, N, C = x.shape
+        H, d = cfg.heads, cfg.head_dim
+        eps = cfg.vit_ln_eps
+        qkv, h = self.lin_ln(x, prefix + "norm1.weight", prefix + "norm1.bias", eps, prefix + "attn.qkv.weight", prefix + "attn.qkv.bias")
+        qkv = q_bf16(qkv).reshape(B, N, 3, H, d).permute(2, 0, 3, 1, 4)
+        o = self.attend(qkv[0][:, :, 0:1], qkv[1], qkv[2], d ** -0.5, round_p=False)       # cls_attention_kernel: fp32 P
+        xc = x[:, 0:1] + self.lin(o, prefix + "attn.proj.weight", prefix + "attn.proj.bias")
+        hc, _ = self.lin_ln(xc, prefix + "norm2.weight", prefix + "norm2.bias", eps, prefix + "mlp.fc1.weight", prefix + "mlp.fc1.bias")
+        hc = q_bf16(gelu_fast(hc))
+        xc = xc + self.lin(hc, prefix + "mlp.fc2.weight", prefix + "mlp.fc2.bias")
+        return torch.cat([xc, x[:, 1:]], dim=1)
+
+    def split_encoder(self, x, taps=None):
+        """engine.encode: norm1 of every block except the very first (and the CLS-only one) is folded when ln_fold >= 1, norm2
+        of every full block when ln_fold >= 2. taps (list): receives (name, stream) after every block."""
+        cfg = self.cfg
+        f1, f2 = self.ln_fold >= 1, self.ln_fold >= 2
+        split_at = cfg.enc_blocks - cfg.split_blocks
+        tag = None
+        for i in range(cfg.enc_blocks):
+            if i == split_at:
+                tag = x
+            x = self.vit_block(x, "module.bert.encoder.blocks.%d." % i, fold1=f1 and i > 0, fold2=f2)
+            if taps is not None:
+                taps.append(("block%d" % i, x))
+        for j in range(cfg.split_blocks):
+            prefix = "module.bert.encoder.tag_blocks.%d." % j
+            if j == cfg.split_blocks - 1 and self.cls_only_last:
+                tag = self.vit_block_cls_only(tag, prefix)
+            else:
+                tag = self.vit_block(tag, prefix, fold1=f1 and (split_at + j) > 0, fold2=f2)
+            if taps is not None:
+                taps.append(("tag_block%d" % j, tag))
+        return x, tag
+
+    def head(self, prefix, h):
+        """engine._head (tag head: bf16 operands) / the x3 branch of engine._decode_layers (vocabulary head)."""
+        cfg = self.cfg
+        x3 = self.decode_x3 and prefix.startswith("module.cls.")
+        ln = (cfg.hidden,), self.p(prefix + "transform.LayerNorm.weight"), self.p(prefix + "transform.LayerNorm.bias"), cfg.bert_ln_eps
+        if x3:
+            t = gelu_fast(self.lin_x3(h, prefix + "transform.dense.weight", prefix + "transform.dense.bias"))
+            t = F.layer_norm(t, *ln)
+            return self.lin_x3(t, prefix + "decoder.weight", None) + self.p(prefix + "bias")
+        t = gelu_fast(self.lin(q_bf16(h), prefix + "transform.dense.weight", prefix + "transform.dense.bias"))
+        t = q_bf16(F.layer_norm(t, *ln))
+        return self.lin(t, prefix + "decoder.weight", None) + self.p(prefix + "bias")
+
+    def tag_head(self, tag_feats):
+        cfg = self.cfg
+        pooled = q_bf16(torch.tanh(self.lin(q_bf16(tag_feats[:, 0]), "module.bert.pooler.dense.weight", "module.bert.pooler.dense.bias")))
+        logit = self.head("module.bert.tag_logit.predictions.", pooled)
+        prob, idx = torch.sigmoid(logit).topk(cfg.topk, dim=1, largest=True)
+        return logit, prob, idx, (prob >= cfg.tag_thresh).sum(dim=1)
+
+    # ---- text side ----------------------------------------------------------------------
+    def qkv_rows(self, idx, h):
+        cfg = self.cfg
+        H, d = cfg.heads, cfg.head_dim
+        p = "module.bert.decoder.layer.%d.attention.self." % idx
+        hq = q_bf16(h)
+
+        def heads(t):
+            return q_bf16(t).view(t.shape[0], t.shape[1], H, d).permute(0, 2, 1, 3)
+        return tuple(heads(self.lin(hq, p + n + ".weight", p + n + ".bias")) for n in ("query", "key", "value"))
+
+    def bert_layer(self, idx, hq, hkv, add_mask):
+        assert hq is hkv
+        q, k, v = self.qkv_rows(idx, hq)
+        return self.bert_layer_from_kv(idx, hq, q, k, v, add_mask), k, v
+
+    def bert_layer_from_kv(self, idx, hq, q, k, v, add_mask, step=False):
+        """hq: fp32 rows (residual); q / k / v hold bf16 values. step=True: a decode step (split-operand MLP when decode_x3)."""
+        cfg = self.cfg
+        p = "module.bert.decoder.layer.%d." % idx
+        C = hq.shape[-1]
+        ctx = self.attend(q, k, v, 1.0 / math.sqrt(cfg.head_dim), add_mask)
+        tmp = self.lin(ctx, p + "attention.output.dense.weight", p + "attention.output.dense.bias") + hq
+        a = F.layer_norm(tmp, (C,), self.p(p + "attention.output.LayerNorm.weight"), self.p(p + "attention.output.LayerNorm.bias"),
+                         cfg.bert_ln_eps)
+        if step and self.decode_x3:
+            m = gelu_fast(self.lin_x3(a, p + "intermediate.dense.weight", p + "intermediate.dense.bias"))
+            m = self.lin_x3(m, p + "output.dense.weight", p + "output.dense.bias")
+        else:
+            m = q_bf16(gelu_fast(self.lin(q_bf16(a), p + "intermediate.dense.weight", p + "intermediate.dense.bias")))
+            m = self.lin(m, p + "output.dense.weight", p + "output.dense.bias")
+        return F.layer_norm(m + a, (C,), self.p(p + "output.LayerNorm.weight"), self.p(p + "output.LayerNorm.bias"), cfg.bert_ln_eps)
 
 
 # =========================================================================================
@@ -362,7 +584,7 @@ class CachedStepper:
                 ka = self.key_add.repeat_interleave(E, dim=0) if E > 1 else self.key_add
                 add = add.repeat(R, 1, 1, 1)
                 add[:, 0, :, :ka.shape[1]] += ka.unsqueeze(1)
-            e = m.bert_layer_from_kv(l, e, q, K, V, add)
+            e = m.bert_layer_from_kv(l, e, q, K, V, add, step=True)
             self.Kt[l] = k[:, :, 0:1] if self.Kt[l] is None else torch.cat([self.Kt[l], k[:, :, 0:1]], dim=2)
             self.Vt[l] = v[:, :, 0:1] if self.Vt[l] is None else torch.cat([self.Vt[l], v[:, :, 0:1]], dim=2)
         return m.head("module.cls.predictions.", e[:, 1])

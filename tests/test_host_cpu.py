@@ -49,10 +49,32 @@ def test_header_symbols_are_exported_and_bound():
     lib = ops.load_library()
     for n in names:
         assert hasattr(lib, n), n
-    simple = {"vc_last_error", "vc_abi_version", "vc_launch_count", "vc_reset_launch_count", "vc_set_pdl", "vc_get_pdl"}
+    simple = {"vc_last_error", "vc_abi_version", "vc_launch_count", "vc_reset_launch_count", "vc_set_pdl", "vc_get_pdl",
+              "vc_set_tuning", "vc_get_tuning", "vc_check_device"}
     assert names - simple == set(ops.SIGNATURES), (names - simple) ^ set(ops.SIGNATURES)
-    assert lib.vc_abi_version() == 5
+    assert lib.vc_abi_version() == 6
     assert isinstance(lib.vc_last_error(), bytes)
+
+
+def test_tuning_knobs_and_arch_guard_without_a_gpu():
+    """vc_set_tuning round-trips and rejects unknown keys; on a box without a usable sm_100 device every compute entry point
+    answers VC_ERR_UNSUPPORTED (-2) with a message instead of failing inside a launch (no GPU here: the guard itself is what is
+    exercised; tests/test_kernels_gpu.py checks the pass-through on a B200 and the VITCAP_FAKE_CC refusal)."""
+    lib = ops.load_library()
+    for key in (ops.TUNE_GEMM_SMEM_KB, ops.TUNE_DATTN_CTAS_PER_SM, ops.TUNE_LAUNCH_PRIORITY):
+        old = ops.get_tuning(key)
+        ops.set_tuning(key, 7)
+        assert ops.get_tuning(key) == 7
+        ops.set_tuning(key, old)
+    with pytest.raises(RuntimeError, match="unknown key"):
+        ops.set_tuning(99, 1)
+    if not torch.cuda.is_available():
+        assert lib.vc_check_device() == -2
+        assert b"CUDA device" in lib.vc_last_error() or b"sm_100a" in lib.vc_last_error()
+        with pytest.raises(RuntimeError, match="-2"):
+            ops.check_device()
+        # a compute entry point (null pointers are never dereferenced: the guard answers first)
+        assert lib.vc_layernorm(1, None, 0, None, None, 1e-6, None, 0, None, 0, 1, 768, None) == -2
 
 
 def test_library_has_no_torch_or_libcuda_link_dependency():
@@ -164,3 +186,48 @@ def test_decode_precision_option(monkeypatch):
     assert FastImageCaptioning(cfg, decode_precision="bf16x3").decode_precision == "bf16x3"
     with pytest.raises(AssertionError):
         FastImageCaptioning(cfg, decode_precision="fp8")
+
+
+def test_generate_limits_are_checked_before_any_kernel():
+    """num_beams / num_keep_best / max_length beyond what the search kernels hold (search.cu VC_MAX_BEAMS = 8, VC_MAX_LEN = 64,
+    keep <= 64) are refused by generate() itself -- on a CPU module, i.e. before the encoder, the prefill or a graph capture."""
+    cfg = vcfg.tiny(max_seq=128)
+    m = FastImageCaptioning(cfg)
+    feats = torch.zeros(1, cfg.n_tokens, cfg.hidden)
+    base = dict(synth.default_test_extra_input(cfg), input_ids=synth.make_text_inputs(cfg, 1)["input_ids"])
+    for bad, msg in ((dict(num_beams=9), "num_beams <= 8"), (dict(num_beams=4, num_keep_best=65), "num_keep_best <= 64"),
+                     (dict(max_length=65), "max_length must be <= 64"), (dict(max_length=1), "max_length must be in")):
+        kw = dict(base)
+        kw.update(bad)
+        with pytest.raises(ValueError, match=msg):
+            m.module(feats, **kw)
+
+
+def test_visible_labels_with_a_non_cls_tag_embedding_are_refused():
+    """config.tagemb != 'cls' takes the reference through encode_tag_to_embedding(cls_emb=None) / extra_embeddings
+    (modeling_bert.py:1466, 1485), which is not built: a visible label region then raises instead of silently using the 'cls'
+    recipes. Without visible labels the setting is irrelevant (the label slots are dead) and accepted."""
+    cfg = vcfg.tiny(tagemb="bert")
+    m = FastImageCaptioning(cfg)
+    ti = synth.make_text_inputs(cfg, 2)
+    assert m._label_counts(ti["attention_mask"], ti["input_ids"], 20) is None
+    ti = synth.make_text_inputs(cfg, 2, n_label=[3, 0])
+    with pytest.raises(NotImplementedError, match="tagemb"):
+        m._label_counts(ti["attention_mask"], ti["input_ids"], 20)
+
+
+def test_packed_weights_are_invalidated_by_moves_and_in_place_updates():
+    """The kernel-side weight copies must follow the parameters: .to() / .float() (new storage) and in-place updates
+    (optimizer step, manual edit) both force a re-pack at the next use."""
+    cfg = vcfg.tiny()
+    m = FastImageCaptioning(cfg)
+    sentinel = object()
+    m._engine, m._packed_version = sentinel, m._param_version()
+    m.double()
+    assert m._engine is None
+    m._engine, m._packed_version = sentinel, m._param_version()
+    with torch.no_grad():
+        m.module.bert.pooler.dense.weight.mul_(0.5)
+    assert m._packed_version != m._param_version()
+    with pytest.raises(RuntimeError, match="CUDA device only"):      # the engine property re-packs, which needs the GPU
+        m.engine

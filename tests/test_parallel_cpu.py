@@ -65,6 +65,10 @@ def _worker(rank, world, port, n_items, q):
         assert ids2[:, 0, 0].tolist() == want.tolist() and tuple(ids2.shape) == (2 * n_items, 1, 20)
         assert torch.equal(tidx, want.view(-1, 1) * 10 + torch.arange(3)) and tidx.dtype == torch.int64
         assert torch.equal(tprob, want.float().view(-1, 1).repeat(1, 3) / 64)
+        # the side-stream gather degrades to the plain collective where there is no CUDA stream (this test): same rows, rank-major
+        rec = torch.full((3, 4), rank, dtype=torch.int32)
+        full, done = parallel.SideStreamGather("cpu")(rec)
+        assert done is None and full[:, 0].tolist() == sum(([r] * 3 for r in range(world)), [])
         q.put((rank, ids[:, 0, 0].tolist(), lp[:, 0].tolist()))
     finally:
         dist.destroy_process_group()

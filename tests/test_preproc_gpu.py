@@ -93,3 +93,21 @@ def test_plan_refuses_bad_geometry():
         ops.resize_crop_plan(torch.tensor([[0, 5]], dtype=torch.int32), 64, 64)
     with pytest.raises(RuntimeError):
         ops.resize_crop_plan(torch.tensor([[50, 50]], dtype=torch.int32), 32, 64)       # resize_to < crop
+
+
+def test_pipelined_calls_do_not_overwrite_a_pending_upload():
+    """The transform's uploads are asynchronous: while the GPU is still busy with earlier work the host may already be packing
+    the next batches. The pinned staging buffers are rotated and guarded by events, so a batch queued behind a long-running
+    kernel is still resized from ITS pixels (a single unguarded buffer would be overwritten by the following call)."""
+    from vitcap_b200.preproc import DeviceTestTransform
+    rng = np.random.default_rng(11)
+    batches = [[rng.integers(0, 256, (int(rng.integers(100, 260)), int(rng.integers(100, 260)), 3), dtype=np.uint8) for _ in range(4)]
+               for _ in range(5)]
+    t = DeviceTestTransform(96)
+    ref = [t(b).cpu().numpy() for b in batches]                  # serial: every call is drained before the next
+    torch.cuda.synchronize()
+    torch.cuda._sleep(int(1.5e9))                                # ~1 s of GPU work ahead of the first upload
+    outs = [t(b) for b in batches]                               # the host runs ahead of the device
+    torch.cuda.synchronize()
+    for r, o in zip(ref, outs):
+        assert np.array_equal(r, o.cpu().numpy())

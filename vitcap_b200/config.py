@@ -28,6 +28,10 @@ class VitCapConfig:
     max_seq_a: int = 20           # caption slots (max_seq_a_length)
     max_seq: int = 70             # caption + od/tag slots (max_seq_length)
     sep_id: int = 102             # [SEP] of bert-base-uncased: forced into the last label slot (modeling_bert.py:1447)
+    # label-slot embedding recipe (modeling_bert.py:1454 / 1480). 'cls' is what the shipped yaml sets and what is implemented;
+    # the pipeline's fallback 'bert' (file line 554: encode_tag_to_embedding(cls_emb=None) / extra_embeddings) only matters when
+    # a label region is VISIBLE, and is refused there (model.py _label_counts)
+    tagemb: str = "cls"
 
     @property
     def head_dim(self):

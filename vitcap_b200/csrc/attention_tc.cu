@@ -259,7 +259,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     const int lab_lim = LABELS ? n_base + n_extra[b] : N;
     for (int tile = 0; tile < nq; ++tile) {
       const uint32_t taddr_o = tmem_base + lane_base + COL_O;
-      float m_ref = -INFINITY;                         // exponent reference (scaled log2 units); lags the true max by < 8
+      // exponent reference (scaled log2 units); lags the true max by < 8 + 1. Always an INTEGER: P = exp2(x - m_ref) is then a
+      // power-of-two multiple of exp2(x - ceil(row max)) and its bf16 rounding -- the one rounding of this kernel whose
+      // realisation would otherwise depend on chunk order and on when the lazy reference moved -- is a function of the scores
+      // alone (oracle/port.py QuantPortModel.attend states it that way; rescale factors become exact powers of two)
+      float m_ref = -INFINITY;
       float l = 0.f;
       const int row_lim = (LABELS && tile * QT + t < n_base) ? n_base : lab_lim;
       for (int j = 0; j < nch; ++j, ++g) {
@@ -319,7 +323,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
               mx0 = fmaxf(mx0, fmaxf(__uint_as_float(r[i]), __uint_as_float(r[i + 1])));
               mx1 = fmaxf(mx1, fmaxf(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])));
             }
-            m_ref = fmaxf(mx0, mx1) * scale_log2;
+            m_ref = ceilf(fmaxf(mx0, mx1) * scale_log2);   // integer reference: see the note at m_ref's declaration
             redo = true;
           } else {
             // speculate that the reference holds (it moves only when the chunk max exceeds it by 2^8): the exponentials
@@ -329,7 +333,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             const bool need = mxs > m_ref + 8.0f;
             redo = __any_sync(0xffffffffu, need);
             if (redo) {
-              const float m_new = need ? mxs : m_ref;
+              const float m_new = need ? ceilf(mxs) : m_ref;
               const float corr = ex2(m_ref - m_new);   // exactly 1 for lanes that keep their reference
               mbar_wait(&pv_done[sb_prev], sph_prev);  // every issued PV has landed in TMEM
               tc_fence_after();
@@ -358,7 +362,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           const float mxs = mx * scale_log2;
           const bool need = mxs > m_ref + 8.0f;        // also covers j == 0 (m_ref = -inf)
           if (__any_sync(0xffffffffu, need)) {
-            const float m_new = need ? mxs : m_ref;
+            const float m_new = need ? ceilf(mxs) : m_ref;
             if (j > 0) {
               const float corr = ex2(m_ref - m_new);
               mbar_wait(&pv_done[sb_prev], sph_prev);

@@ -7,6 +7,7 @@
 
 namespace vc {
 const char* last_error();
+int check_device();
 int gemm_bf16_tc2_ln_emit(const void* A, int lda, const void* W, int ldw, const float* bias, float* out, int ldo, const float* resid,
                           int ldr, void* xb, int ldxb, float* stats, int M, int N, int K, cudaStream_t stream);
 int gemm_bf16_tc2_ln_fold(const void* A, int lda, const void* Wf, int ldw, const float* bias_f, const float* colsum,
@@ -65,13 +66,16 @@ int filter_logits(float* logits, int ld, int rows, int V, float inv_temperature,
 }  // namespace vc
 
 static std::atomic<long long> g_launches{0};
-#define VC_COUNT(n, expr) do { int rc__ = (expr); if (rc__ == 0) g_launches += (n); return rc__; } while (0)
+#define VC_COUNT(n, expr) do { int rc__ = vc::check_device(); if (rc__ == 0) rc__ = (expr); if (rc__ == 0) g_launches += (n); return rc__; } while (0)
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
 
 extern "C" {
 
 const char* vc_last_error(void) { return vc::last_error(); }
-int vc_abi_version(void) { return 5; }
+int vc_abi_version(void) { return 6; }
+int vc_set_tuning(int key, int value) { return vc::set_tuning(key, value); }
+int vc_get_tuning(int key) { return vc::tuning(key); }
+int vc_check_device(void) { return vc::check_device(); }
 long long vc_launch_count(void) { return g_launches.load(); }
 void vc_reset_launch_count(void) { g_launches = 0; }
 void vc_set_pdl(int mode) { vc::set_pdl_mode(mode); }

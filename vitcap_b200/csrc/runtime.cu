@@ -41,6 +41,38 @@ int pdl_mode() {
 }
 void set_pdl_mode(int mode) { g_pdl = mode < 0 ? 0 : (mode > 2 ? 2 : mode); }
 
+static int g_tune[VC_TUNE_COUNT] = {0, 0, 0};
+int tuning(int key) { return (key >= 0 && key < VC_TUNE_COUNT) ? g_tune[key] : 0; }
+int set_tuning(int key, int value) {
+  if (key < 0 || key >= VC_TUNE_COUNT) { set_last_error("vc_set_tuning: unknown key %d", key); return VC_ERR_BAD_ARG; }
+  g_tune[key] = value;
+  return VC_OK;
+}
+
+// The library holds sm_100a code only (tcgen05 / TMEM / TMA): on any other device a launch would fail late with "no kernel
+// image is available". Checked once per process by the first compute entry point (capi.cu VC_COUNT).
+int check_device() {
+  static int state = 0;                       // 0 = not checked, 1 = ok, -1 = unsupported
+  if (state == 0) {
+    int dev = 0, major = 0, minor = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev) != cudaSuccess) {
+      cudaGetLastError();
+      set_last_error("vitcap_b200: no usable CUDA device");
+      return VC_ERR_UNSUPPORTED;
+    }
+    const char* fake = getenv("VITCAP_FAKE_CC");          // test hook: pretend the device reports this compute capability
+    if (fake != nullptr && fake[0] != 0) { major = atoi(fake) / 10; minor = atoi(fake) % 10; }
+    state = (major == 10) ? 1 : -1;
+    if (state < 0) set_last_error("vitcap_b200 is built for sm_100a (B200) only; this device reports compute capability %d.%d", major, minor);
+  }
+  if (state < 0) {
+    if (last_error()[0] == 0) set_last_error("vitcap_b200 is built for sm_100a (B200) only");
+    return VC_ERR_UNSUPPORTED;
+  }
+  return VC_OK;
+}
+
 int sm_count() {
   static int n = 0;
   if (n == 0) {

@@ -146,6 +146,18 @@ class CaptionEngine:
         self.x3_dedup = os.environ.get("VITCAP_X3_DEDUP", "1") != "0"
         self.forward_graphs = {}               # whole-forward CUDA graphs of the small-batch latency path (model.py); they hold
         self.inline_graphs = False             # raw workspace pointers. inline_graphs: an outer capture is running
+        # parity instrumentation (tests / tools only): tap(name, index, tensor) is called with the stream after every ViT block
+        # and with the vocabulary logits after every decode step; while it is set the decode loop runs eagerly (no graph)
+        self.tap = None
+        # decode lanes: the images of a batch are split into `decode_lanes` contiguous groups whose decode loops run on separate
+        # streams (forked and joined inside the captured graph), so that the latency-bound GEMM chain of one lane overlaps the
+        # HBM-bound K/V sweep of another (see greedy_or_sample). 1 = a single stream
+        self.decode_lanes = max(1, int(os.environ.get("VITCAP_DECODE_LANES", "1")))
+        self.min_lane_images = 64              # lanes are not worth their fork/join below this many images per lane
+        # launch priority of the decode-step kernels other than the attention (0 = none; negative = higher): with several lanes
+        # the short GEMM / LayerNorm kernels of one lane should be picked before the next CTAs of another lane's K/V sweep
+        self.lane_gemm_priority = int(os.environ.get("VITCAP_LANE_GEMM_PRIORITY", "0"))
+        self._lane_streams = []
 
     # ------------------------------------------------------------------ workspaces
     def _alloc(self, *shape, dtype=None):
@@ -204,11 +216,8 @@ class CaptionEngine:
         self.forward_graphs.clear()
         return ws
 
-    def _decoder_ws(self, B, E, max_len):
-        key = (B, E, max_len)
-        if key in self._dec_ws:
-            self._dec_ws.move_to_end(key)
-            return self._dec_ws[key]
+    def _new_decoder_ws(self, B, E, max_len):
+        """Buffers of one decode loop over B images x E sequences (one lane)."""
         cfg = self.cfg
         H, F, L = cfg.hidden, cfg.inter, cfg.dec_layers
         R = B * E
@@ -235,15 +244,59 @@ class CaptionEngine:
         ws["unfinished"] = torch.ones(R, device=self.dev, dtype=i32)
         ws["sum_lp"] = torch.zeros(R, device=self.dev, dtype=f32)
         ws["n_steps"] = torch.zeros(R, device=self.dev, dtype=i32)
-        ws["out_ids"] = torch.zeros(R, max_len, device=self.dev, dtype=torch.int64)
-        ws["out_lp"] = torch.zeros(R, device=self.dev, dtype=f32)
         ws["ident_rows"] = torch.arange(R, device=self.dev, dtype=i32)
+        return ws
+
+    def _decoder_ws(self, B, E, max_len, lanes=1):
+        """Decode workspace of a (B, E, max_len) call, cached with its captured graphs. lanes > 1: the images are split into
+        contiguous groups, each with its own buffers (ws['lanes'] = [(first image, images, lane workspace)]); results of all
+        lanes land in the shared out_ids / out_lp."""
+        key = (B, E, max_len, lanes)
+        if key in self._dec_ws:
+            self._dec_ws.move_to_end(key)
+            return self._dec_ws[key]
+        R = B * E
+        if lanes == 1:
+            ws = self._new_decoder_ws(B, E, max_len)
+            ws["lanes"] = [(0, B, ws)]
+        else:
+            ws = {"B": B, "E": E, "R": R, "max_len": max_len, "lanes": []}
+            base, rem = divmod(B, lanes)
+            b0 = 0
+            for i in range(lanes):
+                b = base + (1 if i < rem else 0)
+                ws["lanes"].append((b0, b, self._new_decoder_ws(b, E, max_len)))
+                b0 += b
+        ws["out_ids"] = torch.zeros(R, max_len, device=self.dev, dtype=torch.int64)
+        ws["out_lp"] = torch.zeros(R, device=self.dev, dtype=torch.float32)
         ws["seed"] = torch.zeros(1, device=self.dev, dtype=torch.int64)     # sampling seed, rewritten before every replay
         ws["graphs"] = {}                  # captured decode loops over THIS workspace; they die with it
         self._dec_ws[key] = ws
         while len(self._dec_ws) > self.max_decode_workspaces:
             self._dec_ws.popitem(last=False)
         return ws
+
+    def _n_lanes(self, B):
+        n = self.decode_lanes
+        while n > 1 and B // n < self.min_lane_images:
+            n -= 1
+        return n
+
+    def _lanes_run(self, lanes, fn):
+        """fn(first image, images, lane workspace) for every lane; more than one lane: each on its own stream, forked from and
+        joined to the current stream (inside a capture this becomes parallel branches of the graph)."""
+        if len(lanes) == 1:
+            fn(*lanes[0])
+            return
+        while len(self._lane_streams) < len(lanes):
+            self._lane_streams.append(torch.cuda.Stream(device=self.dev))
+        cur = torch.cuda.current_stream()
+        for lane, st in zip(lanes, self._lane_streams):
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                fn(*lane)
+        for _, st in zip(lanes, self._lane_streams):
+            cur.wait_stream(st)
 
     def reserve(self, B, label_rows=False):
         """Sizes the image-side workspace before a batch starts (growing it later would drop the encoder outputs)."""
@@ -355,6 +408,8 @@ class CaptionEngine:
             wanted = (not last_trunk) or n_cap > 0 or n_tag_fold > 0
             self._vit_block(w.blocks[i], x, rows, B, N, ws, pre=pre, emit=fx if wanted else None)
             pre = fx if wanted else None
+            if self.tap is not None:
+                self.tap("block", i, x.view(B, N, H))
         pre_trunk = pre
         # fork: both branches start from the block-8 input (modeling_bert.py:464-474). The concept branch runs first; its first
         # block reads x and writes xt, so the 0.9 GB stream is never copied
@@ -366,6 +421,8 @@ class CaptionEngine:
                     xt.copy_(x)
                     forked = True
                 self._vit_block_cls_only(w.tag_blocks[j], xt, rows, B, N, ws)
+                if self.tap is not None:
+                    self.tap("tag_block", j, xt.view(B, N, H))
                 continue
             nxt_full = (j + 1 < n_tag_fold)                              # the next concept block consumes the folded form
             emit_t = ft if (self.ln_fold and nxt_full) else None
@@ -376,6 +433,8 @@ class CaptionEngine:
             else:
                 self._vit_block(w.tag_blocks[j], xt, rows, B, N, ws, pre=pre_t, emit=emit_t)
             pre_t = emit_t
+            if self.tap is not None:
+                self.tap("tag_block", j, xt.view(B, N, H))
         if not forked:
             xt.copy_(x)
         if caption_branch:
@@ -384,6 +443,8 @@ class CaptionEngine:
                 emit = fx if (self.ln_fold and i + 1 < cfg.enc_blocks) else None
                 self._vit_block(w.blocks[i], x, rows, B, N, ws, pre=pre, emit=emit)
                 pre = emit
+                if self.tap is not None:
+                    self.tap("block", i, x.view(B, N, H))
         return x.view(B, N, H), xt.view(B, N, H)
 
     def _vit_block_fork(self, p, x, xt, rows, B, N, ws, pre=None, emit=None):
@@ -453,23 +514,31 @@ class CaptionEngine:
             ops.linear(hid, p["f_w"], p["f_b"], tmp, resid=a_f, M=rows)
             self._ln(tmp, p["ln2_w"], p["ln2_b"], cfg.bert_ln_eps, ctx_t, out_f=ctx_f, rows=rows)
 
-    def _decode_layers(self, ws, B, E, cur_len, anc, mask_id, labels=False, head=True):
+    def _decode_layers(self, ws, B, E, cur_len, anc, mask_id, labels=False, head=True, img0=0):
         """One decode step up to the vocabulary logits of the MASK rows. labels: the context holds C + topk rows per image of
-        which ctx_vis[b] are visible. head=False stops after the decoder layers (caption-row replay after a recipe flip)."""
+        which ctx_vis[b] are visible. head=False stops after the decoder layers (caption-row replay after a recipe flip).
+        img0: first image of this lane inside the image-side workspace (its context K/V rows start at img0 * C)."""
         cfg, w = self.cfg, self.w
         R, H = ws["R"], cfg.hidden
         C = cfg.n_ctx + (cfg.topk if labels else 0)
         enc = self._enc_ws
-        ctx_vis = enc["ctx_vis"] if labels else None
+        ctx_vis = enc["ctx_vis"][img0:] if labels else None
         e_f, e_t = ws["e_f"], ws["e_t"]
+        if self.lane_gemm_priority:
+            ops.set_tuning(ops.TUNE_LAUNCH_PRIORITY, self.lane_gemm_priority)
         ops.embed_ln(ws["ids"], cur_len, mask_id, w.word, w.pos, w.type0, w.emb_ln_w, w.emb_ln_b, cfg.bert_ln_eps, e_f, e_t, R)
         scale = 1.0 / math.sqrt(cfg.head_dim)
         x3 = self.decode_x3
         n_layers = len(w.dec)
+        prio = self.lane_gemm_priority
         for l, p in enumerate(w.dec):
             sq = ws["step_qkv"][l]
             ops.linear(e_t, p["qkv_w"], p["qkv_b"], sq[cur_len - 1], M=2 * R)
-            ops.decode_attention(enc["ctx_qkv"][l], sq, anc, ws["att"], B, C, cfg.heads, E, cur_len, scale, ctx_vis=ctx_vis)
+            if prio:
+                ops.set_tuning(ops.TUNE_LAUNCH_PRIORITY, 0)
+            ops.decode_attention(enc["ctx_qkv"][l][img0 * C:], sq, anc, ws["att"], B, C, cfg.heads, E, cur_len, scale, ctx_vis=ctx_vis)
+            if prio:
+                ops.set_tuning(ops.TUNE_LAUNCH_PRIORITY, prio)
             ops.linear(ws["att"], p["o_w"], p["o_b"], ws["tmp"], resid=e_f, M=2 * R)
             if x3:
                 # BertIntermediate / BertOutput (modeling_bert.py:395-419) on split-bf16 operands: the operand rounding of
@@ -506,6 +575,8 @@ class CaptionEngine:
         elif head:
             mask_rows = e_t[1::2]
             self._head(w.cls_head, mask_rows, R, ws["head_f"], ws["head_t"], ws["logits"])
+        if self.lane_gemm_priority:
+            ops.set_tuning(ops.TUNE_LAUNCH_PRIORITY, 0)
 
     def _flip_labels(self, ws, B, E, cur_len, mask_id, anc_table=None):
         """The reference switches the label embedding to the 'raw' recipe at this step (modeling_bert.py:1435) and, having no
@@ -524,12 +595,12 @@ class CaptionEngine:
         outlive every replay (a per-call tensor would be freed and its block reused under the graph's feet)."""
         key = ("eos", tuple(int(e) for e in eos_ids))
         if key not in ws:
-            ws[key] = torch.tensor(list(key[1]), device=ws["ids"].device, dtype=torch.int32)
+            ws[key] = torch.tensor(list(key[1]), device=ws["out_ids"].device, dtype=torch.int32)
         return ws[key]
 
     def _maybe_graph(self, ws, key, fn):
         """Runs fn() eagerly once (warm-up: lazy kernel attribute setup, descriptor cache), then captures and replays it."""
-        if not self.use_cuda_graph or self.inline_graphs:
+        if not self.use_cuda_graph or self.inline_graphs or self.tap is not None:
             fn()
             return
         graphs = ws["graphs"]
@@ -554,32 +625,38 @@ class CaptionEngine:
         recipe (the context must have been prefilled with 'ln' if label_flip > 1, else with 'raw')."""
         labels = label_flip is not None
         cfg = self.cfg
-        ws = self._decoder_ws(B, E, max_len)
+        # lanes: greedy without a label region only (sampling numbers its Philox streams by row, a recipe flip re-prefills
+        # the shared context) and never under a parity tap
+        n_lanes = 1 if (labels or do_sample or self.tap is not None) else self._n_lanes(B)
+        ws = self._decoder_ws(B, E, max_len, lanes=n_lanes)
         R = ws["R"]
         eos = self._eos_tensor(ws, eos_ids)
         filt = do_sample and (top_k > 0 or top_p < 1.0)
 
-        def reset():
-            ws["ids"].zero_()
-            ws["ids"][:, 0] = bos
-            ws["unfinished"].fill_(1)
-            ws["sum_lp"].zero_()
-            ws["n_steps"].zero_()
-
-        def run():
-            reset()
+        def lane_loop(img0, b, lw):
+            r0, r = img0 * E, lw["R"]
+            lw["ids"].zero_()
+            lw["ids"][:, 0] = bos
+            lw["unfinished"].fill_(1)
+            lw["sum_lp"].zero_()
+            lw["n_steps"].zero_()
             for cur_len in range(1, max_len):
                 if labels and cur_len == label_flip and cur_len > 1:
-                    self._flip_labels(ws, B, E, cur_len, mask_id)
-                self._decode_layers(ws, B, E, cur_len, None, mask_id, labels=labels)
+                    self._flip_labels(lw, b, E, cur_len, mask_id)
+                self._decode_layers(lw, b, E, cur_len, None, mask_id, labels=labels, img0=img0)
+                if self.tap is not None:
+                    self.tap("logits", cur_len, lw["logits"][:, :cfg.vocab])
                 t = temperature
                 if filt:
-                    ops.filter_logits(ws["logits"], cfg.vocab, R, 1.0 / temperature, top_k, top_p)
+                    ops.filter_logits(lw["logits"], cfg.vocab, r, 1.0 / temperature, top_k, top_p)
                     t = 1.0
-                ops.token_step(ws["logits"], cfg.vocab, R, do_sample, t, 0, cur_len, pad, eos, ws["ids"], ws["unfinished"],
-                               ws["sum_lp"], ws["n_steps"], seed_dev=ws["seed"] if do_sample else None)
-            ops.greedy_finalize(ws["ids"], ws["unfinished"], ws["sum_lp"], ws["n_steps"], int(eos_ids[0]), R, ws["out_ids"],
-                                ws["out_lp"])
+                ops.token_step(lw["logits"], cfg.vocab, r, do_sample, t, 0, cur_len, pad, eos, lw["ids"], lw["unfinished"],
+                               lw["sum_lp"], lw["n_steps"], seed_dev=ws["seed"] if do_sample else None)
+            ops.greedy_finalize(lw["ids"], lw["unfinished"], lw["sum_lp"], lw["n_steps"], int(eos_ids[0]), r,
+                                ws["out_ids"][r0:r0 + r], ws["out_lp"][r0:r0 + r])
+
+        def run():
+            self._lanes_run(ws["lanes"], lane_loop)
 
         if do_sample:
             # the seed lives in device memory, outside the captured loop: one graph serves every call
@@ -597,8 +674,9 @@ class CaptionEngine:
         ws = self._decoder_ws(B, nb, max_len)
         R, K = ws["R"], 2 * nb
         f32, i32 = torch.float32, torch.int32
-        if "beam" not in ws or ws["beam"]["keep"] != keep:
-            ws["beam"] = {
+        # one state per `keep`: a graph captured for another keep holds raw pointers into ITS state, which must stay alive
+        if ("beam", keep) not in ws:
+            ws[("beam", keep)] = {
                 "keep": keep,
                 "ids": ws["ids"], "beam_scores": torch.zeros(R, device=self.dev, dtype=f32),
                 "done": torch.zeros(B, device=self.dev, dtype=i32), "anc": torch.zeros(max_len, R, device=self.dev, dtype=i32),
@@ -613,7 +691,7 @@ class CaptionEngine:
                 "out_lp": torch.zeros(B, keep, device=self.dev, dtype=f32),
                 "init_scores": torch.tensor(([0.0] + [-1e9] * (nb - 1)) * B, device=self.dev, dtype=f32),
             }
-        st = ws["beam"]
+        st = ws[("beam", keep)]
         eos = self._eos_tensor(ws, eos_ids)
 
         def run():

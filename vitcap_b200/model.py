@@ -207,6 +207,12 @@ class FastViTCAP(nn.Module):
         max_length = int(max_length)
         if max_length > cfg.max_seq or max_length < 2:
             raise ValueError("max_length must be in [2, %d]" % cfg.max_seq)
+        # limits of the search kernels (search.cu VC_MAX_BEAMS / VC_MAX_LEN; decode_attention: cur_len + 1 <= 64), checked
+        # before any kernel or graph capture starts
+        if max_length > 64:
+            raise ValueError("max_length must be <= 64 (caption rows per sequence the decode kernels hold)")
+        if num_beams > 1 and (num_beams > 8 or not 1 <= int(num_keep_best) <= 64):
+            raise ValueError("beam search supports num_beams <= 8 and 1 <= num_keep_best <= 64")
         n_label = owner._label_counts(attention_mask, input_ids, max_length)
         if n_label is not None and not add_od_labels:
             raise NotImplementedError(_UNSUPPORTED % "a visible label region with add_od_labels=False (the reference fails there)")
@@ -259,6 +265,15 @@ class FastImageCaptioning(nn.Module):
     def _invalidate(self):
         self._engine = None
 
+    def _apply(self, fn, *args, **kwargs):
+        # .to() / .cuda() / .float() replace the parameter storage: the packed kernel copies (and an engine bound to the old
+        # device) are stale
+        self._invalidate()
+        return super()._apply(fn, *args, **kwargs)
+
+    def _param_version(self):
+        return sum(p._version for p in self.parameters())
+
     def pack(self):
         """(Re)builds the kernel-side weight copies from the current parameters. Called lazily by forward()."""
         ops.load_library()
@@ -268,11 +283,13 @@ class FastImageCaptioning(nn.Module):
         sd = self.state_dict()
         w = PackedWeights(self.cfg, sd, self.mode, dev, decode_x3=self.decode_precision == "bf16x3")
         self._engine = CaptionEngine(self.cfg, w, dev, use_cuda_graph=self.use_cuda_graph)
+        self._packed_version = self._param_version()
         return self
 
     @property
     def engine(self):
-        if self._engine is None:
+        # in-place parameter updates (an optimizer step, manual edits, re-tying) bump the tensors' version counters
+        if self._engine is None or self._packed_version != self._param_version():
             self.pack()
         return self._engine
 
@@ -318,6 +335,10 @@ class FastImageCaptioning(nn.Module):
             raise NotImplementedError(_UNSUPPORTED % "a text attention mask outside the seq2seq family of dataset.py:395-408")
         if not bool((n > 0).any()):
             return None
+        if cfg.tagemb != "cls":
+            # the visible label rows would come from encode_tag_to_embedding(cls_emb=None) / extra_embeddings
+            # (modeling_bert.py:1466, 1485); only the 'cls' recipes of the shipped configuration are built
+            raise NotImplementedError(_UNSUPPORTED % ("a visible label region with config.tagemb=%r (only 'cls')" % cfg.tagemb))
         if T - a != cfg.topk:
             # modeling_bert.py:1470/1489 writes the topk tag embeddings over the LAST topk input slots
             raise NotImplementedError(_UNSUPPORTED % "a label region whose length differs from config.topk")

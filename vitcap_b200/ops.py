@@ -17,7 +17,8 @@ ACT_NONE, ACT_GELU, ACT_TANH = 0, 1, 2
 _c = ctypes
 _P, _I, _F, _D, _SZ, _U64, _LL = _c.c_void_p, _c.c_int, _c.c_float, _c.c_double, _c.c_size_t, _c.c_uint64, _c.c_longlong
 
-# name -> argtypes; must list every symbol the header declares (checked by tests/test_abi.py)
+# name -> argtypes; must list every symbol the header declares (checked by tests/test_host_cpu.py::
+# test_header_symbols_are_exported_and_bound)
 SIGNATURES = {
     "vc_linear": [_I, _P, _I, _P, _I, _P, _P, _I, _I, _I, _P, _I, _I, _I, _I, _P],
     "vc_linear_simt": [_I, _P, _I, _P, _I, _P, _P, _I, _I, _I, _P, _I, _I, _I, _I, _P],
@@ -85,6 +86,12 @@ def load_library(path=None):
     lib.vc_set_pdl.restype = None
     lib.vc_set_pdl.argtypes = [_I]
     lib.vc_get_pdl.restype = _I
+    lib.vc_set_tuning.restype = _I
+    lib.vc_set_tuning.argtypes = [_I, _I]
+    lib.vc_get_tuning.restype = _I
+    lib.vc_get_tuning.argtypes = [_I]
+    lib.vc_check_device.restype = _I
+    lib.vc_check_device.argtypes = []
     if path is None:
         _lib = lib
     return lib
@@ -123,6 +130,23 @@ def set_pdl(mode):
 
 def get_pdl():
     return int(load_library().vc_get_pdl())
+
+
+TUNE_GEMM_SMEM_KB, TUNE_DATTN_CTAS_PER_SM, TUNE_LAUNCH_PRIORITY = 0, 1, 2
+
+
+def set_tuning(key, value):
+    """Run-time knobs for concurrent decode lanes (include/vitcap_b200.h, vc_set_tuning)."""
+    _check(load_library().vc_set_tuning(int(key), int(value)), "vc_set_tuning")
+
+
+def get_tuning(key):
+    return int(load_library().vc_get_tuning(int(key)))
+
+
+def check_device():
+    """Raises unless the current CUDA device is an sm_100 part (the library holds sm_100a code only)."""
+    _check(load_library().vc_check_device(), "vc_check_device")
 
 
 def _is_bf16(t):

@@ -23,7 +23,7 @@ class DeviceTestTransform:
     crop_size / crop_pct are the reference's ``test_crop_size`` / ``crop_pct`` (1.0 in the shipped yaml).
     ``test_respect_ratio_max`` (MinMaxResizeForTest) is not on the shipped eval path and is refused."""
 
-    def __init__(self, crop_size=384, crop_pct=1.0, device="cuda", test_respect_ratio_max=None):
+    def __init__(self, crop_size=384, crop_pct=1.0, device="cuda", test_respect_ratio_max=None, staging_buffers=2):
         if test_respect_ratio_max:
             raise NotImplementedError("vitcap_b200: MinMaxResizeForTest (test_respect_ratio_max) is not implemented")
         if crop_size % 4:
@@ -32,7 +32,12 @@ class DeviceTestTransform:
         self.crop = int(crop_size)
         self.resize_to = int(math.floor(crop_size / crop_pct))
         self.device = torch.device(device)
-        self._pinned = None
+        # pinned staging buffers, rotated: the upload of a batch is asynchronous, so the host may be packing the next batch while
+        # the copy of this one is still queued behind earlier GPU work. Each buffer carries the event recorded after its last
+        # H2D copy and is rewritten only once that event has completed.
+        self._pinned = [None] * max(2, int(staging_buffers))
+        self._copied = [None] * len(self._pinned)
+        self._slot = 0
         self.h2d_bytes = 0
 
     def _pack(self, images):
@@ -48,15 +53,19 @@ class DeviceTestTransform:
             off[i] = total
             total += (a.size + 15) & ~15                 # 16-byte aligned starts
             arrs.append(a)
-        if self._pinned is None or self._pinned.numel() < total:
-            self._pinned = torch.empty(max(total, 1), dtype=torch.uint8).pin_memory()
-        flat = self._pinned.numpy()
+        slot = self._slot
+        self._slot = (slot + 1) % len(self._pinned)
+        if self._copied[slot] is not None:
+            self._copied[slot].synchronize()             # the previous upload from this buffer has left the host memory
+        if self._pinned[slot] is None or self._pinned[slot].numel() < total:
+            self._pinned[slot] = torch.empty(max(total, 1), dtype=torch.uint8).pin_memory()
+        flat = self._pinned[slot].numpy()
         for a, o in zip(arrs, off.tolist()):
             flat[o:o + a.size] = a.reshape(-1)
-        return self._pinned[:total], off, hw
+        return self._pinned[slot][:total], off, hw, slot
 
     def __call__(self, images):
-        src_h, off_h, hw_h = self._pack(images)
+        src_h, off_h, hw_h, slot = self._pack(images)
         B = hw_h.shape[0]
         kmax, max_rows, tmp_off_h = ops.resize_crop_plan(hw_h, self.resize_to, self.crop)
         dev = self.device
@@ -64,6 +73,9 @@ class DeviceTestTransform:
         meta_h = torch.cat([off_h, tmp_off_h[:B], hw_h.view(-1).to(torch.int64)]).pin_memory()
         meta = meta_h.to(dev, non_blocking=True)
         src = src_h.to(dev, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev))
+        self._copied[slot] = ev
         self.h2d_bytes += src_h.numel() + meta_h.numel() * 8
         hw = meta[2 * B:].to(torch.int32).view(B, 2)
         coef = torch.empty(B * 2 * (kmax + 2) * self.crop, dtype=torch.int32, device=dev)

@@ -23,6 +23,8 @@ class OverlappedCaptioner:
         self.gather = gather
         self.with_tags = with_tags
         self.copy_stream = torch.cuda.Stream(device=self.device)
+        # the cross-rank gather and the read-back of batch i run on a side stream while the compute stream starts batch i+1
+        self.side_gather = parallel.SideStreamGather(self.device) if gather else None
         self._dev = [dict() for _ in range(depth)]       # per-slot device staging buffers
         self._free = [None] * depth                      # event: compute on the slot's buffers has finished
         self._out = [None] * depth                       # per-slot pinned result buffer
@@ -64,16 +66,25 @@ class OverlappedCaptioner:
             rec = parallel.pack_records(ids, lp, tag_idx, tag_prob)
         else:
             rec = parallel.pack_records(ids, lp)
-        full = parallel.all_gather_records(rec) if self.gather else rec
+        free = torch.cuda.Event()                        # the slot's device staging buffers may be refilled after this point
+        free.record(cur)
+        self._free[slot] = free
+        side = self.side_gather is not None and self.side_gather.active()
+        if side:
+            full, gathered = self.side_gather(rec)
+            out_stream = self.side_gather.stream
+        else:
+            full, out_stream = rec, cur
+        n_rows = full.shape[0]
         o = self._out[slot]
         if o is None or o.shape != full.shape:
             o = torch.empty(full.shape, dtype=full.dtype).pin_memory()
             self._out[slot] = o
-        o.copy_(full, non_blocking=True)
-        self.d2h_bytes += o.numel() * o.element_size()
-        done = torch.cuda.Event()
-        done.record(cur)
-        self._free[slot] = done
+        with torch.cuda.stream(out_stream):
+            o.copy_(full, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(out_stream)
+        self.d2h_bytes += n_rows * full.shape[1] * full.element_size()
         return o, done, keep, max_len
 
     def run(self, host_batches):
