@@ -234,7 +234,7 @@ def decode_roofline(torch, ops, cfg, B, dev, peaks, model=None, extra=None):
         kv_bytes = sum(L * B * (C + cl + 1) * 2 * H * 2 for cl in range(1, max_len))
         floor_ms = (kv_bytes + (max_len - 1) * w_bytes) / (peak * 1e9) * 1e3
         loop = {"ms": loop_ms, "floor_ms": floor_ms, "frac": floor_ms / loop_ms, "steps": max_len - 1,
-                "kernels": eng.stats.get("graph_kernels"), "lanes": eng.decode_lanes,
+                "kernels": eng.stats.get("graph_kernels"),
                 "algorithmic_bytes": kv_bytes + (max_len - 1) * w_bytes,
                 "how": "%d-step greedy decode loop replayed 5 times as its CUDA graph right after the timed region (context K/V of "
                        "the last batch), CUDA events; floor = algorithmic bytes / copy bandwidth" % (max_len - 1)}

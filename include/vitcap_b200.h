@@ -49,20 +49,6 @@ int vc_get_pdl(void);
  * TMA code), else VC_ERR_UNSUPPORTED with a message. Every compute entry point performs the same check and returns
  * VC_ERR_UNSUPPORTED instead of failing late inside a launch. (The reference has no counterpart: torch dispatches per device.) */
 int vc_check_device(void);
-/* Run-time tuning knobs for concurrent decode lanes (independent image groups of one batch whose decode loops run on separate
- * streams, vitcap_b200/engine.py): they decide how the latency-bound GEMM kernels of one lane share an SM with the HBM-bound
- * attention kernel of another. Values take effect for launches (and graph captures) made afterwards.
- *   VC_TUNE_GEMM_SMEM_KB     0 = off; else cap (KiB) on the dynamic shared memory of GEMM launches of at most one round of
- *                            tiles (fewer pipeline stages; the decode-step shapes need 12-48 k-blocks)
- *   VC_TUNE_DATTN_CTAS_PER_SM  0 = one CTA per (head, image) work item (up to 4 resident per SM); n > 0 = a persistent grid of
- *                            n CTAs per SM striding over the items, so that the decode-step attention never holds more than
- *                            n x (48 KB shared memory, 16 K registers) of an SM
- *   VC_TUNE_LAUNCH_PRIORITY  0 = the stream's priority; else the cudaLaunchAttributePriority attached to every launch */
-#define VC_TUNE_GEMM_SMEM_KB 0
-#define VC_TUNE_DATTN_CTAS_PER_SM 1
-#define VC_TUNE_LAUNCH_PRIORITY 2
-int vc_set_tuning(int key, int value);
-int vc_get_tuning(int key);
 
 /* out[M,N] = act(A[M,K] * W[N,K]^T + bias[N]) (+ resid[M,N]);  replaces torch.nn.functional.linear behind
  *   vision_transformer.py:152-158 (Mlp fc1/fc2), :169-201 (Attention qkv/proj), :267-275 (PatchEmbed conv as GEMM),

@@ -205,12 +205,23 @@ class QuantPortModel(PortModel):
     cls_only_last: the last concept block is evaluated for the CLS row only with LayerNorm-kernel roundings and an fp32 softmax
     (engine._vit_block_cls_only); False = a full folded block (engine.encode(full_tag_feats=True))."""
 
-    def __init__(self, cfg, state_dict, ln_fold=2, decode_x3=True, cls_only_last=True):
+    def __init__(self, cfg, state_dict, ln_fold=2, decode_x3=True, cls_only_last=True, acc64=False):
         super().__init__(cfg, state_dict, dtype=torch.float32)
         self.ln_fold = ln_fold
         self.decode_x3 = decode_x3
         self.cls_only_last = cls_only_last
+        # acc64: every product is accumulated in fp64 and rounded to fp32 once -- the SAME quantised arithmetic with another
+        # (better) summation. The distance between the acc64 and the plain model is the yardstick for how far two correct
+        # implementations of this spec drift apart end to end: a bf16 rounding turns a relative perturbation e of its input
+        # into ~0.04 sqrt(e) of its output (flipped roundings), so ~1e-7 grows to the quantisation-noise level within a few
+        # stages whatever the implementation (DESIGN.md section 2)
+        self.acc64 = acc64
         self._wq = {}
+
+    def _mm(self, a, w, bias=None):
+        if self.acc64:
+            return F.linear(a.double(), w.double(), bias.double() if bias is not None else None).float()
+        return F.linear(a, w, bias)
 
     def wq(self, key):
         if key not in self._wq:
@@ -220,7 +231,7 @@ class QuantPortModel(PortModel):
     # ---- building blocks ----------------------------------------------------------------
     def lin(self, h_q, wkey, bkey):
         """bf16 operands (h_q already rounded), fp32 accumulate + fp32 bias."""
-        return F.linear(h_q, self.wq(wkey), self.sd[bkey] if bkey else None)
+        return self._mm(h_q, self.wq(wkey), self.sd[bkey] if bkey else None)
 
     def lin_x3(self, a, wkey, bkey):
         """Three-product split-bf16 GEMM (gemm_tc.cu X3 / the K-concatenated form): a_hi w_hi + a_lo w_hi + a_hi w_lo."""
@@ -229,7 +240,11 @@ class QuantPortModel(PortModel):
             self._wq[key] = split_bf16(self.sd[wkey])
         w_hi, w_lo = self._wq[key]
         a_hi, a_lo = split_bf16(a)
-        out = F.linear(a_hi, w_hi) + F.linear(a_lo, w_hi) + F.linear(a_hi, w_lo)
+        if self.acc64:
+            out = (F.linear(a_hi.double(), w_hi.double()) + F.linear(a_lo.double(), w_hi.double()) +
+                   F.linear(a_hi.double(), w_lo.double())).float()
+        else:
+            out = F.linear(a_hi, w_hi) + F.linear(a_lo, w_hi) + F.linear(a_hi, w_lo)
         return out + self.sd[bkey] if bkey else out
 
     def lin_ln(self, x, gkey, bekey, eps, wkey, bkey):
@@ -249,21 +264,21 @@ class QuantPortModel(PortModel):
         mean = x.sum(-1, keepdim=True) / K
         var = torch.clamp((x * x).sum(-1, keepdim=True) / K - mean * mean, min=0.0)     # one-pass, as the GEMM epilogue
         rstd = torch.rsqrt(var + eps)
-        acc = F.linear(q_bf16(x), wf)
+        acc = self._mm(q_bf16(x), wf)
         return rstd * acc + ((-mean * rstd) * colsum + bias_f)
 
-    @staticmethod
-    def attend(q, k, v, scale, add_mask=None, round_p=True):
+    def attend(self, q, k, v, scale, add_mask=None, round_p=True):
         """q, k, v fp32 tensors holding bf16 values, (B, H, S, d). Returns the bf16-rounded attention output (B, Sq, H d)."""
         # exp2 domain with an INTEGER exponent reference, as the kernels (attention_tc.cu, decode_attention_mma.cu): bf16
         # rounding commutes with powers of two, so bf16(P) is the same whichever integer reference (lazy, per chunk, per warp)
         # a kernel happened to use
-        s = torch.matmul(q, k.transpose(-1, -2)) * (scale * 1.4426950408889634)
+        mm = (lambda a, b: torch.matmul(a.double(), b.double()).float()) if self.acc64 else torch.matmul
+        s = mm(q, k.transpose(-1, -2)) * (scale * 1.4426950408889634)
         if add_mask is not None:
             s = s + add_mask
         p = torch.exp2(s - torch.ceil(s.max(dim=-1, keepdim=True).values))
         l = p.sum(dim=-1, keepdim=True)
-        o = torch.matmul(q_bf16(p) if round_p else p, v) / l
+        o = mm(q_bf16(p) if round_p else p, v) / l
         B, H, Sq, d = o.shape
         return q_bf16(o.permute(0, 2, 1, 3).reshape(B, Sq, H * d))
 

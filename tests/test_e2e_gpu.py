@@ -305,31 +305,6 @@ def test_whole_forward_graph_matches_eager_path(kw):
     assert eng.stats.get("forward_graph_replays", 0) == 4
 
 
-@pytest.mark.parametrize("mode", ["bf16", "fp32"])
-@pytest.mark.parametrize("lanes", [2, 3])
-def test_decode_lanes_do_not_change_results(mode, lanes):
-    """engine.decode_lanes: the images of a batch are split into contiguous groups whose decode loops run on separate streams
-    (parallel branches of the captured graph). Images are independent, so ids and log-probs must be bit-identical to the
-    single-stream loop -- eager first call and graph replays, batch sizes that do and do not divide evenly."""
-    cfg = vcfg.tiny()
-    sd = synth.make_state_dict(cfg, seed=7, eos_bias=1.0)
-    extra = synth.default_test_extra_input(cfg)
-    ref = build(cfg, sd, extra, mode, max_batch=8)
-    fast = build(cfg, sd, extra, mode, max_batch=8)
-    fast.engine.decode_lanes = lanes
-    fast.engine.min_lane_images = 1
-    for B, seed in [(7, 1), (7, 2), (8, 3), (2, 4), (7, 5)]:
-        data = synth.make_text_inputs(cfg, B)
-        data["image"] = synth.make_images(cfg, B, seed=seed)
-        d = to_dev(data)
-        i0, l0 = ref(d)
-        i1, l1 = fast(d)
-        assert torch.equal(i0, i1) and torch.equal(l0, l1), (B, seed)
-    keys = list(fast.engine._dec_ws.keys())
-    assert any(k[3] == lanes for k in keys) or lanes > 2          # (B = 2 with 3 lanes falls back to 2)
-    assert fast.engine.stats.get("graph_replays", 0) >= 2
-
-
 def test_alternating_keep_best_on_one_workspace():
     """num_keep_best 1 -> 3 -> 1 on the same (B, beams, max_len) workspace: every captured graph keeps the beam state it was
     captured with (a rebuilt state would leave the old graph replaying into freed memory)."""

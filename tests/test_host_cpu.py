@@ -50,24 +50,17 @@ def test_header_symbols_are_exported_and_bound():
     for n in names:
         assert hasattr(lib, n), n
     simple = {"vc_last_error", "vc_abi_version", "vc_launch_count", "vc_reset_launch_count", "vc_set_pdl", "vc_get_pdl",
-              "vc_set_tuning", "vc_get_tuning", "vc_check_device"}
+              "vc_check_device"}
     assert names - simple == set(ops.SIGNATURES), (names - simple) ^ set(ops.SIGNATURES)
     assert lib.vc_abi_version() == 6
     assert isinstance(lib.vc_last_error(), bytes)
 
 
-def test_tuning_knobs_and_arch_guard_without_a_gpu():
-    """vc_set_tuning round-trips and rejects unknown keys; on a box without a usable sm_100 device every compute entry point
-    answers VC_ERR_UNSUPPORTED (-2) with a message instead of failing inside a launch (no GPU here: the guard itself is what is
-    exercised; tests/test_kernels_gpu.py checks the pass-through on a B200 and the VITCAP_FAKE_CC refusal)."""
+def test_arch_guard_without_a_gpu():
+    """On a box without a usable sm_100 device every compute entry point answers VC_ERR_UNSUPPORTED (-2) with a message instead
+    of failing inside a launch (no GPU here: the guard itself is what is exercised; tests/test_kernels_gpu.py checks the
+    pass-through on a B200 and the refusal under VITCAP_FAKE_CC)."""
     lib = ops.load_library()
-    for key in (ops.TUNE_GEMM_SMEM_KB, ops.TUNE_DATTN_CTAS_PER_SM, ops.TUNE_LAUNCH_PRIORITY):
-        old = ops.get_tuning(key)
-        ops.set_tuning(key, 7)
-        assert ops.get_tuning(key) == 7
-        ops.set_tuning(key, old)
-    with pytest.raises(RuntimeError, match="unknown key"):
-        ops.set_tuning(99, 1)
     if not torch.cuda.is_available():
         assert lib.vc_check_device() == -2
         assert b"CUDA device" in lib.vc_last_error() or b"sm_100a" in lib.vc_last_error()

@@ -73,8 +73,6 @@ extern "C" {
 
 const char* vc_last_error(void) { return vc::last_error(); }
 int vc_abi_version(void) { return 6; }
-int vc_set_tuning(int key, int value) { return vc::set_tuning(key, value); }
-int vc_get_tuning(int key) { return vc::tuning(key); }
 int vc_check_device(void) { return vc::check_device(); }
 long long vc_launch_count(void) { return g_launches.load(); }
 void vc_reset_launch_count(void) { g_launches = 0; }

@@ -40,14 +40,6 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 int pdl_mode();
 void set_pdl_mode(int mode);
 
-// Run-time tuning knobs (vc_set_tuning; include/vitcap_b200.h): they steer how kernels of concurrent decode lanes share an SM.
-#define VC_TUNE_GEMM_SMEM_KB 0
-#define VC_TUNE_DATTN_CTAS_PER_SM 1
-#define VC_TUNE_LAUNCH_PRIORITY 2
-#define VC_TUNE_COUNT 3
-int tuning(int key);
-int set_tuning(int key, int value);
-
 template <typename... KArgs, typename... Args>
 inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
@@ -55,7 +47,9 @@ inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t sme
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[2];
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   const int mode = pdl_mode();
   bool on = (mode == 2);
@@ -63,19 +57,7 @@ inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t sme
     cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
     on = (cudaStreamIsCapturing(stream, &st) == cudaSuccess && st == cudaStreamCaptureStatusActive);
   }
-  unsigned n = 0;
-  if (on) {
-    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[n].val.programmaticStreamSerializationAllowed = 1;
-    ++n;
-  }
-  const int prio = tuning(VC_TUNE_LAUNCH_PRIORITY);        // 0 = the stream's own priority
-  if (prio != 0) {
-    attr[n].id = cudaLaunchAttributePriority;
-    attr[n].val.priority = prio;
-    ++n;
-  }
-  cfg.numAttrs = n;
+  cfg.numAttrs = on ? 1 : 0;
   cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);          // errors are picked up by check_launch()
 }
 

@@ -63,7 +63,7 @@ template <bool UPPER>
 __global__ void __launch_bounds__(128, 4)
 decode_attention_mma_kernel(const bf16* __restrict__ ctx_qkv, const bf16* __restrict__ step_qkv, const int* __restrict__ anc,
                             bf16* __restrict__ out, int Cs, const int* __restrict__ ctx_vis, int H, int R, int E, int cur_len,
-                            float scale_log2, int heads, int items) {
+                            float scale_log2) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint8_t cap_info[MAX_CAP];          // (sequence-in-CTA << 1) | is_mask_key, per caption key
   __shared__ float sm_m[WARPS][16], sm_l[WARPS][16];
@@ -71,19 +71,14 @@ decode_attention_mma_kernel(const bf16* __restrict__ ctx_qkv, const bf16* __rest
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;         // mma fragment coordinates
   const int lane7 = lane & 7, mi = lane >> 3;    // ldmatrix address coordinates
+  const int h = blockIdx.x;
   const int groups = (E + MAX_SEQ - 1) / MAX_SEQ;
-  pdl_launch_dependents();
-  pdl_wait();                                    // programmatic dependent launch: global memory from here on
-  // work item = (head, image x sequence group). Normally one item per CTA (gridDim.x == items); with a capped grid
-  // (vc_set_tuning VC_TUNE_DATTN_CTAS_PER_SM) the CTAs are persistent and stride over the items, which bounds the registers
-  // and shared memory this kernel holds per SM so that a GEMM CTA of a concurrent decode lane fits beside it
-  for (int item = blockIdx.x; item < items; item += gridDim.x) {
-  const int h = item % heads;
-  const int by = item / heads;
-  const int b = by / groups;
-  const int e0 = (by % groups) * MAX_SEQ;
+  const int b = blockIdx.y / groups;
+  const int e0 = (blockIdx.y % groups) * MAX_SEQ;
   const int EC = min(MAX_SEQ, E - e0);           // sequences handled by this CTA
   // context rows of an image: Cs allocated, the first C visible (label-region masks hide a per-image tail, dataset.py:405-408)
+  pdl_launch_dependents();
+  pdl_wait();                                    // programmatic dependent launch: global memory from here on
   const int C = ctx_vis ? ctx_vis[b] : Cs;
   const size_t ld = 3 * (size_t)H;
   const int step = cur_len - 1;
@@ -305,15 +300,13 @@ decode_attention_mma_kernel(const bf16* __restrict__ ctx_qkv, const bf16* __rest
       store8<bf16>(out + (size_t)(2 * r + (row & 1)) * H + h * 64 + pt * 8, acc);
     }
   }
-  __syncthreads();                               // the merge scratch aliases the ring of the next item
-  }
 }
 
 // ctx_qkv [B, C, 3H]; step_qkv [max_len, 2*B*E, 3H]; anc int32 [max_len, B*E] or NULL; out [2*B*E, H]; all bf16
 int decode_attention_mma(const void* ctx_qkv, const void* step_qkv, const int* anc, void* out, int B, int C, const int* ctx_vis,
                          int heads, int E, int cur_len, float scale, cudaStream_t s) {
   const int groups = (E + MAX_SEQ - 1) / MAX_SEQ;
-  if (B <= 0 || C <= 0 || heads <= 0 || E <= 0 || cur_len < 1 || cur_len + 1 > 64 || (long long)B * groups * heads > 0x7fffffffLL) {
+  if (B <= 0 || C <= 0 || heads <= 0 || E <= 0 || cur_len < 1 || cur_len + 1 > 64 || (size_t)B * groups > 65535) {
     set_last_error("decode_attention: bad args B=%d C=%d heads=%d E=%d cur_len=%d", B, C, heads, E, cur_len);
     return VC_ERR_BAD_ARG;
   }
@@ -326,16 +319,13 @@ int decode_attention_mma(const void* ctx_qkv, const void* step_qkv, const int* a
     configured = true;
   }
   const float scale_log2 = scale * 1.4426950408889634f;
-  const int items = heads * B * groups;
-  const int per_sm = tuning(VC_TUNE_DATTN_CTAS_PER_SM);
-  const int cap = per_sm > 0 ? per_sm * sm_count() : items;
-  const dim3 grid(items < cap ? items : cap);
+  const dim3 grid(heads, B * groups);
   if (E > 4)
     launch_pdl(decode_attention_mma_kernel<true>, grid, dim3(128), SMEM_BYTES, s, (const bf16*)ctx_qkv, (const bf16*)step_qkv, anc,
-               (bf16*)out, C, ctx_vis, H, R, E, cur_len, scale_log2, heads, items);
+               (bf16*)out, C, ctx_vis, H, R, E, cur_len, scale_log2);
   else
     launch_pdl(decode_attention_mma_kernel<false>, grid, dim3(128), SMEM_BYTES, s, (const bf16*)ctx_qkv, (const bf16*)step_qkv, anc,
-               (bf16*)out, C, ctx_vis, H, R, E, cur_len, scale_log2, heads, items);
+               (bf16*)out, C, ctx_vis, H, R, E, cur_len, scale_log2);
   return check_launch("decode_attention_mma");
 }
 

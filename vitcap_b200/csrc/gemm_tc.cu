@@ -44,13 +44,11 @@ template <int BN, int ACT, bool OUT_F32, bool RESID, bool X3 = false>
 __global__ void __launch_bounds__(192, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
-               const float* __restrict__ bias, int M, int N, int K, int nst) {
-  // nst: pipeline stages in use (<= C::STAGES; the launcher sizes the dynamic shared memory for it -- a smaller footprint lets
-  // a CTA of this kernel share an SM with CTAs of a concurrent HBM-bound kernel, see vc_set_tuning)
+               const float* __restrict__ bias, int M, int N, int K) {
   using C = GemmCfg<BN, OUT_F32, RESID, X3>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* epi = smem + nst * C::STAGE_BYTES;
+  uint8_t* epi = smem + C::STAGES * C::STAGE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(epi + C::NBUF * C::EPI_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + C::STAGES;
@@ -72,7 +70,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     tma_prefetch_desc(&tmap_b);
     tma_prefetch_desc(&tmap_out);
     if (RESID) tma_prefetch_desc(&tmap_res);
-    for (int i = 0; i < nst; ++i) {
+    for (int i = 0; i < C::STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
@@ -99,7 +97,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       int pre = 0;
       if ((int)blockIdx.x < num_tiles) {
         const int n0 = ((int)blockIdx.x % n_tiles) * BN;
-        pre = num_kb < nst ? num_kb : nst;
+        pre = num_kb < C::STAGES ? num_kb : C::STAGES;
         for (int kb = 0; kb < pre; ++kb) {
           mbar_arrive_expect_tx(&full_bar[kb], C::STAGE_BYTES);
           tma_load_2d(smem + kb * C::STAGE_BYTES + C::A_BYTES, &tmap_b, &full_bar[kb], kb * C::BK, n0);
@@ -133,7 +131,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               tma_load_2d(sb + C::HALF_BYTES, &tmap_b, &full_bar[stage], 2 * Kt + kb * C::BK, n0);
             }
           }
-          if (++stage == nst) { stage = 0; phase ^= 1; }
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -171,7 +169,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             for (int k = 0; k < C::BK / 16; ++k) umma_f16(d_tmem, adesc + 2 * k, bdesc_lo + 2 * k, idesc, true);     // a_hi w_lo
           }
           umma_commit(&empty_bar[stage]);     // frees the smem stage once these MMAs retire
-          if (++stage == nst) { stage = 0; phase ^= 1; }
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tmem_full[as]);          // accumulator complete -> epilogue
         if (++as == 2) { as = 0; aphase ^= 1; }
@@ -323,18 +321,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 // ------------------------------------------------------------------------------------------
 // host launcher
 // ------------------------------------------------------------------------------------------
-// Pipeline depth under the shared-memory cap of vc_set_tuning(VC_TUNE_GEMM_SMEM_KB) (0 = no cap): as many stages as fit, at
-// least 2, never more than the k-blocks of the problem need. Only small GEMMs (at most one round of tiles) are capped: those
-// are the decode-step shapes that run beside another lane's attention kernel.
-int capped_stages(int stages, int stage_bytes, int fixed_bytes, int num_kb) {
-  const int cap_kb = tuning(VC_TUNE_GEMM_SMEM_KB);
-  if (cap_kb <= 0) return stages;
-  int n = (cap_kb * 1024 - fixed_bytes) / stage_bytes;
-  if (n > stages) n = stages;
-  if (n > num_kb && num_kb >= 2) n = num_kb;
-  return n < 2 ? 2 : n;
-}
-
 template <int BN, int ACT, bool OUT_F32, bool RESID>
 static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
                       const float* bias, int M, int N, int K, cudaStream_t stream) {
@@ -349,9 +335,7 @@ static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const CUtens
   }
   const int tiles = ((M + C::BM - 1) / C::BM) * ((N + BN - 1) / BN);
   int grid = tiles < sm_count() ? tiles : sm_count();
-  const int nst = tiles <= sm_count() ? capped_stages(C::STAGES, C::STAGE_BYTES, C::SMEM_BYTES - C::STAGES * C::STAGE_BYTES, K / C::BK)
-                                      : C::STAGES;
-  launch_pdl(kern, dim3(grid), dim3(192), C::SMEM_BYTES - (C::STAGES - nst) * C::STAGE_BYTES, stream, ta, tb, to, tr, bias, M, N, K, nst);
+  launch_pdl(kern, dim3(grid), dim3(192), C::SMEM_BYTES, stream, ta, tb, to, tr, bias, M, N, K);
   return check_launch("gemm_tc");
 }
 
@@ -389,8 +373,7 @@ int gemm_bf16_tc_x3(const void* A, int lda, const void* W, int ldw, const float*
   }
   const int tiles = ((M + C::BM - 1) / C::BM) * ((N + BN - 1) / BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  const int nst = capped_stages(C::STAGES, C::STAGE_BYTES, C::SMEM_BYTES - C::STAGES * C::STAGE_BYTES, K3 / 3 / C::BK);
-  launch_pdl(kern, dim3(grid), dim3(192), C::SMEM_BYTES - (C::STAGES - nst) * C::STAGE_BYTES, stream, ta, tb, to, tr, bias, M, N, K3, nst);
+  launch_pdl(kern, dim3(grid), dim3(192), C::SMEM_BYTES, stream, ta, tb, to, tr, bias, M, N, K3);
   return check_launch("gemm_tc_x3");
 }
 

@@ -141,13 +141,12 @@ template <int ACT, bool OUT_F32, bool RESID, int G, int LN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 128 * G, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                 const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
-                const __grid_constant__ CUtensorMap tmap_xb, const float* __restrict__ bias, LnArgs ln, int M, int N, int K,
-                int nst) {
-  using C = Gemm2Cfg<OUT_F32, RESID, G, LN>;      // nst: pipeline stages in use (<= C::STAGES), see gemm_tc.cu
+                const __grid_constant__ CUtensorMap tmap_xb, const float* __restrict__ bias, LnArgs ln, int M, int N, int K) {
+  using C = Gemm2Cfg<OUT_F32, RESID, G, LN>;
   constexpr bool EMIT = (LN == LN_EMIT || LN == LN_EMIT_TMA);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* epi = smem + nst * C::STAGE_BYTES;
+  uint8_t* epi = smem + C::STAGES * C::STAGE_BYTES;
   uint8_t* xb_stage = epi + C::NBUF * C::EPI_BYTES;     // [XB_BUFS] bf16 staging tiles (LN = 3)
   uint64_t* bars = reinterpret_cast<uint64_t*>(xb_stage + C::XB_BUFS * C::EPI_BYTES);
   uint64_t* full_bar = bars;                            // [STAGES] used in the leader only (both CTAs' TMA bytes land here)
@@ -173,7 +172,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     tma_prefetch_desc(&tmap_out);
     if (RESID) tma_prefetch_desc(&tmap_res);
     if (LN == LN_EMIT_TMA) tma_prefetch_desc(&tmap_xb);
-    for (int i = 0; i < nst; ++i) {
+    for (int i = 0; i < C::STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
@@ -207,7 +206,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
           tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], kb * C::BK, m0);
           tma_load_2d_pair(sb, &tmap_b, &full_bar[stage], kb * C::BK, n0);
-          if (++stage == nst) { stage = 0; phase ^= 1; }
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -233,7 +232,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 #pragma unroll
           for (int k = 0; k < C::BK / 16; ++k) umma_f16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
           umma_commit_pair(&empty_bar[stage]);          // frees this stage in both CTAs
-          if (++stage == nst) { stage = 0; phase ^= 1; }
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit_pair(&tmem_full[as]);               // accumulator complete -> both epilogues
         if (++as == 2) { as = 0; aphase ^= 1; }
@@ -431,8 +430,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 // ------------------------------------------------------------------------------------------
 // host launcher
 // ------------------------------------------------------------------------------------------
-int capped_stages(int stages, int stage_bytes, int fixed_bytes, int num_kb);     // gemm_tc.cu
-
 template <int ACT, bool OUT_F32, bool RESID, int G, int LN = 0>
 static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr, const float* bias,
                    int M, int N, int K, cudaStream_t stream, LnArgs ln = LnArgs(), const CUtensorMap* txb = nullptr) {
@@ -447,11 +444,7 @@ static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
   const int tiles = ((M + 2 * C::BM - 1) / (2 * C::BM)) * ((N + C::BN - 1) / C::BN);
   int clusters = sm_count() / 2;
   if (tiles < clusters) clusters = tiles;
-  // (the cap applies to problems of at most one round of tiles: the decode-step shapes)
-  const int nst = tiles <= clusters ? capped_stages(C::STAGES, C::STAGE_BYTES, C::SMEM_BYTES - C::STAGES * C::STAGE_BYTES, K / C::BK)
-                                    : C::STAGES;
-  launch_pdl(kern, dim3(2 * clusters), dim3(C::THREADS), C::SMEM_BYTES - (C::STAGES - nst) * C::STAGE_BYTES, stream, ta, tb, to, tr,
-             txb ? *txb : to, bias, ln, M, N, K, nst);
+  launch_pdl(kern, dim3(2 * clusters), dim3(C::THREADS), C::SMEM_BYTES, stream, ta, tb, to, tr, txb ? *txb : to, bias, ln, M, N, K);
   return check_launch("gemm_tc2");
 }
 

@@ -41,14 +41,6 @@ int pdl_mode() {
 }
 void set_pdl_mode(int mode) { g_pdl = mode < 0 ? 0 : (mode > 2 ? 2 : mode); }
 
-static int g_tune[VC_TUNE_COUNT] = {0, 0, 0};
-int tuning(int key) { return (key >= 0 && key < VC_TUNE_COUNT) ? g_tune[key] : 0; }
-int set_tuning(int key, int value) {
-  if (key < 0 || key >= VC_TUNE_COUNT) { set_last_error("vc_set_tuning: unknown key %d", key); return VC_ERR_BAD_ARG; }
-  g_tune[key] = value;
-  return VC_OK;
-}
-
 // The library holds sm_100a code only (tcgen05 / TMEM / TMA): on any other device a launch would fail late with "no kernel
 // image is available". Checked once per process by the first compute entry point (capi.cu VC_COUNT).
 int check_device() {

@@ -149,15 +149,6 @@ class CaptionEngine:
         # parity instrumentation (tests / tools only): tap(name, index, tensor) is called with the stream after every ViT block
         # and with the vocabulary logits after every decode step; while it is set the decode loop runs eagerly (no graph)
         self.tap = None
-        # decode lanes: the images of a batch are split into `decode_lanes` contiguous groups whose decode loops run on separate
-        # streams (forked and joined inside the captured graph), so that the latency-bound GEMM chain of one lane overlaps the
-        # HBM-bound K/V sweep of another (see greedy_or_sample). 1 = a single stream
-        self.decode_lanes = max(1, int(os.environ.get("VITCAP_DECODE_LANES", "1")))
-        self.min_lane_images = 64              # lanes are not worth their fork/join below this many images per lane
-        # launch priority of the decode-step kernels other than the attention (0 = none; negative = higher): with several lanes
-        # the short GEMM / LayerNorm kernels of one lane should be picked before the next CTAs of another lane's K/V sweep
-        self.lane_gemm_priority = int(os.environ.get("VITCAP_LANE_GEMM_PRIORITY", "0"))
-        self._lane_streams = []
 
     # ------------------------------------------------------------------ workspaces
     def _alloc(self, *shape, dtype=None):
@@ -217,7 +208,7 @@ class CaptionEngine:
         return ws
 
     def _new_decoder_ws(self, B, E, max_len):
-        """Buffers of one decode loop over B images x E sequences (one lane)."""
+        """Buffers of one decode loop over B images x E sequences."""
         cfg = self.cfg
         H, F, L = cfg.hidden, cfg.inter, cfg.dec_layers
         R = B * E
@@ -247,26 +238,14 @@ class CaptionEngine:
         ws["ident_rows"] = torch.arange(R, device=self.dev, dtype=i32)
         return ws
 
-    def _decoder_ws(self, B, E, max_len, lanes=1):
-        """Decode workspace of a (B, E, max_len) call, cached with its captured graphs. lanes > 1: the images are split into
-        contiguous groups, each with its own buffers (ws['lanes'] = [(first image, images, lane workspace)]); results of all
-        lanes land in the shared out_ids / out_lp."""
-        key = (B, E, max_len, lanes)
+    def _decoder_ws(self, B, E, max_len):
+        """Decode workspace of a (B, E, max_len) call, cached with its captured graphs."""
+        key = (B, E, max_len)
         if key in self._dec_ws:
             self._dec_ws.move_to_end(key)
             return self._dec_ws[key]
         R = B * E
-        if lanes == 1:
-            ws = self._new_decoder_ws(B, E, max_len)
-            ws["lanes"] = [(0, B, ws)]
-        else:
-            ws = {"B": B, "E": E, "R": R, "max_len": max_len, "lanes": []}
-            base, rem = divmod(B, lanes)
-            b0 = 0
-            for i in range(lanes):
-                b = base + (1 if i < rem else 0)
-                ws["lanes"].append((b0, b, self._new_decoder_ws(b, E, max_len)))
-                b0 += b
+        ws = self._new_decoder_ws(B, E, max_len)
         ws["out_ids"] = torch.zeros(R, max_len, device=self.dev, dtype=torch.int64)
         ws["out_lp"] = torch.zeros(R, device=self.dev, dtype=torch.float32)
         ws["seed"] = torch.zeros(1, device=self.dev, dtype=torch.int64)     # sampling seed, rewritten before every replay
@@ -276,33 +255,16 @@ class CaptionEngine:
             self._dec_ws.popitem(last=False)
         return ws
 
-    def _n_lanes(self, B):
-        n = self.decode_lanes
-        while n > 1 and B // n < self.min_lane_images:
-            n -= 1
-        return n
-
-    def _lanes_run(self, lanes, fn):
-        """fn(first image, images, lane workspace) for every lane; more than one lane: each on its own stream, forked from and
-        joined to the current stream (inside a capture this becomes parallel branches of the graph)."""
-        if len(lanes) == 1:
-            fn(*lanes[0])
-            return
-        while len(self._lane_streams) < len(lanes):
-            self._lane_streams.append(torch.cuda.Stream(device=self.dev))
-        cur = torch.cuda.current_stream()
-        for lane, st in zip(lanes, self._lane_streams):
-            st.wait_stream(cur)
-            with torch.cuda.stream(st):
-                fn(*lane)
-        for _, st in zip(lanes, self._lane_streams):
-            cur.wait_stream(st)
-
     def reserve(self, B, label_rows=False):
         """Sizes the image-side workspace before a batch starts (growing it later would drop the encoder outputs)."""
         return self._encoder_ws(B, self.cfg.n_ctx + (self.cfg.topk if label_rows else 0))
 
     # ------------------------------------------------------------------ building blocks
+    def _t(self, name, idx, tensor):
+        """Parity tap (tests / tools): hands a named intermediate to self.tap; free when no tap is set."""
+        if self.tap is not None:
+            self.tap(name, idx, tensor)
+
     def _ln(self, x, g, b, eps, out_t, out_f=None, rows=None):
         """LayerNorm of fp32 rows -> operand copy (and optional fp32 copy). In exact mode both are the same buffer."""
         if self.T == torch.float32:
@@ -312,7 +274,7 @@ class CaptionEngine:
         ops.layernorm(x, g, b, eps, out_t=out_t, out_f=out_f, rows=rows)
         return out_t
 
-    def _vit_block(self, p, x, rows, B, N, ws, out=None, pre=None, emit=None):
+    def _vit_block(self, p, x, rows, B, N, ws, out=None, pre=None, emit=None, tid=("block", -1)):
         """Pre-LN ViT block on the fp32 stream x (in place). vision_transformer.py:233-250.
         out: another stream buffer that receives the block's result while x stays untouched (the fork of the split encoder:
         the first concept block reads the shared trunk's output and starts its own stream without a copy).
@@ -326,7 +288,9 @@ class CaptionEngine:
         else:
             h = self._ln(x, p["n1w"], p["n1b"], cfg.vit_ln_eps, ln, rows=rows)
             ops.linear(h, p["qkv_w"], p["qkv_b"], qkv, M=rows)
+        self._t(tid[0] + ".qkv", tid[1], qkv)
         ops.attention(qkv, att, B, N, cfg.heads, cfg.head_dim ** -0.5, impl=self.attn_impl)
+        self._t(tid[0] + ".att", tid[1], att)
         dst = x if out is None else out
         if self.ln_fold and self.ln_fold2:
             f2 = ws["fold_2"]
@@ -339,6 +303,8 @@ class CaptionEngine:
             x = dst
             h = self._ln(x, p["n2w"], p["n2b"], cfg.vit_ln_eps, ln, rows=rows)
             ops.linear(h, p["fc1_w"], p["fc1_b"], hid, act=ops.ACT_GELU, M=rows)
+        self._t(tid[0] + ".mid", tid[1], x)            # stream after the attention branch (fp32; both taps precede fc2)
+        self._t(tid[0] + ".hid", tid[1], hid)
         if emit is not None:
             ops.linear_ln_emit(hid, p["fc2_w"], p["fc2_b"], x, x, emit[0][:rows], emit[1], M=rows)
         else:
@@ -356,11 +322,16 @@ class CaptionEngine:
         ops.linear(h, p["qkv_w"][H:], p["qkv_b"][H:], qkv[:, H:], M=rows, ldo=3 * H)          # K | V of every row
         h_cls = h.view(B, N * H)[:, :H]                                                        # row 0 of every image
         ops.linear(h_cls, p["qkv_w"][:H], p["qkv_b"][:H], q_cls, M=B)
+        self._t("cls.kv", 0, qkv[:, H:])
+        self._t("cls.q", 0, q_cls)
         ops.cls_attention(q_cls, qkv, att_cls, B, N, cfg.heads, cfg.head_dim ** -0.5)
+        self._t("cls.att", 0, att_cls)
         x_cls = x.view(B, N * H)[:, :H]                                                        # fp32 stream, row 0 of every image
         ops.linear(att_cls, p["proj_w"], p["proj_b"], x_cls, resid=x_cls, M=B)
+        self._t("cls.mid", 0, x_cls)
         h2 = self._ln(x_cls, p["n2w"], p["n2b"], cfg.vit_ln_eps, ln_cls, rows=B)
         ops.linear(h2, p["fc1_w"], p["fc1_b"], hid_cls, act=ops.ACT_GELU, M=B)
+        self._t("cls.hid", 0, hid_cls)
         ops.linear(hid_cls, p["fc2_w"], p["fc2_b"], x_cls, resid=x_cls, M=B)
 
     # ------------------------------------------------------------------ stages
@@ -380,6 +351,7 @@ class CaptionEngine:
         ops.linear(patches, w.patch_w, w.patch_b, po, M=B * P)
         x = ws["x"][:B * N]
         ops.assemble_tokens(po, w.cls_token, w.pos_embed, x, B, P, H)
+        self._t("patch", 0, x.view(B, N, H))
         return x.view(B, N, H)
 
     def encode(self, img_feats, caption_branch=True, full_tag_feats=False):
@@ -406,7 +378,7 @@ class CaptionEngine:
         for i in range(split_at):
             last_trunk = (i == split_at - 1)
             wanted = (not last_trunk) or n_cap > 0 or n_tag_fold > 0
-            self._vit_block(w.blocks[i], x, rows, B, N, ws, pre=pre, emit=fx if wanted else None)
+            self._vit_block(w.blocks[i], x, rows, B, N, ws, pre=pre, emit=fx if wanted else None, tid=("block", i))
             pre = fx if wanted else None
             if self.tap is not None:
                 self.tap("block", i, x.view(B, N, H))
@@ -428,10 +400,10 @@ class CaptionEngine:
             emit_t = ft if (self.ln_fold and nxt_full) else None
             if not forked:
                 # reads the trunk's stream x (and its copy/statistics), writes the concept stream xt out of place
-                self._vit_block_fork(w.tag_blocks[j], x, xt, rows, B, N, ws, pre=pre_t, emit=emit_t)
+                self._vit_block_fork(w.tag_blocks[j], x, xt, rows, B, N, ws, pre=pre_t, emit=emit_t, tid=("tag_block", j))
                 forked = True
             else:
-                self._vit_block(w.tag_blocks[j], xt, rows, B, N, ws, pre=pre_t, emit=emit_t)
+                self._vit_block(w.tag_blocks[j], xt, rows, B, N, ws, pre=pre_t, emit=emit_t, tid=("tag_block", j))
             pre_t = emit_t
             if self.tap is not None:
                 self.tap("tag_block", j, xt.view(B, N, H))
@@ -441,15 +413,15 @@ class CaptionEngine:
             pre = pre_trunk
             for i in range(split_at, cfg.enc_blocks):
                 emit = fx if (self.ln_fold and i + 1 < cfg.enc_blocks) else None
-                self._vit_block(w.blocks[i], x, rows, B, N, ws, pre=pre, emit=emit)
+                self._vit_block(w.blocks[i], x, rows, B, N, ws, pre=pre, emit=emit, tid=("block", i))
                 pre = emit
                 if self.tap is not None:
                     self.tap("block", i, x.view(B, N, H))
         return x.view(B, N, H), xt.view(B, N, H)
 
-    def _vit_block_fork(self, p, x, xt, rows, B, N, ws, pre=None, emit=None):
+    def _vit_block_fork(self, p, x, xt, rows, B, N, ws, pre=None, emit=None, tid=("tag_block", 0)):
         """First block of the concept branch: input = the shared trunk's stream x (left untouched), result -> xt."""
-        self._vit_block(p, x, rows, B, N, ws, out=xt, pre=pre, emit=emit)
+        self._vit_block(p, x, rows, B, N, ws, out=xt, pre=pre, emit=emit, tid=tid)
 
     def _head(self, hp, a_t, rows, th_f, th_t, logits):
         """BertLMPredictionHead (modeling_bert.py:540-563): dense + gelu -> LN(1e-12) -> tied/untied decoder + bias."""
@@ -466,8 +438,10 @@ class CaptionEngine:
         cls_t, pooled = ws["cls_t"][:B], ws["pooled"][:B]
         ops.gather_rows(ws["xt"], N * H, cls_t, B, H)
         ops.linear(cls_t, w.pool_w, w.pool_b, pooled, act=ops.ACT_TANH, M=B)
+        self._t("tag.pooled", 0, pooled)
         logits = ws["tag_logits"][:B]
         self._head(w.tag_head, pooled, B, ws["th_f"][:B], ws["th_t"][:B], logits)
+        self._t("tag.logits", 0, logits[:, :cfg.vocab])
         ops.tag_topk(logits, cfg.vocab, cfg.topk, cfg.tag_thresh, ws["tag_idx"], ws["tag_prob"], ws["tag_len"], rows=B)
         return logits[:, :cfg.vocab], ws["tag_idx"][:B], ws["tag_prob"][:B], ws["tag_len"][:B]
 
@@ -499,46 +473,45 @@ class CaptionEngine:
             ops.label_rows(ws["tag_idx"], cfg.sep_id, label_recipe == "ln", cfg.max_seq_a, w.word, w.pos, w.type0, w.emb_ln_w,
                            w.emb_ln_b, cfg.bert_ln_eps, ctx_f, ctx_t, B, Cp, C)
         att, hid, tmp, a_f, ln = ws["att"][:rows], ws["hid"][:rows], ws["tmp_f"][:rows], ws["a_f"][:rows], ws["ln"][:rows]
+        self._t("prefill.in", 0, ctx_f)
         for l, p in enumerate(w.dec):
             qkv = ws["ctx_qkv"][l][:rows]
             last = (l == cfg.dec_layers - 1)
             if last:
                 # only K and V of the last layer are ever used: project the k|v two thirds of the fused weight
                 ops.linear(ctx_t, p["qkv_w"][H:], p["qkv_b"][H:], qkv[:, H:], M=rows, ldo=3 * H)
+                self._t("prefill.qkv", l, qkv)
                 break
             ops.linear(ctx_t, p["qkv_w"], p["qkv_b"], qkv, M=rows)
+            self._t("prefill.qkv", l, qkv)
             ops.attention(qkv, att, B, Cp, cfg.heads, 1.0 / math.sqrt(cfg.head_dim), impl=self.attn_impl, n_base=C, n_extra=n_extra)
+            self._t("prefill.att", l, att)
             ops.linear(att, p["o_w"], p["o_b"], tmp, resid=ctx_f, M=rows)
             a_t = self._ln(tmp, p["ln1_w"], p["ln1_b"], cfg.bert_ln_eps, ln, out_f=a_f, rows=rows)
+            self._t("prefill.a", l, a_f)
             ops.linear(a_t, p["i_w"], p["i_b"], hid, act=ops.ACT_GELU, M=rows)
+            self._t("prefill.hid", l, hid)
             ops.linear(hid, p["f_w"], p["f_b"], tmp, resid=a_f, M=rows)
             self._ln(tmp, p["ln2_w"], p["ln2_b"], cfg.bert_ln_eps, ctx_t, out_f=ctx_f, rows=rows)
+            self._t("prefill.out", l, ctx_f)
 
-    def _decode_layers(self, ws, B, E, cur_len, anc, mask_id, labels=False, head=True, img0=0):
+    def _decode_layers(self, ws, B, E, cur_len, anc, mask_id, labels=False, head=True):
         """One decode step up to the vocabulary logits of the MASK rows. labels: the context holds C + topk rows per image of
-        which ctx_vis[b] are visible. head=False stops after the decoder layers (caption-row replay after a recipe flip).
-        img0: first image of this lane inside the image-side workspace (its context K/V rows start at img0 * C)."""
+        which ctx_vis[b] are visible. head=False stops after the decoder layers (caption-row replay after a recipe flip)."""
         cfg, w = self.cfg, self.w
         R, H = ws["R"], cfg.hidden
         C = cfg.n_ctx + (cfg.topk if labels else 0)
         enc = self._enc_ws
-        ctx_vis = enc["ctx_vis"][img0:] if labels else None
+        ctx_vis = enc["ctx_vis"] if labels else None
         e_f, e_t = ws["e_f"], ws["e_t"]
-        if self.lane_gemm_priority:
-            ops.set_tuning(ops.TUNE_LAUNCH_PRIORITY, self.lane_gemm_priority)
         ops.embed_ln(ws["ids"], cur_len, mask_id, w.word, w.pos, w.type0, w.emb_ln_w, w.emb_ln_b, cfg.bert_ln_eps, e_f, e_t, R)
         scale = 1.0 / math.sqrt(cfg.head_dim)
         x3 = self.decode_x3
         n_layers = len(w.dec)
-        prio = self.lane_gemm_priority
         for l, p in enumerate(w.dec):
             sq = ws["step_qkv"][l]
             ops.linear(e_t, p["qkv_w"], p["qkv_b"], sq[cur_len - 1], M=2 * R)
-            if prio:
-                ops.set_tuning(ops.TUNE_LAUNCH_PRIORITY, 0)
-            ops.decode_attention(enc["ctx_qkv"][l][img0 * C:], sq, anc, ws["att"], B, C, cfg.heads, E, cur_len, scale, ctx_vis=ctx_vis)
-            if prio:
-                ops.set_tuning(ops.TUNE_LAUNCH_PRIORITY, prio)
+            ops.decode_attention(enc["ctx_qkv"][l], sq, anc, ws["att"], B, C, cfg.heads, E, cur_len, scale, ctx_vis=ctx_vis)
             ops.linear(ws["att"], p["o_w"], p["o_b"], ws["tmp"], resid=e_f, M=2 * R)
             if x3:
                 # BertIntermediate / BertOutput (modeling_bert.py:395-419) on split-bf16 operands: the operand rounding of
@@ -575,8 +548,6 @@ class CaptionEngine:
         elif head:
             mask_rows = e_t[1::2]
             self._head(w.cls_head, mask_rows, R, ws["head_f"], ws["head_t"], ws["logits"])
-        if self.lane_gemm_priority:
-            ops.set_tuning(ops.TUNE_LAUNCH_PRIORITY, 0)
 
     def _flip_labels(self, ws, B, E, cur_len, mask_id, anc_table=None):
         """The reference switches the label embedding to the 'raw' recipe at this step (modeling_bert.py:1435) and, having no
@@ -625,38 +596,30 @@ class CaptionEngine:
         recipe (the context must have been prefilled with 'ln' if label_flip > 1, else with 'raw')."""
         labels = label_flip is not None
         cfg = self.cfg
-        # lanes: greedy without a label region only (sampling numbers its Philox streams by row, a recipe flip re-prefills
-        # the shared context) and never under a parity tap
-        n_lanes = 1 if (labels or do_sample or self.tap is not None) else self._n_lanes(B)
-        ws = self._decoder_ws(B, E, max_len, lanes=n_lanes)
+        ws = self._decoder_ws(B, E, max_len)
         R = ws["R"]
         eos = self._eos_tensor(ws, eos_ids)
         filt = do_sample and (top_k > 0 or top_p < 1.0)
 
-        def lane_loop(img0, b, lw):
-            r0, r = img0 * E, lw["R"]
-            lw["ids"].zero_()
-            lw["ids"][:, 0] = bos
-            lw["unfinished"].fill_(1)
-            lw["sum_lp"].zero_()
-            lw["n_steps"].zero_()
+        def run():
+            ws["ids"].zero_()
+            ws["ids"][:, 0] = bos
+            ws["unfinished"].fill_(1)
+            ws["sum_lp"].zero_()
+            ws["n_steps"].zero_()
             for cur_len in range(1, max_len):
                 if labels and cur_len == label_flip and cur_len > 1:
-                    self._flip_labels(lw, b, E, cur_len, mask_id)
-                self._decode_layers(lw, b, E, cur_len, None, mask_id, labels=labels, img0=img0)
-                if self.tap is not None:
-                    self.tap("logits", cur_len, lw["logits"][:, :cfg.vocab])
+                    self._flip_labels(ws, B, E, cur_len, mask_id)
+                self._decode_layers(ws, B, E, cur_len, None, mask_id, labels=labels)
+                self._t("logits", cur_len, ws["logits"][:, :cfg.vocab])
                 t = temperature
                 if filt:
-                    ops.filter_logits(lw["logits"], cfg.vocab, r, 1.0 / temperature, top_k, top_p)
+                    ops.filter_logits(ws["logits"], cfg.vocab, R, 1.0 / temperature, top_k, top_p)
                     t = 1.0
-                ops.token_step(lw["logits"], cfg.vocab, r, do_sample, t, 0, cur_len, pad, eos, lw["ids"], lw["unfinished"],
-                               lw["sum_lp"], lw["n_steps"], seed_dev=ws["seed"] if do_sample else None)
-            ops.greedy_finalize(lw["ids"], lw["unfinished"], lw["sum_lp"], lw["n_steps"], int(eos_ids[0]), r,
-                                ws["out_ids"][r0:r0 + r], ws["out_lp"][r0:r0 + r])
-
-        def run():
-            self._lanes_run(ws["lanes"], lane_loop)
+                ops.token_step(ws["logits"], cfg.vocab, R, do_sample, t, 0, cur_len, pad, eos, ws["ids"], ws["unfinished"],
+                               ws["sum_lp"], ws["n_steps"], seed_dev=ws["seed"] if do_sample else None)
+            ops.greedy_finalize(ws["ids"], ws["unfinished"], ws["sum_lp"], ws["n_steps"], int(eos_ids[0]), R, ws["out_ids"],
+                                ws["out_lp"])
 
         if do_sample:
             # the seed lives in device memory, outside the captured loop: one graph serves every call

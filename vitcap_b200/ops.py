@@ -86,10 +86,6 @@ def load_library(path=None):
     lib.vc_set_pdl.restype = None
     lib.vc_set_pdl.argtypes = [_I]
     lib.vc_get_pdl.restype = _I
-    lib.vc_set_tuning.restype = _I
-    lib.vc_set_tuning.argtypes = [_I, _I]
-    lib.vc_get_tuning.restype = _I
-    lib.vc_get_tuning.argtypes = [_I]
     lib.vc_check_device.restype = _I
     lib.vc_check_device.argtypes = []
     if path is None:
@@ -130,18 +126,6 @@ def set_pdl(mode):
 
 def get_pdl():
     return int(load_library().vc_get_pdl())
-
-
-TUNE_GEMM_SMEM_KB, TUNE_DATTN_CTAS_PER_SM, TUNE_LAUNCH_PRIORITY = 0, 1, 2
-
-
-def set_tuning(key, value):
-    """Run-time knobs for concurrent decode lanes (include/vitcap_b200.h, vc_set_tuning)."""
-    _check(load_library().vc_set_tuning(int(key), int(value)), "vc_set_tuning")
-
-
-def get_tuning(key):
-    return int(load_library().vc_get_tuning(int(key)))
 
 
 def check_device():
