@@ -298,3 +298,164 @@ def test_beam_kernels_vs_oracle_loop(B, nb, keep, lp, V):
     assert int(anc.min()) >= 0 and int(anc.max()) < B * nb
     rows = torch.arange(B * nb)
     assert torch.equal(anc // nb, (rows // nb).expand_as(anc))        # beams never cross images
+
+
+# ------------------------------------------------------------------------------------------------ fused decode step kernels
+def _bf(x):
+    return x.to(torch.bfloat16)
+
+
+def _split_pair(x):
+    hi = _bf(x)
+    return hi, _bf(x - hi.float())
+
+
+def _x3_operands(M, N, Kt, seed, wscale=0.05):
+    """(a fp32, w fp32, A3 = [a_hi | a_lo | junk], W3 = [w_hi | w_hi | w_lo], fp32 reference of the three products)."""
+    a, w = _rnd(M, Kt, seed=seed), _rnd(N, Kt, seed=seed + 1, scale=wscale)
+    a_hi, a_lo = _split_pair(a)
+    w_hi, w_lo = _split_pair(w)
+    A3 = torch.cat([a_hi, a_lo, _bf(torch.full((M, Kt), 7.0))], 1).contiguous()       # the third block must never be read
+    W3 = ops.split_weight_bf16x3(w)
+    ref = a_hi.float() @ w_hi.float().t() + a_lo.float() @ w_hi.float().t() + a_hi.float() @ w_lo.float().t()
+    return a, w, A3, W3, ref
+
+
+@pytest.mark.parametrize("M,N,Kt,x3,splits", [(1024, 768, 768, False, 1), (1024, 768, 768, False, 6), (1000, 768, 3072, True, 6),
+                                              (512, 768, 768, True, 12), (130, 2304, 768, False, 3), (1, 768, 768, True, 2),
+                                              (5000, 768, 768, False, 2)])
+def test_dec_linear_partial_planes(M, N, Kt, x3, splits):
+    """vc_dec_linear VC_DEC_PARTIAL: plane s = the product over the s-th K slice (fp32, no bias); their sum = the full product.
+    Covers ragged M, a single row, and more tiles than clusters (the producer then waits for the epilogue's staging tiles)."""
+    if x3:
+        a, w, A, W, ref = _x3_operands(M, N, Kt, seed=M + N)
+    else:
+        A, W = _bf(_rnd(M, Kt, seed=M)), _bf(_rnd(N, Kt, seed=N, scale=0.05))
+        ref = A.float() @ W.float().t()
+    m_pad = (M + 127) // 128 * 128
+    out = torch.full((splits, m_pad, N), float("nan"), device=DEV)
+    ops.dec_linear(ops.DEC_PARTIAL, A.to(DEV), W.to(DEV), None, out, M=M, x3=x3, splits=splits, m_pad=m_pad)
+    got = out[:, :M].cpu()
+    assert torch.isfinite(got).all()
+    scale = float(ref.abs().max())
+    assert float((got.sum(0) - ref).abs().max()) <= 3e-5 * scale
+    ks = Kt // splits
+    for s in range(splits):
+        sl = slice(s * ks, (s + 1) * ks)
+        if x3:
+            a_hi, a_lo = A[:, :Kt].float(), A[:, Kt:2 * Kt].float()
+            w_hi, w_lo = W[:, :Kt].float(), W[:, 2 * Kt:].float()
+            part = a_hi[:, sl] @ w_hi[:, sl].t() + a_lo[:, sl] @ w_hi[:, sl].t() + a_hi[:, sl] @ w_lo[:, sl].t()
+        else:
+            part = A[:, sl].float() @ W[:, sl].float().t()
+        assert float((got[s] - part).abs().max()) <= 3e-5 * scale, s
+
+
+@pytest.mark.parametrize("M,N,Kt,x3,mode", [(1024, 2304, 768, False, "bf16"), (1024, 3072, 768, True, "split"), (777, 3072, 768, False, "gelu"),
+                                            (5120, 3072, 768, True, "split"), (200, 768, 768, True, "bf16"), (64, 128, 64, False, "gelu")])
+def test_dec_linear_bf16_and_split_epilogues(M, N, Kt, x3, mode):
+    """VC_DEC_BF16 / VC_DEC_GELU_BF16 / VC_DEC_GELU_SPLIT against fp32 torch on the same operands. The split pair (hi, lo) must
+    carry the GELU output to ~2^-16 where the plain bf16 output stops at 2^-9, and hi must be the plain bf16 rounding."""
+    if x3:
+        a, w, A, W, ref = _x3_operands(M, N, Kt, seed=M + N)
+    else:
+        A, W = _bf(_rnd(M, Kt, seed=M)), _bf(_rnd(N, Kt, seed=N, scale=0.05))
+        ref = A.float() @ W.float().t()
+    bias = _rnd(N, seed=9)
+    ref = ref + bias
+    if mode != "bf16":
+        ref = port.gelu_fast(ref)
+    scale = float(ref.abs().max())
+    if mode == "split":
+        out = torch.full((M, 3 * N), 9.0, device=DEV, dtype=torch.bfloat16)
+        ops.dec_linear(ops.DEC_GELU_SPLIT, A.to(DEV), W.to(DEV), bias.to(DEV), out, M=M, x3=x3)
+        o = out.cpu()
+        hi, lo = o[:, :N].float(), o[:, N:2 * N].float()
+        assert bool((o[:, 2 * N:] == 9.0).all())                               # the third block is left alone
+        assert float((hi + lo - ref).abs().max()) <= 1.2e-3 * scale            # MUFU.TANH (2^-11) dominates
+        assert float((hi - ref).abs().max()) <= 6e-3 * scale
+        assert float((hi + lo - ref).abs().mean()) < 0.2 * float((hi - ref).abs().mean())
+        assert float((lo.abs() > hi.abs() * 2.0 ** -7 + 1e-30).float().mean()) == 0.0      # lo is a rounding remainder
+    else:
+        out = torch.full((M, N), 9.0, device=DEV, dtype=torch.bfloat16)
+        ops.dec_linear(ops.DEC_BF16 if mode == "bf16" else ops.DEC_GELU_BF16, A.to(DEV), W.to(DEV), bias.to(DEV), out, M=M, x3=x3)
+        assert float((out.cpu().float() - ref).abs().max()) <= 6e-3 * scale
+
+
+@pytest.mark.parametrize("rows,splits,gelu,resid,mode", [(1024, 6, False, True, "split"), (1000, 1, False, True, "bf16"),
+                                                         (512, 12, True, False, "split"), (3, 2, False, True, "none")])
+def test_finish_ln(rows, splits, gelu, resid, mode):
+    H = 768
+    m_pad = (rows + 127) // 128 * 128
+    part = _rnd(splits, m_pad, H, seed=rows, scale=0.5)
+    bias, gamma, beta = _rnd(H, seed=1), 1.0 + 0.1 * _rnd(H, seed=2), 0.1 * _rnd(H, seed=3)
+    res = _rnd(rows, H, seed=4) if resid else None
+    x = part[:, :rows].sum(0) + bias
+    if gelu:
+        x = port.gelu_fast(x)
+    if resid:
+        x = x + res
+    ref = torch.nn.functional.layer_norm(x, (H,), gamma, beta, 1e-12)
+    out_f = torch.empty(rows, H, device=DEV)
+    out_t = None if mode == "none" else torch.full((rows, 3 * H if mode == "split" else H), 5.0, device=DEV, dtype=torch.bfloat16)
+    ops.finish_ln(part.to(DEV), splits, bias.to(DEV), gamma.to(DEV), beta.to(DEV), 1e-12, rows, resid=res.to(DEV) if resid else None,
+                  gelu=gelu, out_f=out_f, out_t=out_t, split=(mode == "split"))
+    of = out_f.cpu()
+    assert float((of - ref).abs().max()) <= (2e-3 if gelu else 2e-5) * float(ref.abs().max())
+    if mode == "bf16":
+        assert torch.equal(out_t.cpu(), of.to(torch.bfloat16))
+    elif mode == "split":
+        hi, lo = _split_pair(of)
+        o = out_t.cpu()
+        assert torch.equal(o[:, :H], hi) and torch.equal(o[:, H:2 * H], lo) and bool((o[:, 2 * H:] == 5.0).all())
+
+
+@pytest.mark.parametrize("R,V,x3", [(512, 30522, True), (40, 30522, False), (130, 3000, True), (7, 500, False)])
+def test_vocab_argmax_partials_and_token_step(R, V, x3):
+    """Greedy decoding without materialised logits: vc_dec_vocab_argmax + vc_token_step_partials against the explicit
+    logits -> argmax -> log_softmax -> gather (modeling_utils.py:849-853) and the state update of vc_token_step."""
+    Kt = 768
+    if x3:
+        a, w, A, W, ref = _x3_operands(R, V, Kt, seed=R + V, wscale=0.03)
+    else:
+        A, W = _bf(_rnd(R, Kt, seed=R)), _bf(_rnd(V, Kt, seed=V, scale=0.03))
+        ref = A.float() @ W.float().t()
+    bias = 0.5 * _rnd(V, seed=5)
+    bias[102] += 3.0                                          # a popular [SEP] so that rows finish
+    ref = ref + bias
+    n_part = ops.vocab_partials(V)
+    part = torch.full((R, n_part, 4), float("nan"), device=DEV)
+    ops.dec_vocab_argmax(A.to(DEV), W.to(DEV), bias.to(DEV), part, M=R, x3=x3)
+    p = part.cpu()
+    # every partial: max / arg max / sum over its own columns
+    for tile in (0, n_part // 2 - 1):
+        for g in range(2):
+            T = ops.VOCAB_TILE
+            cols = [c for ch in range(g, 7, 2) for c in range(tile * T + ch * 32, min(tile * T + ch * 32 + 32, (tile + 1) * T)) if c < V]
+            if not cols:
+                assert bool((p[:, 2 * tile + g, 2] == 0).all())
+                continue
+            sub = ref[:, cols]
+            np.testing.assert_allclose(p[:, 2 * tile + g, 0].numpy(), sub.max(1).values.numpy(), atol=2e-4)
+            np.testing.assert_allclose(p[:, 2 * tile + g, 2].numpy(), torch.exp(sub - sub.max(1, keepdim=True).values).sum(1).numpy(), rtol=2e-4)
+    eos = torch.tensor([102], dtype=torch.int32, device=DEV)
+    L = 6
+    ids = torch.zeros(R, L, dtype=torch.int32, device=DEV)
+    unf = torch.ones(R, dtype=torch.int32, device=DEV)
+    unf[::5] = 0
+    slp, nst = torch.zeros(R, device=DEV), torch.zeros(R, dtype=torch.int32, device=DEV)
+    ops.token_step_partials(part, R, 2, 0, eos, ids, unf, slp, nst)
+    top2 = ref.topk(2, dim=1)
+    lsm = torch.log_softmax(ref, dim=1)
+    tok = ids[:, 2].cpu()
+    was_unf = torch.ones(R, dtype=torch.bool)
+    was_unf[::5] = False
+    for r in range(R):
+        if not was_unf[r]:
+            assert int(tok[r]) == 0 and float(slp[r]) == 0.0 and int(nst[r]) == 0 and int(unf[r]) == 0
+            continue
+        if int(tok[r]) != int(top2.indices[r, 0]):
+            assert float(top2.values[r, 0] - top2.values[r, 1]) < 2e-4, r          # only a near-tie may flip
+        assert abs(float(slp[r]) - float(lsm[r, int(tok[r])])) < 3e-4
+        assert int(nst[r]) == 1 and int(unf[r]) == int(int(tok[r]) != 102)
+    assert int((tok == 102).sum()) > 0

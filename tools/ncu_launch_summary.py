@@ -1,5 +1,6 @@
 """Summarises an `ncu --metrics gpu__time_duration.sum --csv` launch list: per-kernel count, total and share.
-usage: python tools/ncu_launch_summary.py gpurun_out/launches.csv [first_id last_id]"""
+usage: python tools/ncu_launch_summary.py gpurun_out/launches.csv [first_id last_id] [--by-grid]
+--by-grid keeps launches of one kernel with different grid sizes apart (e.g. the decode-step GEMMs of different shapes)."""
 import csv
 import re
 import sys
@@ -18,9 +19,11 @@ def short(name):
 
 
 def main():
-    path = sys.argv[1]
-    lo = int(sys.argv[2]) if len(sys.argv) > 2 else 0
-    hi = int(sys.argv[3]) if len(sys.argv) > 3 else 1 << 60
+    by_grid = "--by-grid" in sys.argv
+    argv = [a for a in sys.argv if a != "--by-grid"]
+    path = argv[1]
+    lo = int(argv[2]) if len(argv) > 2 else 0
+    hi = int(argv[3]) if len(argv) > 3 else 1 << 60
     rows = []
     with open(path) as f:
         lines = [l for l in f if l.startswith('"')]
@@ -29,7 +32,10 @@ def main():
             continue
         i = int(r["ID"])
         if lo <= i <= hi:
-            rows.append((i, short(r["Kernel Name"]), float(r["Metric Value"].replace(",", "")), r["Grid Size"], r["Block Size"]))
+            name = short(r["Kernel Name"])
+            if by_grid:
+                name += " grid " + r["Grid Size"].replace(" ", "")
+            rows.append((i, name, float(r["Metric Value"].replace(",", "")), r["Grid Size"], r["Block Size"]))
     agg = OrderedDict()
     for i, n, t, g, b in rows:
         a = agg.setdefault(n, [0, 0.0])

@@ -32,7 +32,7 @@ def _sources():
 
 def _digest(path):
     h = hashlib.sha1()
-    for extra in ("common.cuh",):
+    for extra in ("common.cuh", "pair.cuh"):
         with open(os.path.join(CSRC, extra), "rb") as f:
             h.update(f.read())
     with open(os.path.join(os.path.dirname(HERE), "include", "vitcap_b200.h"), "rb") as f:

@@ -63,6 +63,15 @@ int beam_finalize(const double* hyp_score, const int* hyp_len, const int* hyp_id
                   int pad_id, int eos0, long long* out_ids, float* out_lp, cudaStream_t s);
 int filter_logits(float* logits, int ld, int rows, int V, float inv_temperature, int top_k, float top_p, int min_tokens_to_keep,
                   cudaStream_t s);
+int gemm_dec(int mode, int x3, const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldo, int M, int N,
+             int K, int splits, int m_pad, cudaStream_t stream);
+int gemm_dec_argmax(int x3, const void* A, int lda, const void* W, int ldw, const float* bias, void* part, int n_part, int M, int N,
+                    int K, cudaStream_t stream);
+int finish_ln(const float* part, int splits, size_t plane, int ld_p, const float* bias, int gelu, const float* resid, int ld_r,
+              const float* gamma, const float* beta, float eps, float* out_f, int ld_f, void* out_t, int ld_t, int out_mode, int rows,
+              int H, cudaStream_t s);
+int token_step_partials(const void* part, int n_part, int rows, int cur_len, int max_len, int pad_id, const int* eos_ids, int n_eos,
+                        int* ids, int* unfinished, float* sum_lp, int* n_steps, cudaStream_t s);
 }  // namespace vc
 
 static std::atomic<long long> g_launches{0};
@@ -72,7 +81,7 @@ static std::atomic<long long> g_launches{0};
 extern "C" {
 
 const char* vc_last_error(void) { return vc::last_error(); }
-int vc_abi_version(void) { return 6; }
+int vc_abi_version(void) { return 7; }
 int vc_check_device(void) { return vc::check_device(); }
 long long vc_launch_count(void) { return g_launches.load(); }
 void vc_reset_launch_count(void) { g_launches = 0; }
@@ -218,6 +227,25 @@ int vc_beam_advance(int* ids, float* beam_scores, int* done, int* anc, double* h
 int vc_beam_finalize(const double* hyp_score, const int* hyp_len, const int* hyp_ids, const int* hyp_count, int B, int keep,
                      int max_len, int pad_id, int eos0, long long* out_ids, float* out_lp, void* stream) {
   VC_COUNT(1, vc::beam_finalize(hyp_score, hyp_len, hyp_ids, hyp_count, B, keep, max_len, pad_id, eos0, out_ids, out_lp, ST(stream)));
+}
+int vc_dec_linear(int mode, int x3, const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldo, int M,
+                  int N, int K, int splits, int m_pad, void* stream) {
+  VC_COUNT(1, vc::gemm_dec(mode, x3, A, lda, W, ldw, bias, out, ldo, M, N, K, splits, m_pad, ST(stream)));
+}
+int vc_dec_vocab_argmax(int x3, const void* A, int lda, const void* W, int ldw, const float* bias, void* part, int n_part, int M,
+                        int N, int K, void* stream) {
+  VC_COUNT(1, vc::gemm_dec_argmax(x3, A, lda, W, ldw, bias, part, n_part, M, N, K, ST(stream)));
+}
+int vc_finish_ln(const float* part, int splits, size_t plane, int ld_p, const float* bias, int gelu, const float* resid, int ld_r,
+                 const float* gamma, const float* beta, float eps, float* out_f, int ld_f, void* out_t, int ld_t, int out_mode,
+                 int rows, int H, void* stream) {
+  VC_COUNT(1, vc::finish_ln(part, splits, plane, ld_p, bias, gelu, resid, ld_r, gamma, beta, eps, out_f, ld_f, out_t, ld_t, out_mode,
+                            rows, H, ST(stream)));
+}
+int vc_token_step_partials(const void* part, int n_part, int rows, int cur_len, int max_len, int pad_id, const int* eos_ids,
+                           int n_eos, int* ids, int* unfinished, float* sum_lp, int* n_steps, void* stream) {
+  VC_COUNT(1, vc::token_step_partials(part, n_part, rows, cur_len, max_len, pad_id, eos_ids, n_eos, ids, unfinished, sum_lp, n_steps,
+                                      ST(stream)));
 }
 int vc_filter_logits(float* logits, int ld, int rows, int V, float inv_temperature, int top_k, float top_p, int min_tokens_to_keep,
                      void* stream) {

@@ -1,7 +1,7 @@
 // Bandwidth-bound helper kernels of the caption path: patch extraction, token/context assembly,
 // LayerNorm, row gathers, decode-step embedding. All use 128-bit global accesses and warp-shuffle
 // reductions; one warp owns one row of the hidden dimension.
-#include "common.cuh"
+#include "pair.cuh"
 
 namespace vc {
 
@@ -127,13 +127,6 @@ int assemble_tokens(const float* patch_out, const float* cls, const float* pos, 
 // X3: out_t is the split-bf16 operand [hi | lo | hi] (3H columns, hi = bf16(y), lo = bf16(y - hi)) of the three-product
 // tensor-core GEMM against [w_hi | w_hi | w_lo]; its first H columns are the plain bf16 copy.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  hi = pack_bf16x2(a, b);
-  float ha, hb;
-  unpack_bf16x2(hi, ha, hb);
-  lo = pack_bf16x2(a - ha, b - hb);
-}
-
 template <typename T, bool X3 = false>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ in, int ld_in, const float* __restrict__ gamma, const float* __restrict__ beta,

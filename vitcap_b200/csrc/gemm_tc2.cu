@@ -23,7 +23,7 @@
 //         LN(x) W^T + b  =  rstd * (x (gamma o W)^T  -  mean * colsum(gamma o W))  +  (b + W beta)
 //     (bf16 rounding is relative, so rounding x before instead of after the affine map gives the same error bound as long as
 //     |mean| is not much larger than the row's standard deviation; the statistics are fp32 over the fp32 row).
-#include "common.cuh"
+#include "pair.cuh"
 
 #include <cstdlib>
 
@@ -33,8 +33,6 @@ namespace {
 
 enum { ACT2_NONE = 0, ACT2_GELU = 1, ACT2_TANH = 2 };
 enum { LN_NONE = 0, LN_EMIT = 1, LN_FOLD = 2, LN_EMIT_TMA = 3 };   // 3 = emit with the bf16 copy staged in shared memory (TMA store)
-
-constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;    // clears the CTA-rank bit of a shared::cluster address -> rank 0 of the pair
 
 template <bool OUT_F32, bool RESID, int G, int LN = 0> struct Gemm2Cfg {
   static constexpr int BM = 128;                        // rows per CTA (256 per pair)
@@ -64,58 +62,6 @@ template <bool OUT_F32, bool RESID, int G, int LN = 0> struct Gemm2Cfg {
   static_assert(STAGES >= 4, "pipeline too shallow");
 };
 
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// TMA load into OWN shared memory whose completion bytes are credited to the barrier at the same offset in CTA rank 0
-__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & PEER_MASK), "r"(c0), "r"(c1)
-      : "memory");
-}
-template <int kCols> __device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_slot) {
-  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "n"(kCols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-template <int kCols> __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
-  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
-}
-__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// arrive (once all prior MMAs of this thread retired) on the barrier at this offset in BOTH CTAs of the pair
-__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
-}
-// arrive on the barrier at this offset in CTA rank 0 of the pair (local arrive when executed by rank 0).
-// Default semantics (release at CTA scope, the form CUTLASS's ClusterBarrier::arrive uses): the barrier only tells the MMA thread
-// that this warp's tcgen05.ld reads of the accumulator stage have completed (tcgen05.wait::ld + tcgen05.fence::before_thread_sync
-// precede it); no generic-proxy data is published through it. Spelled .release.cluster, every epilogue warp paid
-// MEMBAR.ALL.CTA + MEMBAR.ALL.GPU + ERRBAR per tile (ncu: 25 % of the kernel's stall samples); this form is one SYNCS.ARRIVE.
-__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
-  asm volatile(
-      "{\n"
-      ".reg .b32 ra;\n"
-      "mapa.shared::cluster.u32 ra, %0, 0;\n"
-      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n"
-      "}\n"
-      ::"r"(smem_u32(bar)) : "memory");
-}
 template <int ACT> __device__ __forceinline__ float apply_act(float v) {
   if (ACT == ACT2_GELU) return gelu_erf_tanh(v);
   if (ACT == ACT2_TANH) return tanhf(v);

@@ -144,6 +144,14 @@ class CaptionEngine:
         # fc2 of a decode step through vc_linear_x3 (distinct tiles loaded once) instead of the K-concatenated plain GEMM
         # (VITCAP_X3_DEDUP=0 for A/B measurements)
         self.x3_dedup = os.environ.get("VITCAP_X3_DEDUP", "1") != "0"
+        # fused decode step (fast mode): the step's Linear layers on the CTA-pair decode kernels (gemm_dec.cu: split-K partial
+        # planes, split-operand epilogues, vocabulary arg-max partials) with bias / residual / LayerNorm / operand split in the
+        # row-wise finish kernel (decode_rowwise.cu). VITCAP_FUSED_DECODE=0 restores the round-1 kernel sequence (A/B runs)
+        self.fused_decode = self.mode == "bf16" and os.environ.get("VITCAP_FUSED_DECODE", "1") != "0"
+        # split-K factors of its partial-plane GEMMs (o-proj, fc2, head transform). CONSTANTS, not functions of the batch: the
+        # summation order of a row must not depend on how many other rows are in flight (every image's result is bit-identical
+        # in any batch, tests/test_fullsize_gpu.py). VITCAP_DEC_SPLITS="o,f,t" overrides them for tuning runs
+        self.dec_splits = tuple(int(v) for v in os.environ.get("VITCAP_DEC_SPLITS", "3,6,6").split(","))
         self.forward_graphs = {}               # whole-forward CUDA graphs of the small-batch latency path (model.py); they hold
         self.inline_graphs = False             # raw workspace pointers. inline_graphs: an outer capture is running
         # parity instrumentation (tests / tools only): tap(name, index, tensor) is called with the stream after every ViT block
@@ -231,6 +239,15 @@ class CaptionEngine:
             ws["hid3"] = self._alloc(2 * R, 3 * F)          # ... and split
             ws["e_t3"] = self._alloc(2 * R, 3 * H)          # last layer's LayerNorm 2 output (feeds the head)
             ws["head_t3"] = self._alloc(R, 3 * H)
+        if self.fused_decode:
+            x3 = self.decode_x3
+            # split-K factors of the partial-plane GEMMs (o-proj, fc2, head transform) and their fp32 planes
+            ws["splits"] = dict(zip("oft", self.dec_splits))
+            assert (H // 64) % ws["splits"]["o"] == 0 and (F // 64) % ws["splits"]["f"] == 0 and (H // 64) % ws["splits"]["t"] == 0
+            ws["m_pad"], ws["m_pad_h"] = _round_up(2 * R, 128), _round_up(R, 128)
+            ws["part"] = self._alloc(max(ws["splits"]["o"], ws["splits"]["f"]), ws["m_pad"], H, dtype=f32)
+            ws["part_h"] = self._alloc(ws["splits"]["t"], ws["m_pad_h"], H, dtype=f32)
+            ws["vpart"] = self._alloc(R, ops.vocab_partials(cfg.vocab), 4, dtype=f32)     # vocabulary arg-max partials
         ws["ids"] = torch.zeros(R, max_len, device=self.dev, dtype=i32)
         ws["unfinished"] = torch.ones(R, device=self.dev, dtype=i32)
         ws["sum_lp"] = torch.zeros(R, device=self.dev, dtype=f32)
@@ -495,9 +512,13 @@ class CaptionEngine:
             self._ln(tmp, p["ln2_w"], p["ln2_b"], cfg.bert_ln_eps, ctx_t, out_f=ctx_f, rows=rows)
             self._t("prefill.out", l, ctx_f)
 
-    def _decode_layers(self, ws, B, E, cur_len, anc, mask_id, labels=False, head=True):
+    def _decode_layers(self, ws, B, E, cur_len, anc, mask_id, labels=False, head=True, vocab="logits"):
         """One decode step up to the vocabulary logits of the MASK rows. labels: the context holds C + topk rows per image of
-        which ctx_vis[b] are visible. head=False stops after the decoder layers (caption-row replay after a recipe flip)."""
+        which ctx_vis[b] are visible. head=False stops after the decoder layers (caption-row replay after a recipe flip).
+        vocab (fused path): 'logits' = ws['logits'] is filled; 'argmax' = only the per-tile (max, arg max, sum exp) partials in
+        ws['vpart'] (greedy decoding); 'both' for parity taps. Returns True when ws['vpart'] holds this step's partials."""
+        if self.fused_decode:
+            return self._decode_layers_fused(ws, B, E, cur_len, anc, mask_id, labels, head, vocab)
         cfg, w = self.cfg, self.w
         R, H = ws["R"], cfg.hidden
         C = cfg.n_ctx + (cfg.topk if labels else 0)
@@ -548,6 +569,62 @@ class CaptionEngine:
         elif head:
             mask_rows = e_t[1::2]
             self._head(w.cls_head, mask_rows, R, ws["head_f"], ws["head_t"], ws["logits"])
+
+    def _decode_layers_fused(self, ws, B, E, cur_len, anc, mask_id, labels, head, vocab):
+        """The same decode step (BertLayer x L + BertLMPredictionHead, modeling_bert.py:303-437, 540-563) on the decode-step
+        kernels. Per layer: q|k|v GEMM -> attention over the K/V cache -> o-proj as split-K partial planes -> finish (bias +
+        residual + LayerNorm 1 -> fp32 row + operand) -> fc1 (+ GELU, written as the split pair) -> fc2 partial planes ->
+        finish (LayerNorm 2). With decode_x3 the MLP and the head run on split operands [hi | lo] (three tensor-core products)."""
+        cfg, w = self.cfg, self.w
+        R, H, F = ws["R"], cfg.hidden, cfg.inter
+        M = 2 * R
+        C = cfg.n_ctx + (cfg.topk if labels else 0)
+        enc = self._enc_ws
+        ctx_vis = enc["ctx_vis"] if labels else None
+        x3 = self.decode_x3
+        eps = cfg.bert_ln_eps
+        scale = 1.0 / math.sqrt(cfg.head_dim)
+        sp, part, m_pad = ws["splits"], ws["part"], ws["m_pad"]
+        e_f, a_f = ws["e_f"], ws["a_f"]
+        # operand copies of the two streams: bf16 rows, or (x3) [hi | lo | .] rows of pitch 3H whose first H columns ARE the
+        # bf16 copy (the q|k|v GEMM reads them with lda = 3H)
+        e_op = ws["e_t3"] if x3 else ws["e_t"]
+        a_op = ws["a_t3"] if x3 else ws["a_t"]
+        hid = ws["hid3"] if x3 else ws["hid"]
+        ops.embed_ln(ws["ids"], cur_len, mask_id, w.word, w.pos, w.type0, w.emb_ln_w, w.emb_ln_b, eps, e_f, ws["e_t"], R)
+        cur = ws["e_t"]                                   # layer 0 reads the embedding rows (bf16, pitch H)
+        for l, p in enumerate(w.dec):
+            sq = ws["step_qkv"][l]
+            ops.dec_linear(ops.DEC_BF16, cur[:, :H], p["qkv_w"], p["qkv_b"], sq[cur_len - 1], M=M)
+            ops.decode_attention(enc["ctx_qkv"][l], sq, anc, ws["att"], B, C, cfg.heads, E, cur_len, scale, ctx_vis=ctx_vis)
+            ops.dec_linear(ops.DEC_PARTIAL, ws["att"], p["o_w"], None, part, M=M, splits=sp["o"], m_pad=m_pad)
+            ops.finish_ln(part, sp["o"], p["o_b"], p["ln1_w"], p["ln1_b"], eps, M, resid=e_f, out_f=a_f, out_t=a_op, split=x3)
+            if x3:
+                ops.dec_linear(ops.DEC_GELU_SPLIT, a_op, p["i_w3"], p["i_b"], hid, M=M, x3=True)
+                ops.dec_linear(ops.DEC_PARTIAL, hid, p["f_w3"], None, part, M=M, x3=True, splits=sp["f"], m_pad=m_pad)
+            else:
+                ops.dec_linear(ops.DEC_GELU_BF16, a_op, p["i_w"], p["i_b"], hid, M=M)
+                ops.dec_linear(ops.DEC_PARTIAL, hid, p["f_w"], None, part, M=M, splits=sp["f"], m_pad=m_pad)
+            ops.finish_ln(part, sp["f"], p["f_b"], p["ln2_w"], p["ln2_b"], eps, M, resid=a_f, out_f=e_f, out_t=e_op, split=x3)
+            cur = e_op
+        if not head:
+            return False
+        # vocabulary head on the MASK rows only (rows 1::2); the reference runs it over all T text rows
+        # (modeling_bert.py:809-810) and keeps one
+        hp = w.cls_head
+        head_op = ws["head_t3"] if x3 else ws["head_t"]
+        ops.dec_linear(ops.DEC_PARTIAL, e_op[1::2], hp["t_w3"] if x3 else hp["t_w"], None, ws["part_h"], M=R, x3=x3,
+                       splits=sp["t"], m_pad=ws["m_pad_h"])
+        # (the K-concatenated GEMM that materialises the logits reads [hi | lo | hi]; the arg-max kernel only [hi | lo])
+        ops.finish_ln(ws["part_h"], sp["t"], hp["t_b"], hp["ln_w"], hp["ln_b"], eps, R, gelu=True, out_t=head_op,
+                      split=(3 if vocab != "argmax" else True) if x3 else False)
+        dec_w = hp["dec_w3"] if x3 else hp["dec_w"]
+        if vocab != "argmax":
+            ops.linear(head_op, dec_w, hp["bias"], ws["logits"][:, :cfg.vocab], M=R, ldo=ws["logits"].stride(0))
+        if vocab != "logits":
+            ops.dec_vocab_argmax(head_op, dec_w, hp["bias"], ws["vpart"], M=R, x3=x3)
+            return True
+        return False
 
     def _flip_labels(self, ws, B, E, cur_len, mask_id, anc_table=None):
         """The reference switches the label embedding to the 'raw' recipe at this step (modeling_bert.py:1435) and, having no
@@ -610,8 +687,15 @@ class CaptionEngine:
             for cur_len in range(1, max_len):
                 if labels and cur_len == label_flip and cur_len > 1:
                     self._flip_labels(ws, B, E, cur_len, mask_id)
-                self._decode_layers(ws, B, E, cur_len, None, mask_id, labels=labels)
-                self._t("logits", cur_len, ws["logits"][:, :cfg.vocab])
+                # greedy decoding on the fused path never materialises the logits (a parity tap asks for both)
+                want = "logits" if do_sample else ("both" if self.tap is not None else "argmax")
+                partials = self._decode_layers(ws, B, E, cur_len, None, mask_id, labels=labels, vocab=want)
+                if want != "argmax" or not partials:
+                    self._t("logits", cur_len, ws["logits"][:, :cfg.vocab])
+                if partials:
+                    ops.token_step_partials(ws["vpart"], R, cur_len, pad, eos, ws["ids"], ws["unfinished"], ws["sum_lp"],
+                                            ws["n_steps"])
+                    continue
                 t = temperature
                 if filt:
                     ops.filter_logits(ws["logits"], cfg.vocab, R, 1.0 / temperature, top_k, top_p)

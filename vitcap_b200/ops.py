@@ -54,6 +54,10 @@ SIGNATURES = {
     "vc_beam_advance": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _D, _I, _P, _I, _P],
     "vc_beam_finalize": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P],
     "vc_filter_logits": [_P, _I, _I, _I, _F, _I, _F, _I, _P],
+    "vc_dec_linear": [_I, _I, _P, _I, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "vc_dec_vocab_argmax": [_I, _P, _I, _P, _I, _P, _P, _I, _I, _I, _I, _P],
+    "vc_finish_ln": [_P, _I, _SZ, _I, _P, _I, _P, _I, _P, _P, _F, _P, _I, _P, _I, _I, _I, _I, _P],
+    "vc_token_step_partials": [_P, _I, _I, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P],
 }
 
 _lib = None
@@ -403,6 +407,65 @@ def beam_finalize(st, B, keep, pad_id, eos0, out_ids, out_lp):
     _check(load_library().vc_beam_finalize(_ptr(st["hyp_score"]), _ptr(st["hyp_len"]), _ptr(st["hyp_ids"]), _ptr(st["hyp_count"]),
                                            B, keep, st["ids"].shape[1], pad_id, eos0, _ptr(out_ids), _ptr(out_lp), _stream()),
            "vc_beam_finalize")
+
+
+DEC_PARTIAL, DEC_BF16, DEC_GELU_BF16, DEC_GELU_SPLIT = 0, 1, 2, 3
+VOCAB_TILE = 208          # columns per tile of vc_dec_vocab_argmax (two partials per tile)
+
+
+def vocab_partials(N):
+    return 2 * ((N + VOCAB_TILE - 1) // VOCAB_TILE)
+
+
+def dec_linear(mode, a, w, bias, out, M=None, x3=False, splits=1, m_pad=0, lda=None, ldo=None):
+    """Decode-step Linear on CTA-pair tiles (include/vitcap_b200.h, vc_dec_linear). a [M, K] / w [N, K] bf16 (K = 3 Kt split
+    layouts with x3). mode DEC_PARTIAL: out fp32 [splits, m_pad, N] partial planes, no bias; DEC_BF16 / DEC_GELU_BF16: out bf16
+    [M, N]; DEC_GELU_SPLIT: out bf16 [M, >= 2N] = [hi | lo] of the GELU output."""
+    N, K = w.shape
+    M = a.shape[0] if M is None else M
+    lda = a.stride(0) if lda is None else lda
+    assert a.dtype == w.dtype == torch.bfloat16 and a.stride(-1) == 1 and w.stride(-1) == 1 and out.stride(-1) == 1
+    if mode == DEC_PARTIAL:
+        assert out.dtype == torch.float32 and out.dim() == 3 and out.shape[0] >= splits and out.shape[1] == m_pad and out.is_contiguous()
+        ldo = out.stride(1)
+    else:
+        assert out.dtype == torch.bfloat16
+        ldo = out.stride(0) if ldo is None else ldo
+    _check(load_library().vc_dec_linear(mode, int(bool(x3)), _ptr(a), lda, _ptr(w), w.stride(0), _ptr(bias), _ptr(out), ldo, M, N, K,
+                                        splits, m_pad, _stream()), "vc_dec_linear")
+    return out
+
+
+def dec_vocab_argmax(a, w, bias, part, M=None, x3=False, lda=None):
+    """part fp32 [M, n_part, 4], n_part = vocab_partials(N): per-tile (max, arg max, sum of exponentials) of a w^T + bias."""
+    N, K = w.shape
+    M = a.shape[0] if M is None else M
+    lda = a.stride(0) if lda is None else lda
+    n_part = vocab_partials(N)
+    assert a.dtype == w.dtype == torch.bfloat16 and part.dtype == torch.float32 and part.is_contiguous()
+    assert part.shape[-1] == 4 and part.shape[-2] == n_part and part.shape[0] >= M
+    _check(load_library().vc_dec_vocab_argmax(int(bool(x3)), _ptr(a), lda, _ptr(w), w.stride(0), _ptr(bias), _ptr(part), n_part, M, N,
+                                              K, _stream()), "vc_dec_vocab_argmax")
+    return part
+
+
+def finish_ln(part, splits, bias, gamma, beta, eps, rows, resid=None, gelu=False, out_f=None, out_t=None, split=False):
+    """LayerNorm(act(sum of `splits` partial planes + bias) + resid) -> out_f (fp32) and out_t (bf16; split=True: the
+    [hi | lo] pair; split=3: [hi | lo | hi])."""
+    assert part.dtype == torch.float32 and part.dim() == 3 and part.shape[0] >= splits
+    H = part.shape[2]
+    mode = 0 if out_t is None else ((3 if split == 3 else 2) if split else 1)
+    _check(load_library().vc_finish_ln(_ptr(part), splits, part.stride(0), part.stride(1), _ptr(bias), int(bool(gelu)), _ptr(resid),
+                                       resid.stride(0) if resid is not None else 0, _ptr(gamma), _ptr(beta), float(eps), _ptr(out_f),
+                                       out_f.stride(0) if out_f is not None else 0, _ptr(out_t),
+                                       out_t.stride(0) if out_t is not None else 0, mode, rows, H, _stream()), "vc_finish_ln")
+
+
+def token_step_partials(part, rows, cur_len, pad_id, eos_ids, ids, unfinished, sum_lp, n_steps):
+    n_part = part.shape[-2]
+    _check(load_library().vc_token_step_partials(_ptr(part), n_part, rows, cur_len, ids.shape[1], pad_id, _ptr(eos_ids),
+                                                 eos_ids.numel(), _ptr(ids), _ptr(unfinished), _ptr(sum_lp), _ptr(n_steps),
+                                                 _stream()), "vc_token_step_partials")
 
 
 def filter_logits(logits, V, rows, inv_temperature, top_k, top_p, min_tokens_to_keep=1):
