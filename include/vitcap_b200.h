@@ -196,6 +196,14 @@ int vc_decode_attention_labels(int bf16, const void* ctx_qkv, const void* step_q
 int vc_decode_attention_labels_simt(int bf16, const void* ctx_qkv, const void* step_qkv, const int* anc, void* out, int B,
                                     int rows_per_image, const int* ctx_vis, int heads, int E, int cur_len, float scale,
                                     void* stream);
+/* fast mode (bf16 K/V): vc_decode_attention_labels (ctx_vis may be NULL) that does no work for finished captions. The reference
+ * keeps computing every row until ALL sequences of the batch have finished (modeling_utils.py:858-867; beam search: until every
+ * image is done, :1003-1011, :1096) and discards what it computed for the finished ones; here a sequence with
+ * seq_unfinished[b * E + e] == 0 (int32 [B * E], may be NULL) or an image with img_done[b] != 0 (int32 [B], may be NULL; takes
+ * precedence) is skipped before its K/V rows are read, and its output rows are left untouched (stale but finite). */
+int vc_decode_attention_skip(const void* ctx_qkv, const void* step_qkv, const int* anc, void* out, int B, int rows_per_image,
+                             const int* ctx_vis, int heads, int E, int cur_len, float scale, const int* seq_unfinished,
+                             const int* img_done, void* stream);
 
 /* greedy / sampled next token + log-prob + state update for `rows` sequences, modeling_utils.py:839-862.
  * logits fp32 [rows, ld]; sampling = Gumbel-max with Philox4x32-10 noise keyed by (seed; vocab idx/4, row, cur_len).

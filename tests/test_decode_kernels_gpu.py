@@ -459,3 +459,38 @@ def test_vocab_argmax_partials_and_token_step(R, V, x3):
         assert abs(float(slp[r]) - float(lsm[r, int(tok[r])])) < 3e-4
         assert int(nst[r]) == 1 and int(unf[r]) == int(int(tok[r]) != 102)
     assert int((tok == 102).sum()) > 0
+
+
+@pytest.mark.parametrize("B,C,heads,E,cur_len", [(6, 578, 12, 1, 7), (3, 198, 12, 5, 4), (2, 146, 12, 10, 9)])
+def test_decode_attention_skips_finished_sequences(B, C, heads, E, cur_len):
+    """vc_decode_attention_skip: a CTA (image, head, group of <= 8 sequences) whose sequences have all finished -- or whose image's
+    beam search is done -- reads no K/V and leaves its output rows untouched; every other row is bit-identical to the plain call."""
+    scale = 0.125
+    ctx, stepq, anc = _da_inputs(B, C, heads, E, cur_len, torch.bfloat16, seed=11)
+    H, R = heads * 64, B * E
+    ctx, stepq, anc = ctx.to(DEV), stepq.to(DEV), anc.to(DEV)
+    full = torch.empty(2 * R, H, dtype=torch.bfloat16, device=DEV)
+    ops.decode_attention(ctx, stepq, anc, full, B, C, heads, E, cur_len, scale)
+    g = torch.Generator().manual_seed(3)
+    unf = (torch.rand(R, generator=g) < 0.5).to(torch.int32)
+    unf[:E] = 0                                               # image 0: every sequence finished
+    done = (torch.rand(B, generator=g) < 0.5).to(torch.int32)
+    done[0], done[-1] = 1, 0
+    groups = (E + 7) // 8
+    for kw, live_seq in ((dict(seq_unfinished=unf.to(DEV)), None), (dict(img_done=done.to(DEV)), None)):
+        out = torch.full((2 * R, H), 123.0, dtype=torch.bfloat16, device=DEV)
+        ops.decode_attention(ctx, stepq, anc, out, B, C, heads, E, cur_len, scale, **kw)
+        o, f = out.cpu(), full.cpu()
+        n_skipped = 0
+        for b in range(B):
+            for grp in range(groups):
+                seqs = range(b * E + grp * 8, b * E + min(E, grp * 8 + 8))
+                live = (int(done[b]) == 0) if "img_done" in kw else any(int(unf[r]) for r in seqs)
+                for r in seqs:
+                    rows = slice(2 * r, 2 * r + 2)
+                    if live:
+                        assert torch.equal(o[rows], f[rows]), (b, r)
+                    else:
+                        assert bool((o[rows] == 123.0).all()), (b, r)
+                        n_skipped += 1
+        assert n_skipped > 0

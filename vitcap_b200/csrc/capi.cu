@@ -48,6 +48,8 @@ int decode_attention(int is_bf16, const void* ctx_qkv, const void* step_qkv, con
                      const int* ctx_vis, int heads, int E, int cur_len, float scale, cudaStream_t s);
 int decode_attention_simt(int is_bf16, const void* ctx_qkv, const void* step_qkv, const int* anc, void* out, int B, int C,
                           const int* ctx_vis, int heads, int E, int cur_len, float scale, cudaStream_t s);
+int decode_attention_skip(const void* ctx_qkv, const void* step_qkv, const int* anc, void* out, int B, int C, const int* ctx_vis,
+                          int heads, int E, int cur_len, float scale, const int* seq_unfinished, const int* img_done, cudaStream_t s);
 int token_step(const float* logits, int ld, int rows, int V, int do_sample, float temperature, uint64_t seed,
                const uint64_t* seed_dev, int cur_len, int max_len, int pad_id, const int* eos_ids, int n_eos, int* ids,
                int* unfinished, float* sum_lp, int* n_steps, cudaStream_t s);
@@ -186,6 +188,12 @@ int vc_embed_ln(int bf16, const int* ids, int max_len, int cur_len, int mask_id,
 int vc_decode_attention(int bf16, const void* ctx_qkv, const void* step_qkv, const int* anc, void* out, int B, int C, int heads,
                         int E, int cur_len, float scale, void* stream) {
   VC_COUNT(1, vc::decode_attention(bf16, ctx_qkv, step_qkv, anc, out, B, C, nullptr, heads, E, cur_len, scale, ST(stream)));
+}
+int vc_decode_attention_skip(const void* ctx_qkv, const void* step_qkv, const int* anc, void* out, int B, int rows_per_image,
+                             const int* ctx_vis, int heads, int E, int cur_len, float scale, const int* seq_unfinished,
+                             const int* img_done, void* stream) {
+  VC_COUNT(1, vc::decode_attention_skip(ctx_qkv, step_qkv, anc, out, B, rows_per_image, ctx_vis, heads, E, cur_len, scale,
+                                        seq_unfinished, img_done, ST(stream)));
 }
 int vc_decode_attention_labels(int bf16, const void* ctx_qkv, const void* step_qkv, const int* anc, void* out, int B,
                                int rows_per_image, const int* ctx_vis, int heads, int E, int cur_len, float scale, void* stream) {

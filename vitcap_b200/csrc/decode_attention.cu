@@ -16,7 +16,7 @@
 namespace vc {
 
 int decode_attention_mma(const void* ctx_qkv, const void* step_qkv, const int* anc, void* out, int B, int C, const int* ctx_vis,
-                         int heads, int E, int cur_len, float scale, cudaStream_t s);
+                         int heads, int E, int cur_len, float scale, const int* seq_unfinished, const int* img_done, cudaStream_t s);
 // CUDA-core variant (exact mode, fp32 storage); also instantiable for bf16 as a cross-check of the mma kernel
 int decode_attention_simt(int is_bf16, const void* ctx_qkv, const void* step_qkv, const int* anc, void* out, int B, int C,
                           const int* ctx_vis, int heads, int E, int cur_len, float scale, cudaStream_t s);
@@ -234,8 +234,16 @@ int decode_attention(int is_bf16, const void* ctx_qkv, const void* step_qkv, con
     set_last_error("decode_attention: bad args B=%d C=%d heads=%d E=%d cur_len=%d", B, C, heads, E, cur_len);
     return VC_ERR_BAD_ARG;
   }
-  if (is_bf16) return decode_attention_mma(ctx_qkv, step_qkv, anc, out, B, C, ctx_vis, heads, E, cur_len, scale, s);
+  if (is_bf16) return decode_attention_mma(ctx_qkv, step_qkv, anc, out, B, C, ctx_vis, heads, E, cur_len, scale, nullptr, nullptr, s);
   return launch_da<float>(ctx_qkv, step_qkv, anc, out, B, C, ctx_vis, heads, E, cur_len, scale, s);
+}
+
+// fast mode only: the same, skipping sequences that have finished (seq_unfinished [B*E], 0 = finished) or images whose beam
+// search is done (img_done [B], != 0 = done); their output rows are left as they are
+int decode_attention_skip(const void* ctx_qkv, const void* step_qkv, const int* anc, void* out, int B, int C, const int* ctx_vis,
+                          int heads, int E, int cur_len, float scale, const int* seq_unfinished, const int* img_done, cudaStream_t s) {
+  if (B <= 0 || C <= 0 || heads <= 0 || E <= 0 || cur_len < 1) { set_last_error("decode_attention_skip: bad args"); return VC_ERR_BAD_ARG; }
+  return decode_attention_mma(ctx_qkv, step_qkv, anc, out, B, C, ctx_vis, heads, E, cur_len, scale, seq_unfinished, img_done, s);
 }
 
 int decode_attention_simt(int is_bf16, const void* ctx_qkv, const void* step_qkv, const int* anc, void* out, int B, int C,

@@ -63,7 +63,7 @@ template <bool UPPER>
 __global__ void __launch_bounds__(128, 4)
 decode_attention_mma_kernel(const bf16* __restrict__ ctx_qkv, const bf16* __restrict__ step_qkv, const int* __restrict__ anc,
                             bf16* __restrict__ out, int Cs, const int* __restrict__ ctx_vis, int H, int R, int E, int cur_len,
-                            float scale_log2) {
+                            float scale_log2, const int* __restrict__ seq_unfinished, const int* __restrict__ img_done) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint8_t cap_info[MAX_CAP];          // (sequence-in-CTA << 1) | is_mask_key, per caption key
   __shared__ float sm_m[WARPS][16], sm_l[WARPS][16];
@@ -79,6 +79,17 @@ decode_attention_mma_kernel(const bf16* __restrict__ ctx_qkv, const bf16* __rest
   // context rows of an image: Cs allocated, the first C visible (label-region masks hide a per-image tail, dataset.py:405-408)
   pdl_launch_dependents();
   pdl_wait();                                    // programmatic dependent launch: global memory from here on
+  // Finished sequences (modeling_utils.py:858-867: their tokens are PAD from now on and their scores frozen; beam search: the
+  // image is `done`, modeling_utils.py:1003-1011) need no attention: a CTA none of whose sequences is live returns before it
+  // touches the K/V cache -- the sweep that dominates a decode step then shrinks with the number of live captions. Their
+  // output rows keep the (finite) values of an earlier step; everything computed from them is discarded by the token step.
+  if (img_done != nullptr) {
+    if (img_done[b] != 0) return;
+  } else if (seq_unfinished != nullptr) {
+    bool live = false;
+    for (int e = 0; e < EC; ++e) live |= (seq_unfinished[b * E + e0 + e] != 0);
+    if (!live) return;
+  }
   const int C = ctx_vis ? ctx_vis[b] : Cs;
   const size_t ld = 3 * (size_t)H;
   const int step = cur_len - 1;
@@ -304,7 +315,7 @@ decode_attention_mma_kernel(const bf16* __restrict__ ctx_qkv, const bf16* __rest
 
 // ctx_qkv [B, C, 3H]; step_qkv [max_len, 2*B*E, 3H]; anc int32 [max_len, B*E] or NULL; out [2*B*E, H]; all bf16
 int decode_attention_mma(const void* ctx_qkv, const void* step_qkv, const int* anc, void* out, int B, int C, const int* ctx_vis,
-                         int heads, int E, int cur_len, float scale, cudaStream_t s) {
+                         int heads, int E, int cur_len, float scale, const int* seq_unfinished, const int* img_done, cudaStream_t s) {
   const int groups = (E + MAX_SEQ - 1) / MAX_SEQ;
   if (B <= 0 || C <= 0 || heads <= 0 || E <= 0 || cur_len < 1 || cur_len + 1 > 64 || (size_t)B * groups > 65535) {
     set_last_error("decode_attention: bad args B=%d C=%d heads=%d E=%d cur_len=%d", B, C, heads, E, cur_len);
@@ -322,10 +333,10 @@ int decode_attention_mma(const void* ctx_qkv, const void* step_qkv, const int* a
   const dim3 grid(heads, B * groups);
   if (E > 4)
     launch_pdl(decode_attention_mma_kernel<true>, grid, dim3(128), SMEM_BYTES, s, (const bf16*)ctx_qkv, (const bf16*)step_qkv, anc,
-               (bf16*)out, C, ctx_vis, H, R, E, cur_len, scale_log2);
+               (bf16*)out, C, ctx_vis, H, R, E, cur_len, scale_log2, seq_unfinished, img_done);
   else
     launch_pdl(decode_attention_mma_kernel<false>, grid, dim3(128), SMEM_BYTES, s, (const bf16*)ctx_qkv, (const bf16*)step_qkv, anc,
-               (bf16*)out, C, ctx_vis, H, R, E, cur_len, scale_log2);
+               (bf16*)out, C, ctx_vis, H, R, E, cur_len, scale_log2, seq_unfinished, img_done);
   return check_launch("decode_attention_mma");
 }
 

@@ -113,6 +113,8 @@ gemm_dec_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   }
   if (warp == 1) tmem_alloc_pair<C::TMEM_COLS>(tmem_slot);
   tc_fence_before();
+  __syncthreads();                                      // (the cluster barrier below already orders the allocator's write of
+                                                        // tmem_slot; this CTA barrier is what compute-sanitizer racecheck models)
   cluster_sync_all();                                   // barriers of both CTAs initialised, TMEM allocated in both
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;

@@ -302,7 +302,7 @@ token_step_kernel(const float* __restrict__ logits, int ld, int V, int do_sample
     const int unf = unfinished[r];
     const int tok = unf ? besti : pad_id;
     ids[(size_t)r * max_len + cur_len] = tok;
-    sum_lp[r] += lp * (float)unf;
+    if (unf) sum_lp[r] += lp;                  // (not lp * unf: a finished row's logits may be stale)
     n_steps[r] += unf;
     int still = unf;
     for (int e = 0; e < n_eos; ++e) still *= (tok != eos_ids[e]);

@@ -512,13 +512,14 @@ class CaptionEngine:
             self._ln(tmp, p["ln2_w"], p["ln2_b"], cfg.bert_ln_eps, ctx_t, out_f=ctx_f, rows=rows)
             self._t("prefill.out", l, ctx_f)
 
-    def _decode_layers(self, ws, B, E, cur_len, anc, mask_id, labels=False, head=True, vocab="logits"):
+    def _decode_layers(self, ws, B, E, cur_len, anc, mask_id, labels=False, head=True, vocab="logits", live=(None, None)):
         """One decode step up to the vocabulary logits of the MASK rows. labels: the context holds C + topk rows per image of
         which ctx_vis[b] are visible. head=False stops after the decoder layers (caption-row replay after a recipe flip).
         vocab (fused path): 'logits' = ws['logits'] is filled; 'argmax' = only the per-tile (max, arg max, sum exp) partials in
-        ws['vpart'] (greedy decoding); 'both' for parity taps. Returns True when ws['vpart'] holds this step's partials."""
+        ws['vpart'] (greedy decoding); 'both' for parity taps. Returns True when ws['vpart'] holds this step's partials.
+        live = (seq_unfinished int32 [R] or None, img_done int32 [B] or None): the attention skips finished captions."""
         if self.fused_decode:
-            return self._decode_layers_fused(ws, B, E, cur_len, anc, mask_id, labels, head, vocab)
+            return self._decode_layers_fused(ws, B, E, cur_len, anc, mask_id, labels, head, vocab, live)
         cfg, w = self.cfg, self.w
         R, H = ws["R"], cfg.hidden
         C = cfg.n_ctx + (cfg.topk if labels else 0)
@@ -570,7 +571,7 @@ class CaptionEngine:
             mask_rows = e_t[1::2]
             self._head(w.cls_head, mask_rows, R, ws["head_f"], ws["head_t"], ws["logits"])
 
-    def _decode_layers_fused(self, ws, B, E, cur_len, anc, mask_id, labels, head, vocab):
+    def _decode_layers_fused(self, ws, B, E, cur_len, anc, mask_id, labels, head, vocab, live=(None, None)):
         """The same decode step (BertLayer x L + BertLMPredictionHead, modeling_bert.py:303-437, 540-563) on the decode-step
         kernels. Per layer: q|k|v GEMM -> attention over the K/V cache -> o-proj as split-K partial planes -> finish (bias +
         residual + LayerNorm 1 -> fp32 row + operand) -> fc1 (+ GELU, written as the split pair) -> fc2 partial planes ->
@@ -596,7 +597,8 @@ class CaptionEngine:
         for l, p in enumerate(w.dec):
             sq = ws["step_qkv"][l]
             ops.dec_linear(ops.DEC_BF16, cur[:, :H], p["qkv_w"], p["qkv_b"], sq[cur_len - 1], M=M)
-            ops.decode_attention(enc["ctx_qkv"][l], sq, anc, ws["att"], B, C, cfg.heads, E, cur_len, scale, ctx_vis=ctx_vis)
+            ops.decode_attention(enc["ctx_qkv"][l], sq, anc, ws["att"], B, C, cfg.heads, E, cur_len, scale, ctx_vis=ctx_vis,
+                                 seq_unfinished=live[0], img_done=live[1])
             ops.dec_linear(ops.DEC_PARTIAL, ws["att"], p["o_w"], None, part, M=M, splits=sp["o"], m_pad=m_pad)
             ops.finish_ln(part, sp["o"], p["o_b"], p["ln1_w"], p["ln1_b"], eps, M, resid=e_f, out_f=a_f, out_t=a_op, split=x3)
             if x3:
@@ -689,7 +691,8 @@ class CaptionEngine:
                     self._flip_labels(ws, B, E, cur_len, mask_id)
                 # greedy decoding on the fused path never materialises the logits (a parity tap asks for both)
                 want = "logits" if do_sample else ("both" if self.tap is not None else "argmax")
-                partials = self._decode_layers(ws, B, E, cur_len, None, mask_id, labels=labels, vocab=want)
+                partials = self._decode_layers(ws, B, E, cur_len, None, mask_id, labels=labels, vocab=want,
+                                               live=(ws["unfinished"], None))
                 if want != "argmax" or not partials:
                     self._t("logits", cur_len, ws["logits"][:, :cfg.vocab])
                 if partials:
@@ -752,7 +755,7 @@ class CaptionEngine:
             for cur_len in range(1, max_len):
                 if labels and cur_len == label_flip and cur_len > 1:
                     self._flip_labels(ws, B, nb, cur_len, mask_id, anc_table=st["anc"])
-                self._decode_layers(ws, B, nb, cur_len, st["anc"], mask_id, labels=labels)
+                self._decode_layers(ws, B, nb, cur_len, st["anc"], mask_id, labels=labels, live=(None, st["done"]))
                 ops.beam_row_topk(ws["logits"], cfg.vocab, R, K, st["cand_val"], st["cand_idx"], st["row_max"], st["row_logsum"])
                 ops.beam_advance(st, st["cand_val"], st["cand_idx"], st["row_max"], st["row_logsum"], B, nb, cfg.vocab, cur_len,
                                  keep, length_penalty, pad, eos)

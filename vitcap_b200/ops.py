@@ -41,6 +41,7 @@ SIGNATURES = {
     "vc_attention_labels": [_I, _P, _P, _I, _I, _I, _F, _I, _P, _P],
     "vc_attention_labels_simt": [_I, _P, _P, _I, _I, _I, _F, _I, _P, _P],
     "vc_decode_attention_labels": [_I, _P, _P, _P, _P, _I, _I, _P, _I, _I, _I, _F, _P],
+    "vc_decode_attention_skip": [_P, _P, _P, _P, _I, _I, _P, _I, _I, _I, _F, _P, _P, _P],
     "vc_decode_attention_labels_simt": [_I, _P, _P, _P, _P, _I, _I, _P, _I, _I, _I, _F, _P],
     "vc_attention_simt": [_I, _P, _P, _I, _I, _I, _F, _P],
     "vc_cls_attention": [_I, _P, _I, _P, _P, _I, _I, _I, _I, _F, _P],
@@ -362,8 +363,18 @@ def embed_ln(ids, cur_len, mask_id, word, pos, type0, gamma, beta, eps, out_f, o
                                       _stream()), "vc_embed_ln")
 
 
-def decode_attention(ctx_qkv, step_qkv, anc, out, B, C, heads, E, cur_len, scale, impl="auto", ctx_vis=None):
-    """ctx_vis (int32 [B]): C context rows are allocated per image, only the first ctx_vis[b] are visible."""
+def decode_attention(ctx_qkv, step_qkv, anc, out, B, C, heads, E, cur_len, scale, impl="auto", ctx_vis=None, seq_unfinished=None,
+                     img_done=None):
+    """ctx_vis (int32 [B]): C context rows are allocated per image, only the first ctx_vis[b] are visible.
+    seq_unfinished (int32 [B*E]) / img_done (int32 [B]): bf16 only -- finished sequences / done images are skipped and their
+    output rows left untouched (vc_decode_attention_skip)."""
+    if (seq_unfinished is not None or img_done is not None) and ctx_qkv.dtype == torch.bfloat16 and impl != "simt":
+        for t in (seq_unfinished, img_done, ctx_vis):
+            assert t is None or t.dtype == torch.int32
+        _check(load_library().vc_decode_attention_skip(_ptr(ctx_qkv), _ptr(step_qkv), _ptr(anc), _ptr(out), B, C, _ptr(ctx_vis), heads, E,
+                                                       cur_len, float(scale), _ptr(seq_unfinished), _ptr(img_done), _stream()),
+               "vc_decode_attention_skip")
+        return
     if ctx_vis is not None:
         assert ctx_vis.dtype == torch.int32 and ctx_vis.numel() >= B
         fn = load_library().vc_decode_attention_labels_simt if impl == "simt" else load_library().vc_decode_attention_labels
