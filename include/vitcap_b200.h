@@ -82,6 +82,14 @@ int vc_linear_tc(const void* A, int lda, const void* W, int ldw, const float* bi
  *   colsum[n] = sum_k Wf[n,k] (fp32), bias_f = b + W beta, prepared by the caller.  act: VC_ACT_NONE / VC_ACT_GELU. */
 int vc_linear_ln_emit(const void* A, int lda, const void* W, int ldw, const float* bias, float* out, int ldo, const float* resid,
                       int ldr, void* xb, int ldxb, float* stats, int M, int N, int K, void* stream);
+/* vc_linear_ln_emit for POST-LN layers (BertSelfOutput / BertOutput, modeling_bert.py:353-357, 415-419: LayerNorm(dense(h) + x)
+ * where x is itself the output of the previous LayerNorm): that LayerNorm output is never materialised. resid_raw [M, N] is the
+ * RAW fp32 row the previous emit produced, rstats [M, rst_tiles, 2] its partial sums, rgamma / rbeta / r_eps its LayerNorm;
+ * the epilogue adds (resid_raw - mean) * rstd * rgamma + rbeta. Together with vc_linear_ln_fold on the consumer side no
+ * stand-alone LayerNorm pass (2.3 GB per pass at 512 images) remains in the decoder prefill. */
+int vc_linear_ln_emit_postln(const void* A, int lda, const void* W, int ldw, const float* bias, float* out, int ldo,
+                             const float* resid_raw, int ldr, const float* rstats, int rst_tiles, const float* rgamma,
+                             const float* rbeta, float r_eps, void* xb, int ldxb, float* stats, int M, int N, int K, void* stream);
 int vc_linear_ln_fold(const void* A, int lda, const void* Wf, int ldw, const float* bias_f, const float* colsum, const float* stats,
                       int st_tiles, float ln_eps, void* out, int ldo, int act, int M, int N, int K, void* stream);
 

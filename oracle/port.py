@@ -205,11 +205,16 @@ class QuantPortModel(PortModel):
     cls_only_last: the last concept block is evaluated for the CLS row only with LayerNorm-kernel roundings and an fp32 softmax
     (engine._vit_block_cls_only); False = a full folded block (engine.encode(full_tag_feats=True))."""
 
-    def __init__(self, cfg, state_dict, ln_fold=2, decode_x3=True, cls_only_last=True, acc64=False):
+    def __init__(self, cfg, state_dict, ln_fold=2, decode_x3=True, cls_only_last=True, acc64=False, prefill_fold=True):
         super().__init__(cfg, state_dict, dtype=torch.float32)
         self.ln_fold = ln_fold
         self.decode_x3 = decode_x3
         self.cls_only_last = cls_only_last
+        # prefill_fold (engine._prefill_folded): in the decoder prefill the intermediate GEMM folds the attention-output
+        # LayerNorm and the q|k|v GEMM of layer i >= 1 folds the output LayerNorm of layer i - 1 (raw bf16 row, gamma-scaled
+        # weights, statistics applied in the epilogue); the residuals are the fp32 LayerNorm outputs as before
+        self.prefill_fold = prefill_fold
+        self._pf_raw = None                    # (layer output tensor, raw pre-LayerNorm rows, gamma key, beta key)
         # acc64: every product is accumulated in fp64 and rounded to fp32 once -- the SAME quantised arithmetic with another
         # (better) summation. The distance between the acc64 and the plain model is the yardstick for how far two correct
         # implementations of this spec drift apart end to end: a bf16 rounding turns a relative perturbation e of its input
@@ -376,26 +381,50 @@ class QuantPortModel(PortModel):
         return tuple(heads(self.lin(hq, p + n + ".weight", p + n + ".bias")) for n in ("query", "key", "value"))
 
     def bert_layer(self, idx, hq, hkv, add_mask):
+        """A prefill layer over the context rows (the decode steps call qkv_rows / bert_layer_from_kv directly)."""
         assert hq is hkv
-        q, k, v = self.qkv_rows(idx, hq)
-        return self.bert_layer_from_kv(idx, hq, q, k, v, add_mask), k, v
+        cfg = self.cfg
+        if idx == 0:
+            self._pf_raw = None
+        if self.prefill_fold and self._pf_raw is not None and self._pf_raw[0] is hq:
+            _, raw, gkey, bekey = self._pf_raw
+            H, d = cfg.heads, cfg.head_dim
+            p = "module.bert.decoder.layer.%d.attention.self." % idx
 
-    def bert_layer_from_kv(self, idx, hq, q, k, v, add_mask, step=False):
-        """hq: fp32 rows (residual); q / k / v hold bf16 values. step=True: a decode step (split-operand MLP when decode_x3)."""
+            def heads(t):
+                return q_bf16(t).view(t.shape[0], t.shape[1], H, d).permute(0, 2, 1, 3)
+            q, k, v = (heads(self.lin_fold(raw, gkey, bekey, cfg.bert_ln_eps, p + n + ".weight", p + n + ".bias"))
+                       for n in ("query", "key", "value"))
+        else:
+            q, k, v = self.qkv_rows(idx, hq)
+        return self.bert_layer_from_kv(idx, hq, q, k, v, add_mask, prefill=True), k, v
+
+    def bert_layer_from_kv(self, idx, hq, q, k, v, add_mask, step=False, prefill=False):
+        """hq: fp32 rows (residual); q / k / v hold bf16 values. step=True: a decode step (split-operand MLP when decode_x3);
+        prefill=True with prefill_fold: the intermediate GEMM folds LayerNorm 1 and the raw output rows are kept for the next
+        layer's folded q|k|v GEMM."""
         cfg = self.cfg
         p = "module.bert.decoder.layer.%d." % idx
         C = hq.shape[-1]
+        ln1 = (p + "attention.output.LayerNorm.weight", p + "attention.output.LayerNorm.bias")
+        ln2 = (p + "output.LayerNorm.weight", p + "output.LayerNorm.bias")
         ctx = self.attend(q, k, v, 1.0 / math.sqrt(cfg.head_dim), add_mask)
         tmp = self.lin(ctx, p + "attention.output.dense.weight", p + "attention.output.dense.bias") + hq
-        a = F.layer_norm(tmp, (C,), self.p(p + "attention.output.LayerNorm.weight"), self.p(p + "attention.output.LayerNorm.bias"),
-                         cfg.bert_ln_eps)
+        a = F.layer_norm(tmp, (C,), self.p(ln1[0]), self.p(ln1[1]), cfg.bert_ln_eps)
         if step and self.decode_x3:
             m = gelu_fast(self.lin_x3(a, p + "intermediate.dense.weight", p + "intermediate.dense.bias"))
             m = self.lin_x3(m, p + "output.dense.weight", p + "output.dense.bias")
         else:
-            m = q_bf16(gelu_fast(self.lin(q_bf16(a), p + "intermediate.dense.weight", p + "intermediate.dense.bias")))
-            m = self.lin(m, p + "output.dense.weight", p + "output.dense.bias")
-        return F.layer_norm(m + a, (C,), self.p(p + "output.LayerNorm.weight"), self.p(p + "output.LayerNorm.bias"), cfg.bert_ln_eps)
+            if prefill and self.prefill_fold:
+                pre = self.lin_fold(tmp, ln1[0], ln1[1], cfg.bert_ln_eps, p + "intermediate.dense.weight", p + "intermediate.dense.bias")
+            else:
+                pre = self.lin(q_bf16(a), p + "intermediate.dense.weight", p + "intermediate.dense.bias")
+            m = self.lin(q_bf16(gelu_fast(pre)), p + "output.dense.weight", p + "output.dense.bias")
+        raw = m + a
+        out = F.layer_norm(raw, (C,), self.p(ln2[0]), self.p(ln2[1]), cfg.bert_ln_eps)
+        if prefill:
+            self._pf_raw = (out, raw, ln2[0], ln2[1])
+        return out
 
 
 # =========================================================================================

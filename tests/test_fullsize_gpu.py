@@ -331,37 +331,47 @@ def test_bf16_mode_every_kernel_vs_quantisation_matched_oracle():
         check("pooler (tanh)", k_pool, port.q_bf16(torch.tanh(qm.lin(port.q_bf16(k_cls), "module.bert.pooler.dense.weight",
                                                                       "module.bert.pooler.dense.bias"))))
         check("concept logits", taps[("tag.logits", 0)], qm.head("module.bert.tag_logit.predictions.", k_pool))
-        # decoder prefill over the context rows, layer by layer
+        # decoder prefill over the context rows, kernel by kernel (engine._prefill_folded: no stand-alone LayerNorm; raw1 / raw2
+        # are the pre-LayerNorm rows, the normalised streams exist only inside the GEMMs that fold / re-apply them)
         ctx = taps[("prefill.in", 0)].view(B, C, H)
         check("context assembly", ctx, torch.cat([k_cls.unsqueeze(1), x], dim=1))
         L = cfg.dec_layers
         Kc, Vc = [], []
+        lnorm = torch.nn.functional.layer_norm
+        hs = lambda t_: t_.reshape(B, C, heads, d).permute(0, 2, 1, 3)                  # noqa: E731
+        resid, raw2, ln2_prev = ctx, None, None              # layer 0: the residual is the context itself
         for l in range(L):
             p = "module.bert.decoder.layer.%d." % l
-            q_, k_, v_ = qm.qkv_rows(l, ctx)
+            if l == 0:
+                q_, k_, v_ = qm.qkv_rows(l, ctx)
+            else:
+                q_, k_, v_ = (hs(port.q_bf16(qm.lin_fold(raw2, ln2_prev[0], ln2_prev[1], cfg.bert_ln_eps,
+                                                         p + "attention.self.%s.weight" % n, p + "attention.self.%s.bias" % n)))
+                              for n in ("query", "key", "value"))
             k_qkv = taps[("prefill.qkv", l)].float().view(B, C, 3 * H)
-            hs = lambda t_: t_.reshape(B, C, heads, d).permute(0, 2, 1, 3)              # noqa: E731
             kq, kk_, kv = hs(k_qkv[..., :H]), hs(k_qkv[..., H:2 * H]), hs(k_qkv[..., 2 * H:])
             Kc.append(kk_)
             Vc.append(kv)
-            check("prefill %d k|v" % l, torch.cat([kk_, kv], 1), torch.cat([k_, v_], 1))
+            how = "plain" if l == 0 else "folded output LayerNorm of layer %d" % (l - 1)
+            check("prefill %d k|v (%s)" % (l, how), torch.cat([kk_, kv], 1), torch.cat([k_, v_], 1))
             if l == L - 1:
                 break
-            check("prefill %d q" % l, kq, q_)
+            check("prefill %d q (%s)" % (l, how), kq, q_)
             k_att = taps[("prefill.att", l)].float().view(B, C, H)
             check("prefill %d attention" % l, k_att, qm.attend(kq, kk_, kv, 1.0 / (d ** 0.5)))
-            ln1 = ((H,), qm.p(p + "attention.output.LayerNorm.weight"), qm.p(p + "attention.output.LayerNorm.bias"), cfg.bert_ln_eps)
-            k_a = taps[("prefill.a", l)].view(B, C, H)
-            check("prefill %d o-proj + residual + LayerNorm" % l, k_a, torch.nn.functional.layer_norm(
-                qm.lin(k_att, p + "attention.output.dense.weight", p + "attention.output.dense.bias") + ctx, *ln1))
+            ln1 = (p + "attention.output.LayerNorm.weight", p + "attention.output.LayerNorm.bias")
+            ln2 = (p + "output.LayerNorm.weight", p + "output.LayerNorm.bias")
+            k_raw1 = taps[("prefill.raw1", l)].view(B, C, H)
+            check("prefill %d o-proj + residual%s" % (l, "" if l == 0 else " (LayerNorm re-applied to the raw tile)"), k_raw1,
+                  qm.lin(k_att, p + "attention.output.dense.weight", p + "attention.output.dense.bias") + resid)
             k_hid = taps[("prefill.hid", l)].float().view(B, C, F_)
-            check("prefill %d intermediate + GELU" % l, k_hid, port.q_bf16(port.gelu_fast(
-                qm.lin(port.q_bf16(k_a), p + "intermediate.dense.weight", p + "intermediate.dense.bias"))))
-            ln2 = ((H,), qm.p(p + "output.LayerNorm.weight"), qm.p(p + "output.LayerNorm.bias"), cfg.bert_ln_eps)
-            k_out = taps[("prefill.out", l)].view(B, C, H)
-            check("prefill %d output + residual + LayerNorm" % l, k_out, torch.nn.functional.layer_norm(
-                qm.lin(k_hid, p + "output.dense.weight", p + "output.dense.bias") + k_a, *ln2))
-            ctx = k_out
+            check("prefill %d intermediate + GELU (folded attention-output LayerNorm)" % l, k_hid, port.q_bf16(port.gelu_fast(
+                qm.lin_fold(k_raw1, ln1[0], ln1[1], cfg.bert_ln_eps, p + "intermediate.dense.weight", p + "intermediate.dense.bias"))))
+            a_norm = lnorm(k_raw1, (H,), qm.p(ln1[0]), qm.p(ln1[1]), cfg.bert_ln_eps)
+            raw2 = taps[("prefill.raw2", l)].view(B, C, H)
+            check("prefill %d output + residual (LayerNorm re-applied to the raw tile)" % l, raw2,
+                  qm.lin(k_hid, p + "output.dense.weight", p + "output.dense.bias") + a_norm)
+            resid, ln2_prev = lnorm(raw2, (H,), qm.p(ln2[0]), qm.p(ln2[1]), cfg.bert_ln_eps), ln2
         # first decode step from the kernel's OWN context K/V cache: rows [BOS, MASK] through the four layers and the head
         inp = torch.tensor([[int(extra["bos_token_id"]), int(extra["mask_token_id"])]]).expand(B, 2)
         e = qm.embeddings(inp, torch.tensor([[0, 1]]).expand(B, 2))

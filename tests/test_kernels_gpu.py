@@ -347,6 +347,32 @@ def test_linear_ln_emit_and_fold(M, act, row_mean, K1):
     torch.testing.assert_close(got.float(), ref, rtol=3e-2, atol=3e-2)
 
 
+@pytest.mark.parametrize("M", [578 * 2, 9000])
+@pytest.mark.parametrize("K1", [3072, 768])
+def test_linear_ln_emit_postln_residual(M, K1):
+    """vc_linear_ln_emit_postln: the residual added is LayerNorm(raw rows) evaluated in the epilogue from the raw fp32 tile and
+    the partial sums a previous emit left -- equal to materialising the LayerNorm first (post-LN BertLayer, the decoder prefill)."""
+    H = 768
+    a, w, b = rnd(M, K1, seed=5, dtype=torch.bfloat16), rnd(H, K1, seed=6, scale=0.03, dtype=torch.bfloat16), rnd(H, seed=7)
+    raw = rnd(M, H, seed=8) * 1.7 + 0.4
+    gamma, beta, eps = 1.0 + 0.1 * rnd(H, seed=11), 0.05 * rnd(H, seed=12), 1e-12
+    # the statistics exactly as a producer would have emitted them: per-256-column partial (sum, sum of squares)
+    rstats = torch.stack([raw.view(M, 3, 256).sum(2), (raw.view(M, 3, 256) ** 2).sum(2)], dim=2).contiguous()
+    resid = torch.nn.functional.layer_norm(raw, (H,), gamma, beta, eps)
+    plain = torch.empty(M, H, device=dev())
+    ops.linear(a, w, b, plain, resid=resid, impl="tc", tile_n=512)
+    out = torch.empty(M, H, device=dev())
+    xb = torch.zeros(M, H, device=dev(), dtype=torch.bfloat16)
+    stats = torch.zeros(M, 3, 2, device=dev())
+    ops.linear_ln_emit(a, w, b, out, raw, xb, stats, resid_ln=(rstats, 3, gamma, beta, eps))
+    scale = float(plain.abs().max())
+    assert float((out - plain).abs().max()) <= 2e-5 * scale
+    assert torch.equal(xb, out.to(torch.bfloat16))
+    s = stats.sum(1)
+    torch.testing.assert_close(s[:, 0], out.double().sum(1).float(), rtol=1e-5, atol=1e-3)
+    torch.testing.assert_close(s[:, 1], (out.double() ** 2).sum(1).float(), rtol=1e-5, atol=1e-3)
+
+
 # ---- split-bf16 operands of the decode-step GEMMs (include/vitcap_b200.h, VC_OPERAND_BF16X3) ---------------------------------
 def _split_ref(y):
     hi = y.to(torch.bfloat16)

@@ -232,6 +232,27 @@ def x3_probe(B):
     print("x3probe split_bf16x3 [%d, 3072]: %.1f us" % (2 * R, timeit(lambda: ops.split_bf16x3(x, o), iters=20, warm=3) * 1e3))
 
 
+def prefill_fold_ab_probe(B, variant="16_384"):
+    """A/B of the folded decoder prefill (engine.prefill_fold) in one process, alternating, steady state (20 iterations)."""
+    cfg = vcfg.variant(variant)
+    sd = synth.make_state_dict(cfg, seed=0)
+    m = FastImageCaptioning(cfg, mode="bf16", max_batch=B)
+    m.load_state_dict(sd)
+    m = m.to(dev)
+    eng = m.engine
+    data = {k: v.to(dev) for k, v in synth.make_text_inputs(cfg, B).items()}
+    data["image"] = synth.make_images(cfg, B, seed=1).to(dev)
+    m(data)
+    for rnd in range(3):
+        for fold in (True, False):
+            eng.prefill_fold = fold
+            t_pre = timeit(lambda: eng.prefill(B), iters=20, warm=3)
+            t_all = timeit(lambda: m(data), iters=20, warm=3)
+            print("prefill_fold=%d round %d: prefill %.2f ms  full forward %.2f ms  (%.1f images/s)" % (fold, rnd, t_pre, t_all, B / t_all * 1e3),
+                  flush=True)
+    eng.prefill_fold = True
+
+
 if __name__ == "__main__":
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 512
     what = sys.argv[2] if len(sys.argv) > 2 else "all"
@@ -254,3 +275,5 @@ if __name__ == "__main__":
         fold_probe(B)
     if what == "foldab":
         fold_ab_probe(B)
+    if what == "prefillab":
+        prefill_fold_ab_probe(B)

@@ -9,7 +9,9 @@ namespace vc {
 const char* last_error();
 int check_device();
 int gemm_bf16_tc2_ln_emit(const void* A, int lda, const void* W, int ldw, const float* bias, float* out, int ldo, const float* resid,
-                          int ldr, void* xb, int ldxb, float* stats, int M, int N, int K, cudaStream_t stream);
+                          int ldr, void* xb, int ldxb, float* stats, int M, int N, int K, cudaStream_t stream,
+                          const float* rstats = nullptr, int rst_tiles = 0, const float* rgamma = nullptr, const float* rbeta = nullptr,
+                          float r_eps = 0.f);
 int gemm_bf16_tc2_ln_fold(const void* A, int lda, const void* Wf, int ldw, const float* bias_f, const float* colsum,
                           const float* stats, int st_tiles, float ln_eps, void* out, int ldo, int act, int M, int N, int K,
                           cudaStream_t stream);
@@ -98,6 +100,13 @@ int vc_linear(int bf16, const void* A, int lda, const void* W, int ldw, const fl
 int vc_linear_ln_emit(const void* A, int lda, const void* W, int ldw, const float* bias, float* out, int ldo, const float* resid,
                       int ldr, void* xb, int ldxb, float* stats, int M, int N, int K, void* stream) {
   VC_COUNT(1, vc::gemm_bf16_tc2_ln_emit(A, lda, W, ldw, bias, out, ldo, resid, ldr, xb, ldxb, stats, M, N, K, ST(stream)));
+}
+int vc_linear_ln_emit_postln(const void* A, int lda, const void* W, int ldw, const float* bias, float* out, int ldo,
+                             const float* resid_raw, int ldr, const float* rstats, int rst_tiles, const float* rgamma,
+                             const float* rbeta, float r_eps, void* xb, int ldxb, float* stats, int M, int N, int K, void* stream) {
+  if (rstats == nullptr) { vc::set_last_error("vc_linear_ln_emit_postln: rstats is NULL"); return VC_ERR_BAD_ARG; }
+  VC_COUNT(1, vc::gemm_bf16_tc2_ln_emit(A, lda, W, ldw, bias, out, ldo, resid_raw, ldr, xb, ldxb, stats, M, N, K, ST(stream), rstats,
+                                        rst_tiles, rgamma, rbeta, r_eps));
 }
 int vc_linear_ln_fold(const void* A, int lda, const void* Wf, int ldw, const float* bias_f, const float* colsum, const float* stats,
                       int st_tiles, float ln_eps, void* out, int ldo, int act, int M, int N, int K, void* stream) {

@@ -73,6 +73,9 @@ template <int ACT> __device__ __forceinline__ float apply_act(float v) {
 // LN = 1: xb = bf16 [M, N] copy of the output row (pitch ldxb), stats = float [M, n_tiles, 2] partial (sum, sum of squares)
 // LN = 2: stats = the producer's partials [M, st_tiles, 2] of the K-wide input row, colsum = float [N] row sums of W (bf16
 //         values, fp32 sum), inv_k = 1 / K, ln_eps; bias already holds b + W beta
+// RLN (post-LN layers, BertSelfOutput / BertOutput, modeling_bert.py:353-357, 415-419): the residual is itself a LayerNorm output
+//         that is never materialised: the residual tile holds the RAW fp32 row of the producer, rstats its partial sums
+//         [M, rst_tiles, 2] (over r_inv_n = 1 / row width), and the epilogue adds (raw - mean) * rstd * rgamma + rbeta
 struct LnArgs {
   bf16* xb;
   int ldxb;
@@ -81,15 +84,22 @@ struct LnArgs {
   float ln_eps;
   float inv_k;
   int st_tiles;
+  const float* rstats;
+  const float* rgamma;
+  const float* rbeta;
+  float r_eps;
+  float r_inv_n;
+  int rst_tiles;
 };
 
-template <int ACT, bool OUT_F32, bool RESID, int G, int LN>
+template <int ACT, bool OUT_F32, bool RESID, int G, int LN, bool RLN = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 128 * G, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                 const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
                 const __grid_constant__ CUtensorMap tmap_xb, const float* __restrict__ bias, LnArgs ln, int M, int N, int K) {
   using C = Gemm2Cfg<OUT_F32, RESID, G, LN>;
   constexpr bool EMIT = (LN == LN_EMIT || LN == LN_EMIT_TMA);
+  static_assert(!RLN || (RESID && OUT_F32), "a normalised residual needs the fp32 residual epilogue");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* epi = smem + C::STAGES * C::STAGE_BYTES;
@@ -240,6 +250,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         if (nt < num_tiles) load_row_stats((nt / n_tiles) * (2 * C::BM) + (int)rank * C::BM + t, nx_s, nx_q);
       }
       float st_s = 0.f, st_q = 0.f;                      // LN = 1: this row's partial statistics over the tile's columns
+      float r_rstd = 0.f, r_nm = 0.f;                    // RLN: the residual row's 1 / std and -mean / std
+      if (RLN && m0 + t < M) {
+        const float2* sp = reinterpret_cast<const float2*>(ln.rstats) + (size_t)(m0 + t) * ln.rst_tiles;
+        float rs = 0.f, rq = 0.f;
+        for (int i = 0; i < ln.rst_tiles; ++i) { const float2 pq = __ldg(sp + i); rs += pq.x; rq += pq.y; }
+        const float mean = rs * ln.r_inv_n;
+        r_rstd = rsqrtf(fmaxf(fmaf(rq, ln.r_inv_n, -mean * mean), 0.f) + ln.r_eps);
+        r_nm = -mean * r_rstd;
+      }
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
 #pragma unroll 1
@@ -306,7 +325,19 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 const float4 rr = *reinterpret_cast<const float4*>(myrow + ((j ^ sw) << 4));
-                v[4 * j] += rr.x; v[4 * j + 1] += rr.y; v[4 * j + 2] += rr.z; v[4 * j + 3] += rr.w;
+                if (RLN) {
+                  float4 gg = make_float4(0.f, 0.f, 0.f, 0.f), bb = gg;
+                  if (full || cb + 4 * j < N) {
+                    gg = __ldg(reinterpret_cast<const float4*>(ln.rgamma + cb + 4 * j));
+                    bb = __ldg(reinterpret_cast<const float4*>(ln.rbeta + cb + 4 * j));
+                  }
+                  v[4 * j] += fmaf(fmaf(rr.x, r_rstd, r_nm), gg.x, bb.x);
+                  v[4 * j + 1] += fmaf(fmaf(rr.y, r_rstd, r_nm), gg.y, bb.y);
+                  v[4 * j + 2] += fmaf(fmaf(rr.z, r_rstd, r_nm), gg.z, bb.z);
+                  v[4 * j + 3] += fmaf(fmaf(rr.w, r_rstd, r_nm), gg.w, bb.w);
+                } else {
+                  v[4 * j] += rr.x; v[4 * j + 1] += rr.y; v[4 * j + 2] += rr.z; v[4 * j + 3] += rr.w;
+                }
               }
             }
 #pragma unroll
@@ -378,11 +409,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 // ------------------------------------------------------------------------------------------
 // host launcher
 // ------------------------------------------------------------------------------------------
-template <int ACT, bool OUT_F32, bool RESID, int G, int LN = 0>
+template <int ACT, bool OUT_F32, bool RESID, int G, int LN = 0, bool RLN = false>
 static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr, const float* bias,
                    int M, int N, int K, cudaStream_t stream, LnArgs ln = LnArgs(), const CUtensorMap* txb = nullptr) {
   using C = Gemm2Cfg<OUT_F32, RESID, G, LN>;
-  auto kern = gemm_tc2_kernel<ACT, OUT_F32, RESID, G, LN>;
+  auto kern = gemm_tc2_kernel<ACT, OUT_F32, RESID, G, LN, RLN>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
@@ -436,7 +467,8 @@ int gemm_bf16_tc2(const void* A, int lda, const void* W, int ldw, const float* b
 // out (fp32) = A W^T + bias + resid, plus xb = bf16(out) and stats[M, ceil(N/256), 2] = per-256-column partial (sum, sum of
 // squares) of every output row: the producer half of the folded LayerNorm
 int gemm_bf16_tc2_ln_emit(const void* A, int lda, const void* W, int ldw, const float* bias, float* out, int ldo, const float* resid,
-                          int ldr, void* xb, int ldxb, float* stats, int M, int N, int K, cudaStream_t stream) {
+                          int ldr, void* xb, int ldxb, float* stats, int M, int N, int K, cudaStream_t stream, const float* rstats,
+                          int rst_tiles, const float* rgamma, const float* rbeta, float r_eps) {
   if (M <= 0 || N <= 0 || K <= 0 || (K % 64) != 0 || (N % 64) != 0 || resid == nullptr || xb == nullptr || stats == nullptr) {
     set_last_error("gemm_tc2_ln_emit: need K %% 64 == 0, N %% 64 == 0, a residual, xb and stats (N=%d K=%d)", N, K);
     return VC_ERR_BAD_ARG;
@@ -460,13 +492,29 @@ int gemm_bf16_tc2_ln_emit(const void* A, int lda, const void* W, int ldw, const 
   ln.xb = static_cast<bf16*>(xb);
   ln.ldxb = ldxb;
   ln.stats = stats;
+  const bool rln = (rstats != nullptr);
+  if (rln) {
+    if (rst_tiles < 1 || rgamma == nullptr || rbeta == nullptr || (reinterpret_cast<uintptr_t>(rstats) & 7) ||
+        (reinterpret_cast<uintptr_t>(rgamma) & 15) || (reinterpret_cast<uintptr_t>(rbeta) & 15)) {
+      set_last_error("gemm_tc2_ln_emit: a normalised residual needs rstats (8-byte aligned), rst_tiles >= 1, rgamma and rbeta");
+      return VC_ERR_BAD_ARG;
+    }
+    ln.rstats = rstats;
+    ln.rst_tiles = rst_tiles;
+    ln.rgamma = rgamma;
+    ln.rbeta = rbeta;
+    ln.r_eps = r_eps;
+    ln.r_inv_n = 1.0f / (float)N;                        // the residual row is as wide as the output row
+  }
   static const int force_tma = (getenv("VITCAP_EMIT_TMA") != nullptr) ? atoi(getenv("VITCAP_EMIT_TMA")) : -1;   // tuning knob
   if (force_tma == 1 || (force_tma != 0 && K <= 768)) {                       // HBM-bound shape: stage the copy in shared memory
     CUtensorMap tx;
     rc = get_tmap_2d_bf16(&tx, xb, (uint64_t)M, (uint64_t)N, (uint64_t)ldxb, 128, 64);
     if (rc) return rc;
+    if (rln) return launch2<ACT2_NONE, true, true, 1, LN_EMIT_TMA, true>(ta, tb, to, tr, bias, M, N, K, stream, ln, &tx);
     return launch2<ACT2_NONE, true, true, 1, LN_EMIT_TMA>(ta, tb, to, tr, bias, M, N, K, stream, ln, &tx);
   }
+  if (rln) return launch2<ACT2_NONE, true, true, 1, LN_EMIT, true>(ta, tb, to, tr, bias, M, N, K, stream, ln);
   return launch2<ACT2_NONE, true, true, 1, LN_EMIT>(ta, tb, to, tr, bias, M, N, K, stream, ln);
 }
 

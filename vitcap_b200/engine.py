@@ -55,12 +55,14 @@ class PackedWeights:
         self.cls_token = Fp(ie + "cls_token").reshape(H).contiguous()
         self.pos_embed = Fp(ie + "pos_embed").reshape(cfg.n_tokens, H).contiguous()
 
-        def folded(w_key, b_key, g_key, beta_key):
+        def folded_t(w32, b32, g32, be32):
             """LayerNorm folded into the consuming Linear (vc_linear_ln_fold): Wf = bf16(gamma o W), colsum = fp32 row sums of
             the ROUNDED Wf (so that mean * colsum cancels what the tensor cores accumulate), bias_f = b + W beta."""
-            w32, b32, g32, be32 = Fp(w_key), Fp(b_key), Fp(g_key), Fp(beta_key)
             wf = (w32 * g32.unsqueeze(0)).to(torch.bfloat16).contiguous()
             return wf, wf.float().sum(1).contiguous(), (b32 + w32 @ be32).contiguous()
+
+        def folded(w_key, b_key, g_key, beta_key):
+            return folded_t(Fp(w_key), Fp(b_key), Fp(g_key), Fp(beta_key))
 
         def block(prefix):
             d = {
@@ -117,6 +119,17 @@ class PackedWeights:
             if self.decode_x3:
                 self.dec[-1]["i_w3"] = ops.split_weight_bf16x3(Fp(p + "intermediate.dense.weight"))
                 self.dec[-1]["f_w3"] = ops.split_weight_bf16x3(Fp(p + "output.dense.weight"))
+            if mode == "bf16":
+                # prefill with folded LayerNorms (engine.prefill): the intermediate GEMM folds this layer's attention-output
+                # LayerNorm, the q|k|v GEMM of layer i >= 1 folds the output LayerNorm of layer i - 1
+                d = self.dec[-1]
+                d["i_wf"], d["i_cf"], d["i_bf"] = folded(p + "intermediate.dense.weight", p + "intermediate.dense.bias",
+                                                         p + "attention.output.LayerNorm.weight", p + "attention.output.LayerNorm.bias")
+                if i > 0:
+                    pp = "module.bert.decoder.layer.%d." % (i - 1)
+                    d["qkv_wf"], d["qkv_cf"], d["qkv_bf"] = folded_t(qkv_w.to(device=device, dtype=torch.float32),
+                                                                     qkv_b.to(device=device, dtype=torch.float32),
+                                                                     Fp(pp + "output.LayerNorm.weight"), Fp(pp + "output.LayerNorm.bias"))
 
 
 class CaptionEngine:
@@ -152,6 +165,8 @@ class CaptionEngine:
         # summation order of a row must not depend on how many other rows are in flight (every image's result is bit-identical
         # in any batch, tests/test_fullsize_gpu.py). VITCAP_DEC_SPLITS="o,f,t" overrides them for tuning runs
         self.dec_splits = tuple(int(v) for v in os.environ.get("VITCAP_DEC_SPLITS", "3,6,6").split(","))
+        # decoder prefill with every LayerNorm folded into the GEMMs around it (post-LN variant of the ViT fold; prefill())
+        self.prefill_fold = self.mode == "bf16" and os.environ.get("VITCAP_PREFILL_FOLD", "1") != "0"
         self.forward_graphs = {}               # whole-forward CUDA graphs of the small-batch latency path (model.py); they hold
         self.inline_graphs = False             # raw workspace pointers. inline_graphs: an outer capture is running
         # parity instrumentation (tests / tools only): tap(name, index, tensor) is called with the stream after every ViT block
@@ -188,6 +203,9 @@ class CaptionEngine:
         ws["tmp_f"] = self._alloc(B * C, H, dtype=f32)
         ws["a_f"] = self._alloc(B * C, H, dtype=f32)
         ws["ctx_qkv"] = self._alloc(L, B * C, 3 * H)
+        if self.mode == "bf16":
+            st = (H + 255) // 256                  # per-256-column (sum, sum of squares) of the two raw prefill streams
+            ws["pf_st"] = (self._alloc(B * C, st, 2, dtype=f32), self._alloc(B * C, st, 2, dtype=f32), st)
         # tag head
         ws["cls_t"] = self._alloc(B, H)
         ws["pooled"] = self._alloc(B, H, dtype=f32 if self.T == f32 else self.T)
@@ -491,6 +509,8 @@ class CaptionEngine:
                            w.emb_ln_b, cfg.bert_ln_eps, ctx_f, ctx_t, B, Cp, C)
         att, hid, tmp, a_f, ln = ws["att"][:rows], ws["hid"][:rows], ws["tmp_f"][:rows], ws["a_f"][:rows], ws["ln"][:rows]
         self._t("prefill.in", 0, ctx_f)
+        if self.prefill_fold:
+            return self._prefill_folded(ws, B, Cp, C, rows, n_extra)
         for l, p in enumerate(w.dec):
             qkv = ws["ctx_qkv"][l][:rows]
             last = (l == cfg.dec_layers - 1)
@@ -511,6 +531,43 @@ class CaptionEngine:
             ops.linear(hid, p["f_w"], p["f_b"], tmp, resid=a_f, M=rows)
             self._ln(tmp, p["ln2_w"], p["ln2_b"], cfg.bert_ln_eps, ctx_t, out_f=ctx_f, rows=rows)
             self._t("prefill.out", l, ctx_f)
+
+    def _prefill_folded(self, ws, B, Cp, C, rows, n_extra):
+        """The same layers without a stand-alone LayerNorm pass (each one re-read and re-wrote 2.3 GB at 512 images). BertLayer
+        is post-LN: a = LN1(o(att) + x), y = LN2(f(gelu(i(a))) + a). Both normalised streams only ever feed (1) a GEMM -- which
+        folds the normalisation (vc_linear_ln_fold on the raw bf16 copy + row statistics the producing GEMM emitted) -- and
+        (2) the residual input of the next residual GEMM, which re-applies it to the raw fp32 tile in its epilogue
+        (vc_linear_ln_emit_postln). raw1 / raw2 are the pre-LayerNorm rows o(att) + x and f(.) + a."""
+        cfg, w = self.cfg, self.w
+        H, eps = cfg.hidden, cfg.bert_ln_eps
+        ctx_f, ctx_t = ws["ctx_f"][:rows], ws["ctx_t"][:rows]
+        att, hid = ws["att"][:rows], ws["hid"][:rows]
+        raw1, raw2 = ws["tmp_f"][:rows], ws["a_f"][:rows]
+        xb1, xb2 = ws["ln"][:rows], ctx_t                  # ctx_t is free once layer 0 has projected it
+        st1, st2, nst = ws["pf_st"]
+        L = cfg.dec_layers
+        for l, p in enumerate(w.dec):
+            qkv = ws["ctx_qkv"][l][:rows]
+            lo = H if l == L - 1 else 0                    # the last layer only ever serves K and V
+            if l == 0:
+                ops.linear(ctx_t, p["qkv_w"][lo:], p["qkv_b"][lo:], qkv[:, lo:], M=rows, ldo=3 * H)
+            else:
+                ops.linear_ln_fold(xb2, p["qkv_wf"][lo:], p["qkv_bf"][lo:], p["qkv_cf"][lo:], st2, nst, eps, qkv[:, lo:], M=rows, ldo=3 * H)
+            self._t("prefill.qkv", l, qkv)
+            if l == L - 1:
+                break
+            ops.attention(qkv, att, B, Cp, cfg.heads, 1.0 / math.sqrt(cfg.head_dim), impl=self.attn_impl, n_base=C, n_extra=n_extra)
+            self._t("prefill.att", l, att)
+            if l == 0:
+                ops.linear_ln_emit(att, p["o_w"], p["o_b"], raw1, ctx_f, xb1, st1, M=rows)
+            else:
+                q = w.dec[l - 1]
+                ops.linear_ln_emit(att, p["o_w"], p["o_b"], raw1, raw2, xb1, st1, M=rows, resid_ln=(st2, nst, q["ln2_w"], q["ln2_b"], eps))
+            self._t("prefill.raw1", l, raw1)
+            ops.linear_ln_fold(xb1, p["i_wf"], p["i_bf"], p["i_cf"], st1, nst, eps, hid, act=ops.ACT_GELU, M=rows)
+            self._t("prefill.hid", l, hid)
+            ops.linear_ln_emit(hid, p["f_w"], p["f_b"], raw2, raw1, xb2, st2, M=rows, resid_ln=(st1, nst, p["ln1_w"], p["ln1_b"], eps))
+            self._t("prefill.raw2", l, raw2)
 
     def _decode_layers(self, ws, B, E, cur_len, anc, mask_id, labels=False, head=True, vocab="logits", live=(None, None)):
         """One decode step up to the vocabulary logits of the MASK rows. labels: the context holds C + topk rows per image of

@@ -25,6 +25,7 @@ SIGNATURES = {
     "vc_linear_tc": [_P, _I, _P, _I, _P, _P, _I, _I, _I, _P, _I, _I, _I, _I, _I, _P],
     "vc_linear_ln_emit": [_P, _I, _P, _I, _P, _P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _P],
     "vc_linear_ln_fold": [_P, _I, _P, _I, _P, _P, _P, _I, _F, _P, _I, _I, _I, _I, _I, _P],
+    "vc_linear_ln_emit_postln": [_P, _I, _P, _I, _P, _P, _I, _P, _I, _P, _I, _P, _P, _F, _P, _I, _P, _I, _I, _I, _P],
     "vc_patchify": [_I, _P, _P, _I, _I, _I, _P],
     "vc_patchify_u8": [_I, _P, _P, _I, _I, _I, _I, _P],
     "vc_resize_crop_plan": [_P, _I, _I, _I, _P, _P, _P],
@@ -189,14 +190,23 @@ def _profiled(flops, call):
         call()
 
 
-def linear_ln_emit(a, w, bias, out, resid, xb, stats, M=None):
+def linear_ln_emit(a, w, bias, out, resid, xb, stats, M=None, resid_ln=None):
     """out (fp32) = a @ w^T + bias + resid, plus xb = bf16(out) and stats [M, ceil(N/256), 2] = partial (sum, sum of squares) per
-    256-column tile of every output row (the producer half of the folded LayerNorm, vc_linear_ln_emit)."""
+    256-column tile of every output row (the producer half of the folded LayerNorm, vc_linear_ln_emit).
+    resid_ln = (rstats, rst_tiles, gamma, beta, eps): ``resid`` holds the RAW rows of a previous emit and the residual added is
+    their LayerNorm, evaluated on the fly (vc_linear_ln_emit_postln)."""
     lib = load_library()
     N, K = w.shape
     M = a.shape[0] if M is None else M
     assert a.dtype == w.dtype == xb.dtype == torch.bfloat16 and out.dtype == resid.dtype == stats.dtype == torch.float32
     assert stats.is_contiguous() and stats.numel() >= M * ((N + 255) // 256) * 2
+    if resid_ln is not None:
+        rstats, rst_tiles, g, b, eps = resid_ln
+        assert rstats.dtype == g.dtype == b.dtype == torch.float32 and rstats.is_contiguous() and rstats.numel() >= M * rst_tiles * 2
+        _profiled(2.0 * M * N * K, lambda: _check(lib.vc_linear_ln_emit_postln(
+            _ptr(a), a.stride(0), _ptr(w), w.stride(0), _ptr(bias), _ptr(out), out.stride(0), _ptr(resid), resid.stride(0), _ptr(rstats),
+            rst_tiles, _ptr(g), _ptr(b), float(eps), _ptr(xb), xb.stride(0), _ptr(stats), M, N, K, _stream()), "vc_linear_ln_emit_postln"))
+        return out
     _profiled(2.0 * M * N * K, lambda: _check(lib.vc_linear_ln_emit(
         _ptr(a), a.stride(0), _ptr(w), w.stride(0), _ptr(bias), _ptr(out), out.stride(0), _ptr(resid), resid.stride(0), _ptr(xb),
         xb.stride(0), _ptr(stats), M, N, K, _stream()), "vc_linear_ln_emit"))
