@@ -170,7 +170,8 @@ def test_attention_exact_fp32(B, N, heads):
 
 
 @pytest.mark.parametrize("impl", ["auto", "simt"])
-@pytest.mark.parametrize("B,N,heads", [(2, 577, 12), (3, 197, 12), (1, 578, 12), (2, 145, 12), (2, 17, 2), (1, 128, 1), (1, 129, 1), (1, 256, 3)])
+@pytest.mark.parametrize("B,N,heads", [(2, 577, 12), (3, 197, 12), (1, 578, 12), (2, 145, 12), (2, 17, 2), (1, 128, 1), (1, 129, 1), (1, 256, 3),
+                                       (2, 288, 2), (1, 289, 3), (2, 290, 1), (1, 385, 2), (1, 674, 2), (1, 576, 1)])
 def test_attention_bf16(B, N, heads, impl):
     """bf16 operands; P is rounded to bf16 before the PV product (as any flash kernel does): 2e-2 abs on O(1) outputs."""
     qkv = rnd(B, N, 3 * heads * 64, seed=3, dtype=torch.bfloat16)
@@ -191,6 +192,54 @@ def test_attention_bf16_many_ctas():
     torch.cuda.synchronize()
     ref = ref_attention(qkv, heads, 0.125)
     torch.testing.assert_close(out.float(), ref, rtol=2e-2, atol=2e-2)
+
+
+def _ref_attention_rounded_p(qkv, heads, scale):
+    """The kernels' own statement of the arithmetic (oracle/port.py QuantPortModel.attend): exp2 domain, integer exponent
+    reference, P rounded to bf16 for the V product, row sum of the unrounded P, bf16 output."""
+    B, N, H3 = qkv.shape
+    q, k, v = qkv.double().view(B, N, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    s = (q @ k.transpose(-1, -2)) * (scale * 1.4426950408889634)
+    p = torch.exp2(s - torch.ceil(s.max(-1, keepdim=True).values))
+    o = (p.float().to(torch.bfloat16).double() @ v) / p.sum(-1, keepdim=True)
+    return o.transpose(1, 2).reshape(B, N, heads * 64).float()
+
+
+@pytest.mark.parametrize("B,N,heads", [(3, 577, 12), (2, 578, 12), (2, 288, 2), (2, 197, 3), (1, 674, 1)])
+@pytest.mark.parametrize("gain", [1.0, 2.5])
+def test_attention_bf16_vs_rounded_p_statement(B, N, heads, gain):
+    """Both tensor-core attention kernels (64-key chunks; 96-key chunks with the leading keys peeled off onto the CUDA cores for
+    N = p + 96 m) against the quantisation-matched statement: what is left is the final bf16 rounding of the output (2^-8
+    relative) and the rare P whose bf16 rounding flips under MUFU.EX2's 2^-22 error. A mishandled peeled key (a missing score
+    in the row maximum / row sum, an unrounded P) shows as a 1e-2 .. 1e-1 error here."""
+    qkv = rnd(B, N, 3 * heads * 64, seed=11, scale=gain, dtype=torch.bfloat16)
+    out = torch.zeros(B, N, heads * 64, device=dev(), dtype=torch.bfloat16)
+    ops.attention(qkv, out, B, N, heads, 0.125)
+    ref = _ref_attention_rounded_p(qkv, heads, 0.125)
+    err = (out.float() - ref).abs()
+    # element-wise: one bf16 ulp of the output plus one flipped P rounding of a dominating key (2^-9 of the row's scale)
+    assert float((err - (2.0 ** -7) * ref.abs()).max()) <= 2.0 ** -8 * float(ref.abs().max()), float(err.max())
+    assert float(err.norm() / ref.norm()) < 3e-3
+
+
+def test_attention_96_key_kernel_equals_64_key_kernel():
+    """VITCAP_ATTN96=0 routes N = 577 / 578 to the 64-key kernel: same P roundings (integer exponent reference), different
+    summation order only."""
+    import os
+    for N in (577, 578):
+        qkv = rnd(4, N, 3 * 12 * 64, seed=13, dtype=torch.bfloat16)
+        a = torch.zeros(4, N, 768, device=dev(), dtype=torch.bfloat16)
+        b = torch.zeros_like(a)
+        ops.attention(qkv, a, 4, N, 12, 0.125)
+        os.environ["VITCAP_ATTN96"] = "0"
+        try:
+            ops.attention(qkv, b, 4, N, 12, 0.125)
+        finally:
+            del os.environ["VITCAP_ATTN96"]
+        torch.cuda.synchronize()
+        d = (a.float() - b.float()).abs()
+        assert float(d.max()) <= 2.0 ** -7 * float(b.float().abs().max())      # at most one bf16 ulp of the largest output
+        assert float((d > 0).float().mean()) < 0.05
 
 
 def test_attention_bf16_peaky_scores():

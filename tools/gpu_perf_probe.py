@@ -56,9 +56,22 @@ def attn_probe(B):
     N, heads = 577, 12
     qkv = torch.randn(B, N, 3 * 768, device=dev).to(torch.bfloat16)
     out = torch.empty(B, N, 768, device=dev, dtype=torch.bfloat16)
-    ms = timeit(lambda: ops.attention(qkv, out, B, N, heads, 0.125))
     fl = 4.0 * B * heads * N * N * 64
-    print("attention_tc B=%d N=%d: %.3f ms  %.1f TFLOP/s (algorithmic)" % (B, N, ms, fl / ms / 1e9), flush=True)
+    for rnd in range(2):
+        for knob, name in (("1", "attention_tc96 (96-key chunks, CLS key peeled)"), ("0", "attention_tc (64-key chunks)")):
+            os.environ["VITCAP_ATTN96"] = knob
+            ms = timeit(lambda: ops.attention(qkv, out, B, N, heads, 0.125), iters=20, warm=3)
+            print("%s B=%d N=%d: %.3f ms  %.1f TFLOP/s (algorithmic)" % (name, B, N, ms, fl / ms / 1e9), flush=True)
+    del os.environ["VITCAP_ATTN96"]
+    qkv2 = torch.randn(B, 578, 3 * 768, device=dev).to(torch.bfloat16)
+    out2 = torch.empty(B, 578, 768, device=dev, dtype=torch.bfloat16)
+    for knob in ("1", "0"):
+        os.environ["VITCAP_ATTN96"] = knob
+        ms = timeit(lambda: ops.attention(qkv2, out2, B, 578, heads, 0.125), iters=20, warm=3)
+        print("N=578 (decoder context) VITCAP_ATTN96=%s: %.3f ms" % (knob, ms), flush=True)
+    del os.environ["VITCAP_ATTN96"]
+    del qkv2, out2
+    ms = timeit(lambda: ops.attention(qkv, out, B, N, heads, 0.125))
     q, k, v = qkv.view(B, N, 3, heads, 64).permute(2, 0, 3, 1, 4)
     ms2 = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(q, k, v))
     print("     torch SDPA same shape: %.3f ms  %.1f TFLOP/s" % (ms2, fl / ms2 / 1e9), flush=True)

@@ -437,7 +437,12 @@ static int launch_attention(dim3 grid, const CUtensorMap& tq, const CUtensorMap&
   return check_launch("attention_tc");
 }
 
+int attention_tc96_peel(int N);
+int attention_tc96(const void* qkv, void* out, int B, int N, int heads, float scale, cudaStream_t s);
+
 int attention_tc(const void* qkv, void* out, int B, int N, int heads, float scale, int n_base, const int* n_extra, cudaStream_t s) {
+  // N = p + 96 m (577, 578: the ViT-B/16-384 shapes): the 96-key kernel with p peeled keys (attention_tc96.cu)
+  if (n_extra == nullptr && N > 0 && attention_tc96_peel(N) >= 0) return attention_tc96(qkv, out, B, N, heads, scale, s);
   if (B <= 0 || N <= 0 || heads <= 0 || B > 65535 || (n_extra && (n_base < 1 || n_base > N))) {
     set_last_error("attention_tc: bad args"); return VC_ERR_BAD_ARG;
   }
