@@ -262,6 +262,20 @@ int vc_token_step_partials(const void* part, int n_part, int rows, int cur_len, 
 int vc_greedy_finalize(const int* ids, const int* unfinished, const float* sum_lp, const int* n_steps, int eos0, int max_len, int R,
                        long long* out_ids, float* out_lp, void* stream);
 
+/* Early exit of a CAPTURED decode loop without a host round trip (modeling_utils.py:865-867 `if cur_unfinished.max() == 0:
+ * break`, :1071-1073 `if all(done): break`). `capture_stream` must be capturing into a CUDA graph (e.g. torch.cuda.graph):
+ * vc_graph_if_any_begin appends a one-block kernel that evaluates any(flags[i] != 0) (invert = 0: per-sequence `unfinished`)
+ * or any(flags[i] == 0) (invert = 1: per-image `done`) over n int32 flags on the device, then a conditional IF node on that
+ * value, and starts capturing `body_stream` (another stream, not capturing) into the IF node's body: everything the caller
+ * launches on body_stream until vc_graph_if_end(body_stream) is skipped by a replay in which no flag is live.
+ * Bodies hold kernel launches only (no allocations, no host-pageable copies). */
+int vc_graph_if_any_begin(const int* flags, int n, int invert, void* capture_stream, void* body_stream);
+int vc_graph_if_end(void* body_stream);
+/* a non-blocking stream of the current device that belongs to the caller alone (a framework's pooled streams may alias the
+ * capturing stream or carry other work): the body stream of vc_graph_if_any_begin. *stream_out receives the cudaStream_t. */
+int vc_stream_create(void** stream_out);
+int vc_stream_destroy(void* stream);
+
 /* beam search step, modeling_utils.py:988-1065: (1) per-row log-sum-exp + top-(2*beams) logits, (2) per-image candidate
  * walk, hypothesis pool (BeamHypotheses, :1138-1180), next beams, ancestor table update. */
 int vc_beam_row_topk(const float* logits, int ld, int rows, int V, int K, float* cand_val, int* cand_idx, float* row_max,

@@ -91,6 +91,57 @@ def test_tiny_greedy_vs_oracle(mode, gap, graph):
         compare_ids_gap_aware(ids.cpu().numpy()[:, 0], rids.numpy()[:, 0], top, gap, "%s rep%d" % (mode, rep))
 
 
+@pytest.mark.parametrize("search", ["greedy", "sample", "beam"])
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_captured_decode_loop_exits_early_on_the_device(search, mode, monkeypatch):
+    """`if cur_unfinished.max() == 0: break` / `if all(done): break` (modeling_utils.py:865-867, 1071-1073) inside the captured
+    loop: every step after the first is the body of a conditional graph node. With an EOS planted so strongly that every caption
+    ends within a few tokens, (1) ids and log-probs equal the loop without the conditional nodes (VITCAP_EARLY_EXIT=0) bit for
+    bit, (2) the steps after the last live one did NOT run: the q|k|v rows they would have written keep a sentinel."""
+    cfg = vcfg.tiny()
+    sd = synth.make_state_dict(cfg, seed=7, eos_bias=9.0)
+    B = 5
+    data = synth.make_text_inputs(cfg, B)
+    data["image"] = synth.make_images(cfg, B, seed=3)
+    kw = {"greedy": {}, "sample": dict(do_sample=True, num_return_sequences=3, temperature=0.8),
+          "beam": dict(num_beams=3, num_keep_best=2, length_penalty=0.8)}[search]
+    extra = synth.default_test_extra_input(cfg, **kw)
+    E = {"greedy": 1, "sample": 3, "beam": 3}[search]
+    out = {}
+    for early in ("0", "1"):
+        monkeypatch.setenv("VITCAP_EARLY_EXIT", early)
+        m = build(cfg, sd, extra, mode, sample_seed=11, use_cuda_graph=True)
+        assert m.engine.early_exit == (early == "1")
+        m(to_dev(data))                                   # eager warm-up + capture
+        ws = m.engine._decoder_ws(B, E, 20)
+        ws["step_qkv"].fill_(7.0)                         # sentinel in every step's q|k|v rows
+        ids, lp = m(to_dev(data))                         # replay
+        torch.cuda.synchronize()
+        out[early] = (ids.clone(), lp.clone(), ws["step_qkv"].float().clone())
+    assert torch.equal(out["0"][0], out["1"][0]) and torch.equal(out["0"][1], out["1"][1])
+    ids = out["1"][0]
+    if search == "beam":
+        n_live = 19                                       # beams end when the pool is full and cannot improve: count from the rows
+    else:
+        eos = int(extra["eos_token_ids"][0])
+        first = (ids[:, 0] == eos).float().argmax(1)      # position of the first EOS of every caption
+        assert bool((ids[:, 0] == eos).any(1).all()), "the planted EOS must end every caption"
+        n_live = int(first.max())                         # steps 1..n_live ran (the step that emits the last EOS included)
+        assert n_live <= 6
+    touched0 = (out["0"][2] != 7.0).flatten(2).any(2)     # [L, max_len]: did step s+1 write its rows?
+    touched1 = (out["1"][2] != 7.0).flatten(2).any(2)
+    assert bool(touched0[:, :19].all())                   # without the conditional nodes all 19 steps run
+    if search != "beam":
+        assert bool(touched1[:, :n_live].all()) and not bool(touched1[:, n_live:].any()), touched1
+    else:
+        assert bool(touched1[:, 0].all()) and not bool(touched1[:, 18].any()), touched1
+    # PAD after the end, as the reference pads after its break
+    if search != "beam":
+        pad = int(extra["pad_token_id"])
+        for r in range(ids.shape[0]):
+            assert bool((ids[r, 0, int(first[r]) + 1:] == pad).all())
+
+
 def test_tiny_sampling_matches_oracle_with_same_noise():
     """do_sample: Gumbel-max with Philox noise == multinomial(softmax); with the oracle drawing the same counter-based
     noise the sampled ids agree token for token (exact mode)."""

@@ -52,7 +52,7 @@ def test_header_symbols_are_exported_and_bound():
     simple = {"vc_last_error", "vc_abi_version", "vc_launch_count", "vc_reset_launch_count", "vc_set_pdl", "vc_get_pdl",
               "vc_check_device"}
     assert names - simple == set(ops.SIGNATURES), (names - simple) ^ set(ops.SIGNATURES)
-    assert lib.vc_abi_version() == 7
+    assert lib.vc_abi_version() == 8
     assert isinstance(lib.vc_last_error(), bytes)
 
 

@@ -40,10 +40,17 @@ def main():
         torch.cuda.synchronize()
         ln = caption_lengths(ids)
         eng = m.engine
-        t_dec = timeit(lambda: eng.greedy_or_sample(B, 1, 20, 101, 0, [102], 103), iters=8, warm=2)
-        t_all = timeit(lambda: m(data), iters=8, warm=2)
-        print("eos_bias %.2f: mean length %.2f (min %d max %d, %d of %d reach 20)  decode loop %.2f ms  full step %.2f ms (%.1f images/s)"
-              % (eb, float(ln.mean()), int(ln.min()), int(ln.max()), int((ln >= 20).sum()), B, t_dec, t_all, B / t_all * 1e3), flush=True)
+        for early in (True, False, True, False):
+            eng.early_exit = early
+            eng._dec_ws.clear()                          # drop the captured loops: the next call captures with / without IF nodes
+            m(data)
+            m(data)
+            t_dec = timeit(lambda: eng.greedy_or_sample(B, 1, 20, 101, 0, [102], 103), iters=8, warm=2)
+            t_all = timeit(lambda: m(data), iters=8, warm=2)
+            print("eos_bias %.3f early_exit=%d: mean length %.2f (min %d max %d, %d of %d reach 20)  decode loop %.2f ms  full step %.2f ms "
+                  "(%.1f images/s)" % (eb, early, float(ln.mean()), int(ln.min()), int(ln.max()), int((ln >= 20).sum()), B, t_dec, t_all,
+                                       B / t_all * 1e3), flush=True)
+        eng.early_exit = True
 
 
 if __name__ == "__main__":

@@ -300,6 +300,18 @@ attention_tc96_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             sx[x] = a;
           }
         }
+        // the peeled keys give every row an exponent reference BEFORE its first chunk arrives: chunk 0 then runs speculatively
+        // like every other chunk (one pass over S instead of a maximum pass followed by an exponential pass)
+        float mxp = sx[0];
+#pragma unroll
+        for (int x = 1; x < PEEL; ++x) mxp = fmaxf(mxp, sx[x]);
+        m_ref = ceilf(mxp * scale_log2);
+#pragma unroll
+        for (int x = 0; x < PEEL; ++x) {
+          const float p = ex2(fmaf(sx[x], scale_log2, -m_ref));
+          l += p;
+          px[x] = __bfloat162float(__float2bfloat16_rn(p));
+        }
       }
       for (int j = 0; j < nch; ++j) {
         const uint32_t taddr_s = tmem_base + lane_base + COL_S + sb * KT;
@@ -344,8 +356,8 @@ attention_tc96_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             csum += (a0 + a1) + (a2 + a3);
           };
           bool redo;
-          if (j == 0) {
-            // first chunk of a tile: no reference yet, the maximum (peeled keys included) has to come first
+          if (PEEL == 0 && j == 0) {
+            // first chunk of a tile without peeled keys: no reference yet, the maximum has to come first
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
               uint32_t r[HALF];
@@ -356,15 +368,7 @@ attention_tc96_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
                 mx1 = fmaxf(mx1, fmaxf(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])));
               }
             }
-#pragma unroll
-            for (int x = 0; x < PEEL; ++x) mx0 = fmaxf(mx0, sx[x]);
             m_ref = ceilf(fmaxf(mx0, mx1) * scale_log2);
-#pragma unroll
-            for (int x = 0; x < PEEL; ++x) {
-              const float p = ex2(fmaf(sx[x], scale_log2, -m_ref));
-              l += p;
-              px[x] = __bfloat162float(__float2bfloat16_rn(p));
-            }
             redo = true;
           } else {
             // speculate that the reference holds (it moves only when the chunk max exceeds it by 2^8): the exponentials run
@@ -377,9 +381,11 @@ attention_tc96_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             if (redo) {
               const float m_new = need ? ceilf(mxs) : m_ref;
               const float corr = ex2(m_ref - m_new);   // exactly 1 for lanes that keep their reference, else a power of two
-              mbar_wait(&pv_done[sb_prev], sph_prev);  // every issued PV has landed in TMEM
-              tc_fence_after();
-              rescale_o(taddr_o, corr);
+              if (j > 0) {                             // (at j == 0 the accumulator still holds the PREVIOUS tile's rows)
+                mbar_wait(&pv_done[sb_prev], sph_prev);  // every issued PV has landed in TMEM
+                tc_fence_after();
+                rescale_o(taddr_o, corr);
+              }
               l *= corr;
 #pragma unroll
               for (int x = 0; x < PEEL; ++x) px[x] *= corr;

@@ -76,6 +76,8 @@ int finish_ln(const float* part, int splits, size_t plane, int ld_p, const float
               int H, cudaStream_t s);
 int token_step_partials(const void* part, int n_part, int rows, int cur_len, int max_len, int pad_id, const int* eos_ids, int n_eos,
                         int* ids, int* unfinished, float* sum_lp, int* n_steps, cudaStream_t s);
+int graph_if_any_begin(const int* flags, int n, int invert, cudaStream_t cap, cudaStream_t body);
+int graph_if_end(cudaStream_t body);
 }  // namespace vc
 
 static std::atomic<long long> g_launches{0};
@@ -85,12 +87,29 @@ static std::atomic<long long> g_launches{0};
 extern "C" {
 
 const char* vc_last_error(void) { return vc::last_error(); }
-int vc_abi_version(void) { return 7; }
+int vc_abi_version(void) { return 8; }
 int vc_check_device(void) { return vc::check_device(); }
 long long vc_launch_count(void) { return g_launches.load(); }
 void vc_reset_launch_count(void) { g_launches = 0; }
 void vc_set_pdl(int mode) { vc::set_pdl_mode(mode); }
 int vc_get_pdl(void) { return vc::pdl_mode(); }
+
+int vc_graph_if_any_begin(const int* flags, int n, int invert, void* capture_stream, void* body_stream) {
+  VC_COUNT(1, vc::graph_if_any_begin(flags, n, invert, ST(capture_stream), ST(body_stream)));
+}
+int vc_graph_if_end(void* body_stream) { return vc::graph_if_end(ST(body_stream)); }
+int vc_stream_create(void** stream_out) {
+  cudaStream_t s = nullptr;
+  if (stream_out == nullptr) { vc::set_last_error("vc_stream_create: NULL"); return VC_ERR_BAD_ARG; }
+  const cudaError_t e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { vc::set_last_error("vc_stream_create: %s", cudaGetErrorString(e)); cudaGetLastError(); return VC_ERR_DRIVER; }
+  *stream_out = s;
+  return VC_OK;
+}
+int vc_stream_destroy(void* stream) {
+  if (stream != nullptr && cudaStreamDestroy(ST(stream)) != cudaSuccess) { cudaGetLastError(); return VC_ERR_DRIVER; }
+  return VC_OK;
+}
 
 int vc_linear(int bf16, const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldo, int out_f32, int act,
               const float* resid, int ldr, int M, int N, int K, void* stream) {

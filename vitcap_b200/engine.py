@@ -167,6 +167,10 @@ class CaptionEngine:
         self.dec_splits = tuple(int(v) for v in os.environ.get("VITCAP_DEC_SPLITS", "3,6,6").split(","))
         # decoder prefill with every LayerNorm folded into the GEMMs around it (post-LN variant of the ViT fold; prefill())
         self.prefill_fold = self.mode == "bf16" and os.environ.get("VITCAP_PREFILL_FOLD", "1") != "0"
+        # early exit of the captured decode loops (modeling_utils.py:865-867, 1071-1073): every step after the first is the body
+        # of a conditional graph node keyed on "any caption unfinished", evaluated on the device (ops.graph_if_any)
+        self.early_exit = os.environ.get("VITCAP_EARLY_EXIT", "1") != "0"
+        self._body_stream = None
         self.forward_graphs = {}               # whole-forward CUDA graphs of the small-batch latency path (model.py); they hold
         self.inline_graphs = False             # raw workspace pointers. inline_graphs: an outer capture is running
         # parity instrumentation (tests / tools only): tap(name, index, tensor) is called with the stream after every ViT block
@@ -705,6 +709,12 @@ class CaptionEngine:
             ws[key] = torch.tensor(list(key[1]), device=ws["out_ids"].device, dtype=torch.int32)
         return ws[key]
 
+    def _if_stream(self):
+        """The stream the bodies of the conditional decode steps are captured on (ops.body_stream: one per device)."""
+        if self._body_stream is None:
+            self._body_stream = ops.body_stream(self.dev)
+        return self._body_stream
+
     def _maybe_graph(self, ws, key, fn):
         """Runs fn() eagerly once (warm-up: lazy kernel attribute setup, descriptor cache), then captures and replays it."""
         if not self.use_cuda_graph or self.inline_graphs or self.tap is not None:
@@ -737,31 +747,39 @@ class CaptionEngine:
         eos = self._eos_tensor(ws, eos_ids)
         filt = do_sample and (top_k > 0 or top_p < 1.0)
 
+        def step(cur_len):
+            if labels and cur_len == label_flip and cur_len > 1:
+                self._flip_labels(ws, B, E, cur_len, mask_id)
+            # greedy decoding on the fused path never materialises the logits (a parity tap asks for both)
+            want = "logits" if do_sample else ("both" if self.tap is not None else "argmax")
+            partials = self._decode_layers(ws, B, E, cur_len, None, mask_id, labels=labels, vocab=want,
+                                           live=(ws["unfinished"], None))
+            if want != "argmax" or not partials:
+                self._t("logits", cur_len, ws["logits"][:, :cfg.vocab])
+            if partials:
+                ops.token_step_partials(ws["vpart"], R, cur_len, pad, eos, ws["ids"], ws["unfinished"], ws["sum_lp"],
+                                        ws["n_steps"])
+                return
+            t = temperature
+            if filt:
+                ops.filter_logits(ws["logits"], cfg.vocab, R, 1.0 / temperature, top_k, top_p)
+                t = 1.0
+            ops.token_step(ws["logits"], cfg.vocab, R, do_sample, t, 0, cur_len, pad, eos, ws["ids"], ws["unfinished"],
+                           ws["sum_lp"], ws["n_steps"], seed_dev=ws["seed"] if do_sample else None)
+
         def run():
-            ws["ids"].zero_()
+            # positions a finished batch never reaches stay PAD (the reference pads after its break, modeling_utils.py:879-883)
+            ws["ids"].fill_(pad)
             ws["ids"][:, 0] = bos
             ws["unfinished"].fill_(1)
             ws["sum_lp"].zero_()
             ws["n_steps"].zero_()
             for cur_len in range(1, max_len):
-                if labels and cur_len == label_flip and cur_len > 1:
-                    self._flip_labels(ws, B, E, cur_len, mask_id)
-                # greedy decoding on the fused path never materialises the logits (a parity tap asks for both)
-                want = "logits" if do_sample else ("both" if self.tap is not None else "argmax")
-                partials = self._decode_layers(ws, B, E, cur_len, None, mask_id, labels=labels, vocab=want,
-                                               live=(ws["unfinished"], None))
-                if want != "argmax" or not partials:
-                    self._t("logits", cur_len, ws["logits"][:, :cfg.vocab])
-                if partials:
-                    ops.token_step_partials(ws["vpart"], R, cur_len, pad, eos, ws["ids"], ws["unfinished"], ws["sum_lp"],
-                                            ws["n_steps"])
-                    continue
-                t = temperature
-                if filt:
-                    ops.filter_logits(ws["logits"], cfg.vocab, R, 1.0 / temperature, top_k, top_p)
-                    t = 1.0
-                ops.token_step(ws["logits"], cfg.vocab, R, do_sample, t, 0, cur_len, pad, eos, ws["ids"], ws["unfinished"],
-                               ws["sum_lp"], ws["n_steps"], seed_dev=ws["seed"] if do_sample else None)
+                # `if cur_unfinished.max() == 0: break` (modeling_utils.py:865-867) on the device: in a captured loop every step
+                # after the first is the body of a conditional node (the label-recipe flip re-runs the prefill with torch
+                # copies in it: those loops keep the plain sequence)
+                with ops.graph_if_any(ws["unfinished"], self._if_stream(), enabled=self.early_exit and cur_len > 1 and not labels):
+                    step(cur_len)
             ops.greedy_finalize(ws["ids"], ws["unfinished"], ws["sum_lp"], ws["n_steps"], int(eos_ids[0]), R, ws["out_ids"],
                                 ws["out_lp"])
 
@@ -810,12 +828,14 @@ class CaptionEngine:
             st["hyp_count"].zero_()
             st["worst"].fill_(1e9)
             for cur_len in range(1, max_len):
-                if labels and cur_len == label_flip and cur_len > 1:
-                    self._flip_labels(ws, B, nb, cur_len, mask_id, anc_table=st["anc"])
-                self._decode_layers(ws, B, nb, cur_len, st["anc"], mask_id, labels=labels, live=(None, st["done"]))
-                ops.beam_row_topk(ws["logits"], cfg.vocab, R, K, st["cand_val"], st["cand_idx"], st["row_max"], st["row_logsum"])
-                ops.beam_advance(st, st["cand_val"], st["cand_idx"], st["row_max"], st["row_logsum"], B, nb, cfg.vocab, cur_len,
-                                 keep, length_penalty, pad, eos)
+                # `if all(done): break` (modeling_utils.py:1071-1073) on the device, as in greedy_or_sample
+                with ops.graph_if_any(st["done"], self._if_stream(), invert=True, enabled=self.early_exit and cur_len > 1 and not labels):
+                    if labels and cur_len == label_flip and cur_len > 1:
+                        self._flip_labels(ws, B, nb, cur_len, mask_id, anc_table=st["anc"])
+                    self._decode_layers(ws, B, nb, cur_len, st["anc"], mask_id, labels=labels, live=(None, st["done"]))
+                    ops.beam_row_topk(ws["logits"], cfg.vocab, R, K, st["cand_val"], st["cand_idx"], st["row_max"], st["row_logsum"])
+                    ops.beam_advance(st, st["cand_val"], st["cand_idx"], st["row_max"], st["row_logsum"], B, nb, cfg.vocab, cur_len,
+                                     keep, length_penalty, pad, eos)
             ops.beam_finalize(st, B, keep, pad, int(eos_ids[0]), st["out_ids"], st["out_lp"])
 
         self._maybe_graph(ws, ("beam", B, nb, max_len, keep, float(length_penalty), bos, pad, tuple(eos_ids), mask_id, label_flip), run)

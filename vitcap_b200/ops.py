@@ -52,6 +52,10 @@ SIGNATURES = {
     "vc_decode_attention_simt": [_I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
     "vc_token_step": [_P, _I, _I, _I, _I, _F, _U64, _P, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P],
     "vc_greedy_finalize": [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P],
+    "vc_graph_if_any_begin": [_P, _I, _I, _P, _P],
+    "vc_graph_if_end": [_P],
+    "vc_stream_create": [_P],
+    "vc_stream_destroy": [_P],
     "vc_beam_row_topk": [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P],
     "vc_beam_advance": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _D, _I, _P, _I, _P],
     "vc_beam_finalize": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P],
@@ -122,6 +126,51 @@ def launch_count():
 
 def reset_launch_count():
     load_library().vc_reset_launch_count()
+
+
+_BODY_STREAMS = {}
+
+
+def body_stream(device):
+    """The stream conditional-node bodies are captured on: one per device, created through the library (not a pooled torch
+    stream, which may alias the capturing stream or carry a loader's copies) and kept for the life of the process."""
+    idx = torch.device(device).index
+    idx = torch.cuda.current_device() if idx is None else idx
+    if idx not in _BODY_STREAMS:
+        with torch.cuda.device(idx):
+            h = ctypes.c_void_p()
+            _check(load_library().vc_stream_create(ctypes.byref(h)), "vc_stream_create")
+        _BODY_STREAMS[idx] = torch.cuda.ExternalStream(h.value, device=torch.device("cuda", idx))
+    return _BODY_STREAMS[idx]
+
+
+class graph_if_any:
+    """Context manager: while the current stream is being captured into a CUDA graph, the kernels launched inside the block become
+    the body of a conditional IF node that a replay executes only when any(flags != 0) (invert: any(flags == 0)) holds on the
+    device at that point (vc_graph_if_any_begin / vc_graph_if_end); the block runs on `body_stream`. Outside a capture (eager
+    runs) the block simply executes."""
+
+    def __init__(self, flags, body_stream, invert=False, enabled=True):
+        self.flags, self.body, self.invert = flags, body_stream, invert
+        self.active = bool(enabled) and body_stream is not None and torch.cuda.is_current_stream_capturing()
+        self._ctx = None
+
+    def __enter__(self):
+        if self.active:
+            assert self.flags.dtype == torch.int32 and self.flags.is_contiguous()
+            _check(load_library().vc_graph_if_any_begin(_ptr(self.flags), self.flags.numel(), int(self.invert), _stream(),
+                                                        self.body.cuda_stream), "vc_graph_if_any_begin")
+            self._ctx = torch.cuda.stream(self.body)
+            self._ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.active:
+            self._ctx.__exit__(*exc)
+            rc = load_library().vc_graph_if_end(self.body.cuda_stream)
+            if exc[0] is None:
+                _check(rc, "vc_graph_if_end")
+        return False
 
 
 def set_pdl(mode):
