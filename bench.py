@@ -590,6 +590,46 @@ def main():
         del m12
         torch.cuda.empty_cache()
 
+    if not args.no_extras and world == 1 and args.mode == "bf16":
+        # the same step on EOS-planted weights (cls.predictions.bias[SEP] += 1.825: captions end after 11 tokens on average, as
+        # with a trained checkpoint; with the bench's plain random weights no caption ever ends). Finished captions are skipped
+        # by the decode-step attention, and the captured loop leaves through its conditional nodes once all have ended
+        # (modeling_utils.py:865-867)
+        eos_bias = 1.825
+        model.load_state_dict(synth.make_state_dict(cfg, seed=0, eos_bias=eos_bias))
+        for _ in range(3):
+            ids_e, _lp = model(data_dev)
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(5):
+            ids_e, _lp = model(data_dev)
+        a1.record()
+        torch.cuda.synchronize()
+        ms_e = a0.elapsed_time(a1) / 5
+        eos_id = int(extra["eos_token_ids"][0])
+        hit = ids_e[:, 0] == eos_id
+        length = torch.where(hit.any(1), hit.float().argmax(1) + 1, torch.full_like(ids_e[:, 0, 0], ids_e.shape[-1])).float()
+        eng = model.engine
+        max_len = int(extra["max_length"])
+        loop = lambda: eng.greedy_or_sample(B, 1, max_len, int(extra["bos_token_id"]), int(extra["pad_token_id"]),   # noqa: E731
+                                            [int(e) for e in extra["eos_token_ids"]], int(extra["mask_token_id"]))
+        loop()
+        torch.cuda.synchronize()
+        a0.record()
+        for _ in range(5):
+            loop()
+        a1.record()
+        torch.cuda.synchronize()
+        extras["eos_planted"] = {"value": B / ms_e * 1e3, "unit": UNIT, "ms_per_step": ms_e, "steps": 5, "warmup": 3,
+                                 "eos_bias": eos_bias, "mean_caption_tokens": float(length.mean()),
+                                 "captions_reaching_max_length": int((length >= max_len).sum()),
+                                 "decode_loop_ms": a0.elapsed_time(a1) / 5,
+                                 "decode_loop_ms_no_eos": (roofline_decode or {}).get("loop", {}).get("ms"),
+                                 "note": "device-resident inputs; BOS and the closing EOS count as caption tokens"}
+        model.load_state_dict(sd)
+        del ids_e
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
