@@ -191,8 +191,11 @@ def test_bf16_mode_features_and_tags_16_224():
     e_lg = rel_err(lg, logit_r)
     overlap = np.mean([len(set(a) & set(b)) / 50.0 for a, b in zip(idx.cpu().tolist(), idx_r.tolist())])
     print("bf16 rel err: cap %.3g tag %.3g tag_logits %.3g top50 overlap %.3f" % (e_cap, e_tag, e_lg, overlap))
-    assert e_cap < 1e-2 and e_tag < 1e-2 and e_lg < 2e-2
-    assert overlap >= 0.9
+    # against the fp32 arithmetic (operand quantisation included): the measured values (5.0e-3 / 5.0e-3 / 8.3e-3, overlap 0.99)
+    # + 30 %; the 1e-3 bound of the north star is held kernel by kernel against the quantisation-matched oracle
+    # (tests/test_fullsize_gpu.py::test_bf16_mode_every_kernel_vs_quantisation_matched_oracle)
+    assert e_cap < 6.5e-3 and e_tag < 6.5e-3 and e_lg < 1.1e-2
+    assert overlap >= 0.95
 
 
 def test_overlapped_host_loop_matches_direct_forward():
