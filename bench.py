@@ -117,9 +117,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Samples that arrived inside [t0, t1] (the timed region); the sampler is started before the warm-up steps because
+        nvidia-smi needs a few hundred ms to deliver its first line. A timed region shorter than the sampling period (strong
+        scaling at 8 GPUs: 0.2 s) falls back to the samples of the warm-up steps right before it and says so."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -127,9 +130,13 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
+        rows = [r for t, r in self.rows if (t0 is None or t >= t0) and (t1 is None or t <= t1 + 0.2)]
+        window = "timed region"
+        if not rows:
+            rows, window = [r for t, r in self.rows], "warm-up steps + timed region (timed region shorter than the sampling period)"
         sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
                 continue
@@ -142,7 +149,7 @@ class ClockSampler:
                     reasons.add(n)
         load = [s for s, p in zip(sm, pw) if p > 300] or sm
         return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 # ------------------------------------------------------------------------------------------------ CPU baseline
@@ -420,24 +427,26 @@ def main():
     # ---- GEMM profiler: CUDA events around every eager tensor-core GEMM launch of the timed steps
     prof = []
     ops.GEMM_PROFILE = None
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         step_device()
     sync_all()
     ops.reset_launch_count()
     replays0 = model.engine.stats.get("graph_replays", 0)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     ops.GEMM_PROFILE = prof
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
+    t_region0 = time.time()
     ev0.record()
     for _ in range(args.steps):
         out = step_device()
     join_gather()                                         # the timed region ends when the last batch's records are gathered
     ev1.record()
     sync_all()
+    t_region1 = time.time()
     ops.GEMM_PROFILE = None
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_region0, t_region1)
     ms = ev0.elapsed_time(ev1)
     t = torch.tensor([ms], device=dev)
     if world > 1:
