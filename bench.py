@@ -473,11 +473,11 @@ def main():
     # DRAM traffic of the largest GEMM launch (MLP fc1 + GELU, M = 512 x 577) from the committed ncu --set full capture
     traffic, traffic_note = None, "no ncu capture committed"
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
-        k = next(k for k in tj if "gemm_tc2_kernel<1, 0, 0, 2" in k)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")))
+        k = next(k for k in tj if "gemm_tc2_kernel<1, 0, 0, 2, 2" in k)
         traffic = tj[k]["dram_bytes"]
-        traffic_note = "dram__bytes_read+write of one fc1+GELU launch (M=295424, N=3072, K=768; algorithmic 2.27 GB), " \
-                       "profiles/r01_ncu_summary.md"
+        traffic_note = "dram__bytes_read+write of one fc1+GELU launch with the folded LayerNorm (M=295424, N=3072, K=768; " \
+                       "algorithmic 2.27 GB), profiles/r02_ncu_summary.md"
     except Exception:
         pass
     roofline = {

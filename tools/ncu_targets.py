@@ -1,5 +1,5 @@
 """Launches single hot kernels at the bench shapes (B=512) for `ncu --set full -k regex:...` captures.
-usage: python tools/ncu_targets.py [attn|gemm_qkv|gemm_proj|gemm_fc1|gemm_fc2|x3_fc1|x3_fc2|x3_vocab|dattn|ln] [reps]"""
+usage: python tools/ncu_targets.py [attn|gemm_qkv|gemm_qkv_fold|gemm_fc1_fold|gemm_proj|gemm_fc1|gemm_fc2|x3_fc1|x3_fc2|x3_vocab|dattn|ln] [reps]"""
 import os
 import sys
 
@@ -44,6 +44,20 @@ elif what in ("gemm_qkv_fold", "gemm_fc2_emit"):
     for _ in range(reps):
         ops.linear_ln_emit(hid, w2, b2, x, x, xb, stats)
         ops.linear_ln_fold(xb, wq, bq, cq, stats, 3, 1e-6, qkv)
+elif what in ("gemm_fc1_fold", "gemm_proj_emit"):
+    # the bench's dominant pair inside a ViT block: proj + residual emitting (bf16 row, statistics) -> fc1 + GELU folding norm2
+    att = torch.randn(M, 768, device=dev).to(torch.bfloat16)
+    wp = (torch.randn(768, 768, device=dev) * 0.02).to(torch.bfloat16)
+    bp = torch.randn(768, device=dev)
+    x = torch.randn(M, 768, device=dev)
+    xb = torch.empty(M, 768, device=dev, dtype=torch.bfloat16)
+    stats = torch.empty(M, 3, 2, device=dev)
+    w1 = (torch.randn(3072, 768, device=dev) * 0.02).to(torch.bfloat16)
+    b1, c1 = torch.randn(3072, device=dev), torch.randn(3072, device=dev)
+    hid = torch.empty(M, 3072, device=dev, dtype=torch.bfloat16)
+    for _ in range(reps):
+        ops.linear_ln_emit(att, wp, bp, x, x, xb, stats)
+        ops.linear_ln_fold(xb, w1, b1, c1, stats, 3, 1e-6, hid, act=ops.ACT_GELU)
 elif what == "gemm_proj":
     gemm(768, 768, 0, True, True)
 elif what == "gemm_fc1":
