@@ -258,6 +258,11 @@ class FastImageCaptioning(nn.Module):
         self._sample_calls = 0
         self._label_flip_hold = None        # None: decide per generate() call; False: forward() in progress, not decided yet
         self._tag_parts = None              # list while forward() runs: per-chunk concept top-k collected by _generate
+        # greedy / sampling: the tokens the search actually chose at every step, int64 (B*K, L), BEFORE the forced EOS of rows
+        # that ran to max_length (modeling_utils.py:869-871 overwrites the last position of the returned ids, while the
+        # returned log-prob belongs to the token that was chosen there): what a teacher-forced re-scoring needs (scst.py)
+        self.last_raw_ids = None
+        self._raw_parts = None
         self.register_load_state_dict_post_hook(lambda m, keys: m._invalidate())
         self.eval()
 
@@ -384,6 +389,8 @@ class FastImageCaptioning(nn.Module):
                 ids, lp = eng.greedy_or_sample(b, nret, max_length, bos, pad, eos_ids, mask_id, do_sample, temperature, top_k,
                                                top_p, seed=(seed + s) if do_sample else 0,
                                                label_flip=flip if n_label is not None else None)
+                if self._raw_parts is not None:
+                    self._raw_parts.append(eng._decoder_ws(b, nret, max_length)["ids"].to(torch.int64))
             outs_i.append(ids)
             outs_l.append(lp)
         return torch.cat(outs_i, 0), torch.cat(outs_l, 0)
@@ -444,6 +451,7 @@ class FastImageCaptioning(nn.Module):
             return out
         ent["image"].copy_(image, non_blocking=True)
         ent["graph"].replay()
+        self.last_raw_ids = None
         eng.stats["forward_graph_replays"] = eng.stats.get("forward_graph_replays", 0) + 1
         self.last_tags = (ent["tags"][0].clone(), ent["tags"][1].clone()) if ent["tags"] is not None else None
         return ent["out"][0].clone(), ent["out"][1].clone()
@@ -453,6 +461,7 @@ class FastImageCaptioning(nn.Module):
         ids_all, lp_all = [], []
         self._label_flip_hold = False              # the label recipe follows the first sample of the WHOLE batch (see _generate)
         self._tag_parts = []
+        self._raw_parts = [] if not self.engine.inline_graphs else None
         try:
             for s in range(0, B, self.max_batch):      # the image stream buffer holds max_batch images
                 sub = {k: (v[s:s + self.max_batch] if torch.is_tensor(v) and v.shape[:1] == (B,) else v) for k, v in data.items()}
@@ -465,6 +474,8 @@ class FastImageCaptioning(nn.Module):
         finally:
             self._label_flip_hold = None
             parts, self._tag_parts = self._tag_parts, None
+            raw, self._raw_parts = self._raw_parts, None
+        self.last_raw_ids = torch.cat(raw, 0) if raw else None
         self.last_tags = (torch.cat([p[0] for p in parts], 0), torch.cat([p[1] for p in parts], 0)) if parts else None
         return torch.cat(ids_all, 0), torch.cat(lp_all, 0)
 
