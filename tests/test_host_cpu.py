@@ -73,6 +73,7 @@ def test_arch_guard_without_a_gpu():
 def test_library_has_no_torch_or_libcuda_link_dependency():
     import subprocess
     out = subprocess.run(["ldd", ops.LIB_PATH], capture_output=True, text=True).stdout
+    out = re.sub(r"\(0x[0-9a-f]+\)", "", out)            # load addresses are random hex: they may spell "c10"
     assert "torch" not in out and "libcuda.so" not in out and "c10" not in out
 
 
