@@ -160,6 +160,23 @@ def fold_probe(B):
         print("%-16s burst %.3f ms   steady %.3f ms" % (name, ms_burst, ms), flush=True)
 
 
+def fold_consumers_probe(B):
+    """The two LayerNorm-folding consumer GEMMs of a ViT block at the bench shape: q|k|v (N = 2304) and fc1 + GELU (N = 3072)."""
+    M, H = B * 577, 768
+    xb = torch.randn(M, H, device=dev).to(torch.bfloat16)
+    stats = torch.stack([xb.float().view(M, 3, 256).sum(2), (xb.float().view(M, 3, 256) ** 2).sum(2)], dim=2).contiguous()
+    for name, N, act in (("qkv fold", 2304, ops.ACT_NONE), ("fc1+GELU fold", 3072, ops.ACT_GELU)):
+        w = (torch.randn(N, H, device=dev) * 0.02).to(torch.bfloat16)
+        bq, cq = torch.randn(N, device=dev), torch.randn(N, device=dev)
+        out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        fn = lambda: ops.linear_ln_fold(xb, w, bq, cq, stats, 3, 1e-6, out, act=act)   # noqa: E731
+        for rnd in range(2):
+            ms_burst = timeit(fn, iters=5, warm=2)
+            ms = timeit(fn, iters=300, warm=20)
+            print("%-14s round %d: burst %.3f ms   steady %.3f ms  (%.0f TFLOP/s steady)" % (name, rnd, ms_burst, ms, 2.0 * M * N * H / ms / 1e9),
+                  flush=True)
+
+
 def fold_ab_probe(B, variant="16_384"):
     """A/B of the folded norm1 (engine.ln_fold) in one process, alternating, steady state (20 forwards per sample)."""
     cfg = vcfg.variant(variant)
@@ -286,6 +303,8 @@ if __name__ == "__main__":
         pdl_probe(B)
     if what == "fold":
         fold_probe(B)
+    if what == "foldc":
+        fold_consumers_probe(B)
     if what == "foldab":
         fold_ab_probe(B)
     if what == "prefillab":

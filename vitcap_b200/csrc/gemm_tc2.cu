@@ -225,13 +225,22 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     if (RESID && leader) {
       for (int i = 0; i < C::NBUF_G - 2; ++i) prefetch_resid();
     }
+    // LN = 2: the partial (sum, sum of squares) of the NEXT tile's row are requested one tile ahead and only SUMMED when that
+    // tile starts: the loads stay in flight behind the current tile's epilogue (round-2 profile: summing them at once put
+    // 5 % of the epilogue warps' samples on the first add). Up to four partials in registers (K <= 1024), the rest summed at once.
+    float2 nx_p[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
     float nx_s = 0.f, nx_q = 0.f;
-    auto load_row_stats = [&](int row, float& s, float& q) {
-      s = 0.f;
-      q = 0.f;
+    auto load_row_stats = [&](int row) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) nx_p[i] = make_float2(0.f, 0.f);
+      nx_s = 0.f;
+      nx_q = 0.f;
       if (row < M) {
         const float2* sp = reinterpret_cast<const float2*>(ln.stats) + (size_t)row * ln.st_tiles;
-        for (int i = 0; i < ln.st_tiles; ++i) { const float2 pq = __ldg(sp + i); s += pq.x; q += pq.y; }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (i < ln.st_tiles) nx_p[i] = __ldg(sp + i);
+        for (int i = 4; i < ln.st_tiles; ++i) { const float2 pq = __ldg(sp + i); nx_s += pq.x; nx_q += pq.y; }
       }
     };
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
@@ -241,13 +250,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       // requested here and consumed one tile later, so their latency never sits in front of the accumulator read
       float ln_rstd = 0.f, ln_nm = 0.f;
       if (LN == LN_FOLD) {
-        if (tile == cluster_id) load_row_stats(m0 + t, nx_s, nx_q);
-        const float mean = nx_s * ln.inv_k;
-        const float var = fmaxf(fmaf(nx_q, ln.inv_k, -mean * mean), 0.f);
+        if (tile == cluster_id) load_row_stats(m0 + t);
+        // (the same left-to-right order as a running sum over the partials)
+        const float row_s = (((nx_p[0].x + nx_p[1].x) + nx_p[2].x) + nx_p[3].x) + nx_s;
+        const float row_q = (((nx_p[0].y + nx_p[1].y) + nx_p[2].y) + nx_p[3].y) + nx_q;
+        const float mean = row_s * ln.inv_k;
+        const float var = fmaxf(fmaf(row_q, ln.inv_k, -mean * mean), 0.f);
         ln_rstd = (m0 + t < M) ? rsqrtf(var + ln.ln_eps) : 0.f;
         ln_nm = -mean * ln_rstd;
         const int nt = tile + num_clusters;
-        if (nt < num_tiles) load_row_stats((nt / n_tiles) * (2 * C::BM) + (int)rank * C::BM + t, nx_s, nx_q);
+        if (nt < num_tiles) load_row_stats((nt / n_tiles) * (2 * C::BM) + (int)rank * C::BM + t);
       }
       float st_s = 0.f, st_q = 0.f;                      // LN = 1: this row's partial statistics over the tile's columns
       float r_rstd = 0.f, r_nm = 0.f;                    // RLN: the residual row's 1 / std and -mean / std
@@ -278,26 +290,35 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         // (2) accumulator row -> registers -> bias / activation / residual -> swizzled staging row
 #pragma unroll
         for (int hh = 0; hh < C::CW / 32; ++hh) {
+          const int cb = col0 + hh * 32;
+          // LN = 2: the chunk's bias' and column sums are requested BEFORE the accumulator read (the TMEM load's "memory"
+          // clobber would otherwise pin them behind its wait: 6 % of the epilogue warps' samples sat on the first use)
+          float4 fb[LN == LN_FOLD ? 8 : 1], fc[LN == LN_FOLD ? 8 : 1];
+          if (LN == LN_FOLD) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              fb[j] = fc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (full || cb + 4 * j < N) {             // N % 4 == 0 is checked by the launcher
+                fb[j] = __ldg(reinterpret_cast<const float4*>(bias + cb + 4 * j));
+                fc[j] = __ldg(reinterpret_cast<const float4*>(ln.colsum + cb + 4 * j));
+              }
+            }
+          }
           uint32_t r[32];
           tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + as * C::BN + c * C::CW + hh * 32, r);
           tmem_ld_wait();
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          const int cb = col0 + hh * 32;
           if (LN == LN_FOLD) {
-            // v = rstd * acc + (nm * colsum + bias'),  nm = -mean * rstd   (N % 4 == 0 is checked by the launcher)
+            // v = rstd * acc + (nm * colsum + bias'),  nm = -mean * rstd   (columns past N: clipped by the TMA store)
             const uint64_t r2 = pack_f32x2(ln_rstd, ln_rstd), n2 = pack_f32x2(ln_nm, ln_nm);
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (full || cb + j < N) {
-                const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + cb + j));
-                const float4 cc = __ldg(reinterpret_cast<const float4*>(ln.colsum + cb + j));
-                unpack_f32x2(fma_f32x2(r2, pack_f32x2(v[j], v[j + 1]), fma_f32x2(n2, pack_f32x2(cc.x, cc.y), pack_f32x2(bb.x, bb.y))),
-                             v[j], v[j + 1]);
-                unpack_f32x2(fma_f32x2(r2, pack_f32x2(v[j + 2], v[j + 3]), fma_f32x2(n2, pack_f32x2(cc.z, cc.w), pack_f32x2(bb.z, bb.w))),
-                             v[j + 2], v[j + 3]);
-              }
+            for (int j = 0; j < 8; ++j) {
+              unpack_f32x2(fma_f32x2(r2, pack_f32x2(v[4 * j], v[4 * j + 1]), fma_f32x2(n2, pack_f32x2(fc[j].x, fc[j].y), pack_f32x2(fb[j].x, fb[j].y))),
+                           v[4 * j], v[4 * j + 1]);
+              unpack_f32x2(fma_f32x2(r2, pack_f32x2(v[4 * j + 2], v[4 * j + 3]), fma_f32x2(n2, pack_f32x2(fc[j].z, fc[j].w), pack_f32x2(fb[j].z, fb[j].w))),
+                           v[4 * j + 2], v[4 * j + 3]);
             }
           } else if (bias != nullptr) {
             if (full) {

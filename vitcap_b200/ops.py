@@ -10,7 +10,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libvitcap_b200.so")
+# VITCAP_LIB: another build of the same ABI (A/B measurements of a kernel change in tools/)
+LIB_PATH = os.environ.get("VITCAP_LIB") or os.path.join(_HERE, "lib", "libvitcap_b200.so")
 
 ACT_NONE, ACT_GELU, ACT_TANH = 0, 1, 2
 
