@@ -160,6 +160,24 @@ def fold_probe(B):
         print("%-16s burst %.3f ms   steady %.3f ms" % (name, ms_burst, ms), flush=True)
 
 
+def prefill_probe(B, variant="16_384"):
+    """The decoder prefill alone (steady state), for old / new library comparisons (VITCAP_LIB)."""
+    cfg = vcfg.variant(variant)
+    m = FastImageCaptioning(cfg, mode="bf16", max_batch=B)
+    m.load_state_dict(synth.make_state_dict(cfg, seed=0))
+    m = m.to(dev)
+    data = {k: v.to(dev) for k, v in synth.make_text_inputs(cfg, B).items()}
+    data["image"] = synth.make_images(cfg, B, seed=1).to(dev)
+    m(data)
+    f = m.engine.patch_embed(data["image"])
+    for rnd in range(3):
+        t_enc = timeit(lambda: m.engine.encode(f), iters=20, warm=3)
+        t_pre = timeit(lambda: m.engine.prefill(B), iters=40, warm=5)
+        t_all = timeit(lambda: m(data), iters=20, warm=3)
+        print("round %d: encode %.3f ms  prefill %.3f ms  full forward %.2f ms (%.1f images/s)" % (rnd, t_enc, t_pre, t_all, B / t_all * 1e3),
+              flush=True)
+
+
 def fold_consumers_probe(B):
     """The two LayerNorm-folding consumer GEMMs of a ViT block at the bench shape: q|k|v (N = 2304) and fc1 + GELU (N = 3072)."""
     M, H = B * 577, 768
@@ -303,6 +321,8 @@ if __name__ == "__main__":
         pdl_probe(B)
     if what == "fold":
         fold_probe(B)
+    if what == "prefill":
+        prefill_probe(B)
     if what == "foldc":
         fold_consumers_probe(B)
     if what == "foldab":

@@ -304,6 +304,18 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
               }
             }
           }
+          // RLN: likewise the previous LayerNorm's gamma / beta of the chunk (re-applied to the raw residual tile below)
+          float4 rg[RLN ? 8 : 1], rb[RLN ? 8 : 1];
+          if (RLN) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              rg[j] = rb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (full || cb + 4 * j < N) {
+                rg[j] = __ldg(reinterpret_cast<const float4*>(ln.rgamma + cb + 4 * j));
+                rb[j] = __ldg(reinterpret_cast<const float4*>(ln.rbeta + cb + 4 * j));
+              }
+            }
+          }
           uint32_t r[32];
           tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + as * C::BN + c * C::CW + hh * 32, r);
           tmem_ld_wait();
@@ -347,11 +359,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
               for (int j = 0; j < 8; ++j) {
                 const float4 rr = *reinterpret_cast<const float4*>(myrow + ((j ^ sw) << 4));
                 if (RLN) {
-                  float4 gg = make_float4(0.f, 0.f, 0.f, 0.f), bb = gg;
-                  if (full || cb + 4 * j < N) {
-                    gg = __ldg(reinterpret_cast<const float4*>(ln.rgamma + cb + 4 * j));
-                    bb = __ldg(reinterpret_cast<const float4*>(ln.rbeta + cb + 4 * j));
-                  }
+                  const float4 gg = rg[j], bb = rb[j];
                   v[4 * j] += fmaf(fmaf(rr.x, r_rstd, r_nm), gg.x, bb.x);
                   v[4 * j + 1] += fmaf(fmaf(rr.y, r_rstd, r_nm), gg.y, bb.y);
                   v[4 * j + 2] += fmaf(fmaf(rr.z, r_rstd, r_nm), gg.z, bb.z);
