@@ -213,7 +213,7 @@ def decode_roofline(torch, ops, cfg, B, dev, peaks, model=None, extra=None):
     ach = byt / (ms * 1e-3) / 1e9
     traffic = None
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")))
         traffic = next(v["dram_bytes"] for k, v in tj.items() if "decode_attention_mma_kernel" in k)
     except Exception:
         pass
@@ -250,7 +250,7 @@ def decode_roofline(torch, ops, cfg, B, dev, peaks, model=None, extra=None):
             "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": src,
             "algorithmic_bytes_per_launch": byt, "us_per_launch": ms * 1e3, "traffic": traffic,
             "traffic_note": "dram__bytes_read+write of one launch at B=512 from the committed ncu --set full capture "
-                            "(profiles/r01_ncu_summary.md)",
+                            "(profiles/r02_ncu_summary.md)",
             "how": "eager launches after the timed region (the decode loop itself is one CUDA graph): one launch per decoder "
                    "layer over distinct %0.2f GB caches, CUDA events, %d iterations" % (byt / 1e9, iters)}
 
