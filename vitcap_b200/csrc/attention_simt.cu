@@ -121,11 +121,28 @@ int attention_simt(int is_bf16, const void* qkv, void* out, int B, int N, int he
 // ------------------------------------------------------------------------------------------
 namespace vc {
 
+// 8 consecutive elements as loaded (16 B of bf16 / 32 B of fp32): kept raw until use so that many loads fit in registers
+template <typename T> struct Raw8;
+template <> struct Raw8<bf16> {
+  uint4 v;
+  __device__ __forceinline__ void load(const bf16* p) { v = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void zero() { v = make_uint4(0u, 0u, 0u, 0u); }
+  __device__ __forceinline__ void get(float* f) const {
+    unpack_bf16x2(v.x, f[0], f[1]); unpack_bf16x2(v.y, f[2], f[3]); unpack_bf16x2(v.z, f[4], f[5]); unpack_bf16x2(v.w, f[6], f[7]);
+  }
+};
+template <> struct Raw8<float> {
+  float4 a, b;
+  __device__ __forceinline__ void load(const float* p) { a = *reinterpret_cast<const float4*>(p); b = *reinterpret_cast<const float4*>(p + 4); }
+  __device__ __forceinline__ void zero() { a = b = make_float4(0.f, 0.f, 0.f, 0.f); }
+  __device__ __forceinline__ void get(float* f) const { f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w; }
+};
+
 template <typename T>
 __global__ void __launch_bounds__(128)
 cls_attention_kernel(const T* __restrict__ q, int ldq, const T* __restrict__ qkv, T* __restrict__ out, int ldo, int N, int H,
                      float scale) {
-  constexpr int D = 64, U = 4;
+  constexpr int D = 64, U = 8;          // keys per lane group and iteration: 16 vector loads in flight per thread
   const int h = blockIdx.x, b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int grp = lane >> 3, part = lane & 7;
@@ -139,25 +156,27 @@ cls_attention_kernel(const T* __restrict__ q, int ldq, const T* __restrict__ qkv
   const T* vbase = kbase + H;
   for (int kb = warp * 4; kb < N; kb += 16 * U) {        // warp-uniform trip count (shuffles inside)
     const int k0 = kb + grp;
-    float kf[U][8], vf[U][8];
+    Raw8<T> kr[U], vr[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int k = k0 + 16 * u;
       if (k < N) {
-        load8<T>(kbase + (size_t)k * ld, kf[u]);
-        load8<T>(vbase + (size_t)k * ld, vf[u]);
+        kr[u].load(kbase + (size_t)k * ld);
+        vr[u].load(vbase + (size_t)k * ld);
       } else {
-#pragma unroll
-        for (int d = 0; d < 8; ++d) { kf[u][d] = 0.f; vf[u][d] = 0.f; }
+        kr[u].zero();
+        vr[u].zero();
       }
     }
     float s[U];
     float mx = m;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
+      float kf[8];
+      kr[u].get(kf);
       float a = 0.f;
 #pragma unroll
-      for (int d = 0; d < 8; ++d) a = fmaf(qf[d], kf[u][d], a);
+      for (int d = 0; d < 8; ++d) a = fmaf(qf[d], kf[d], a);
       a += __shfl_xor_sync(0xffffffffu, a, 1);
       a += __shfl_xor_sync(0xffffffffu, a, 2);
       a += __shfl_xor_sync(0xffffffffu, a, 4);
@@ -173,8 +192,10 @@ cls_attention_kernel(const T* __restrict__ q, int ldq, const T* __restrict__ qkv
     for (int u = 0; u < U; ++u) {
       const float p = (k0 + 16 * u < N) ? expf(s[u] - mx) : 0.f;
       l += p;
+      float vf[8];
+      vr[u].get(vf);
 #pragma unroll
-      for (int d = 0; d < 8; ++d) o[d] = fmaf(p, vf[u][d], o[d]);
+      for (int d = 0; d < 8; ++d) o[d] = fmaf(p, vf[d], o[d]);
     }
   }
   // merge the 4 lane groups of the warp, then the 4 warps
