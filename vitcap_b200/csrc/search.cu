@@ -25,6 +25,7 @@ struct TopkSmem {
   int idxs[64];
   uint32_t prefix, need, cnt_gt, cnt_eq;
   int last_idx, best_idx;
+  uint32_t wsum[32];
 };
 
 __device__ void block_topk(const float* __restrict__ row, int V, int K, TopkSmem& sm, float* out_val, int* out_idx) {
@@ -43,15 +44,39 @@ __device__ void block_topk(const float* __restrict__ row, int V, int K, TopkSmem
       if ((k & mask_bits) == prefix) atomicAdd(&sm.hist[(k >> sh) & ((1u << wd) - 1)], 1u);
     }
     __syncthreads();
-    if (tid == 0) {
-      uint32_t need = sm.need, acc = 0;
-      int bin = (1 << wd) - 1;
-      for (; bin > 0; --bin) {
-        if (acc + sm.hist[bin] >= need) break;
-        acc += sm.hist[bin];
+    {
+      // the bin in which the count from the top reaches `need`: every thread sums a run of bins (taken from the top), a block
+      // scan over those sums finds the run that crosses, and its owner walks it (a serial walk of 2048 bins by one thread
+      // was most of this kernel: 3 x ~60k cycles)
+      const int nb = 1 << wd;
+      const int run = (nb + nt - 1) / nt;                // bins per thread
+      const int hi = nb - 1 - tid * run;                 // this thread's bins: hi, hi-1, .., hi-run+1 (those >= 0)
+      uint32_t mine = 0;
+      for (int j = 0; j < run; ++j)
+        if (hi - j >= 0) mine += sm.hist[hi - j];
+      uint32_t incl = mine;                              // inclusive scan in thread order == from the top bin downwards
+      const int lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += n;
       }
-      sm.need = need - acc;            // how many are still needed from inside this bin
-      sm.prefix = prefix | ((uint32_t)bin << sh);
+      if (lane == 31) sm.wsum[wid] = incl;
+      __syncthreads();
+      uint32_t above = incl - mine;                      // count in the bins above this thread's run
+      for (int w2 = 0; w2 < wid; ++w2) above += sm.wsum[w2];
+      const uint32_t need = sm.need;
+      __syncthreads();                                   // every thread has read sm.need / sm.wsum before they are rewritten
+      if (above < need && above + mine >= need) {        // exactly one thread: the crossing lies in its run
+        uint32_t acc = above;
+        int bin = hi;
+        for (; bin > 0 && bin > hi - run + 1; --bin) {
+          if (acc + sm.hist[bin] >= need) break;
+          acc += sm.hist[bin];
+        }
+        sm.need = need - acc;          // how many are still needed from inside this bin
+        sm.prefix = prefix | ((uint32_t)bin << sh);
+      }
     }
     mask_bits |= ((1u << wd) - 1) << sh;
     __syncthreads();
