@@ -153,32 +153,62 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU baseline
-def cpu_baseline(cfg, sd, n_images, extra):
-    """The reference's algorithm as shipped (every decode step re-runs the ViT trunk, the tag head and the whole decoder;
-    oracle/port.py 'faithful', pinned against the reference's own outputs in tests/golden) on the host cores, as BASELINE.md
-    section 4 prescribes: all host threads, one untimed B = 1 warm-up, one timed run of B = n_images (configs[0]: 8)."""
+def cpu_captioner(cfg, sd, extra, variant):
+    """The CPU implementation both CPU legs time: the UNMODIFIED reference when it can be imported here -- from /root/reference
+    in the build container, from the bytecode tree oracle/build_ref.py staged under oracle/_ref on the GPU box -- through its
+    own public entry (ImageCaptioning.forward under no_grad, uni_pipeline.py:745-746); otherwise the restatement
+    oracle/port.py 'faithful' (pinned to the reference's outputs by tests/golden). Returns (fn(data) -> (ids, logprobs),
+    kind, what)."""
     import torch
+    from vitcap_b200 import config as vcfg
+    try:
+        from oracle import ref_loader
+        if ref_loader.reference_available() and vcfg.variant(variant, dec_layers=cfg.dec_layers) == cfg:
+            ref, _ = ref_loader.build_reference(variant, decoder_layer=cfg.dec_layers)
+            ref.load_state_dict(sd, strict=True)
+            ref.test_extra_input = extra
+
+            def run_ref(data):
+                d = dict(data)
+                d["key"] = ["k%d" % i for i in range(d["image"].shape[0])]
+                with torch.no_grad():
+                    return ref(d)
+            return run_ref, "reference", "the unmodified reference (ImageCaptioning.forward, imported from %s: %s)" \
+                % (ref_loader.REF_ROOT, ref_loader.REF_KIND)
+    except Exception as e:  # noqa: BLE001 -- a reference tree that does not import falls back to the pinned restatement
+        print("reference import failed (%s: %s): timing oracle/port.py instead" % (type(e).__name__, e), file=sys.stderr)
     from oracle import port
+    pm = port.PortModel(cfg, sd)
+
+    def run_port(data):
+        with torch.no_grad():
+            return port.caption(pm, data, extra, algorithm="faithful")
+    return run_port, "port", "oracle/port.py 'faithful' (restatement of the reference algorithm, pinned by tests/golden)"
+
+
+def cpu_baseline(cfg, sd, n_images, extra, variant):
+    """The reference as shipped (every decode step re-runs the ViT trunk, the tag head and the whole decoder) on the host
+    cores, as BASELINE.md section 4 prescribes: all host threads, one untimed B = 1 warm-up, one timed run of B = n_images
+    (configs[0]: 8)."""
+    import torch
     from vitcap_b200 import synth
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    pm = port.PortModel(cfg, sd)
+    fn, kind, what = cpu_captioner(cfg, sd, extra, variant)
     warm = synth.make_text_inputs(cfg, 1)
     warm["image"] = synth.make_images(cfg, 1, seed=1233)
     t0 = time.time()
-    with torch.no_grad():
-        port.caption(pm, warm, extra, algorithm="faithful")
+    fn(warm)
     t_warm = time.time() - t0
     data = synth.make_text_inputs(cfg, n_images)
     data["image"] = synth.make_images(cfg, n_images, seed=1234)
     t0 = time.time()
-    with torch.no_grad():
-        ids, lp = port.caption(pm, data, extra, algorithm="faithful")
+    ids, lp = fn(data)
     dt = time.time() - t0
-    return {"value": n_images / dt, "unit": UNIT, "cores": threads, "kind": "port",
+    return {"value": n_images / dt, "unit": UNIT, "cores": threads, "kind": kind,
             "sample": "BASELINE.json configs[0]: one batch of %d image(s) of the same workload (ViT-B/16-%d, 20-token greedy, fp32, "
-                      "reference algorithm without KV cache: 19 full-model calls), %.1f s, after one untimed B=1 warm-up (%.1f s)"
-                      % (n_images, cfg.img_size, dt, t_warm)}, ids
+                      "no KV cache: 19 full-model calls) through %s, %.1f s, after one untimed B=1 warm-up (%.1f s)"
+                      % (n_images, cfg.img_size, what, dt, t_warm)}, ids
 
 
 def decode_roofline(torch, ops, cfg, B, dev, peaks, model=None, extra=None):
@@ -313,20 +343,18 @@ def run_reference_arm(args):
         return run_reference_on_gpu(args)
     from vitcap_b200 import config as vcfg
     from vitcap_b200 import synth
-    from oracle import port
     cfg = vcfg.variant(args.variant, dec_layers=args.dec_layers)
     sd = synth.make_state_dict(cfg, seed=0)
     extra = synth.default_test_extra_input(cfg)
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    pm = port.PortModel(cfg, sd)
+    fn, kind, what = cpu_captioner(cfg, sd, extra, args.variant)
 
     def run(n, seed):
         data = synth.make_text_inputs(cfg, n)
         data["image"] = synth.make_images(cfg, n, seed=seed)
         t0 = time.time()
-        with torch.no_grad():
-            port.caption(pm, data, extra, algorithm="faithful")
+        fn(data)
         return time.time() - t0
 
     # Warm-up: W untimed B = 1 captions ("one untimed B=1 warm-up"); their median also sizes the timed
@@ -343,9 +371,9 @@ def run_reference_arm(args):
     rates = sorted(per_step / t for t in times)
     spread = {"min": rates[0], "median": statistics.median(rates), "max": rates[-1], "unit": UNIT, "timed_steps": len(times)}
     sample = "%d timed step(s) of %d image(s) each (BASELINE.json configs[0] is B=8; the per-step batch is the largest <= 8 that " \
-             "keeps %d steps within ~4 min at this host's %.2f s per B=1 caption), reference algorithm (no KV cache, 19 full-model " \
-             "calls per caption), fp32, %d host threads; per-step rate min/median/max %.3f/%.3f/%.3f images/s" \
-             % (len(times), per_step, args.steps, t_img, threads, spread["min"], spread["median"], spread["max"])
+             "keeps %d steps within ~4 min at this host's %.2f s per B=1 caption) through %s: no KV cache, 19 full-model " \
+             "calls per caption, fp32, %d host threads; per-step rate min/median/max %.3f/%.3f/%.3f images/s" \
+             % (len(times), per_step, args.steps, t_img, what, threads, spread["min"], spread["median"], spread["max"])
     wl = workload_config(args, cfg)
     wl["batch_per_step"] = per_step
     wl["reference_sample"] = "the reference arm captions %d image(s) per step, not %d: a bounded sample of the workload" \
@@ -354,7 +382,7 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": wl,
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample, "spread": spread},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample, "spread": spread},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -650,7 +678,7 @@ def main():
         line["config"]["host_binding"] = ("rank bound to the %d CPU cores NVML reports as local to its GPU" % len(numa_cores)
                                           if numa_cores else "none (NVML affinity unavailable)")
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cb, _ = cpu_baseline(cfg, sd, args.cpu_sample_images, extra)
+        cb, _ = cpu_baseline(cfg, sd, args.cpu_sample_images, extra, args.variant)
         line["cpu_baseline"] = cb
     if rank == 0:
         print(json.dumps(line), flush=True)

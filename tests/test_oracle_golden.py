@@ -85,3 +85,41 @@ def test_faithful_port_matches_reference(name):
     assert np.array_equal(ids.numpy(), z["ids"])
     np.testing.assert_allclose(lp.numpy(), z["logprobs"], atol=5e-5)
     assert info["n_calls"] == meta["n_model_calls"]
+
+
+_STAGED_CHECK = r"""
+import sys, numpy as np, torch
+from oracle import ref_loader
+from tests.helpers import golden_setup, load_golden
+assert ref_loader.REF_KIND == "env" and ref_loader.REF_ROOT.endswith("_ref"), (ref_loader.REF_ROOT, ref_loader.REF_KIND)
+z, meta = load_golden(sys.argv[1])
+cfg, sd, data, extra = golden_setup(meta)
+ref, tok = ref_loader.build_reference(meta["variant"])
+import src.layers.bert.modeling_bert as mb
+assert mb.__file__.endswith(".pyc"), mb.__file__            # the bytecode tree, not /root/reference
+ref.load_state_dict(sd, strict=True)
+ref.test_extra_input = extra
+data = dict(data)
+data["key"] = ["k%d" % i for i in range(data["image"].shape[0])]
+with torch.no_grad():
+    ids, lp = ref(data)
+assert np.array_equal(ids.numpy(), z["ids"]) and np.array_equal(lp.numpy(), z["logprobs"])
+print("STAGED-REFERENCE-OK")
+"""
+
+
+def test_staged_reference_bytecode_reproduces_the_golden():
+    """oracle/_ref (oracle/build_ref.py: the unmodified reference compiled to bytecode, what bench.py's CPU legs time on the GPU
+    box) is the reference: imported without /root/reference it returns the committed golden bit for bit."""
+    import os
+    import subprocess
+    import sys
+    from oracle import build_ref
+    staged = build_ref.staged_root()
+    if staged is None:
+        pytest.skip("oracle/_ref not staged (python -m oracle.build_ref needs the reference tree)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, VITCAP_REFERENCE_ROOT=staged, PYTHONPATH=root)
+    r = subprocess.run([sys.executable, "-W", "ignore", "-c", _STAGED_CHECK, "g9_greedy_refinit_16_224"], cwd=root, env=env,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "STAGED-REFERENCE-OK" in r.stdout, r.stderr[-2000:]
