@@ -171,7 +171,7 @@ def cpu_captioner(cfg, sd, extra, variant):
             def run_ref(data):
                 d = dict(data)
                 d["key"] = ["k%d" % i for i in range(d["image"].shape[0])]
-                with torch.no_grad():
+                with torch.no_grad(), ref_loader.on_cpu():
                     return ref(d)
             return run_ref, "reference", "the unmodified reference (ImageCaptioning.forward, imported from %s: %s)" \
                 % (ref_loader.REF_ROOT, ref_loader.REF_KIND)

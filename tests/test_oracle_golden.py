@@ -101,7 +101,7 @@ ref.load_state_dict(sd, strict=True)
 ref.test_extra_input = extra
 data = dict(data)
 data["key"] = ["k%d" % i for i in range(data["image"].shape[0])]
-with torch.no_grad():
+with torch.no_grad(), ref_loader.on_cpu():
     ids, lp = ref(data)
 assert np.array_equal(ids.numpy(), z["ids"]) and np.array_equal(lp.numpy(), z["logprobs"])
 print("STAGED-REFERENCE-OK")
