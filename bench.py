@@ -36,8 +36,8 @@ def parse():
     ap.add_argument("--variant", default="16_384")
     ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--dec-layers", type=int, default=4)
-    ap.add_argument("--decode-precision", default=None, choices=["bf16", "bf16x3"],
-                    help="operands of the decode-step MLP / vocabulary-head GEMMs (default: the model's, bf16x3)")
+    ap.add_argument("--decode-precision", default=None, choices=["bf16", "bf16x3", "fp16"],
+                    help="operands of the decode-step MLP / vocabulary-head GEMMs (default: the model's, fp16)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-sample-images", type=int, default=8, help="cpu_baseline leg: BASELINE.json configs[0] is B = 8")
@@ -74,7 +74,7 @@ def workload_config(args, cfg):
         "variant": args.variant, "batch_per_gpu": b, "global_batch": b * max(1, args.gpus), "batch_per_step": b * max(1, args.gpus),
         "max_length": 20, "num_beams": 1, "decoder_layers": cfg.dec_layers, "parallelism": "dp%d" % max(1, args.gpus),
         "weights": "random-init (synth.make_state_dict seed 0, reference layout)",
-        "decode_precision": getattr(args, "decode_precision", None) or "bf16x3",
+        "decode_precision": getattr(args, "decode_precision", None) or "fp16",
         "l2": "inputs larger than L2 (906 MB of images and >10 GB of activations per step vs 126 MB L2)",
     }
 

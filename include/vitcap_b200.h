@@ -223,13 +223,19 @@ int vc_token_step(const float* logits, int ld, int rows, int V, int do_sample, f
 /* ---- fused decode step (fast mode): the Linear layers of a decode step on CTA-pair tiles sized for M = 2 x sequences rows.
  * They replace the same reference operators as vc_linear (modeling_bert.py:307-313 q/k/v, :353-357 BertSelfOutput.dense,
  * :402-405 BertIntermediate, :415-419 BertOutput.dense, :524-563 prediction head); what differs is the boundary between kernels.
- * A [M, K] and W [N, K] bf16, row pitches lda / ldw. x3 = 1: split operands, A = [a_hi | a_lo | (unused)] and
- * W = [w_hi | w_hi | w_lo] along K (K = 3 Kt, VC_OPERAND_BF16X3): out = a_hi w_hi + a_lo w_hi + a_hi w_lo, every distinct tile
- * loaded once.
+ * A [M, K] and W [N, K] 16-bit, row pitches lda / ldw. Operand format `fmt`:
+ *   VC_DEC_FMT_BF16   bf16 x bf16
+ *   VC_DEC_FMT_BF16X3 split operands, A = [a_hi | a_lo | (unused)] and W = [w_hi | w_hi | w_lo] along K (K = 3 Kt,
+ *                     VC_OPERAND_BF16X3): out = a_hi w_hi + a_lo w_hi + a_hi w_lo, every distinct tile loaded once
+ *   VC_DEC_FMT_F16    IEEE half x IEEE half (ABI 9): 11-bit significands in ONE product at the rate and bytes of bf16; the
+ *                     range (6e-8 .. 65504) holds LayerNorm / GELU outputs and weights, conversions saturate
  *   mode VC_DEC_PARTIAL    out = fp32 [splits, m_pad, N] (pitch ldo): plane s = A W^T over the s-th slice of K, NO bias
- *                          (split-K over the SMs a 2-sequence-row GEMM leaves idle; vc_finish_ln sums the planes)
+ *                          (split-K over the SMs a 2-sequence-row GEMM leaves idle; vc_finish_ln sums the planes).
+ *                          splits == 1 accepts a bias and any N: out = fp32 [M, N] = A W^T + bias, the materialised
+ *                          vocabulary logits of beam search / sampling (the store works in 16-byte units: columns
+ *                          [N, round_up(N, 4)) of a row, which the pitch ldo % 4 == 0 guarantees to exist, may receive zeros)
  *   mode VC_DEC_BF16       out = bf16 (A W^T + bias)
- *   mode VC_DEC_GELU_BF16  out = bf16 GELU(A W^T + bias)
+ *   mode VC_DEC_GELU_BF16  out = GELU(A W^T + bias) as bf16 (as IEEE halves with VC_DEC_FMT_F16: the next GEMM's operand)
  *   mode VC_DEC_GELU_SPLIT out = bf16 [M, >= 2N]: columns [0, N) = hi, [N, 2N) = lo of GELU(A W^T + bias) (the split operand
  *                          of the next x3 GEMM, written by the epilogue instead of an fp32 round trip + vc_split_bf16x3)
  * splits must divide K / 64 (Kt / 64) and be 1 for the bf16 modes; m_pad >= M, multiple of 128. */
@@ -237,21 +243,25 @@ int vc_token_step(const float* logits, int ld, int rows, int V, int do_sample, f
 #define VC_DEC_BF16 1
 #define VC_DEC_GELU_BF16 2
 #define VC_DEC_GELU_SPLIT 3
-int vc_dec_linear(int mode, int x3, const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldo, int M,
+#define VC_DEC_FMT_BF16 0
+#define VC_DEC_FMT_BF16X3 1
+#define VC_DEC_FMT_F16 2
+int vc_dec_linear(int mode, int fmt, const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldo, int M,
                   int N, int K, int splits, int m_pad, void* stream);
 /* vocabulary projection of greedy decoding WITHOUT materialising the logits (BertLMPredictionHead.decoder + bias,
  * modeling_bert.py:551-563, then argmax -> log_softmax -> gather, modeling_utils.py:849-853): part = float4 [M, n_part],
  * n_part = 2 * ceil(N / 208); entry (row, 2 * tile + g) = (max, first arg max as int bits, sum of exp(x - max), 0) of
  * A W^T + bias over the 32-column chunks g, g + 2, ... of the 208-column tile (208: the 30522-word vocabulary then makes 3.97
  * rounds of tiles over the 74 CTA pairs). vc_token_step_partials reduces them. */
-int vc_dec_vocab_argmax(int x3, const void* A, int lda, const void* W, int ldw, const float* bias, void* part, int n_part, int M,
+int vc_dec_vocab_argmax(int fmt, const void* A, int lda, const void* W, int ldw, const float* bias, void* part, int n_part, int M,
                         int N, int K, void* stream);
 /* y = LayerNorm(act(sum_s part[s] + bias) + resid) per row: the split-K reduction, bias / residual of BertSelfOutput /
  * BertOutput (modeling_bert.py:353-357, 415-419), their LayerNorm -- or, with gelu = 1 and resid = NULL, the GELU + LayerNorm
  * of the prediction-head transform (modeling_bert.py:524-537) -- and the operand copy for the next GEMM in one pass.
  * part: `splits` fp32 planes [rows, ld_p], `plane` elements apart; out_f (fp32, may be NULL) the normalised row;
  * out_mode 0 = no operand copy, 1 = bf16 [rows, ld_t], 2 = split pair: columns [0, H) = hi, [H, 2H) = lo (ld_t >= 2H),
- * 3 = [hi | lo | hi] (ld_t >= 3H; the K-concatenated form vc_linear reads for VC_OPERAND_BF16X3). */
+ * 3 = [hi | lo | hi] (ld_t >= 3H; the K-concatenated form vc_linear reads for VC_OPERAND_BF16X3), 4 = IEEE half [rows, ld_t],
+ * 5 = [bf16 | half] (ld_t >= 2H: the q|k|v projection reads the bf16 columns, a VC_DEC_FMT_F16 GEMM the half columns). */
 int vc_finish_ln(const float* part, int splits, size_t plane, int ld_p, const float* bias, int gelu, const float* resid, int ld_r,
                  const float* gamma, const float* beta, float eps, float* out_f, int ld_f, void* out_t, int ld_t, int out_mode,
                  int rows, int H, void* stream);

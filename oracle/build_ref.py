@@ -1,14 +1,15 @@
 """TEST INFRASTRUCTURE ONLY -- never imported by the product path.
 
 Recipe for oracle/_ref: compiles the UNMODIFIED reference (every module under /root/reference/src, where the sources lie)
-to CPython bytecode and stages the result -- bytecode only, no source text -- under oracle/_ref/, next to the two data
-files per model variant the reference's own from_pretrained calls read (vocab.txt, config.json of yaml/<variant>/).
+to CPython bytecode and stages the result -- bytecode only, no source text -- as ONE archive, oracle/_ref/reference_pyc.zip
+(imported through zipimport; loose .pyc files do not survive the copy to the GPU box), next to the two data files per model
+variant the reference's own from_pretrained calls read (vocab.txt, config.json of yaml/<variant>/).
 
     python -m oracle.build_ref          # in the build container; __graft_entry__.build() runs it when /root/reference exists
 
 oracle/_ref is git-ignored (it stays out of history) and NOT gpurun-ignored: like the built .so it travels to the GPU box,
-where /root/reference does not exist. oracle/ref_loader.py then imports the reference from it (sourceless import of the
-.pyc tree), which is what lets `bench.py --impl reference` and the cpu_baseline leg time the reference's own code on the
+where /root/reference does not exist. oracle/ref_loader.py then imports the reference from it (sourceless import from the
+archive), which is what lets `bench.py --impl reference` and the cpu_baseline leg time the reference's own code on the
 box's host cores (cpu_baseline.kind "reference") instead of the restatement in oracle/port.py.
 
 The bytecode is tied to this interpreter's magic number; the GPU box runs the same image. ref_loader checks the number
@@ -22,10 +23,12 @@ import py_compile
 import shutil
 import sys
 import warnings
+import zipfile
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC_ROOT = os.environ.get("VITCAP_REFERENCE_SRC", "/root/reference")
 OUT = os.path.join(HERE, "_ref")
+ARCHIVE = "reference_pyc.zip"
 DATA_FILES = ("vocab.txt", "config.json")
 
 
@@ -40,6 +43,8 @@ def build(verbose=False):
         return None
     tmp = OUT + ".tmp"
     shutil.rmtree(tmp, ignore_errors=True)
+    os.makedirs(tmp)
+    pyc = os.path.join(tmp, "_pyc")
     n_mod, digest = 0, hashlib.sha256()
     for root, dirs, files in os.walk(src):
         dirs.sort()
@@ -48,7 +53,7 @@ def build(verbose=False):
             if not f.endswith(".py"):
                 continue
             s = os.path.join(root, f)
-            d = os.path.join(tmp, rel, f + "c")          # legacy layout: module.pyc where module.py would be
+            d = os.path.join(pyc, rel, f + "c")          # legacy layout: module.pyc where module.py would be
             os.makedirs(os.path.dirname(d), exist_ok=True)
             try:
                 with warnings.catch_warnings():
@@ -62,6 +67,15 @@ def build(verbose=False):
             with open(s, "rb") as fh:
                 digest.update(hashlib.sha256(fh.read()).digest())
             n_mod += 1
+    with zipfile.ZipFile(os.path.join(tmp, ARCHIVE), "w", zipfile.ZIP_DEFLATED) as z:
+        for root, dirs, files in os.walk(pyc):
+            dirs.sort()
+            if root != pyc:                              # explicit directory entries: zipimport finds namespace packages
+                z.write(root, os.path.relpath(root, pyc) + "/")     # (directories without __init__) only through them
+            for f in sorted(files):
+                full = os.path.join(root, f)
+                z.write(full, os.path.relpath(full, pyc))
+    shutil.rmtree(pyc)
     ydir = os.path.join(SRC_ROOT, "yaml")
     variants = []
     for v in sorted(os.listdir(ydir)) if os.path.isdir(ydir) else []:
@@ -70,8 +84,8 @@ def build(verbose=False):
             for f in DATA_FILES:
                 shutil.copyfile(os.path.join(ydir, v, f), os.path.join(tmp, "yaml", v, f))
             variants.append(v)
-    man = {"what": "CPython bytecode of the unmodified reference's src/ tree (no source text) + vocab.txt / config.json of "
-                   "its model variants; built by oracle/build_ref.py",
+    man = {"what": "CPython bytecode of the unmodified reference's src/ tree (no source text; %s) + vocab.txt / config.json "
+                   "of its model variants; built by oracle/build_ref.py" % ARCHIVE,
            "python_magic": magic_hex(), "python": sys.version.split()[0], "modules": n_mod, "variants": variants,
            "sources_sha256": digest.hexdigest()}
     with open(os.path.join(tmp, "MANIFEST.json"), "w") as fh:
@@ -88,9 +102,16 @@ def staged_root():
             man = json.load(fh)
     except (OSError, ValueError):
         return None
-    if man.get("python_magic") != magic_hex() or not os.path.isdir(os.path.join(OUT, "src", "layers", "bert")):
+    if man.get("python_magic") != magic_hex() or not os.path.isfile(os.path.join(OUT, ARCHIVE)):
         return None
     return OUT
+
+
+def code_root(root):
+    """The sys.path entry under which ``src.*`` of a reference root imports: the root itself for a source tree, the bytecode
+    archive for a staged one."""
+    arc = os.path.join(root, ARCHIVE)
+    return arc if os.path.isfile(arc) else root
 
 
 if __name__ == "__main__":

@@ -170,6 +170,11 @@ def q_bf16(x):
     return x.to(torch.bfloat16).to(torch.float32)
 
 
+def q_f16(x):
+    """Round to IEEE half (nearest even, saturating at +-65504 as cvt.rn.satfinite.f16.f32) and back to fp32."""
+    return x.clamp(-65504.0, 65504.0).to(torch.float16).to(torch.float32)
+
+
 def split_bf16(x):
     """x ~ hi + lo with hi = bf16(x), lo = bf16(x - hi): the split operand of the decode-step GEMMs (engine.py, bf16x3)."""
     hi = q_bf16(x)
@@ -198,17 +203,21 @@ class QuantPortModel(PortModel):
                        rstd (bf16(x) bf16(gamma o W)^T - mean colsum) + (b + W beta), colsum over the rounded weight
       attention        S = Q K^T fp32, P = exp(S - max) rounded to bf16 for the P V product, row sum from the unrounded P
       decoder prefill  post-LN BertLayer: LayerNorm kernel output bf16 (operand) + fp32 (residual), qkv / attention / GELU bf16
-      decode step      the same; with decode_x3 the MLP and the vocabulary head run on split operands (hi + lo, three products)
+      decode step      the same; with decode_x3 the MLP and the vocabulary head run on split operands (hi + lo, three products),
+                       with decode_f16 on operands rounded to IEEE half (one product; decode_precision='fp16')
       heads            dense + fast GELU fp32 -> LayerNorm -> bf16 (tag head) or split (vocabulary head) -> decoder GEMM
 
     ln_fold: 0 = LayerNorm kernel everywhere, 1 = norm1 folded, 2 = norm1 and norm2 folded (the engine's default).
     cls_only_last: the last concept block is evaluated for the CLS row only with LayerNorm-kernel roundings and an fp32 softmax
     (engine._vit_block_cls_only); False = a full folded block (engine.encode(full_tag_feats=True))."""
 
-    def __init__(self, cfg, state_dict, ln_fold=2, decode_x3=True, cls_only_last=True, acc64=False, prefill_fold=True):
+    def __init__(self, cfg, state_dict, ln_fold=2, decode_x3=True, cls_only_last=True, acc64=False, prefill_fold=True,
+                 decode_f16=False):
         super().__init__(cfg, state_dict, dtype=torch.float32)
         self.ln_fold = ln_fold
-        self.decode_x3 = decode_x3
+        # decode_f16 takes the split-operand route through the layers (lin_x3 is the GEMM of both forms)
+        self.decode_f16 = decode_f16
+        self.decode_x3 = decode_x3 or decode_f16
         self.cls_only_last = cls_only_last
         # prefill_fold (engine._prefill_folded): in the decoder prefill the intermediate GEMM folds the attention-output
         # LayerNorm and the q|k|v GEMM of layer i >= 1 folds the output LayerNorm of layer i - 1 (raw bf16 row, gamma-scaled
@@ -239,7 +248,14 @@ class QuantPortModel(PortModel):
         return self._mm(h_q, self.wq(wkey), self.sd[bkey] if bkey else None)
 
     def lin_x3(self, a, wkey, bkey):
-        """Three-product split-bf16 GEMM (gemm_tc.cu X3 / the K-concatenated form): a_hi w_hi + a_lo w_hi + a_hi w_lo."""
+        """Three-product split-bf16 GEMM (gemm_tc.cu X3 / the K-concatenated form): a_hi w_hi + a_lo w_hi + a_hi w_lo; with
+        decode_f16 the one-product IEEE-half GEMM of gemm_dec.cu (operands rounded to nearest even, saturating)."""
+        if self.decode_f16:
+            key = ("f16", wkey)
+            if key not in self._wq:
+                self._wq[key] = q_f16(self.sd[wkey])
+            out = self._mm(q_f16(a), self._wq[key])
+            return out + self.sd[bkey] if bkey else out
         key = ("x3", wkey)
         if key not in self._wq:
             self._wq[key] = split_bf16(self.sd[wkey])

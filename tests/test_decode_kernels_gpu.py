@@ -494,3 +494,108 @@ def test_decode_attention_skips_finished_sequences(B, C, heads, E, cur_len):
                         assert bool((o[rows] == 123.0).all()), (b, r)
                         n_skipped += 1
         assert n_skipped > 0
+
+
+# ------------------------------------------------------------------------------------------------ IEEE-half operand format
+def _h(x):
+    return x.clamp(-65504.0, 65504.0).to(torch.float16)
+
+
+@pytest.mark.parametrize("M,N,K,splits", [(1024, 768, 3072, 6), (777, 768, 768, 3), (1, 768, 768, 6), (512, 768, 768, 1)])
+def test_dec_linear_half_partial_planes(M, N, K, splits):
+    """VC_DEC_FMT_F16 (decode_precision='fp16'): the product of IEEE-half operands, fp32 accumulation -- against fp32 torch on
+    the SAME half values, so the only difference is the summation order; and it must be the half product, not a bf16 one."""
+    a, w = _rnd(M, K, seed=M + 1), _rnd(N, K, seed=N + 2, scale=0.05)
+    A, W = _h(a), _h(w)
+    ref = A.float() @ W.float().t()
+    m_pad = (M + 127) // 128 * 128
+    out = torch.full((splits, m_pad, N), float("nan"), device=DEV)
+    ops.dec_linear(ops.DEC_PARTIAL, A.to(DEV), W.to(DEV), None, out, M=M, splits=splits, m_pad=m_pad)
+    got = out[:, :M].cpu().sum(0)
+    scale = float(ref.abs().max())
+    assert float((got - ref).abs().max()) <= 3e-5 * scale
+    # the same bits read as bf16 would be another number altogether; the operand rounding itself is 8 x finer than bf16's
+    e_half = float((ref - a @ w.t()).abs().mean())
+    e_bf16 = float((_bf(a).float() @ _bf(w).float().t() - a @ w.t()).abs().mean())
+    assert e_half < 0.2 * e_bf16
+
+
+@pytest.mark.parametrize("M,N,K", [(1024, 3072, 768), (130, 3072, 768), (64, 128, 64)])
+def test_dec_linear_half_gelu_epilogue(M, N, K):
+    """VC_DEC_GELU_BF16 with half operands writes GELU(A W^T + bias) as IEEE halves (the operand of the next half GEMM)."""
+    A, W = _h(_rnd(M, K, seed=M)), _h(_rnd(N, K, seed=N, scale=0.05))
+    bias = _rnd(N, seed=9)
+    ref = port.gelu_fast(A.float() @ W.float().t() + bias)
+    out = torch.full((M, N), 9.0, device=DEV, dtype=torch.float16)
+    ops.dec_linear(ops.DEC_GELU_BF16, A.to(DEV), W.to(DEV), bias.to(DEV), out, M=M)
+    got = out.cpu().float()
+    scale = float(ref.abs().max())
+    assert float((got - ref).abs().max()) <= 1.2e-3 * scale                  # MUFU.TANH (2^-11) + the half rounding (2^-12)
+    assert float((got - ref).abs().mean()) <= 1.5e-4 * scale
+
+
+@pytest.mark.parametrize("R,V", [(512, 30522), (5, 30522), (130, 3000)])
+def test_dec_linear_half_logits_plane_with_bias(R, V):
+    """VC_DEC_PARTIAL with splits = 1 and a bias = the materialised fp32 vocabulary logits (beam search / sampling with
+    decode_precision='fp16'): any N (30522 is not a multiple of 4), rows clipped at M. The TMA store works in 16-byte units: the
+    pad columns up to the next multiple of 4 may receive zeros (the pitch is a multiple of 4, so they exist), the rest is
+    untouched."""
+    K = 768
+    A, W = _h(_rnd(R, K, seed=R)), _h(_rnd(V, K, seed=V, scale=0.03))
+    bias = 0.5 * _rnd(V, seed=5)
+    ref = A.float() @ W.float().t() + bias
+    ldl = (V + 63) // 64 * 64
+    logits = torch.full((R + 3, ldl), 7.0, device=DEV)
+    ops.dec_linear(ops.DEC_PARTIAL, A.to(DEV), W.to(DEV), bias.to(DEV), logits[:, :V], M=R)
+    got = logits.cpu()
+    assert float((got[:R, :V] - ref).abs().max()) <= 3e-5 * float(ref.abs().max())
+    V4 = (V + 3) // 4 * 4
+    assert bool((got[R:] == 7.0).all()) and bool((got[:, V4:] == 7.0).all())
+    assert bool(((got[:R, V:V4] == 7.0) | (got[:R, V:V4] == 0.0)).all())
+
+
+@pytest.mark.parametrize("rows,splits,gelu,mode", [(1024, 3, False, "f16"), (1000, 6, False, "bf16+f16"), (512, 6, True, "f16"),
+                                                   (3, 2, False, "bf16+f16")])
+def test_finish_ln_half_operand_copies(rows, splits, gelu, mode):
+    H = 768
+    m_pad = (rows + 127) // 128 * 128
+    part = _rnd(splits, m_pad, H, seed=rows, scale=0.5)
+    bias, gamma, beta = _rnd(H, seed=1), 1.0 + 0.1 * _rnd(H, seed=2), 0.1 * _rnd(H, seed=3)
+    res = None if gelu else _rnd(rows, H, seed=4)
+    out_f = torch.empty(rows, H, device=DEV)
+    if mode == "f16":
+        out_t = torch.full((rows, H), 5.0, device=DEV, dtype=torch.float16)
+    else:
+        out_t = torch.full((rows, 3 * H), 5.0, device=DEV, dtype=torch.bfloat16)
+    ops.finish_ln(part.to(DEV), splits, bias.to(DEV), gamma.to(DEV), beta.to(DEV), 1e-12, rows, resid=None if gelu else res.to(DEV),
+                  gelu=gelu, out_f=out_f, out_t=out_t, split=mode)
+    of = out_f.cpu()
+    if mode == "f16":
+        assert torch.equal(out_t.cpu(), _h(of))
+    else:
+        o = out_t.cpu()
+        assert torch.equal(o[:, :H], _bf(of))
+        assert torch.equal(o.view(torch.float16)[:, H:2 * H], _h(of))
+        assert bool((o[:, 2 * H:] == 5.0).all())
+
+
+@pytest.mark.parametrize("R,V", [(512, 30522), (40, 3000)])
+def test_vocab_argmax_half_operands(R, V):
+    K = 768
+    A, W = _h(_rnd(R, K, seed=R)), _h(_rnd(V, K, seed=V, scale=0.03))
+    bias = 0.5 * _rnd(V, seed=5)
+    ref = A.float() @ W.float().t() + bias
+    n_part = ops.vocab_partials(V)
+    part = torch.full((R, n_part, 4), float("nan"), device=DEV)
+    ops.dec_vocab_argmax(A.to(DEV), W.to(DEV), bias.to(DEV), part, M=R)
+    p = part.cpu()
+    mx = p[:, :, 0].max(1).values
+    np.testing.assert_allclose(mx.numpy(), ref.max(1).values.numpy(), atol=2e-4)
+    lse = torch.log((p[:, :, 2] * torch.exp(p[:, :, 0] - mx[:, None])).nan_to_num(0.0).sum(1)) + mx
+    np.testing.assert_allclose(lse.numpy(), torch.logsumexp(ref, 1).numpy(), atol=3e-4)
+    best = p[:, :, 0].argmax(1)
+    idx = p[torch.arange(R), best, 1].contiguous().view(torch.int32)
+    top2 = ref.topk(2, dim=1)
+    for r in range(R):
+        if int(idx[r]) != int(top2.indices[r, 0]):
+            assert float(top2.values[r, 0] - top2.values[r, 1]) < 2e-4, r

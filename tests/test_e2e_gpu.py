@@ -177,6 +177,69 @@ def test_tiny_beam_vs_oracle():
         np.testing.assert_allclose(lp.cpu().numpy(), rlp.numpy(), atol=2e-4)
 
 
+def _matched_oracle_f16(cfg, sd, data, extra, sampler=None):
+    """oracle/port.py QuantPortModel with the decode-step MLP / vocabulary head on IEEE-half operands: the executable spec of
+    decode_precision='fp16'."""
+    qm = port.QuantPortModel(cfg, sd, decode_f16=True)
+    trace = []
+    with torch.no_grad():
+        ids, lp = port.caption(qm, data, extra, algorithm="cached", trace=trace, sampler=sampler)
+    return ids, lp, trace
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_tiny_greedy_fp16_decode_vs_matched_oracle(graph):
+    """decode_precision='fp16' (decode-step MLP and vocabulary head as ONE product on IEEE-half operands) against its
+    quantisation-matched oracle: identical greedy ids except at near-ties of that oracle, close log-probs; chunked batch,
+    eager and captured loop (the arg-max epilogue path: no logits)."""
+    cfg = vcfg.tiny()
+    sd = synth.make_state_dict(cfg, seed=7, eos_bias=1.0)
+    B = 5
+    data = synth.make_text_inputs(cfg, B)
+    data["image"] = synth.make_images(cfg, B, seed=3)
+    extra = synth.default_test_extra_input(cfg)
+    rids, rlp, trace = _matched_oracle_f16(cfg, sd, data, extra)
+    m = build(cfg, sd, extra, "bf16", max_batch=3, use_cuda_graph=graph, decode_precision="fp16")
+    assert m.engine.decode_f16 and not m.engine.decode_x3
+    top = torch.stack([t.topk(2).values for t in trace]).numpy()
+    for rep in range(2):
+        ids, lp = m(to_dev(data))
+        excused = compare_ids_gap_aware(ids.cpu().numpy()[:, 0], rids.numpy()[:, 0], top, 2e-2, "fp16 rep%d" % rep)
+        if excused == 0:
+            np.testing.assert_allclose(lp.cpu().numpy(), rlp.numpy(), atol=5e-3)
+
+
+def test_tiny_fp16_decode_beam_and_sampling_read_the_half_logits():
+    """Beam search and sampling need the logits: with decode_precision='fp16' they come from the decode-step kernel itself
+    (VC_DEC_PARTIAL, one plane + bias). Beam search against the matched oracle (most rows identical, the others excused by a
+    close score), sampling against the matched oracle drawing the same Philox noise."""
+    cfg = vcfg.tiny()
+    sd = synth.make_state_dict(cfg, seed=7, eos_bias=1.0)
+    B = 4
+    data = synth.make_text_inputs(cfg, B)
+    data["image"] = synth.make_images(cfg, B, seed=3)
+    extra = synth.default_test_extra_input(cfg, num_beams=4, num_keep_best=2, length_penalty=0.7)
+    rids, rlp, _ = _matched_oracle_f16(cfg, sd, data, extra)
+    m = build(cfg, sd, extra, "bf16", use_cuda_graph=True, decode_precision="fp16")
+    for rep in range(2):
+        ids, lp = m(to_dev(data))
+        same = (ids.cpu() == rids).all(dim=-1)                       # (B, keep)
+        assert float(same.float().mean()) >= 0.75, (ids.cpu(), rids)
+        np.testing.assert_allclose(lp.cpu().numpy()[same.numpy()], rlp.numpy()[same.numpy()], atol=5e-3)
+        # a hypothesis that differs must score within a near-tie of the oracle's
+        np.testing.assert_allclose(lp.cpu().numpy(), rlp.numpy(), atol=5e-2)
+    K, seed = 4, 1234
+    sd2 = synth.make_state_dict(cfg, seed=7, eos_bias=0.5)
+    extra2 = synth.default_test_extra_input(cfg, do_sample=True, num_return_sequences=K, temperature=0.9)
+    rids, rlp, _ = _matched_oracle_f16(cfg, sd2, data, extra2, sampler=philox.make_sampler(seed))
+    m = build(cfg, sd2, extra2, "bf16", sample_seed=seed, use_cuda_graph=False, decode_precision="fp16")
+    ids, lp = m(to_dev(data))
+    agree = float((ids.cpu() == rids).float().mean())
+    assert agree >= 0.9, agree
+    same = (ids.cpu() == rids).all(dim=-1).squeeze(1)
+    np.testing.assert_allclose(lp.cpu().numpy()[same.numpy()], rlp.numpy()[same.numpy()], atol=5e-3)
+
+
 def test_bf16_mode_features_and_tags_16_224():
     """Fast mode accuracy on the 16_224 variant: encoder features / tag logits relative error and top-50 overlap."""
     z, meta = load_golden("g3_greedy_eos_16_224")

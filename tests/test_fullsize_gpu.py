@@ -156,6 +156,7 @@ def _oracle_on_gpu(cfg, sd, data, extra):
 
 
 @pytest.mark.parametrize("precision,vocab_gain,min_agree,max_gap", [("bf16x3", 1.0, 0.99, 2.5e-2), ("bf16", 1.0, 0.975, 2.5e-2),
+                                                                    ("fp16", 1.0, 0.99, 2.5e-2),
                                                                     ("bf16x3", 4.0, 0.98, 1e-1), ("bf16", 4.0, 0.96, 1e-1)])
 def test_bf16_mode_token_agreement_fullsize_vs_oracle(precision, vocab_gain, min_agree, max_gap):
     """North-star criterion for the fast mode: >= 99 % greedy-token agreement with the fp32 reference algorithm. Full-size
@@ -232,8 +233,8 @@ def _rel(a, b):
     return float((a - b).norm() / b.norm())
 
 
-def _tapped_forward(cfg, sd, extra, data, B):
-    m = FastImageCaptioning(cfg, test_extra_input=extra, mode="bf16", max_batch=B)
+def _tapped_forward(cfg, sd, extra, data, B, decode_precision=None):
+    m = FastImageCaptioning(cfg, test_extra_input=extra, mode="bf16", max_batch=B, decode_precision=decode_precision)
     m.load_state_dict(sd)
     m = m.to(DEV)
     taps = {}
@@ -264,7 +265,7 @@ def test_bf16_mode_every_kernel_vs_quantisation_matched_oracle():
     extra = synth.default_test_extra_input(cfg)
     B = 8
     data = _data(cfg, B, seed=2024)
-    m, taps, ids, lp = _tapped_forward(cfg, sd, extra, data, B)
+    m, taps, ids, lp = _tapped_forward(cfg, sd, extra, data, B, decode_precision="bf16x3")
     sd_dev = {k: v.to(DEV) for k, v in sd.items()}
     N, C, H, heads, d, F_ = cfg.n_tokens, cfg.n_ctx, cfg.hidden, cfg.heads, cfg.head_dim, cfg.inter
     split_at = cfg.enc_blocks - cfg.split_blocks
@@ -392,8 +393,50 @@ def test_bf16_mode_every_kernel_vs_quantisation_matched_oracle():
         assert e <= 1e-3, (name, e)
 
 
-def test_bf16_mode_end_to_end_vs_quantisation_matched_oracle():
-    """The same comparison END TO END (32 images, full-size model, benchmarked configuration): caption / concept features, concept
+def test_fp16_decode_step_vs_quantisation_matched_oracle():
+    """decode_precision='fp16' at full size, the kernel-level statement: the first decode step (embeddings, four layers on the
+    kernel's OWN context K/V cache, head, vocabulary logits through the one-plane + bias form of vc_dec_linear) against
+    QuantPortModel(decode_f16=True) -- the same arithmetic with the MLP / head operands rounded to IEEE half where the kernels
+    round (finish_ln operand copies, GELU epilogue, packed weights): <= 1e-3 norm-wise, and the greedy token of every row equals
+    the arg max of those logits (the arg-max epilogue and the logits plane are the same GEMM)."""
+    from oracle import port
+    cfg = vcfg.variant("16_384")
+    sd = synth.make_state_dict(cfg, seed=0, eos_bias=1.0)
+    extra = synth.default_test_extra_input(cfg)
+    B = 8
+    data = _data(cfg, B, seed=2024)
+    m, taps, ids, lp = _tapped_forward(cfg, sd, extra, data, B, decode_precision="fp16")
+    assert m.engine.decode_f16
+    sd_dev = {k: v.to(DEV) for k, v in sd.items()}
+    C, H, heads, d, L = cfg.n_ctx, cfg.hidden, cfg.heads, cfg.head_dim, cfg.dec_layers
+    res = {}
+
+    def run():
+        qm = port.QuantPortModel(cfg, sd_dev, decode_f16=True)
+        hs = lambda t_: t_.reshape(B, C, heads, d).permute(0, 2, 1, 3)                  # noqa: E731
+        inp = torch.tensor([[int(extra["bos_token_id"]), int(extra["mask_token_id"])]]).expand(B, 2)
+        e = qm.embeddings(inp, torch.tensor([[0, 1]]).expand(B, 2))
+        for l in range(L):
+            k_qkv = taps[("prefill.qkv", l)].float().view(B, C, 3 * H)
+            q_, k_, v_ = qm.qkv_rows(l, e)
+            add = torch.zeros(1, 1, 2, C + 2)
+            add[..., 0, -1] = port.NEG_MASK
+            e = qm.bert_layer_from_kv(l, e, q_, torch.cat([hs(k_qkv[..., H:2 * H]), k_], 2),
+                                      torch.cat([hs(k_qkv[..., 2 * H:]), v_], 2), add, step=True)
+        res["want"] = qm.head("module.cls.predictions.", e[:, 1])
+
+    _on_gpu(run)
+    got = taps[("logits", 1)].float()
+    err = _rel(got.reshape(res["want"].shape), res["want"])
+    print("fp16 decode step 1 vs its quantisation-matched oracle: %.3g" % err)
+    assert err <= 1e-3
+    assert torch.equal(got.argmax(-1).reshape(-1).cpu(), ids[:, 0, 1].cpu())
+
+
+@pytest.mark.parametrize("precision", ["fp16", "bf16x3"])
+def test_bf16_mode_end_to_end_vs_quantisation_matched_oracle(precision):
+    """(precision: operands of the decode-step MLP / vocabulary head; the quantised oracle rounds them the same way.)
+    The same comparison END TO END (32 images, full-size model, benchmarked configuration): caption / concept features, concept
     logits and the vocabulary logits of all 19 decode steps against (a) QuantPortModel and (b) the fp32 oracle.
       * vocabulary logits (rows whose prefix equals the oracle's): <= 1e-3 against the quantised oracle, the north star's
         figure (measured 6e-4: the decode steps keep their MLP / head operands as split bf16 pairs);
@@ -407,7 +450,8 @@ def test_bf16_mode_end_to_end_vs_quantisation_matched_oracle():
     extra = synth.default_test_extra_input(cfg)
     B = int(os.environ.get("VITCAP_QPARITY_B", "32"))
     data = _data(cfg, B, seed=2024)
-    m, taps, ids, lp = _tapped_forward(cfg, sd, extra, data, B)
+    m, taps, ids, lp = _tapped_forward(cfg, sd, extra, data, B, decode_precision=precision)
+    f16 = precision == "fp16"
     taps = {k: v for k, v in taps.items() if k[0] in ("block", "tag_block", "logits")}
     tag_logits, tag_idx, tag_prob, tag_n = m.forward_tags(data["image"])
     sd_dev = {k: v.to(DEV) for k, v in sd.items()}
@@ -418,8 +462,8 @@ def test_bf16_mode_end_to_end_vs_quantisation_matched_oracle():
         out = port.caption(model, data, extra, algorithm="cached", trace=trace, info=info)
         return out, trace, info
 
-    (q_ids, q_lp), q_trace, q_info = _on_gpu(lambda: run_oracle(port.QuantPortModel(cfg, sd_dev)))
-    (d_ids, d_lp), d_trace, d_info = _on_gpu(lambda: run_oracle(port.QuantPortModel(cfg, sd_dev, acc64=True)))
+    (q_ids, q_lp), q_trace, q_info = _on_gpu(lambda: run_oracle(port.QuantPortModel(cfg, sd_dev, decode_f16=f16)))
+    (d_ids, d_lp), d_trace, d_info = _on_gpu(lambda: run_oracle(port.QuantPortModel(cfg, sd_dev, acc64=True, decode_f16=f16)))
     (f_ids, f_lp), f_trace, f_info = _on_gpu(lambda: run_oracle(port.PortModel(cfg, sd_dev)))
     k_cap, k_cls = taps[("block", n_enc - 1)], taps[("tag_block", n_tag - 1)][:, 0]
     rows = {"caption features": (k_cap, "cap", None), "concept CLS feature": (k_cls, "tag_feats", 0), "concept logits": (tag_logits, "tag", None)}
@@ -443,6 +487,7 @@ def test_bf16_mode_end_to_end_vs_quantisation_matched_oracle():
     for name, (vq, vself, vf) in e.items():
         print("bf16 mode end to end, %-20s vs quantised oracle %.3g (oracle vs its fp64-accumulating self %.3g)   vs fp32 oracle %.3g"
               % (name, vq, vself, vf))
+    print("decode_precision %s:" % precision)
     print("bf16 mode end to end, vocabulary logits (worst of 19 steps) vs quantised oracle %.3g   vs fp32 oracle %.3g" % (worst_q, worst_f))
     print("greedy tokens equal to the quantised oracle's: %.4f, to the fp32 oracle's: %.4f (rows with identical prefix per step: "
           "min %d of %d)" % (float((a == qa).float().mean()), float((a == fa).float().mean()), min(rows_q), B))

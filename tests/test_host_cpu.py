@@ -52,7 +52,7 @@ def test_header_symbols_are_exported_and_bound():
     simple = {"vc_last_error", "vc_abi_version", "vc_launch_count", "vc_reset_launch_count", "vc_set_pdl", "vc_get_pdl",
               "vc_check_device"}
     assert names - simple == set(ops.SIGNATURES), (names - simple) ^ set(ops.SIGNATURES)
-    assert lib.vc_abi_version() == 8
+    assert lib.vc_abi_version() == 9
     assert isinstance(lib.vc_last_error(), bytes)
 
 
@@ -166,14 +166,15 @@ def test_three_product_split_bf16_arithmetic_spec():
 
 
 def test_decode_precision_option(monkeypatch):
-    """decode_precision: 'bf16x3' by default in the fast mode, overridable by argument or VITCAP_DECODE_PRECISION; the exact mode
+    """decode_precision: 'fp16' by default in the fast mode, overridable by argument or VITCAP_DECODE_PRECISION; the exact mode
     ignores it; anything else is refused at construction."""
     from vitcap_b200 import config as vcfg
     from vitcap_b200.model import FastImageCaptioning
     cfg = vcfg.tiny()
     monkeypatch.delenv("VITCAP_DECODE_PRECISION", raising=False)
-    assert FastImageCaptioning(cfg).decode_precision == "bf16x3"
+    assert FastImageCaptioning(cfg).decode_precision == "fp16"
     assert FastImageCaptioning(cfg, decode_precision="bf16").decode_precision == "bf16"
+    assert FastImageCaptioning(cfg, decode_precision="bf16x3").decode_precision == "bf16x3"
     assert FastImageCaptioning(cfg, mode="fp32", decode_precision="bf16x3").decode_precision == "fp32"
     monkeypatch.setenv("VITCAP_DECODE_PRECISION", "bf16")
     assert FastImageCaptioning(cfg).decode_precision == "bf16"

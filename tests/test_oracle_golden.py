@@ -96,7 +96,7 @@ z, meta = load_golden(sys.argv[1])
 cfg, sd, data, extra = golden_setup(meta)
 ref, tok = ref_loader.build_reference(meta["variant"])
 import src.layers.bert.modeling_bert as mb
-assert mb.__file__.endswith(".pyc"), mb.__file__            # the bytecode tree, not /root/reference
+assert "reference_pyc.zip" in mb.__file__ and mb.__file__.endswith(".pyc"), mb.__file__     # the archive, not /root/reference
 ref.load_state_dict(sd, strict=True)
 ref.test_extra_input = extra
 data = dict(data)

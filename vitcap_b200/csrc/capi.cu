@@ -87,7 +87,7 @@ static std::atomic<long long> g_launches{0};
 extern "C" {
 
 const char* vc_last_error(void) { return vc::last_error(); }
-int vc_abi_version(void) { return 8; }
+int vc_abi_version(void) { return 9; }
 int vc_check_device(void) { return vc::check_device(); }
 long long vc_launch_count(void) { return g_launches.load(); }
 void vc_reset_launch_count(void) { g_launches = 0; }
@@ -264,13 +264,13 @@ int vc_beam_finalize(const double* hyp_score, const int* hyp_len, const int* hyp
                      int max_len, int pad_id, int eos0, long long* out_ids, float* out_lp, void* stream) {
   VC_COUNT(1, vc::beam_finalize(hyp_score, hyp_len, hyp_ids, hyp_count, B, keep, max_len, pad_id, eos0, out_ids, out_lp, ST(stream)));
 }
-int vc_dec_linear(int mode, int x3, const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldo, int M,
+int vc_dec_linear(int mode, int fmt, const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldo, int M,
                   int N, int K, int splits, int m_pad, void* stream) {
-  VC_COUNT(1, vc::gemm_dec(mode, x3, A, lda, W, ldw, bias, out, ldo, M, N, K, splits, m_pad, ST(stream)));
+  VC_COUNT(1, vc::gemm_dec(mode, fmt, A, lda, W, ldw, bias, out, ldo, M, N, K, splits, m_pad, ST(stream)));
 }
-int vc_dec_vocab_argmax(int x3, const void* A, int lda, const void* W, int ldw, const float* bias, void* part, int n_part, int M,
+int vc_dec_vocab_argmax(int fmt, const void* A, int lda, const void* W, int ldw, const float* bias, void* part, int n_part, int M,
                         int N, int K, void* stream) {
-  VC_COUNT(1, vc::gemm_dec_argmax(x3, A, lda, W, ldw, bias, part, n_part, M, N, K, ST(stream)));
+  VC_COUNT(1, vc::gemm_dec_argmax(fmt, A, lda, W, ldw, bias, part, n_part, M, N, K, ST(stream)));
 }
 int vc_finish_ln(const float* part, int splits, size_t plane, int ld_p, const float* bias, int gelu, const float* resid, int ld_r,
                  const float* gamma, const float* beta, float eps, float* out_f, int ld_f, void* out_t, int ld_t, int out_mode,

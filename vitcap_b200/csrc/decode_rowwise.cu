@@ -97,7 +97,7 @@ finish_ln_kernel(const float* __restrict__ part, int splits, size_t plane, int l
       if (out_f != nullptr) *reinterpret_cast<float4*>(out_f + (size_t)row * ld_f + c) = o;
       if (out_mode == 1) {
         *reinterpret_cast<uint2*>(out_t + (size_t)row * ld_t + c) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
-      } else if (out_mode >= 2) {
+      } else if (out_mode == 2 || out_mode == 3) {
         uint2 hi, lo;
         split_bf16x2(o.x, o.y, hi.x, lo.x);
         split_bf16x2(o.z, o.w, hi.y, lo.y);
@@ -106,16 +106,26 @@ finish_ln_kernel(const float* __restrict__ part, int splits, size_t plane, int l
         *reinterpret_cast<uint2*>(op + H) = lo;
         if (out_mode == 3) *reinterpret_cast<uint2*>(op + 2 * H) = hi;     // the K-concatenated GEMM form reads [hi | lo | hi]
       }
+      if (out_mode == 4 || out_mode == 5) {             // IEEE-half operand copy (the one-product half GEMMs of gemm_dec.cu)
+        bf16* op = out_t + (size_t)row * ld_t + c;
+        if (out_mode == 5) {                             // [bf16 | half]: the q|k|v projection reads the first H columns
+          *reinterpret_cast<uint2*>(op) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+          op += H;
+        }
+        *reinterpret_cast<uint2*>(op) = make_uint2(pack_f16x2(o.x, o.y), pack_f16x2(o.z, o.w));
+      }
     }
 }
 
 // part: [splits] planes of [>= rows, ld_p] fp32, `plane` elements apart; out_mode 0 = no operand copy, 1 = bf16 [rows, ld_t],
-// 2 = split pair: columns [0, H) = hi, [H, 2H) = lo (ld_t >= 2H), 3 = [hi | lo | hi] (ld_t >= 3H)
+// 2 = split pair: columns [0, H) = hi, [H, 2H) = lo (ld_t >= 2H), 3 = [hi | lo | hi] (ld_t >= 3H), 4 = IEEE half [rows, ld_t],
+// 5 = [bf16 | half] (ld_t >= 2H)
 int finish_ln(const float* part, int splits, size_t plane, int ld_p, const float* bias, int gelu, const float* resid, int ld_r,
               const float* gamma, const float* beta, float eps, float* out_f, int ld_f, void* out_t, int ld_t, int out_mode, int rows,
               int H, cudaStream_t s) {
   if (H % 128 || H > 1024 || rows <= 0 || splits < 1 || (ld_p % 4) || (plane % 4) || (resid && (ld_r % 4)) || (out_f && (ld_f % 4)) ||
-      out_mode < 0 || out_mode > 3 || (out_mode && (out_t == nullptr || (ld_t % 4) || ld_t < out_mode * H)) || part == nullptr ||
+      out_mode < 0 || out_mode > 5 || part == nullptr ||
+      (out_mode && (out_t == nullptr || (ld_t % 4) || ld_t < (out_mode == 4 ? 1 : out_mode == 5 ? 2 : out_mode) * H)) ||
       gamma == nullptr || beta == nullptr) {
     set_last_error("finish_ln: need H %% 128 == 0, H <= 1024, pitches %% 4 == 0, ld_t >= H (2H for the split pair) (H=%d)", H);
     return VC_ERR_BAD_ARG;

@@ -54,12 +54,13 @@ template <bool X3, int BN_> struct DecCfg {
 };
 
 struct DecArgs {
-  const float* bias;    // [N] or NULL (EPI_PARTIAL ignores it)
+  const float* bias;    // [N] or NULL (EPI_PARTIAL: added only to a single plane, splits == 1 -- the fp32 logits form)
   float4* part;         // EPI_ARGMAX: [M, n_part] (max, arg max as int bits, sum of exp(x - max), unused)
   int n_part;
   int M, N, K;          // K = operand pitch along K (3 Kt with X3)
   int splits;           // split-K factor (EPI_PARTIAL); tiles are (m, n, split) triples
   int m_pad;            // rows per partial plane (multiple of 128)
+  int f16;              // operands are IEEE halves (one product); the GELU epilogue then writes halves as well
 };
 
 }  // namespace
@@ -170,7 +171,7 @@ gemm_dec_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     // ===================== MMA issuer (leader CTA only) =====================
     if (rank == 0 && lane == 0) {
       pdl_wait();
-      constexpr uint32_t idesc = make_idesc_bf16(2 * C::BM, C::BN, 0, 0);
+      const uint32_t idesc = ar.f16 ? make_idesc_f16(2 * C::BM, C::BN, 0, 0) : make_idesc_bf16(2 * C::BM, C::BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -285,6 +286,12 @@ gemm_dec_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
             if (EPI == EPI_PARTIAL) {
+              if (ar.bias != nullptr) {                 // single plane with bias = the fp32 logits (N need not be a multiple of 4)
+                const int cb = col0 + hh * 32;
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (cb + j < ar.N) v[j] += __ldg(ar.bias + cb + j);
+              }
 #pragma unroll
               for (int j = 0; j < 8; ++j)
                 *reinterpret_cast<float4*>(row_hi + ((j ^ sw) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -312,6 +319,9 @@ gemm_dec_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                   split_bf16x2(v[8 * j + 4], v[8 * j + 5], hi.z, lo.z);
                   split_bf16x2(v[8 * j + 6], v[8 * j + 7], hi.w, lo.w);
                   *reinterpret_cast<uint4*>(row_lo + (((hh * 4 + j) ^ sw) << 4)) = lo;
+                } else if (EPI == EPI_GELU_BF16 && ar.f16) {
+                  hi = make_uint4(pack_f16x2(v[8 * j], v[8 * j + 1]), pack_f16x2(v[8 * j + 2], v[8 * j + 3]),
+                                  pack_f16x2(v[8 * j + 4], v[8 * j + 5]), pack_f16x2(v[8 * j + 6], v[8 * j + 7]));
                 } else {
                   hi = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
                                   pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
@@ -369,8 +379,10 @@ static int launch_dec(const CUtensorMap& ta, const CUtensorMap& tb, const CUtens
 
 constexpr int VOCAB_BN = 208;
 
-static int dec_check(const char* what, const void* A, int lda, const void* W, int ldw, int M, int N, int K, int x3) {
-  const int unit = x3 ? 192 : 64;
+// operand format `fmt`: 0 = bf16, 1 = split bf16 (three products, K = 3 Kt), 2 = IEEE half (one product)
+static int dec_check(const char* what, const void* A, int lda, const void* W, int ldw, int M, int N, int K, int fmt) {
+  if (fmt < 0 || fmt > 2) { set_last_error("%s: operand format %d (0 bf16, 1 split bf16, 2 half)", what, fmt); return VC_ERR_BAD_ARG; }
+  const int unit = fmt == 1 ? 192 : 64;
   if (M <= 0 || N <= 0 || K <= 0 || (K % unit) != 0) {
     set_last_error("%s: need K %% %d == 0 (M=%d N=%d K=%d)", what, unit, M, N, K);
     return VC_ERR_BAD_ARG;
@@ -382,20 +394,23 @@ static int dec_check(const char* what, const void* A, int lda, const void* W, in
   return VC_OK;
 }
 
-// mode 0: out = fp32 partial planes [splits, m_pad, N] of A W^T (no bias), plane s = the s-th slice of K
-// mode 1: out = bf16 (A W^T + bias);  mode 2: out = bf16 GELU(A W^T + bias)
+// mode 0: out = fp32 partial planes [splits, m_pad, N] of A W^T, plane s = the s-th slice of K; no bias -- except that a single
+//         plane (splits == 1) takes one: out = fp32 A W^T + bias with any N (the materialised vocabulary logits)
+// mode 1: out = bf16 (A W^T + bias);  mode 2: out = GELU(A W^T + bias) as bf16 (as halves with fmt 2: the next GEMM's operand)
 // mode 3: out = bf16 [M, >= 2N]: columns [0, N) = hi, [N, 2N) = lo of the split of GELU(A W^T + bias)
-int gemm_dec(int mode, int x3, const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldo, int M, int N,
+int gemm_dec(int mode, int fmt, const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldo, int M, int N,
              int K, int splits, int m_pad, cudaStream_t stream) {
-  int rc = dec_check("gemm_dec", A, lda, W, ldw, M, N, K, x3);
+  int rc = dec_check("gemm_dec", A, lda, W, ldw, M, N, K, fmt);
   if (rc) return rc;
+  const int x3 = fmt == 1;
   const int num_kb = (x3 ? K / 3 : K) / 64;
   if (mode < 0 || mode > 3 || out == nullptr || (reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(bias) & 15)) {
     set_last_error("gemm_dec: bad mode / output"); return VC_ERR_BAD_ARG;
   }
   if (mode == EPI_PARTIAL) {
-    if (splits < 1 || num_kb % splits || m_pad < M || (m_pad % 128) || (ldo % 4) || (N % 4)) {
-      set_last_error("gemm_dec: partial planes need splits | k-blocks (%d), m_pad %% 128 == 0 >= M, N %% 4 == 0", num_kb);
+    if (splits < 1 || num_kb % splits || m_pad < M || (m_pad % 128) || (ldo % 4) || ((N % 4) && splits > 1) || (bias && splits > 1)) {
+      set_last_error("gemm_dec: partial planes need splits | k-blocks (%d), m_pad %% 128 == 0 >= M, N %% 4 == 0, a bias only with "
+                     "splits == 1", num_kb);
       return VC_ERR_BAD_ARG;
     }
   } else {
@@ -413,10 +428,11 @@ int gemm_dec(int mode, int x3, const void* A, int lda, const void* W, int ldw, c
   if (rc) return rc;
   rc = get_tmap_2d_bf16(&tb, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, narrow ? 64 : 128, 64);
   if (rc) return rc;
-  if (mode == EPI_PARTIAL) rc = get_tmap_2d_f32(&to, out, (uint64_t)splits * m_pad, (uint64_t)N, (uint64_t)ldo, 128, 32);
+  // (a single plane is clipped at M rows: the logits buffer has no padding rows)
+  if (mode == EPI_PARTIAL) rc = get_tmap_2d_f32(&to, out, splits == 1 ? (uint64_t)M : (uint64_t)splits * m_pad, (uint64_t)N, (uint64_t)ldo, 128, 32);
   else rc = get_tmap_2d_bf16(&to, out, (uint64_t)M, (uint64_t)(mode == EPI_GELU_SPLIT ? 2 * N : N), (uint64_t)ldo, 128, 64);
   if (rc) return rc;
-  DecArgs ar = {bias, nullptr, 0, M, N, K, splits, m_pad};
+  DecArgs ar = {mode == EPI_PARTIAL && splits > 1 ? nullptr : bias, nullptr, 0, M, N, K, splits, m_pad, fmt == 2};
   if (x3) {
     switch (mode) {
       case EPI_PARTIAL: return launch_dec<true, EPI_PARTIAL, 256>(ta, tb, to, ar, stream);
@@ -436,10 +452,11 @@ int gemm_dec(int mode, int x3, const void* A, int lda, const void* W, int ldw, c
 
 // part [M, n_part] float4, n_part = 2 * ceil(N / 208): per (row, 208-column tile, epilogue group) the maximum of
 // A W^T + bias over the group's columns, its first arg max, and the sum of exp(x - max)
-int gemm_dec_argmax(int x3, const void* A, int lda, const void* W, int ldw, const float* bias, void* part, int n_part, int M, int N,
+int gemm_dec_argmax(int fmt, const void* A, int lda, const void* W, int ldw, const float* bias, void* part, int n_part, int M, int N,
                     int K, cudaStream_t stream) {
-  int rc = dec_check("gemm_dec_argmax", A, lda, W, ldw, M, N, K, x3);
+  int rc = dec_check("gemm_dec_argmax", A, lda, W, ldw, M, N, K, fmt);
   if (rc) return rc;
+  const int x3 = fmt == 1;
   if (part == nullptr || (reinterpret_cast<uintptr_t>(part) & 15) || n_part != 2 * ((N + VOCAB_BN - 1) / VOCAB_BN)) {
     set_last_error("gemm_dec_argmax: part must be 16-byte aligned with n_part = 2 * ceil(N / 208)"); return VC_ERR_BAD_ARG;
   }
@@ -448,7 +465,7 @@ int gemm_dec_argmax(int x3, const void* A, int lda, const void* W, int ldw, cons
   if (rc) return rc;
   rc = get_tmap_2d_bf16(&tb, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, VOCAB_BN / 2, 64);
   if (rc) return rc;
-  DecArgs ar = {bias, static_cast<float4*>(part), n_part, M, N, K, 1, 0};
+  DecArgs ar = {bias, static_cast<float4*>(part), n_part, M, N, K, 1, 0, fmt == 2};
   if (x3) return launch_dec<true, EPI_ARGMAX, VOCAB_BN>(ta, tb, ta, ar, stream);
   return launch_dec<false, EPI_ARGMAX, VOCAB_BN>(ta, tb, ta, ar, stream);
 }

@@ -34,11 +34,14 @@ def _round_up(a, b):
 class PackedWeights:
     """Weights re-laid for the kernels from a reference-layout state_dict (fp32 masters stay in the nn.Module)."""
 
-    def __init__(self, cfg: VitCapConfig, sd, mode, device, decode_x3=False):
+    def __init__(self, cfg: VitCapConfig, sd, mode, device, decode_x3=False, decode_f16=False):
         self.cfg = cfg
         self.mode = mode
         # split-bf16 copies [w_hi | w_hi | w_lo] of the decode-step MLP and vocabulary-head weights (see _decode_layers)
         self.decode_x3 = bool(decode_x3) and mode == "bf16"
+        # IEEE-half copies of the same weights (decode_precision='fp16': one product on 11-bit significands)
+        self.decode_f16 = bool(decode_f16) and mode == "bf16"
+        assert not (self.decode_x3 and self.decode_f16)
         wt = torch.bfloat16 if mode == "bf16" else torch.float32
         self.wt = wt
 
@@ -47,6 +50,9 @@ class PackedWeights:
 
         def Fp(key):
             return sd[key].detach().to(device=device, dtype=torch.float32).contiguous()
+
+        def Hf(key):
+            return Fp(key).clamp_(-65504.0, 65504.0).to(torch.float16).contiguous()
 
         H = cfg.hidden
         ie = "image_encoder.module."
@@ -95,6 +101,9 @@ class PackedWeights:
         if self.decode_x3:
             self.cls_head["t_w3"] = ops.split_weight_bf16x3(Fp("module.cls.predictions.transform.dense.weight"))
             self.cls_head["dec_w3"] = ops.split_weight_bf16x3(Fp("module.cls.predictions.decoder.weight"))
+        if self.decode_f16:
+            self.cls_head["t_wh"] = Hf("module.cls.predictions.transform.dense.weight")
+            self.cls_head["dec_wh"] = Hf("module.cls.predictions.decoder.weight")
 
         e = "module.bert.embeddings."
         self.word = Fp(e + "word_embeddings.weight")
@@ -119,6 +128,9 @@ class PackedWeights:
             if self.decode_x3:
                 self.dec[-1]["i_w3"] = ops.split_weight_bf16x3(Fp(p + "intermediate.dense.weight"))
                 self.dec[-1]["f_w3"] = ops.split_weight_bf16x3(Fp(p + "output.dense.weight"))
+            if self.decode_f16:
+                self.dec[-1]["i_wh"] = Hf(p + "intermediate.dense.weight")
+                self.dec[-1]["f_wh"] = Hf(p + "output.dense.weight")
             if mode == "bf16":
                 # prefill with folded LayerNorms (engine.prefill): the intermediate GEMM folds this layer's attention-output
                 # LayerNorm, the q|k|v GEMM of layer i >= 1 folds the output LayerNorm of layer i - 1
@@ -154,6 +166,8 @@ class CaptionEngine:
         self.ln_fold2 = level >= 2             # the same for norm2: the proj GEMM emits, the fc1 + GELU GEMM folds
         # decode-step MLP and vocabulary head on split-bf16 operands (three tensor-core products, ~fp32 operand precision)
         self.decode_x3 = weights.decode_x3
+        # ... or on IEEE-half operands (one product, 11-bit significands; fused decode step only)
+        self.decode_f16 = weights.decode_f16
         # fc2 of a decode step through vc_linear_x3 (distinct tiles loaded once) instead of the K-concatenated plain GEMM
         # (VITCAP_X3_DEDUP=0 for A/B measurements)
         self.x3_dedup = os.environ.get("VITCAP_X3_DEDUP", "1") != "0"
@@ -161,6 +175,8 @@ class CaptionEngine:
         # planes, split-operand epilogues, vocabulary arg-max partials) with bias / residual / LayerNorm / operand split in the
         # row-wise finish kernel (decode_rowwise.cu). VITCAP_FUSED_DECODE=0 restores the round-1 kernel sequence (A/B runs)
         self.fused_decode = self.mode == "bf16" and os.environ.get("VITCAP_FUSED_DECODE", "1") != "0"
+        if self.decode_f16 and not self.fused_decode:
+            raise NotImplementedError("decode_precision='fp16' exists on the fused decode step only (VITCAP_FUSED_DECODE=0 is set)")
         # split-K factors of its partial-plane GEMMs (o-proj, fc2, head transform). CONSTANTS, not functions of the batch: the
         # summation order of a row must not depend on how many other rows are in flight (every image's result is bit-identical
         # in any batch, tests/test_fullsize_gpu.py). VITCAP_DEC_SPLITS="o,f,t" overrides them for tuning runs
@@ -261,6 +277,11 @@ class CaptionEngine:
             ws["hid3"] = self._alloc(2 * R, 3 * F)          # ... and split
             ws["e_t3"] = self._alloc(2 * R, 3 * H)          # last layer's LayerNorm 2 output (feeds the head)
             ws["head_t3"] = self._alloc(R, 3 * H)
+        if self.decode_f16:
+            ws["a_th"] = self._alloc(2 * R, H, dtype=torch.float16)       # LayerNorm 1 output as halves
+            ws["hid_h"] = self._alloc(2 * R, F, dtype=torch.float16)      # GELU output as halves
+            ws["e_t2"] = self._alloc(2 * R, 2 * H)                        # LayerNorm 2 output: [bf16 | bit patterns of the halves]
+            ws["head_th"] = self._alloc(R, H, dtype=torch.float16)
         if self.fused_decode:
             x3 = self.decode_x3
             # split-K factors of the partial-plane GEMMs (o-proj, fc2, head transform) and their fp32 planes
@@ -643,16 +664,20 @@ class CaptionEngine:
         C = cfg.n_ctx + (cfg.topk if labels else 0)
         enc = self._enc_ws
         ctx_vis = enc["ctx_vis"] if labels else None
-        x3 = self.decode_x3
+        x3, f16 = self.decode_x3, self.decode_f16
         eps = cfg.bert_ln_eps
         scale = 1.0 / math.sqrt(cfg.head_dim)
         sp, part, m_pad = ws["splits"], ws["part"], ws["m_pad"]
         e_f, a_f = ws["e_f"], ws["a_f"]
-        # operand copies of the two streams: bf16 rows, or (x3) [hi | lo | .] rows of pitch 3H whose first H columns ARE the
-        # bf16 copy (the q|k|v GEMM reads them with lda = 3H)
-        e_op = ws["e_t3"] if x3 else ws["e_t"]
-        a_op = ws["a_t3"] if x3 else ws["a_t"]
-        hid = ws["hid3"] if x3 else ws["hid"]
+        # operand copies of the two streams: bf16 rows; (x3) [hi | lo | .] rows of pitch 3H whose first H columns ARE the bf16
+        # copy (the q|k|v GEMM reads them with lda = 3H); (f16) IEEE halves -- the LayerNorm 2 stream as [bf16 | half] rows of
+        # pitch 2H, because the q|k|v projection stays a bf16 product
+        e_op = ws["e_t3"] if x3 else (ws["e_t2"] if f16 else ws["e_t"])
+        a_op = ws["a_t3"] if x3 else (ws["a_th"] if f16 else ws["a_t"])
+        hid = ws["hid3"] if x3 else (ws["hid_h"] if f16 else ws["hid"])
+        split1 = "f16" if f16 else x3
+        split2 = "bf16+f16" if f16 else x3
+        wi, wf = ("i_w3", "f_w3") if x3 else (("i_wh", "f_wh") if f16 else ("i_w", "f_w"))
         ops.embed_ln(ws["ids"], cur_len, mask_id, w.word, w.pos, w.type0, w.emb_ln_w, w.emb_ln_b, eps, e_f, ws["e_t"], R)
         cur = ws["e_t"]                                   # layer 0 reads the embedding rows (bf16, pitch H)
         for l, p in enumerate(w.dec):
@@ -661,29 +686,35 @@ class CaptionEngine:
             ops.decode_attention(enc["ctx_qkv"][l], sq, anc, ws["att"], B, C, cfg.heads, E, cur_len, scale, ctx_vis=ctx_vis,
                                  seq_unfinished=live[0], img_done=live[1])
             ops.dec_linear(ops.DEC_PARTIAL, ws["att"], p["o_w"], None, part, M=M, splits=sp["o"], m_pad=m_pad)
-            ops.finish_ln(part, sp["o"], p["o_b"], p["ln1_w"], p["ln1_b"], eps, M, resid=e_f, out_f=a_f, out_t=a_op, split=x3)
+            ops.finish_ln(part, sp["o"], p["o_b"], p["ln1_w"], p["ln1_b"], eps, M, resid=e_f, out_f=a_f, out_t=a_op, split=split1)
             if x3:
-                ops.dec_linear(ops.DEC_GELU_SPLIT, a_op, p["i_w3"], p["i_b"], hid, M=M, x3=True)
-                ops.dec_linear(ops.DEC_PARTIAL, hid, p["f_w3"], None, part, M=M, x3=True, splits=sp["f"], m_pad=m_pad)
+                ops.dec_linear(ops.DEC_GELU_SPLIT, a_op, p[wi], p["i_b"], hid, M=M, x3=True)
             else:
-                ops.dec_linear(ops.DEC_GELU_BF16, a_op, p["i_w"], p["i_b"], hid, M=M)
-                ops.dec_linear(ops.DEC_PARTIAL, hid, p["f_w"], None, part, M=M, splits=sp["f"], m_pad=m_pad)
-            ops.finish_ln(part, sp["f"], p["f_b"], p["ln2_w"], p["ln2_b"], eps, M, resid=a_f, out_f=e_f, out_t=e_op, split=x3)
+                ops.dec_linear(ops.DEC_GELU_BF16, a_op, p[wi], p["i_b"], hid, M=M)
+            ops.dec_linear(ops.DEC_PARTIAL, hid, p[wf], None, part, M=M, x3=x3, splits=sp["f"], m_pad=m_pad)
+            ops.finish_ln(part, sp["f"], p["f_b"], p["ln2_w"], p["ln2_b"], eps, M, resid=a_f, out_f=e_f, out_t=e_op, split=split2)
             cur = e_op
         if not head:
             return False
         # vocabulary head on the MASK rows only (rows 1::2); the reference runs it over all T text rows
         # (modeling_bert.py:809-810) and keeps one
         hp = w.cls_head
-        head_op = ws["head_t3"] if x3 else ws["head_t"]
-        ops.dec_linear(ops.DEC_PARTIAL, e_op[1::2], hp["t_w3"] if x3 else hp["t_w"], None, ws["part_h"], M=R, x3=x3,
-                       splits=sp["t"], m_pad=ws["m_pad_h"])
+        if f16:
+            mask_rows = e_op.view(torch.float16)[1::2, H:2 * H]          # the half columns of the [bf16 | half] rows
+            head_op, t_w, dec_w = ws["head_th"], hp["t_wh"], hp["dec_wh"]
+        else:
+            mask_rows = e_op[1::2]
+            head_op = ws["head_t3"] if x3 else ws["head_t"]
+            t_w, dec_w = (hp["t_w3"], hp["dec_w3"]) if x3 else (hp["t_w"], hp["dec_w"])
+        ops.dec_linear(ops.DEC_PARTIAL, mask_rows, t_w, None, ws["part_h"], M=R, x3=x3, splits=sp["t"], m_pad=ws["m_pad_h"])
         # (the K-concatenated GEMM that materialises the logits reads [hi | lo | hi]; the arg-max kernel only [hi | lo])
         ops.finish_ln(ws["part_h"], sp["t"], hp["t_b"], hp["ln_w"], hp["ln_b"], eps, R, gelu=True, out_t=head_op,
-                      split=(3 if vocab != "argmax" else True) if x3 else False)
-        dec_w = hp["dec_w3"] if x3 else hp["dec_w"]
+                      split="f16" if f16 else ((3 if vocab != "argmax" else True) if x3 else False))
         if vocab != "argmax":
-            ops.linear(head_op, dec_w, hp["bias"], ws["logits"][:, :cfg.vocab], M=R, ldo=ws["logits"].stride(0))
+            if f16:       # fp32 logits from the decode-step kernel itself: one plane with the bias (no half form of vc_linear)
+                ops.dec_linear(ops.DEC_PARTIAL, head_op, dec_w, hp["bias"], ws["logits"][:, :cfg.vocab], M=R)
+            else:
+                ops.linear(head_op, dec_w, hp["bias"], ws["logits"][:, :cfg.vocab], M=R, ldo=ws["logits"].stride(0))
         if vocab != "logits":
             ops.dec_vocab_argmax(head_op, dec_w, hp["bias"], ws["vpart"], M=R, x3=x3)
             return True

@@ -488,21 +488,41 @@ def vocab_partials(N):
     return 2 * ((N + VOCAB_TILE - 1) // VOCAB_TILE)
 
 
+DEC_FMT_BF16, DEC_FMT_BF16X3, DEC_FMT_F16 = 0, 1, 2
+
+
+def _dec_fmt(a, w, x3):
+    """Operand format of a decode-step GEMM from the operand dtype: torch.float16 tensors select the IEEE-half product."""
+    assert a.dtype == w.dtype and a.stride(-1) == 1 and w.stride(-1) == 1
+    if a.dtype == torch.float16:
+        assert not x3, "half operands run as one product"
+        return DEC_FMT_F16
+    assert a.dtype == torch.bfloat16
+    return DEC_FMT_BF16X3 if x3 else DEC_FMT_BF16
+
+
 def dec_linear(mode, a, w, bias, out, M=None, x3=False, splits=1, m_pad=0, lda=None, ldo=None):
     """Decode-step Linear on CTA-pair tiles (include/vitcap_b200.h, vc_dec_linear). a [M, K] / w [N, K] bf16 (K = 3 Kt split
-    layouts with x3). mode DEC_PARTIAL: out fp32 [splits, m_pad, N] partial planes, no bias; DEC_BF16 / DEC_GELU_BF16: out bf16
-    [M, N]; DEC_GELU_SPLIT: out bf16 [M, >= 2N] = [hi | lo] of the GELU output."""
+    layouts with x3) or float16 (one product on IEEE halves). mode DEC_PARTIAL: out fp32 [splits, m_pad, N] partial planes, no
+    bias -- or, with splits = 1 and a 2-d out, fp32 [M, N] = a w^T + bias (the materialised logits); DEC_BF16: out bf16 [M, N];
+    DEC_GELU_BF16: out [M, N] in the operand dtype; DEC_GELU_SPLIT: out bf16 [M, >= 2N] = [hi | lo] of the GELU output."""
     N, K = w.shape
     M = a.shape[0] if M is None else M
     lda = a.stride(0) if lda is None else lda
-    assert a.dtype == w.dtype == torch.bfloat16 and a.stride(-1) == 1 and w.stride(-1) == 1 and out.stride(-1) == 1
-    if mode == DEC_PARTIAL:
+    fmt = _dec_fmt(a, w, x3)
+    assert out.stride(-1) == 1
+    if mode == DEC_PARTIAL and out.dim() == 2:
+        assert out.dtype == torch.float32 and splits == 1 and out.shape[0] >= M
+        ldo = out.stride(0)
+        m_pad = -(-M // 128) * 128
+    elif mode == DEC_PARTIAL:
         assert out.dtype == torch.float32 and out.dim() == 3 and out.shape[0] >= splits and out.shape[1] == m_pad and out.is_contiguous()
+        assert bias is None
         ldo = out.stride(1)
     else:
-        assert out.dtype == torch.bfloat16
+        assert out.dtype == (torch.float16 if (fmt == DEC_FMT_F16 and mode == DEC_GELU_BF16) else torch.bfloat16)
         ldo = out.stride(0) if ldo is None else ldo
-    _check(load_library().vc_dec_linear(mode, int(bool(x3)), _ptr(a), lda, _ptr(w), w.stride(0), _ptr(bias), _ptr(out), ldo, M, N, K,
+    _check(load_library().vc_dec_linear(mode, fmt, _ptr(a), lda, _ptr(w), w.stride(0), _ptr(bias), _ptr(out), ldo, M, N, K,
                                         splits, m_pad, _stream()), "vc_dec_linear")
     return out
 
@@ -513,19 +533,31 @@ def dec_vocab_argmax(a, w, bias, part, M=None, x3=False, lda=None):
     M = a.shape[0] if M is None else M
     lda = a.stride(0) if lda is None else lda
     n_part = vocab_partials(N)
-    assert a.dtype == w.dtype == torch.bfloat16 and part.dtype == torch.float32 and part.is_contiguous()
+    fmt = _dec_fmt(a, w, x3)
+    assert part.dtype == torch.float32 and part.is_contiguous()
     assert part.shape[-1] == 4 and part.shape[-2] == n_part and part.shape[0] >= M
-    _check(load_library().vc_dec_vocab_argmax(int(bool(x3)), _ptr(a), lda, _ptr(w), w.stride(0), _ptr(bias), _ptr(part), n_part, M, N,
+    _check(load_library().vc_dec_vocab_argmax(fmt, _ptr(a), lda, _ptr(w), w.stride(0), _ptr(bias), _ptr(part), n_part, M, N,
                                               K, _stream()), "vc_dec_vocab_argmax")
     return part
 
 
 def finish_ln(part, splits, bias, gamma, beta, eps, rows, resid=None, gelu=False, out_f=None, out_t=None, split=False):
-    """LayerNorm(act(sum of `splits` partial planes + bias) + resid) -> out_f (fp32) and out_t (bf16; split=True: the
-    [hi | lo] pair; split=3: [hi | lo | hi])."""
+    """LayerNorm(act(sum of `splits` partial planes + bias) + resid) -> out_f (fp32) and the operand copy out_t: bf16;
+    split=True: the [hi | lo] pair; split=3: [hi | lo | hi]; split='f16': IEEE halves (out_t float16);
+    split='bf16+f16': columns [0, H) bf16, [H, 2H) the bit patterns of the halves (out_t bf16, pitch >= 2H)."""
     assert part.dtype == torch.float32 and part.dim() == 3 and part.shape[0] >= splits
     H = part.shape[2]
-    mode = 0 if out_t is None else ((3 if split == 3 else 2) if split else 1)
+    if out_t is None:
+        mode = 0
+    elif split == "f16":
+        assert out_t.dtype == torch.float16
+        mode = 4
+    elif split == "bf16+f16":
+        assert out_t.dtype == torch.bfloat16
+        mode = 5
+    else:
+        assert out_t.dtype == torch.bfloat16
+        mode = (3 if split == 3 else 2) if split else 1
     _check(load_library().vc_finish_ln(_ptr(part), splits, part.stride(0), part.stride(1), _ptr(bias), int(bool(gelu)), _ptr(resid),
                                        resid.stride(0) if resid is not None else 0, _ptr(gamma), _ptr(beta), float(eps), _ptr(out_f),
                                        out_f.stride(0) if out_f is not None else 0, _ptr(out_t),
