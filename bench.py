@@ -75,6 +75,9 @@ def workload_config(args, cfg):
         "max_length": 20, "num_beams": 1, "decoder_layers": cfg.dec_layers, "parallelism": "dp%d" % max(1, args.gpus),
         "weights": "random-init (synth.make_state_dict seed 0, reference layout)",
         "decode_precision": getattr(args, "decode_precision", None) or "fp16",
+        "precision": "bf16 operands / fp32 accumulation throughout (fp32 residual stream); decode_precision names the operands of "
+                     "the decode-step MLP and vocabulary-head GEMMs: fp16 = IEEE half (11-bit significand, one product), "
+                     "bf16x3 = split bf16 (three products), bf16 = plain",
         "l2": "inputs larger than L2 (906 MB of images and >10 GB of activations per step vs 126 MB L2)",
     }
 
