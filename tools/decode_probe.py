@@ -38,7 +38,7 @@ def precisions(B, names):
             m = models[n]
             t_dec = timeit(lambda: m.engine.greedy_or_sample(B, 1, 20, 101, 0, [102], 103), iters=8, warm=2)
             t_all = timeit(lambda: m(data), iters=4, warm=1)
-            print("decode_precision=%-7s round %d: decode(graph) %.2f ms  full forward %.2f ms (%.1f images/s)  kernels=%s" % (
+            print("decode_precision=%-9s round %d: decode(graph) %.2f ms  full forward %.2f ms (%.1f images/s)  kernels=%s" % (
                 n, rnd, t_dec, t_all, B / t_all * 1e3, m.engine.stats.get("graph_kernels")), flush=True)
 
 
