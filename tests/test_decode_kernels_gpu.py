@@ -599,3 +599,26 @@ def test_vocab_argmax_half_operands(R, V):
     for r in range(R):
         if int(idx[r]) != int(top2.indices[r, 0]):
             assert float(top2.values[r, 0] - top2.values[r, 1]) < 2e-4, r
+
+
+def test_half_conversions_saturate_instead_of_overflowing():
+    """Values beyond the IEEE-half range become +-65504, never infinities (cvt.rn.satfinite): LayerNorm outputs under an absurd
+    gain through vc_finish_ln, GELU outputs of a GEMM with huge weights through vc_dec_linear."""
+    rows, H = 64, 768
+    part = _rnd(1, 128, H, seed=1)
+    gamma, beta = torch.full((H,), 1.0e5), torch.zeros(H)
+    out_f = torch.empty(rows, H, device=DEV)
+    out_t = torch.empty(rows, H, device=DEV, dtype=torch.float16)
+    ops.finish_ln(part.to(DEV), 1, None, gamma.to(DEV), beta.to(DEV), 1e-12, rows, out_f=out_f, out_t=out_t, split="f16")
+    of, ot = out_f.cpu(), out_t.cpu()
+    assert float(of.abs().max()) > 65504.0 and bool(torch.isfinite(ot.float()).all())
+    assert torch.equal(ot, _h(of)) and float(ot.float().abs().max()) == 65504.0
+    M, N, K = 128, 128, 64
+    A, W = _h(_rnd(M, K, seed=2) * 100.0), _h(_rnd(N, K, seed=3) * 100.0)
+    ref = port.gelu_fast(A.float() @ W.float().t())
+    out = torch.empty(M, N, device=DEV, dtype=torch.float16)
+    ops.dec_linear(ops.DEC_GELU_BF16, A.to(DEV), W.to(DEV), None, out, M=M)
+    got = out.cpu().float()
+    assert float(ref.max()) > 65504.0 and bool(torch.isfinite(got).all()) and float(got.max()) == 65504.0
+    big = ref.abs() > 70000.0
+    assert bool((got[big] == 65504.0).all())

@@ -226,3 +226,37 @@ def test_packed_weights_are_invalidated_by_moves_and_in_place_updates():
     assert m._packed_version != m._param_version()
     with pytest.raises(RuntimeError, match="CUDA device only"):      # the engine property re-packs, which needs the GPU
         m.engine
+
+
+def test_half_range_bounds_of_the_fp16_decode_operands():
+    """decode_precision='fp16' stores LayerNorm / GELU outputs and four weight matrices as IEEE halves. engine.half_range_bounds
+    derives worst-case magnitudes from the weights alone; below 65504 they prove that no conversion can saturate. The synthetic
+    'stress' and reference-style weights are far inside; the bounds really are bounds (checked against the oracle's activations);
+    an absurd LayerNorm gain is reported."""
+    import torch
+    from oracle import port
+    from vitcap_b200 import config as vcfg, synth
+    from vitcap_b200.engine import HALF_MAX, half_range_bounds
+    cfg = vcfg.tiny()
+    for style in ("stress", "reference"):
+        sd = synth.make_state_dict(cfg, seed=3, style=style)
+        b = half_range_bounds(cfg, sd)
+        assert 0 < b["weights"] < 10 and b["layernorm"] < HALF_MAX / 10 and b["gelu"] < HALF_MAX / 2, (style, b)
+    # the bounds hold for what the model actually computes: LayerNorm outputs and GELU outputs of a decode step
+    sd = synth.make_state_dict(cfg, seed=3)
+    b = half_range_bounds(cfg, sd)
+    seen = {"ln": 0.0, "gelu": 0.0}
+
+    class Spy(port.QuantPortModel):
+        def lin_x3(self, a, wkey, bkey):
+            kind = "gelu" if wkey.endswith("output.dense.weight") else "ln"
+            seen[kind] = max(seen[kind], float(a.abs().max()))
+            return super().lin_x3(a, wkey, bkey)
+
+    data = synth.make_text_inputs(cfg, 2)
+    data["image"] = synth.make_images(cfg, 2, seed=5)
+    with torch.no_grad():
+        port.caption(Spy(cfg, sd, decode_f16=True), data, synth.default_test_extra_input(cfg), algorithm="cached")
+    assert 0 < seen["ln"] <= b["layernorm"] and 0 < seen["gelu"] <= b["gelu"], (seen, b)
+    sd["module.bert.decoder.layer.0.output.LayerNorm.weight"] = sd["module.bert.decoder.layer.0.output.LayerNorm.weight"] * 1e5
+    assert half_range_bounds(cfg, sd)["layernorm"] > HALF_MAX

@@ -19,6 +19,7 @@ HBM layout (T = bf16 in fast mode, fp32 in exact mode; all row-major, rows = tok
 """
 import math
 import os
+import warnings
 from collections import OrderedDict
 
 import torch
@@ -29,6 +30,40 @@ from .config import VitCapConfig
 
 def _round_up(a, b):
     return (a + b - 1) // b * b
+
+
+HALF_MAX = 65504.0
+
+
+def half_range_bounds(cfg: VitCapConfig, sd):
+    """Worst-case magnitudes of everything decode_precision='fp16' stores as an IEEE half, from the weights alone:
+      * the four weight matrices themselves (BertIntermediate / BertOutput of every decoder layer, head transform, vocabulary);
+      * LayerNorm outputs (operands of fc1 and of the head GEMMs): |y_j| <= |gamma_j| sqrt(H - 1) + |beta_j|;
+      * GELU outputs of fc1 (operand of fc2): |gelu(x)| <= |x| <= sum_j |W_ij| |y_j| + |b_i|  with the bound on y above.
+    Returns {'weights': ..., 'layernorm': ..., 'gelu': ...}; a value below 65504 PROVES that the conversion never saturates for
+    any input. (The conversions saturate instead of producing infinities in any case.)"""
+    H = cfg.hidden
+    root = math.sqrt(H - 1.0)
+
+    def f(key):
+        return sd[key].detach().float()
+
+    def ln_bound(prefix):
+        return f(prefix + "weight").abs() * root + f(prefix + "bias").abs()
+
+    w_max, ln_max, gelu_max = 0.0, 0.0, 0.0
+    for i in range(cfg.dec_layers):
+        p = "module.bert.decoder.layer.%d." % i
+        y1 = ln_bound(p + "attention.output.LayerNorm.")
+        y2 = ln_bound(p + "output.LayerNorm.")
+        wi, wo = f(p + "intermediate.dense.weight"), f(p + "output.dense.weight")
+        w_max = max(w_max, float(wi.abs().max()), float(wo.abs().max()))
+        ln_max = max(ln_max, float(y1.max()), float(y2.max()))
+        gelu_max = max(gelu_max, float((wi.abs() @ y1 + f(p + "intermediate.dense.bias").abs()).max()))
+    h = "module.cls.predictions."
+    w_max = max(w_max, float(f(h + "transform.dense.weight").abs().max()), float(f(h + "decoder.weight").abs().max()))
+    ln_max = max(ln_max, float(ln_bound(h + "transform.LayerNorm.").max()))
+    return {"weights": w_max, "layernorm": ln_max, "gelu": gelu_max}
 
 
 class PackedWeights:
@@ -102,6 +137,16 @@ class PackedWeights:
             self.cls_head["t_w3"] = ops.split_weight_bf16x3(Fp("module.cls.predictions.transform.dense.weight"))
             self.cls_head["dec_w3"] = ops.split_weight_bf16x3(Fp("module.cls.predictions.decoder.weight"))
         if self.decode_f16:
+            # range proof of the half operands from the weights (half_range_bounds): weights beyond the half range are refused,
+            # activations that COULD saturate (no checkpoint of this model family comes close) are reported once
+            self.half_range = half_range_bounds(cfg, sd)
+            if self.half_range["weights"] > HALF_MAX:
+                raise ValueError("decode_precision='fp16': a decode-step weight of magnitude %.3g does not fit an IEEE half; use "
+                                 "decode_precision='bf16x3'" % self.half_range["weights"])
+            if max(self.half_range["layernorm"], self.half_range["gelu"]) > HALF_MAX:
+                warnings.warn("decode_precision='fp16': the weights allow LayerNorm / GELU outputs up to %.3g / %.3g, beyond the IEEE-half "
+                              "range (65504): such values would saturate. decode_precision='bf16x3' has bf16's range."
+                              % (self.half_range["layernorm"], self.half_range["gelu"]))
             self.cls_head["t_wh"] = Hf("module.cls.predictions.transform.dense.weight")
             self.cls_head["dec_wh"] = Hf("module.cls.predictions.decoder.weight")
 
