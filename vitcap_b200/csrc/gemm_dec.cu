@@ -47,7 +47,9 @@ template <bool X3, int BN_> struct DecCfg {
   static constexpr int THREADS = 64 + 128 * G;
   static constexpr int ACC_COLS = 256;                  // TMEM columns per accumulator stage
   static constexpr int TMEM_COLS = 512;                 // two accumulator stages
-  static constexpr int SMEM_BYTES = PIPE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int BIAS_PAD = 256;                  // floats per staged bias slice (EPI_ARGMAX: [G][2 accumulator stages][256])
+  static constexpr int BIAS_BYTES = G * 2 * BIAS_PAD * 4;
+  static constexpr int SMEM_BYTES = PIPE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + BIAS_BYTES;
   static_assert(BN % 16 == 0 && BN >= 32 && BN <= 256, "UMMA N of a CTA pair: multiple of 16, at most 256");
   static_assert(STAGES >= 3, "pipeline too shallow");
   static_assert((BN / 32) * TILE_BYTES <= PIPE_BYTES, "the staging tiles of one output tile must fit in the pipeline memory");
@@ -81,6 +83,7 @@ gemm_dec_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   uint64_t* tmem_empty = bars + 2 * C::STAGES + 2;      // [2] leader only: 2 CTAs x 4G warps arrive
   uint64_t* epi_free = bars + 2 * C::STAGES + 4;        // [1] per CTA: the staging tiles have been read by their TMA stores
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 5);
+  float* sbias = reinterpret_cast<float*>(smem + C::PIPE_BYTES + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -219,6 +222,18 @@ gemm_dec_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       const int m0 = tile_m(tile) * (2 * C::BM) + (int)rank * C::BM;
       const int n0 = tile_n(tile) * C::BN;
       const int row = m0 + t;
+      const float* sb = sbias + (grp * 2 + as) * C::BIAS_PAD;
+      if (EPI == EPI_ARGMAX) {
+        // the tile's bias slice goes to shared memory WHILE its MMAs run: every thread of a warp needs the same 32 values per
+        // chunk, and as 32 scalar global loads per chunk they were what the epilogue waited for (ncu, session 4 of round 2:
+        // 37 % of the kernel's stall samples on the FADD that consumes them, 21 000 cycles per tile against 5 000 of tensor
+        // work). One buffer per (group, accumulator stage): the group's barrier of the NEXT tile separates reuse from reads.
+        float* sw = sbias + (grp * 2 + as) * C::BIAS_PAD;
+#pragma unroll
+        for (int i = t; i < C::BIAS_PAD; i += 128)
+          sw[i] = (ar.bias != nullptr && i < C::BN && n0 + i < ar.N) ? __ldg(ar.bias + n0 + i) : 0.f;
+        named_bar_sync(bar_id, 128);
+      }
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
       const uint32_t tacc = tmem_base + ((uint32_t)(quad * 32) << 16) + as * C::ACC_COLS;
@@ -250,7 +265,7 @@ gemm_dec_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const bool in = (col0 + j < lim);
-            v[j] = in ? __uint_as_float(r[j]) + (ar.bias ? __ldg(ar.bias + col0 + j) : 0.f) : -INFINITY;
+            v[j] = in ? __uint_as_float(r[j]) + sb[c * 32 + j] : -INFINITY;
             if (v[j] > cm) { cm = v[j]; ci = j; }       // ascending scan: the first index on ties
           }
           if (cm > mx) {
