@@ -14,86 +14,108 @@
 
 namespace vc {
 
-// One warp per row; H <= 1024, H % 128 == 0. S = number of partial planes as a compile-time constant (0 = run-time loop): with
-// the plane loop unrolled all S x 3 loads of a half row are in flight together -- the rows are L2 resident and the kernel is
-// pure latency (round-2 profile: 13.7 us per launch with the run-time loop, whose loads serialised behind their adds).
-// Two rows per 64-thread block: 2 x rows / 148 blocks per SM keeps every SM busy at 1024 rows.
+// TWO warps per row (interleaved float4 columns), two rows per 128-thread block; H <= 1024, H % 128 == 0. S = number of partial
+// planes as a compile-time constant (0 = run-time loop).
+// The kernel is pure latency (the rows are L2 resident, 1024 rows x 3 KB x a few planes): what counts is how many dependent
+// memory round trips a row makes. ncu of the one-warp-per-row form (session 4 of round 2): 75-80 % of the stall samples on the
+// first use of four successive load groups (first half of the planes, second half, bias / residual, gamma / beta after the
+// reductions). Now: bias, gamma and beta -- parameters, not products of the previous kernel -- are requested BEFORE the
+// programmatic-dependency wait, and every plane and the residual of a thread's columns right after it, all in flight together
+// (half the columns per thread keeps that within the register file): one round trip.
 template <bool GELU, int S>
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(128)
 finish_ln_kernel(const float* __restrict__ part, int splits, size_t plane, int ld_p, const float* __restrict__ bias,
                  const float* __restrict__ resid, int ld_r, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                  float* __restrict__ out_f, int ld_f, bf16* __restrict__ out_t, int ld_t, int out_mode, int rows, int H) {
+  __shared__ float red[2][2][2];                      // [row in block][pass][warp of the row]
   pdl_launch_dependents();
-  pdl_wait();
-  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int rb = threadIdx.x >> 6;                   // row inside the block
+  const int w = (threadIdx.x >> 5) & 1;              // which of the row's two warps
   const int lane = threadIdx.x & 31;
-  if (row >= rows) return;
-  const int nv = H / 128;                    // float4 per lane
-  const int ns = S > 0 ? S : splits;
-  const float* prow = part + (size_t)row * ld_p;
-  float4 v[8];
-  float s = 0.f;
+  const int row_raw = blockIdx.x * 2 + rb;
+  const bool active = row_raw < rows;
+  const int row = active ? row_raw : rows - 1;       // an odd tail row: compute on a valid row, store nothing (barriers below)
+  const int nv = H / 128;                            // float4 per lane over the whole row; this thread owns ii = 2 i + w
+  float4 g[4], be[4], bi[4];
 #pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    float4 acc[4][S > 0 ? S : 1];
-    if (S > 0) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int sp = 0; sp < S; ++sp)
-          if (half * 4 + i < nv) acc[i][sp] = *reinterpret_cast<const float4*>(prow + sp * plane + ((half * 4 + i) * 32 + lane) * 4);
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int ii = half * 4 + i;
-      if (ii < nv) {
-        const int c = (ii * 32 + lane) * 4;
-        float4 a;
-        if (S > 0) {
-          a = acc[i][0];
-#pragma unroll
-          for (int sp = 1; sp < S; ++sp) { a.x += acc[i][sp].x; a.y += acc[i][sp].y; a.z += acc[i][sp].z; a.w += acc[i][sp].w; }
-        } else {
-          a = *reinterpret_cast<const float4*>(prow + c);
-          for (int sp = 1; sp < ns; ++sp) {  // fixed summation order: plane 0, 1, ... (as the unrolled form)
-            const float4 b = *reinterpret_cast<const float4*>(prow + sp * plane + c);
-            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-          }
-        }
-        if (bias != nullptr) {
-          const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c));
-          a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-        }
-        if (GELU) {
-          gelu_erf_tanh_x2(a.x, a.y);
-          gelu_erf_tanh_x2(a.z, a.w);
-        }
-        if (resid != nullptr) {
-          const float4 b = *reinterpret_cast<const float4*>(resid + (size_t)row * ld_r + c);
-          a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-        }
-        v[ii] = a;
-        s += (a.x + a.y) + (a.z + a.w);
-      }
+  for (int i = 0; i < 4; ++i) {
+    const int ii = 2 * i + w;
+    if (ii < nv) {
+      const int c = (ii * 32 + lane) * 4;
+      g[i] = __ldg(reinterpret_cast<const float4*>(gamma + c));
+      be[i] = __ldg(reinterpret_cast<const float4*>(beta + c));
+      bi[i] = bias != nullptr ? __ldg(reinterpret_cast<const float4*>(bias + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
-  const float mean = warp_sum(s) / (float)H;
+  pdl_wait();
+  const int ns = S > 0 ? S : splits;
+  const float* prow = part + (size_t)row * ld_p;
+  float4 acc[4][S > 0 ? S : 1];
+  float4 rs[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int ii = 2 * i + w;
+    if (ii < nv) {
+      const int c = (ii * 32 + lane) * 4;
+      if (S > 0) {
+#pragma unroll
+        for (int sp = 0; sp < S; ++sp) acc[i][sp] = *reinterpret_cast<const float4*>(prow + sp * plane + c);
+      } else {
+        acc[i][0] = *reinterpret_cast<const float4*>(prow + c);
+      }
+      rs[i] = resid != nullptr ? *reinterpret_cast<const float4*>(resid + (size_t)row * ld_r + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  float4 v[4];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int ii = 2 * i + w;
+    if (ii < nv) {
+      const int c = (ii * 32 + lane) * 4;
+      float4 a = acc[i][0];
+      if (S > 0) {
+#pragma unroll
+        for (int sp = 1; sp < S; ++sp) { a.x += acc[i][sp].x; a.y += acc[i][sp].y; a.z += acc[i][sp].z; a.w += acc[i][sp].w; }
+      } else {
+        for (int sp = 1; sp < ns; ++sp) {    // fixed summation order: plane 0, 1, ... (as the unrolled form)
+          const float4 b = *reinterpret_cast<const float4*>(prow + sp * plane + c);
+          a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        }
+      }
+      a.x += bi[i].x; a.y += bi[i].y; a.z += bi[i].z; a.w += bi[i].w;
+      if (GELU) {
+        gelu_erf_tanh_x2(a.x, a.y);
+        gelu_erf_tanh_x2(a.z, a.w);
+      }
+      a.x += rs[i].x; a.y += rs[i].y; a.z += rs[i].z; a.w += rs[i].w;
+      v[i] = a;
+      s += (a.x + a.y) + (a.z + a.w);
+    }
+  }
+  s = warp_sum(s);
+  if (lane == 0) red[rb][0][w] = s;
+  __syncthreads();
+  const float mean = (red[rb][0][0] + red[rb][0][1]) / (float)H;
   float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
-    if (i < nv) {
+  for (int i = 0; i < 4; ++i)
+    if (2 * i + w < nv) {
       const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
       q += a * a + b * b + c * c + d * d;
     }
-  const float rstd = rsqrtf(warp_sum(q) / (float)H + eps);
+  q = warp_sum(q);
+  if (lane == 0) red[rb][1][w] = q;
+  __syncthreads();
+  const float rstd = rsqrtf((red[rb][1][0] + red[rb][1][1]) / (float)H + eps);
+  if (!active) return;
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
-    if (i < nv) {
-      const int c = (i * 32 + lane) * 4;
-      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
-      const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
-      const float4 o = make_float4((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y,
-                                   (v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
+  for (int i = 0; i < 4; ++i) {
+    const int ii = 2 * i + w;
+    if (ii < nv) {
+      const int c = (ii * 32 + lane) * 4;
+      const float4 o = make_float4((v[i].x - mean) * rstd * g[i].x + be[i].x, (v[i].y - mean) * rstd * g[i].y + be[i].y,
+                                   (v[i].z - mean) * rstd * g[i].z + be[i].z, (v[i].w - mean) * rstd * g[i].w + be[i].w);
       if (out_f != nullptr) *reinterpret_cast<float4*>(out_f + (size_t)row * ld_f + c) = o;
       if (out_mode == 1) {
         *reinterpret_cast<uint2*>(out_t + (size_t)row * ld_t + c) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
@@ -115,6 +137,7 @@ finish_ln_kernel(const float* __restrict__ part, int splits, size_t plane, int l
         *reinterpret_cast<uint2*>(op) = make_uint2(pack_f16x2(o.x, o.y), pack_f16x2(o.z, o.w));
       }
     }
+  }
 }
 
 // part: [splits] planes of [>= rows, ld_p] fp32, `plane` elements apart; out_mode 0 = no operand copy, 1 = bf16 [rows, ld_t],
@@ -130,7 +153,7 @@ int finish_ln(const float* part, int splits, size_t plane, int ld_p, const float
     set_last_error("finish_ln: need H %% 128 == 0, H <= 1024, pitches %% 4 == 0, ld_t >= H (2H for the split pair) (H=%d)", H);
     return VC_ERR_BAD_ARG;
   }
-  const dim3 grid((rows + 1) / 2), block(64);
+  const dim3 grid((rows + 1) / 2), block(128);
   bf16* ot = static_cast<bf16*>(out_t);
 #define VC_FIN(G, S) launch_pdl(finish_ln_kernel<G, S>, grid, block, 0, s, part, splits, plane, ld_p, bias, resid, ld_r, gamma, beta, \
                                 eps, out_f, ld_f, ot, ld_t, out_mode, rows, H)
