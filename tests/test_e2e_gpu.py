@@ -92,8 +92,8 @@ def test_tiny_greedy_vs_oracle(mode, gap, graph):
 
 
 @pytest.mark.parametrize("search", ["greedy", "sample", "beam"])
-@pytest.mark.parametrize("mode", ["fp32", "bf16"])
-def test_captured_decode_loop_exits_early_on_the_device(search, mode, monkeypatch):
+@pytest.mark.parametrize("mode,every", [("fp32", 1), ("bf16", 1), ("bf16", 3)])
+def test_captured_decode_loop_exits_early_on_the_device(search, mode, every, monkeypatch):
     """`if cur_unfinished.max() == 0: break` / `if all(done): break` (modeling_utils.py:865-867, 1071-1073) inside the captured
     loop: every step after the first is the body of a conditional graph node. With an EOS planted so strongly that every caption
     ends within a few tokens, (1) ids and log-probs equal the loop without the conditional nodes (VITCAP_EARLY_EXIT=0) bit for
@@ -108,6 +108,8 @@ def test_captured_decode_loop_exits_early_on_the_device(search, mode, monkeypatc
     extra = synth.default_test_extra_input(cfg, **kw)
     E = {"greedy": 1, "sample": 3, "beam": 3}[search]
     out = {}
+    # every: decode steps per condition (engine._exit_every: 1 for small batches, 2 / 4 for large ones; forced here)
+    monkeypatch.setenv("VITCAP_EARLY_EXIT_EVERY", str(every))
     for early in ("0", "1"):
         monkeypatch.setenv("VITCAP_EARLY_EXIT", early)
         m = build(cfg, sd, extra, mode, sample_seed=11, use_cuda_graph=True)
@@ -132,7 +134,11 @@ def test_captured_decode_loop_exits_early_on_the_device(search, mode, monkeypatc
     touched1 = (out["1"][2] != 7.0).flatten(2).any(2)
     assert bool(touched0[:, :19].all())                   # without the conditional nodes all 19 steps run
     if search != "beam":
-        assert bool(touched1[:, :n_live].all()) and not bool(touched1[:, n_live:].any()), touched1
+        # step 1 always runs; a group of `every` steps starting at step f runs iff a caption was unfinished after step f - 1
+        ran = [s == 1 or (2 + (s - 2) // every * every) <= n_live for s in range(1, 20)]
+        assert ran[:n_live] == [True] * n_live and sum(ran) <= n_live + every - 1
+        for s_ in range(1, 20):
+            assert bool(touched1[:, s_ - 1].all()) == ran[s_ - 1] and bool(touched1[:, s_ - 1].any()) == ran[s_ - 1], (s_, touched1)
     else:
         assert bool(touched1[:, 0].all()) and not bool(touched1[:, 18].any()), touched1
     # PAD after the end, as the reference pads after its break

@@ -260,3 +260,17 @@ def test_half_range_bounds_of_the_fp16_decode_operands():
     assert 0 < seen["ln"] <= b["layernorm"] and 0 < seen["gelu"] <= b["gelu"], (seen, b)
     sd["module.bert.decoder.layer.0.output.LayerNorm.weight"] = sd["module.bert.decoder.layer.0.output.LayerNorm.weight"] * 1e5
     assert half_range_bounds(cfg, sd)["layernorm"] > HALF_MAX
+
+
+def test_early_exit_step_groups():
+    """engine._step_groups: step 1 unconditional, then `every` steps per condition, covering 1 .. max_len - 1 exactly once."""
+    from vitcap_b200.engine import CaptionEngine
+    eng = CaptionEngine.__new__(CaptionEngine)
+    for n, every in ((1, 1), (16, 1), (17, 2), (128, 2), (129, 4), (512, 4)):
+        assert eng._exit_every(n) == every
+        for max_len in (2, 3, 7, 20):
+            groups = eng._step_groups(max_len, n, True)
+            steps = [s for f, l, c in groups for s in range(f, l)]
+            assert steps == list(range(1, max_len)) and groups[0] == (1, 2, False)
+            assert all(c and l - f <= every for f, l, c in groups[1:])
+    assert eng._step_groups(20, 512, False) == [(1, 20, False)]

@@ -791,6 +791,24 @@ class CaptionEngine:
             self._body_stream = ops.body_stream(self.dev)
         return self._body_stream
 
+    def _exit_every(self, n):
+        """Decode steps per early-exit condition. A conditional node costs ~15 us per replay (condition kernel + node), and the
+        chance that ALL n captions have finished at a given step falls quickly with n: one node per step for small batches
+        (serving: the call returns at the first step after its last EOS), one per 2 / 4 steps for larger ones. Steps that run
+        after every caption has finished change nothing (finished rows receive PAD, their attention is skipped).
+        VITCAP_EARLY_EXIT_EVERY overrides."""
+        env = os.environ.get("VITCAP_EARLY_EXIT_EVERY")
+        if env:
+            return max(1, int(env))
+        return 1 if n <= 16 else (2 if n <= 128 else 4)
+
+    def _step_groups(self, max_len, n, conditional):
+        """[(first step, last step + 1, behind a condition?)] covering steps 1 .. max_len - 1: step 1 always runs."""
+        if not conditional:
+            return [(1, max_len, False)]
+        every = self._exit_every(n)
+        return [(1, 2, False)] + [(f, min(f + every, max_len), True) for f in range(2, max_len, every)]
+
     def _maybe_graph(self, ws, key, fn):
         """Runs fn() eagerly once (warm-up: lazy kernel attribute setup, descriptor cache), then captures and replays it."""
         if not self.use_cuda_graph or self.inline_graphs or self.tap is not None:
@@ -850,12 +868,13 @@ class CaptionEngine:
             ws["unfinished"].fill_(1)
             ws["sum_lp"].zero_()
             ws["n_steps"].zero_()
-            for cur_len in range(1, max_len):
-                # `if cur_unfinished.max() == 0: break` (modeling_utils.py:865-867) on the device: in a captured loop every step
-                # after the first is the body of a conditional node (the label-recipe flip re-runs the prefill with torch
-                # copies in it: those loops keep the plain sequence)
-                with ops.graph_if_any(ws["unfinished"], self._if_stream(), enabled=self.early_exit and cur_len > 1 and not labels):
-                    step(cur_len)
+            # `if cur_unfinished.max() == 0: break` (modeling_utils.py:865-867) on the device: in a captured loop the steps
+            # after the first are bodies of conditional nodes, `every` steps per node (_exit_every; the label-recipe flip
+            # re-runs the prefill with torch copies in it: those loops keep the plain sequence)
+            for first, last, cond in self._step_groups(max_len, R, self.early_exit and not labels):
+                with ops.graph_if_any(ws["unfinished"], self._if_stream(), enabled=cond):
+                    for cur_len in range(first, last):
+                        step(cur_len)
             ops.greedy_finalize(ws["ids"], ws["unfinished"], ws["sum_lp"], ws["n_steps"], int(eos_ids[0]), R, ws["out_ids"],
                                 ws["out_lp"])
 
@@ -903,15 +922,16 @@ class CaptionEngine:
             st["anc"].zero_()
             st["hyp_count"].zero_()
             st["worst"].fill_(1e9)
-            for cur_len in range(1, max_len):
-                # `if all(done): break` (modeling_utils.py:1071-1073) on the device, as in greedy_or_sample
-                with ops.graph_if_any(st["done"], self._if_stream(), invert=True, enabled=self.early_exit and cur_len > 1 and not labels):
-                    if labels and cur_len == label_flip and cur_len > 1:
-                        self._flip_labels(ws, B, nb, cur_len, mask_id, anc_table=st["anc"])
-                    self._decode_layers(ws, B, nb, cur_len, st["anc"], mask_id, labels=labels, live=(None, st["done"]))
-                    ops.beam_row_topk(ws["logits"], cfg.vocab, R, K, st["cand_val"], st["cand_idx"], st["row_max"], st["row_logsum"])
-                    ops.beam_advance(st, st["cand_val"], st["cand_idx"], st["row_max"], st["row_logsum"], B, nb, cfg.vocab, cur_len,
-                                     keep, length_penalty, pad, eos)
+            # `if all(done): break` (modeling_utils.py:1071-1073) on the device, as in greedy_or_sample (B images decide)
+            for first, last, cond in self._step_groups(max_len, B, self.early_exit and not labels):
+                with ops.graph_if_any(st["done"], self._if_stream(), invert=True, enabled=cond):
+                    for cur_len in range(first, last):
+                        if labels and cur_len == label_flip and cur_len > 1:
+                            self._flip_labels(ws, B, nb, cur_len, mask_id, anc_table=st["anc"])
+                        self._decode_layers(ws, B, nb, cur_len, st["anc"], mask_id, labels=labels, live=(None, st["done"]))
+                        ops.beam_row_topk(ws["logits"], cfg.vocab, R, K, st["cand_val"], st["cand_idx"], st["row_max"], st["row_logsum"])
+                        ops.beam_advance(st, st["cand_val"], st["cand_idx"], st["row_max"], st["row_logsum"], B, nb, cfg.vocab,
+                                         cur_len, keep, length_penalty, pad, eos)
             ops.beam_finalize(st, B, keep, pad, int(eos_ids[0]), st["out_ids"], st["out_lp"])
 
         self._maybe_graph(ws, ("beam", B, nb, max_len, keep, float(length_penalty), bos, pad, tuple(eos_ids), mask_id, label_flip), run)
