@@ -511,6 +511,29 @@ def main():
                        "algorithmic 2.27 GB), profiles/r02_ncu_summary.md"
     except Exception:
         pass
+    # the same launches shape by shape, each against the roof that bounds IT: max(flops / tensor peak, bytes / copy bandwidth).
+    # (The o-proj GEMMs carry the fp32 residual stream -- 2.7 GB per launch for 0.35 TFLOP -- and are HBM bound; folded into the
+    # family's tensor-roof figure above they read as a low tensor fraction.)
+    hbm_peak = peaks.get("hbm_gbs") or 6500.0
+    by_shape = {}
+    for pr in prof:
+        if len(pr) < 5:
+            continue
+        d = by_shape.setdefault(pr[4], {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+        d["launches"] += 1
+        d["ms"] += pr[1].elapsed_time(pr[2])
+        d["flops"] += pr[0]
+        d["bytes"] += pr[3]
+    shapes, floor_ms = [], 0.0
+    for tag, d in sorted(by_shape.items(), key=lambda kv: -kv[1]["ms"]):
+        t_tensor = d["flops"] / (peak * 1e12) * 1e3
+        t_hbm = d["bytes"] / (hbm_peak * 1e9) * 1e3
+        floor_ms += max(t_tensor, t_hbm)
+        if d["ms"] / max(gemm_ms, 1e-9) < 0.01:
+            continue
+        shapes.append({"gemm": tag, "launches_per_step": d["launches"] / max(1, args.steps), "us_per_launch": 1e3 * d["ms"] / d["launches"],
+                       "tflops": d["flops"] / (d["ms"] * 1e-3) / 1e12, "gbs": d["bytes"] / (d["ms"] * 1e-3) / 1e9,
+                       "bound": "tensor" if t_tensor >= t_hbm else "hbm", "frac_of_its_roof": max(t_tensor, t_hbm) / d["ms"]})
     roofline = {
         "kernel": "gemm_tc2_kernel / gemm_tc_kernel (tcgen05 bf16 GEMM, cta_group::2 pairs for the large shapes; %d eager "
                   "launches/step: ViT qkv/proj/fc1/fc2, patch embed, decoder prefill, heads)" % (len(prof) // max(1, args.steps)),
@@ -518,6 +541,11 @@ def main():
         "peak_source": peak_src, "traffic": traffic, "traffic_note": traffic_note,
         "share_of_step": gemm_ms / ms if ms > 0 else None,
         "algorithmic_flops_per_step": flops / max(1, args.steps),
+        "by_shape": shapes,
+        "frac_per_kernel_roof": floor_ms / gemm_ms if gemm_ms > 0 else None,
+        "by_shape_note": "every eager GEMM launch of the timed region grouped by epilogue / N / K, against max(algorithmic flops / "
+                         "%.0f TFLOP/s, algorithmic bytes / %.0f GB/s); frac_per_kernel_roof = sum of those floors / measured time "
+                         "(shapes below 1 %% of the GEMM time are counted but not listed)" % (peak, hbm_peak),
     }
 
     # ---- second roofline object: the HBM-bound kernel of the decode steps (single-token attention over the KV cache). It runs

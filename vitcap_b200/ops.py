@@ -222,20 +222,23 @@ def linear(a, w, bias, out, act=ACT_NONE, resid=None, M=None, lda=None, ldo=None
             e0.record()
             _check(lib.vc_linear(1, *args, _stream()), "vc_linear")
             e1.record()
-            prof.append((2.0 * M * N * K, e0, e1))
+            nbytes = 2.0 * M * K + 2.0 * N * K + (4.0 if out_f32 else 2.0) * M * N + (4.0 * M * N if resid is not None else 0.0)
+            tag = "linear%s%s N=%d K=%d" % ("+act" if act != ACT_NONE else "", "+residual (fp32 stream)" if resid is not None else "", N, K)
+            prof.append((2.0 * M * N * K, e0, e1, nbytes, tag))
         else:
             _check(lib.vc_linear(_is_bf16(a), *args, _stream()), "vc_linear")
     return out
 
 
-def _profiled(flops, call):
+def _profiled(flops, call, nbytes=0.0, tag=""):
+    """(flops, start event, end event, algorithmic bytes, shape tag) of an eager tensor-core GEMM launch -> GEMM_PROFILE."""
     prof = GEMM_PROFILE
     if prof is not None and not torch.cuda.is_current_stream_capturing():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         call()
         e1.record()
-        prof.append((flops, e0, e1))
+        prof.append((flops, e0, e1, nbytes, tag))
     else:
         call()
 
@@ -255,11 +258,13 @@ def linear_ln_emit(a, w, bias, out, resid, xb, stats, M=None, resid_ln=None):
         assert rstats.dtype == g.dtype == b.dtype == torch.float32 and rstats.is_contiguous() and rstats.numel() >= M * rst_tiles * 2
         _profiled(2.0 * M * N * K, lambda: _check(lib.vc_linear_ln_emit_postln(
             _ptr(a), a.stride(0), _ptr(w), w.stride(0), _ptr(bias), _ptr(out), out.stride(0), _ptr(resid), resid.stride(0), _ptr(rstats),
-            rst_tiles, _ptr(g), _ptr(b), float(eps), _ptr(xb), xb.stride(0), _ptr(stats), M, N, K, _stream()), "vc_linear_ln_emit_postln"))
+            rst_tiles, _ptr(g), _ptr(b), float(eps), _ptr(xb), xb.stride(0), _ptr(stats), M, N, K, _stream()), "vc_linear_ln_emit_postln"),
+            2.0 * M * K + 2.0 * N * K + 10.0 * M * N, "ln_emit (post-LN residual) N=%d K=%d" % (N, K))
         return out
     _profiled(2.0 * M * N * K, lambda: _check(lib.vc_linear_ln_emit(
         _ptr(a), a.stride(0), _ptr(w), w.stride(0), _ptr(bias), _ptr(out), out.stride(0), _ptr(resid), resid.stride(0), _ptr(xb),
-        xb.stride(0), _ptr(stats), M, N, K, _stream()), "vc_linear_ln_emit"))
+        xb.stride(0), _ptr(stats), M, N, K, _stream()), "vc_linear_ln_emit"),
+        2.0 * M * K + 2.0 * N * K + 10.0 * M * N, "ln_emit N=%d K=%d" % (N, K))      # fp32 residual in, fp32 row + bf16 copy out
     return out
 
 
@@ -273,7 +278,8 @@ def linear_ln_fold(xb, wf, bias_f, colsum, stats, st_tiles, eps, out, act=ACT_NO
     assert xb.dtype == wf.dtype == out.dtype == torch.bfloat16 and bias_f.dtype == colsum.dtype == stats.dtype == torch.float32
     _profiled(2.0 * M * N * K, lambda: _check(lib.vc_linear_ln_fold(
         _ptr(xb), xb.stride(0), _ptr(wf), wf.stride(0), _ptr(bias_f), _ptr(colsum), _ptr(stats), st_tiles, float(eps), _ptr(out), ldo,
-        act, M, N, K, _stream()), "vc_linear_ln_fold"))
+        act, M, N, K, _stream()), "vc_linear_ln_fold"),
+        2.0 * M * K + 2.0 * N * K + 2.0 * M * N, "ln_fold%s N=%d K=%d" % ("+act" if act != ACT_NONE else "", N, K))
     return out
 
 
