@@ -1,4 +1,2 @@
-timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 4 --warmup 3 > gpurun_out/s4_bench_n2.log 2>&1
-tail -c 600 gpurun_out/s4_bench_n2.log
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29518 bench.py --impl reference --variant 16_224 --gpus 2 --steps 1 --warmup 1 > gpurun_out/s4_ref_n2.log 2>&1
-grep -c '"impl": "reference"' gpurun_out/s4_ref_n2.log
+timeout 800 ncu --metrics gpu__time_duration.sum --clock-control none -c 2400 --csv --log-file gpurun_out/r02_launches_bench_final_s4.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-extras > gpurun_out/r02_launches_bench_final_s4.log 2>&1
+wc -l gpurun_out/r02_launches_bench_final_s4.csv
