@@ -87,7 +87,7 @@ class PackedWeights:
             return sd[key].detach().to(device=device, dtype=torch.float32).contiguous()
 
         def Hf(key):
-            return Fp(key).clamp_(-65504.0, 65504.0).to(torch.float16).contiguous()
+            return Fp(key).clamp(-HALF_MAX, HALF_MAX).to(torch.float16).contiguous()      # (out of place: Fp may alias the master)
 
         H = cfg.hidden
         ie = "image_encoder.module."
