@@ -3,10 +3,14 @@ for different operand formats of the decode-step MLP and the vocabulary head. Th
 spec, oracle/port.py QuantPortModel (pinned to the kernels by tests/test_fullsize_gpu.py); the variants only replace its
 `lin_x3` (the GEMMs of BertIntermediate / BertOutput of a decode step and of BertLMPredictionHead):
 
-    bf16x3   split-bf16 operands, three products (the shipped default)
+    bf16x3   split-bf16 operands, three products (decode_precision='bf16x3', the default until session 4 of round 2)
     bf16     plain bf16 operands, one product (decode_precision='bf16')
     fp16     operands rounded to IEEE half (11-bit significand), one product -- same tensor-core rate and bytes as plain bf16
+             (decode_precision='fp16', the default)
     fp16x2   activations split into two halves (hi + lo), weights one half: two products
+    fp16all  NOT a shipped mode: EVERY bf16 rounding point of the fast mode (encoder, prefill, K/V cache, attention
+             probabilities, decode steps) replaced by an IEEE-half rounding -- what half-precision storage of all operands would
+             buy (candidate for a later round; the kernels store bf16 today)
 
 Counting as tests/test_fullsize_gpu.py::test_bf16_mode_token_agreement_fullsize_vs_oracle (same weights, same images):
 tokens produced under an identical prefix, every row up to and including its first divergence.
@@ -51,7 +55,21 @@ class Fp16x2Decode(port.QuantPortModel):
         return out + self.sd[bkey] if bkey else out
 
 
+class AllHalf(port.QuantPortModel):
+    """Every operand rounding of QuantPortModel as an IEEE-half rounding (port.q_bf16 is swapped while this model runs)."""
+
+    def run(self, fn):
+        saved = port.q_bf16
+        port.q_bf16 = port.q_f16
+        try:
+            return fn()
+        finally:
+            port.q_bf16 = saved
+
+
 def build(name, cfg, sd):
+    if name == "fp16all":
+        return AllHalf(cfg, sd, decode_f16=True)
     if name == "bf16x3":
         return port.QuantPortModel(cfg, sd, decode_x3=True)
     if name == "bf16":
@@ -80,16 +98,20 @@ def main():
         hi = min(n, lo + chunk)
         data = synth.make_text_inputs(cfg, hi - lo)
         data["image"] = images[lo:hi]
-        trace = []
+        trace, r_info = [], {}
         with torch.no_grad():
-            r_ids, _ = port.caption(ref, data, extra, algorithm="cached", trace=trace)
+            r_ids, _ = port.caption(ref, data, extra, algorithm="cached", trace=trace, info=r_info)
         r = r_ids[:, 0].numpy()
         gaps = torch.stack([tr.float().topk(2).values for tr in trace])
         gaps = (gaps[..., 0] - gaps[..., 1]).numpy()
         for v in variants:
+            info = {}
             with torch.no_grad():
-                ids, _ = port.caption(models[v], data, extra, algorithm="cached")
+                call = lambda: port.caption(models[v], data, extra, algorithm="cached", info=info)      # noqa: E731
+                ids, _ = models[v].run(call) if hasattr(models[v], "run") else call()
             a = ids[:, 0].numpy()
+            s_ = stats[v]
+            s_.setdefault("cap_err", []).append(float((info["cap"] - r_info["cap"]).norm() / r_info["cap"].norm()))
             s = stats[v]
             for row in range(hi - lo):
                 neq = np.nonzero(a[row] != r[row])[0]
@@ -103,8 +125,9 @@ def main():
                 s["agree"] += t - 1
                 s["div"] += 1
                 s["worst"] = max(s["worst"], float(gaps[t - 1, row]))
-        line = "  ".join("%s %d/%d (%.4f, %d rows, worst gap %.3g)" % (v, s["agree"], s["same"], s["agree"] / max(1, s["same"]),
-                                                                       s["div"], s["worst"]) for v, s in stats.items())
+        line = "  ".join("%s %d/%d (%.4f, %d rows, worst gap %.3g, caption features vs fp32 %.2e)"
+                         % (v, s["agree"], s["same"], s["agree"] / max(1, s["same"]), s["div"], s["worst"],
+                            sum(s["cap_err"]) / len(s["cap_err"])) for v, s in stats.items())
         print("images %d..%d  %.0f s  %s" % (lo, hi, time.time() - t0, line), flush=True)
 
 
