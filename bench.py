@@ -75,6 +75,8 @@ def workload_config(args, cfg):
         "max_length": 20, "num_beams": 1, "decoder_layers": cfg.dec_layers, "parallelism": "dp%d" % max(1, args.gpus),
         "weights": "random-init (synth.make_state_dict seed 0, reference layout)",
         "decode_precision": getattr(args, "decode_precision", None) or "fp16",
+        "operand_storage": "fp16 (VITCAP_STORE=fp16: every 16-bit operand an IEEE half)" if os.environ.get("VITCAP_STORE", "bf16").lower()
+                           in ("fp16", "f16", "half") else "bf16",
         "precision": "bf16 operands / fp32 accumulation throughout (fp32 residual stream); decode_precision names the operands of "
                      "the decode-step MLP and vocabulary-head GEMMs: fp16 = IEEE half (11-bit significand, one product), "
                      "bf16x3 = split bf16 (three products), bf16 = plain",
@@ -219,9 +221,9 @@ def decode_roofline(torch, ops, cfg, B, dev, peaks, model=None, extra=None):
     duration of decode_attention_mma_kernel at the middle decode step, against the measured copy bandwidth."""
     H, heads, C, L = cfg.hidden, cfg.heads, cfg.n_ctx, cfg.dec_layers
     cur_len = 10
-    ctx = [torch.randn(B, C, 3 * H, device=dev).to(torch.bfloat16) for _ in range(L)]
-    stepq = [torch.randn(20, 2 * B, 3 * H, device=dev).to(torch.bfloat16) for _ in range(L)]
-    out = torch.empty(2 * B, H, device=dev, dtype=torch.bfloat16)
+    ctx = [torch.randn(B, C, 3 * H, device=dev).to(ops.STORE) for _ in range(L)]       # (ops.STORE: bf16, or halves under VITCAP_STORE=fp16)
+    stepq = [torch.randn(20, 2 * B, 3 * H, device=dev).to(ops.STORE) for _ in range(L)]
+    out = torch.empty(2 * B, H, device=dev, dtype=ops.STORE)
 
     def run():
         for l in range(L):

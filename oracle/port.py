@@ -19,6 +19,7 @@ restatements are pinned against the reference *itself*, imported and run in the 
 by ``oracle/make_golden.py``; the outputs are committed under ``tests/golden/`` and checked by
 ``tests/test_oracle_golden.py`` (which needs no reference tree).
 """
+import contextlib
 import math
 
 import numpy as np
@@ -173,6 +174,20 @@ def q_bf16(x):
 def q_f16(x):
     """Round to IEEE half (nearest even, saturating at +-65504 as cvt.rn.satfinite.f16.f32) and back to fp32."""
     return x.clamp(-65504.0, 65504.0).to(torch.float16).to(torch.float32)
+
+
+@contextlib.contextmanager
+def half_store():
+    """Inside the block every operand rounding of QuantPortModel is an IEEE-half rounding (q_bf16 IS q_f16): the executable spec
+    of a VITCAP_STORE=fp16 process, where the kernels store every 16-bit operand as a half (csrc/common.cuh VC_STORE_F16).
+    Build AND run the model inside the block (rounded weights are cached per instance)."""
+    global q_bf16
+    saved = q_bf16
+    q_bf16 = q_f16
+    try:
+        yield
+    finally:
+        q_bf16 = saved
 
 
 def split_bf16(x):

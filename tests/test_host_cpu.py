@@ -274,3 +274,24 @@ def test_early_exit_step_groups():
             assert steps == list(range(1, max_len)) and groups[0] == (1, 2, False)
             assert all(c and l - f <= every for f, l, c in groups[1:])
     assert eng._step_groups(20, 512, False) == [(1, 20, False)]
+
+
+def test_half_storage_library_exports_the_same_abi():
+    """libvitcap_b200_f16.so (the same sources built with -DVC_STORE_F16, selected by VITCAP_STORE=fp16) exports every entry
+    point of the header under the same ABI version; the process-wide switch picks it and torch.float16."""
+    import ctypes
+    import subprocess
+    import sys
+    from vitcap_b200 import build as b
+    assert os.path.exists(b.LIB_F16), "python -m vitcap_b200.build builds both libraries"
+    lib = ctypes.CDLL(b.LIB_F16)
+    lib.vc_abi_version.restype = ctypes.c_int
+    assert lib.vc_abi_version() == 9
+    for n in ops.SIGNATURES:
+        assert hasattr(lib, n), n
+    assert ops.STORE == torch.bfloat16 and not ops.HALF_STORE and ops.LIB_PATH.endswith("libvitcap_b200.so")     # this process
+    code = "from vitcap_b200 import ops; import torch; assert ops.HALF_STORE and ops.STORE == torch.float16; " \
+           "assert ops.LIB_PATH.endswith('_f16.so'); ops.load_library(); print('ok')"
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=dict(os.environ, VITCAP_STORE="fp16", PYTHONPATH=ROOT),
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-1500:]

@@ -12,6 +12,9 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIBDIR, "libvitcap_b200.so")
+# the same sources with IEEE-half storage of every 16-bit operand (csrc/common.cuh, VC_STORE_F16; selected by VITCAP_STORE=fp16)
+LIB_F16 = os.path.join(LIBDIR, "libvitcap_b200_f16.so")
+OBJDIR_F16 = os.path.join(HERE, "build", "f16")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -43,14 +46,14 @@ def _digest(path):
     return h.hexdigest()
 
 
-def _compile(src, verbose):
+def _compile(src, verbose, objdir=OBJDIR, defines=()):
     path = os.path.join(CSRC, src)
-    obj = os.path.join(OBJDIR, src[:-3] + ".o")
+    obj = os.path.join(objdir, src[:-3] + ".o")
     stamp = obj + ".sha1"
-    dg = _digest(path)
+    dg = _digest(path) + "".join(defines)
     if os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == dg:
         return obj, False, ""
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-c", path, "-o", obj]
+    cmd = [_nvcc()] + NVCC_FLAGS + list(defines) + ["-c", path, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
@@ -59,30 +62,34 @@ def _compile(src, verbose):
     return obj, True, r.stderr
 
 
-def build(verbose=False, force=False):
+def build(verbose=False, force=False, half_store=False):
+    """half_store: the VC_STORE_F16 build (libvitcap_b200_f16.so) instead of the default library."""
+    objdir, lib, defines = (OBJDIR_F16, LIB_F16, ("-DVC_STORE_F16",)) if half_store else (OBJDIR, LIB, ())
     os.makedirs(LIBDIR, exist_ok=True)
-    os.makedirs(OBJDIR, exist_ok=True)
+    os.makedirs(objdir, exist_ok=True)
     if force:
-        for f in os.listdir(OBJDIR):
-            os.remove(os.path.join(OBJDIR, f))
+        for f in os.listdir(objdir):
+            if os.path.isfile(os.path.join(objdir, f)):
+                os.remove(os.path.join(objdir, f))
     srcs = _sources()
     with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
-        results = list(ex.map(lambda s: _compile(s, verbose), srcs))
+        results = list(ex.map(lambda s: _compile(s, verbose, objdir, defines), srcs))
     objs = [o for o, _, _ in results]
     changed = any(c for _, c, _ in results)
     log = "\n".join("== %s ==\n%s" % (s, l) for s, (_, c, l) in zip(srcs, results) if c and l)
     if log:
-        with open(os.path.join(OBJDIR, "ptxas.log"), "w") as f:
+        with open(os.path.join(objdir, "ptxas.log"), "w") as f:
             f.write(log)
         if verbose:
             print(log)
-    if changed or not os.path.exists(LIB):
-        cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-cudart", "static", "-Xcompiler", "-fPIC"]
+    if changed or not os.path.exists(lib):
+        cmd = [_nvcc(), "-shared", "-o", lib] + objs + ["-cudart", "static", "-Xcompiler", "-fPIC"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
     print(build(verbose="-v" in sys.argv, force="-f" in sys.argv))
+    print(build(verbose="-v" in sys.argv, force="-f" in sys.argv, half_store=True))

@@ -230,7 +230,7 @@ attention_tc96_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
       const int col = (t < 64 ? H : 2 * H) + h * D + d;
 #pragma unroll
       for (int x = 0; x < PEEL; ++x)
-        (t < 64 ? kx : vx)[x * D + d] = __bfloat162float(qkv[((size_t)b * N + x) * (3 * H) + col]);
+        (t < 64 ? kx : vx)[x * D + d] = to_f32<bf16>(qkv[((size_t)b * N + x) * (3 * H) + col]);
       named_bar_sync(1, 128);
     }
     int sb = 0, sb_prev = NS - 1;                      // g % NS, (g - 1) % NS
@@ -310,7 +310,7 @@ attention_tc96_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         for (int x = 0; x < PEEL; ++x) {
           const float p = ex2(fmaf(sx[x], scale_log2, -m_ref));
           l += p;
-          px[x] = __bfloat162float(__float2bfloat16_rn(p));
+          px[x] = to_f32<bf16>(from_f32<bf16>(p));
         }
       }
       for (int j = 0; j < nch; ++j) {

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda.h>
 #include <stdint.h>
 
@@ -14,7 +15,15 @@
 
 namespace vc {
 
+// The 16-bit storage / operand type of the fast mode. Default: bfloat16. Built with -DVC_STORE_F16 (libvitcap_b200_f16.so,
+// selected by VITCAP_STORE=fp16) the SAME sources store IEEE halves everywhere -- weights, q|k|v, attention probabilities and
+// outputs, GELU outputs, LayerNorm-fold row copies, K/V cache: 11-bit significands at the same bytes and tensor-core rate (the
+// type keeps its historical name `bf16`; conversions saturate at +-65504).
+#ifdef VC_STORE_F16
+typedef __half bf16;
+#else
 typedef __nv_bfloat16 bf16;
+#endif
 
 // ------------------------------------------------------------------------------------------
 // error plumbing (host)
@@ -98,6 +107,27 @@ __device__ __forceinline__ float gelu_erf(float x) {
 
 template <typename T> __device__ __forceinline__ float to_f32(T v);
 template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+// two floats -> packed IEEE halves (round to nearest even, saturating at +-65504 instead of producing infinities)
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+#ifdef VC_STORE_F16
+template <> __device__ __forceinline__ float to_f32<bf16>(bf16 v) { return __half2float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f32<bf16>(float v) {
+  const uint32_t r = pack_f16x2(v, 0.f);
+  return __ushort_as_half((unsigned short)(r & 0xffffu));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) { return pack_f16x2(lo, hi); }
+__device__ __forceinline__ void unpack_bf16x2(uint32_t v, float& lo, float& hi) {
+  const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&v));
+  lo = f.x;
+  hi = f.y;
+}
+#else
 template <> __device__ __forceinline__ float to_f32<bf16>(bf16 v) { return __bfloat162float(v); }
 template <typename T> __device__ __forceinline__ T from_f32(float v);
 template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
@@ -107,16 +137,11 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);
 }
-// two floats -> packed IEEE halves (round to nearest even, saturating at +-65504 instead of producing infinities)
-__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
-  uint32_t r;
-  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  return r;
-}
 __device__ __forceinline__ void unpack_bf16x2(uint32_t v, float& lo, float& hi) {
   lo = __uint_as_float(v << 16);
   hi = __uint_as_float(v & 0xffff0000u);
 }
+#endif
 
 // loads 8 consecutive elements (16 B for bf16, 32 B for fp32) as floats
 template <typename T> __device__ __forceinline__ void load8(const T* p, float* f);
@@ -343,8 +368,14 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uin
   return d;
 }
 // instruction descriptor for kind::f16, bf16 x bf16 -> fp32 (UMMA::InstrDescriptor bit layout)
+// (a_format / b_format, bits 7-9 / 10-12: 1 = BF16, 0 = F16 -- the storage type of this build)
+#ifdef VC_STORE_F16
+constexpr uint32_t IDESC_AB_FORMAT = 0u;
+#else
+constexpr uint32_t IDESC_AB_FORMAT = (1u << 7) | (1u << 10);
+#endif
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+  return (1u << 4) | IDESC_AB_FORMAT | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 // the same with IEEE half operands (a_format = b_format = 0 = F16): 11-bit significands at the rate and bytes of bf16

@@ -108,7 +108,11 @@ static std::mutex g_tmap_mu;
 
 static int encode(CUtensorMap* out, const TmapKey& key, int rank, const void* base, const cuuint64_t* dims,
                   const cuuint64_t* strides_bytes, const cuuint32_t* box,
+#ifdef VC_STORE_F16
+                  CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_FLOAT16) {
+#else
                   CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16) {
+#endif
   {
     std::lock_guard<std::mutex> g(g_tmap_mu);
     auto it = g_tmaps.find(key);

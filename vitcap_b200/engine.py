@@ -77,7 +77,7 @@ class PackedWeights:
         # IEEE-half copies of the same weights (decode_precision='fp16': one product on 11-bit significands)
         self.decode_f16 = bool(decode_f16) and mode == "bf16"
         assert not (self.decode_x3 and self.decode_f16)
-        wt = torch.bfloat16 if mode == "bf16" else torch.float32
+        wt = ops.STORE if mode == "bf16" else torch.float32        # (IEEE halves in a VITCAP_STORE=fp16 process)
         self.wt = wt
 
         def W(key):
@@ -99,7 +99,7 @@ class PackedWeights:
         def folded_t(w32, b32, g32, be32):
             """LayerNorm folded into the consuming Linear (vc_linear_ln_fold): Wf = bf16(gamma o W), colsum = fp32 row sums of
             the ROUNDED Wf (so that mean * colsum cancels what the tensor cores accumulate), bias_f = b + W beta."""
-            wf = (w32 * g32.unsqueeze(0)).to(torch.bfloat16).contiguous()
+            wf = (w32 * g32.unsqueeze(0)).to(ops.STORE).contiguous()
             return wf, wf.float().sum(1).contiguous(), (b32 + w32 @ be32).contiguous()
 
         def folded(w_key, b_key, g_key, beta_key):

@@ -245,6 +245,11 @@ class FastImageCaptioning(nn.Module):
         if decode_precision is None:
             decode_precision = os.environ.get("VITCAP_DECODE_PRECISION", "fp16")
         assert decode_precision in ("bf16", "bf16x3", "fp16")
+        if ops.HALF_STORE and mode == "bf16":
+            # VITCAP_STORE=fp16: EVERY 16-bit operand of the fast mode is an IEEE half already (ops.STORE); the decode step then
+            # runs its plain one-product path on them, which is what 'fp16' asks for and more
+            decode_precision = "plain"
+        self.operand_storage = ("fp16" if ops.HALF_STORE else "bf16") if mode == "bf16" else "fp32"
         self.decode_precision = decode_precision if mode == "bf16" else "fp32"
         self.module = FastViTCAP(cfg, self)
         self.image_encoder = FastImageEncoder(cfg, self)

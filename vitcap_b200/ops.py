@@ -10,8 +10,14 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
+# VITCAP_STORE=fp16 (process-wide, read at import): the fast mode stores EVERY 16-bit operand -- weights, q|k|v, attention
+# probabilities and outputs, GELU outputs, LayerNorm-fold row copies, K/V cache -- as IEEE halves instead of bfloat16
+# (libvitcap_b200_f16.so: the same sources built with -DVC_STORE_F16; DESIGN.md section 4a''). STORE is the torch dtype of those
+# tensors; every "bf16" in the names of this module then reads "the 16-bit storage type".
+HALF_STORE = os.environ.get("VITCAP_STORE", "bf16").lower() in ("fp16", "f16", "half")
+STORE = torch.float16 if HALF_STORE else torch.bfloat16
 # VITCAP_LIB: another build of the same ABI (A/B measurements of a kernel change in tools/)
-LIB_PATH = os.environ.get("VITCAP_LIB") or os.path.join(_HERE, "lib", "libvitcap_b200.so")
+LIB_PATH = os.environ.get("VITCAP_LIB") or os.path.join(_HERE, "lib", "libvitcap_b200_f16.so" if HALF_STORE else "libvitcap_b200.so")
 
 ACT_NONE, ACT_GELU, ACT_TANH = 0, 1, 2
 
@@ -190,7 +196,13 @@ def check_device():
 
 
 def _is_bf16(t):
-    return 1 if t.dtype == torch.bfloat16 else 0
+    """1 = the 16-bit storage type of this process (ops.STORE), 0 = fp32. The OTHER 16-bit float type is refused: the library
+    would otherwise read it as fp32 and run off the end of the buffer."""
+    if t.dtype == STORE:
+        return 1
+    if t.dtype in (torch.float16, torch.bfloat16):
+        raise TypeError("this process stores 16-bit operands as %s (VITCAP_STORE); got a %s tensor" % (STORE, t.dtype))
+    return 0
 
 
 def linear(a, w, bias, out, act=ACT_NONE, resid=None, M=None, lda=None, ldo=None, impl="auto", tile_n=0):
@@ -211,13 +223,13 @@ def linear(a, w, bias, out, act=ACT_NONE, resid=None, M=None, lda=None, ldo=None
     if impl == "simt":
         _check(lib.vc_linear_simt(_is_bf16(a), *args, _stream()), "vc_linear_simt")
     elif impl == "tc":
-        assert a.dtype == torch.bfloat16
+        assert a.dtype == STORE
         _check(lib.vc_linear_tc(*args, tile_n, _stream()), "vc_linear_tc")
     else:
         if a.dtype == torch.float32:
             assert out_f32, "exact mode writes fp32"
         prof = GEMM_PROFILE
-        if prof is not None and a.dtype == torch.bfloat16 and not torch.cuda.is_current_stream_capturing():
+        if prof is not None and a.dtype == STORE and not torch.cuda.is_current_stream_capturing():
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             _check(lib.vc_linear(1, *args, _stream()), "vc_linear")
@@ -251,7 +263,7 @@ def linear_ln_emit(a, w, bias, out, resid, xb, stats, M=None, resid_ln=None):
     lib = load_library()
     N, K = w.shape
     M = a.shape[0] if M is None else M
-    assert a.dtype == w.dtype == xb.dtype == torch.bfloat16 and out.dtype == resid.dtype == stats.dtype == torch.float32
+    assert a.dtype == w.dtype == xb.dtype == STORE and out.dtype == resid.dtype == stats.dtype == torch.float32
     assert stats.is_contiguous() and stats.numel() >= M * ((N + 255) // 256) * 2
     if resid_ln is not None:
         rstats, rst_tiles, g, b, eps = resid_ln
@@ -275,7 +287,7 @@ def linear_ln_fold(xb, wf, bias_f, colsum, stats, st_tiles, eps, out, act=ACT_NO
     N, K = wf.shape
     M = xb.shape[0] if M is None else M
     ldo = out.stride(0) if ldo is None else ldo
-    assert xb.dtype == wf.dtype == out.dtype == torch.bfloat16 and bias_f.dtype == colsum.dtype == stats.dtype == torch.float32
+    assert xb.dtype == wf.dtype == out.dtype == STORE and bias_f.dtype == colsum.dtype == stats.dtype == torch.float32
     _profiled(2.0 * M * N * K, lambda: _check(lib.vc_linear_ln_fold(
         _ptr(xb), xb.stride(0), _ptr(wf), wf.stride(0), _ptr(bias_f), _ptr(colsum), _ptr(stats), st_tiles, float(eps), _ptr(out), ldo,
         act, M, N, K, _stream()), "vc_linear_ln_fold"),
@@ -434,7 +446,7 @@ def decode_attention(ctx_qkv, step_qkv, anc, out, B, C, heads, E, cur_len, scale
     """ctx_vis (int32 [B]): C context rows are allocated per image, only the first ctx_vis[b] are visible.
     seq_unfinished (int32 [B*E]) / img_done (int32 [B]): bf16 only -- finished sequences / done images are skipped and their
     output rows left untouched (vc_decode_attention_skip)."""
-    if (seq_unfinished is not None or img_done is not None) and ctx_qkv.dtype == torch.bfloat16 and impl != "simt":
+    if (seq_unfinished is not None or img_done is not None) and ctx_qkv.dtype == STORE and impl != "simt":
         for t in (seq_unfinished, img_done, ctx_vis):
             assert t is None or t.dtype == torch.int32
         _check(load_library().vc_decode_attention_skip(_ptr(ctx_qkv), _ptr(step_qkv), _ptr(anc), _ptr(out), B, C, _ptr(ctx_vis), heads, E,
@@ -498,8 +510,12 @@ DEC_FMT_BF16, DEC_FMT_BF16X3, DEC_FMT_F16 = 0, 1, 2
 
 
 def _dec_fmt(a, w, x3):
-    """Operand format of a decode-step GEMM from the operand dtype: torch.float16 tensors select the IEEE-half product."""
+    """Operand format of a decode-step GEMM from the operand dtype: torch.float16 tensors select the IEEE-half product. (In a
+    VITCAP_STORE=fp16 process the library's plain format IS the half: format 0.)"""
     assert a.dtype == w.dtype and a.stride(-1) == 1 and w.stride(-1) == 1
+    if HALF_STORE:
+        assert a.dtype == torch.float16 and not x3, "half storage: one product on halves, no split operands"
+        return DEC_FMT_BF16
     if a.dtype == torch.float16:
         assert not x3, "half operands run as one product"
         return DEC_FMT_F16
@@ -526,7 +542,7 @@ def dec_linear(mode, a, w, bias, out, M=None, x3=False, splits=1, m_pad=0, lda=N
         assert bias is None
         ldo = out.stride(1)
     else:
-        assert out.dtype == (torch.float16 if (fmt == DEC_FMT_F16 and mode == DEC_GELU_BF16) else torch.bfloat16)
+        assert out.dtype == (torch.float16 if (fmt == DEC_FMT_F16 and mode == DEC_GELU_BF16) else STORE)
         ldo = out.stride(0) if ldo is None else ldo
     _check(load_library().vc_dec_linear(mode, fmt, _ptr(a), lda, _ptr(w), w.stride(0), _ptr(bias), _ptr(out), ldo, M, N, K,
                                         splits, m_pad, _stream()), "vc_dec_linear")
@@ -562,7 +578,7 @@ def finish_ln(part, splits, bias, gamma, beta, eps, rows, resid=None, gelu=False
         assert out_t.dtype == torch.bfloat16
         mode = 5
     else:
-        assert out_t.dtype == torch.bfloat16
+        assert out_t.dtype == STORE
         mode = (3 if split == 3 else 2) if split else 1
     _check(load_library().vc_finish_ln(_ptr(part), splits, part.stride(0), part.stride(1), _ptr(bias), int(bool(gelu)), _ptr(resid),
                                        resid.stride(0) if resid is not None else 0, _ptr(gamma), _ptr(beta), float(eps), _ptr(out_f),
