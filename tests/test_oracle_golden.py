@@ -123,3 +123,32 @@ def test_staged_reference_bytecode_reproduces_the_golden():
     r = subprocess.run([sys.executable, "-W", "ignore", "-c", _STAGED_CHECK, "g9_greedy_refinit_16_224"], cwd=root, env=env,
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "STAGED-REFERENCE-OK" in r.stdout, r.stderr[-2000:]
+
+
+def test_half_storage_oracle_is_eight_times_closer_to_the_fp32_algorithm():
+    """port.half_store(): every operand rounding of QuantPortModel as an IEEE-half rounding (the spec of a VITCAP_STORE=fp16
+    process). On the tiny model the caption features sit ~8 x closer to the fp32 algorithm than with bf16 roundings (11-bit
+    against 8-bit significands), and leaving the block restores the bf16 roundings."""
+    from vitcap_b200 import config as vcfg
+    from vitcap_b200 import synth
+    cfg = vcfg.tiny()
+    sd = synth.make_state_dict(cfg, seed=7, eos_bias=1.0)
+    data = synth.make_text_inputs(cfg, 2)
+    data["image"] = synth.make_images(cfg, 2, seed=3)
+    extra = synth.default_test_extra_input(cfg)
+    out = {}
+    with torch.no_grad():
+        for name in ("fp32", "half", "bf16"):
+            info = {}
+            if name == "fp32":
+                port.caption(port.PortModel(cfg, sd), data, extra, algorithm="cached", info=info)
+            elif name == "half":
+                with port.half_store():
+                    port.caption(port.QuantPortModel(cfg, sd, decode_x3=False), data, extra, algorithm="cached", info=info)
+            else:
+                port.caption(port.QuantPortModel(cfg, sd, decode_x3=False), data, extra, algorithm="cached", info=info)
+            out[name] = info["cap"]
+    rel = lambda a, b: float((a - b).norm() / b.norm())                     # noqa: E731
+    e_half, e_bf16 = rel(out["half"], out["fp32"]), rel(out["bf16"], out["fp32"])
+    assert e_half < 1e-3 and 4.0 * e_half < e_bf16 < 1e-2, (e_half, e_bf16)
+    assert float(port.q_bf16(torch.tensor([1.003]))[0]) == 1.0              # bf16 roundings are back
