@@ -2,8 +2,8 @@
 
 Recipe for oracle/_ref: compiles the UNMODIFIED reference (every module under /root/reference/src, where the sources lie)
 to CPython bytecode and stages the result -- bytecode only, no source text -- as ONE archive, oracle/_ref/reference_pyc.zip
-(imported through zipimport; loose .pyc files do not survive the copy to the GPU box), next to the two data files per model
-variant the reference's own from_pretrained calls read (vocab.txt, config.json of yaml/<variant>/).
+(imported through zipimport; loose .pyc files do not survive the copy to the GPU box), which also carries the two data files
+per model variant the reference's own from_pretrained calls read (vocab.txt, config.json of yaml/<variant>/).
 
     python -m oracle.build_ref          # in the build container; __graft_entry__.build() runs it when /root/reference exists
 
@@ -75,15 +75,16 @@ def build(verbose=False):
             for f in sorted(files):
                 full = os.path.join(root, f)
                 z.write(full, os.path.relpath(full, pyc))
+        # the two data files per model variant the reference's from_pretrained calls read ride in the same archive
+        # (ref_loader extracts them to a temporary directory when it builds a model)
+        ydir = os.path.join(SRC_ROOT, "yaml")
+        variants = []
+        for v in sorted(os.listdir(ydir)) if os.path.isdir(ydir) else []:
+            if all(os.path.isfile(os.path.join(ydir, v, f)) for f in DATA_FILES):
+                for f in DATA_FILES:
+                    z.write(os.path.join(ydir, v, f), "yaml/%s/%s" % (v, f))
+                variants.append(v)
     shutil.rmtree(pyc)
-    ydir = os.path.join(SRC_ROOT, "yaml")
-    variants = []
-    for v in sorted(os.listdir(ydir)) if os.path.isdir(ydir) else []:
-        if all(os.path.isfile(os.path.join(ydir, v, f)) for f in DATA_FILES):
-            os.makedirs(os.path.join(tmp, "yaml", v), exist_ok=True)
-            for f in DATA_FILES:
-                shutil.copyfile(os.path.join(ydir, v, f), os.path.join(tmp, "yaml", v, f))
-            variants.append(v)
     man = {"what": "CPython bytecode of the unmodified reference's src/ tree (no source text; %s) + vocab.txt / config.json "
                    "of its model variants; built by oracle/build_ref.py" % ARCHIVE,
            "python_magic": magic_hex(), "python": sys.version.split()[0], "modules": n_mod, "variants": variants,
@@ -105,6 +106,21 @@ def staged_root():
     if man.get("python_magic") != magic_hex() or not os.path.isfile(os.path.join(OUT, ARCHIVE)):
         return None
     return OUT
+
+
+def data_dir(root, variant_dir):
+    """Directory holding vocab.txt / config.json of a model variant: yaml/<variant> of a source tree, or a temporary directory
+    the two files are extracted to from the staged archive."""
+    arc = os.path.join(root, ARCHIVE)
+    if not os.path.isfile(arc):
+        return os.path.join(root, "yaml", variant_dir)
+    import tempfile
+    out = tempfile.mkdtemp(prefix="vitcap_ref_%s_" % variant_dir[-6:])
+    with zipfile.ZipFile(arc) as z:
+        for f in DATA_FILES:
+            with z.open("yaml/%s/%s" % (variant_dir, f)) as src, open(os.path.join(out, f), "wb") as dst:
+                shutil.copyfileobj(src, dst)
+    return out
 
 
 def code_root(root):
